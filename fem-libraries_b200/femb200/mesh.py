@@ -1,0 +1,209 @@
+"""Synthetic meshes, dof maps and problem data for the mechanic2d hot path.
+
+Input generation only (host side, numpy): nothing here is on the timed path.
+Conventions are the ones fixed in SURVEY.md 8c:
+
+* unit square [0,1]^2 (or [0,1] x [0,ny/nx]), structured nx x ny cells; triangles
+  are each cell split by the "right" diagonal into {v0,v1,v3}, {v0,v2,v3};
+* P2/Q2 nodes live on the (2nx+1) x (2ny+1) lattice, numbered lexicographically
+  (x fastest); P1 nodes on the (nx+1) x (ny+1) lattice;
+* P2 local dof order is basix': three vertices, then the midpoint of the edge
+  opposite to vertex i; Q2 local order is tensor / lexicographic (ix + 3 iy);
+* global dof = 2 * node + component (blocked, bs = 2: `M.cc:1107`, `F.cc:691`);
+* materials: the reference's 200 Young moduli (`M.cc:1076-1085`) indexed by
+  `cell_id % 200`, nu = 0.3 (`M.cc:1074`);
+* Dirichlet: all dofs on x = 0 clamped, on x = 1: ux = +0.01, uy = 0
+  (`F.cc:627-664`); body force `M.cc:1431-1440`.
+
+All `file:line` citations are relative to /root/reference (M.cc =
+MFEM/mechanic2d/asym_elasto_damage_model.cc, F.cc = FEniCSx/mechanic2d/...).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+P1, P2, Q2 = 0, 1, 2
+ELEM_ND = {P1: 3, P2: 6, Q2: 9}
+ELEM_NV = {P1: 3, P2: 3, Q2: 4}
+ELEM_NAME = {P1: "P1", P2: "P2", Q2: "Q2"}
+
+
+@dataclass
+class Mesh:
+    """A 2-D mesh with one vector-valued Lagrange space on it.
+
+    x        (nnodes, 2) float64   coordinates of every node of the space
+    xdofmap  (ncells, nv) int32    geometry vertices of each cell (node ids)
+    dofmap   (ncells, nd) int32    scalar dofs (node ids) of each cell
+    """
+
+    etype: int
+    x: np.ndarray
+    xdofmap: np.ndarray
+    dofmap: np.ndarray
+    nx: int = 0
+    ny: int = 0
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def nnodes(self) -> int:
+        return int(self.x.shape[0])
+
+    @property
+    def ncells(self) -> int:
+        return int(self.dofmap.shape[0])
+
+    @property
+    def ndofs(self) -> int:
+        return 2 * self.nnodes
+
+    @property
+    def nd(self) -> int:
+        return ELEM_ND[self.etype]
+
+    @property
+    def nv(self) -> int:
+        return ELEM_NV[self.etype]
+
+
+def young_table() -> np.ndarray:
+    """The reference's 200 Young moduli: glibc `srand(6575)`, `rand() % 200`
+    (`M.cc:1076-1085`, `F.cc:533-541`, `F.py:213-222`)."""
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(6575)
+    a = (1.0e8 - 5.0e6) / 199.0
+    tab = np.array([a * (libc.rand() % 200) + 5.0e6 for _ in range(200)], dtype=np.float64)
+    # E_range[1], E_range[2] with glibc 2.39
+    assert abs(tab[1] - 70402010.05025125) < 1e-6 and abs(tab[2] - 26005025.12562814) < 1e-6, \
+        "libc rand() does not reproduce the reference's Young-modulus table"
+    return tab
+
+
+def young_per_cell(ncells: int, first_cell: int = 0) -> np.ndarray:
+    """E per cell = table[cell_id % 200]."""
+    tab = young_table()
+    return tab[(np.arange(first_cell, first_cell + ncells, dtype=np.int64) % 200)].copy()
+
+
+def _lattice(nx: int, ny: int, sub: int, ly: float, y0: float = 0.0):
+    mx, my = sub * nx + 1, sub * ny + 1
+    xs = np.linspace(0.0, 1.0, mx)
+    ys = y0 + np.linspace(0.0, ly, my)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    x = np.stack([X.ravel(), Y.ravel()], axis=1).astype(np.float64)
+    return x, mx, my
+
+
+def structured_triangles(nx: int, ny: int | None = None, order: int = 2, ly: float | None = None,
+                         y0: float = 0.0) -> Mesh:
+    """nx x ny cells, right-diagonal split, P1 (order 1) or P2 (order 2)."""
+    ny = nx if ny is None else ny
+    ly = (ny / nx) if ly is None else ly
+    sub = 1 if order == 1 else 2
+    x, mx, _ = _lattice(nx, ny, sub, ly, y0)
+    cx, cy = np.meshgrid(np.arange(nx, dtype=np.int64), np.arange(ny, dtype=np.int64), indexing="xy")
+    cx, cy = cx.ravel(), cy.ravel()
+    node = lambda i, j: i + mx * j
+    v0 = node(sub * cx, sub * cy)
+    v1 = node(sub * cx + sub, sub * cy)
+    v2 = node(sub * cx, sub * cy + sub)
+    v3 = node(sub * cx + sub, sub * cy + sub)
+    ncell = 2 * nx * ny
+    tri = np.empty((ncell, 3), dtype=np.int64)
+    tri[0::2] = np.stack([v0, v1, v3], axis=1)
+    tri[1::2] = np.stack([v0, v2, v3], axis=1)
+    if order == 1:
+        dm = tri
+        et = P1
+    else:
+        # midpoint lattice node of two vertex lattice nodes = their average index
+        mid = lambda a, b: (a + b) // 2
+        dm = np.empty((ncell, 6), dtype=np.int64)
+        dm[:, :3] = tri
+        dm[:, 3] = mid(tri[:, 1], tri[:, 2])
+        dm[:, 4] = mid(tri[:, 0], tri[:, 2])
+        dm[:, 5] = mid(tri[:, 0], tri[:, 1])
+        et = P2
+    return Mesh(et, x, tri.astype(np.int32), dm.astype(np.int32), nx, ny,
+                {"kind": "structured-tri-right", "order": order})
+
+
+def structured_quads_q2(nx: int, ny: int | None = None, ly: float | None = None, y0: float = 0.0) -> Mesh:
+    """nx x ny Q2 quads on the (2nx+1) x (2ny+1) lattice; local order ix + 3 iy."""
+    ny = nx if ny is None else ny
+    ly = (ny / nx) if ly is None else ly
+    x, mx, _ = _lattice(nx, ny, 2, ly, y0)
+    cx, cy = np.meshgrid(np.arange(nx, dtype=np.int64), np.arange(ny, dtype=np.int64), indexing="xy")
+    cx, cy = cx.ravel(), cy.ravel()
+    dm = np.empty((nx * ny, 9), dtype=np.int64)
+    for iy in range(3):
+        for ix in range(3):
+            dm[:, ix + 3 * iy] = (2 * cx + ix) + mx * (2 * cy + iy)
+    xd = dm[:, [0, 2, 6, 8]]
+    return Mesh(Q2, x, xd.astype(np.int32), dm.astype(np.int32), nx, ny, {"kind": "structured-quad"})
+
+
+def jitter(mesh: Mesh, amp: float = 0.2, seed: int = 1234) -> Mesh:
+    """Move interior *vertex* nodes by U(-amp*h, amp*h); edge
+    (and Q2 face) nodes are re-placed at the average of their vertices so that
+    triangles stay straight-sided and quads bilinear."""
+    nx, ny = mesh.nx, mesh.ny
+    h = 1.0 / nx
+    rng = np.random.default_rng(seed)
+    x = mesh.x.copy()
+    if mesh.etype == P1:
+        mx, my = nx + 1, ny + 1
+        I, J = np.meshgrid(np.arange(mx), np.arange(my), indexing="xy")
+        interior = ((I > 0) & (I < mx - 1) & (J > 0) & (J < my - 1)).ravel()
+        x[interior] += rng.uniform(-amp * h, amp * h, size=(int(interior.sum()), 2))
+        return Mesh(mesh.etype, x, mesh.xdofmap, mesh.dofmap, nx, ny, dict(mesh.meta, jitter=amp))
+    mx, my = 2 * nx + 1, 2 * ny + 1
+    I, J = np.meshgrid(np.arange(mx), np.arange(my), indexing="xy")
+    isv = ((I % 2 == 0) & (J % 2 == 0))
+    interior = (isv & (I > 0) & (I < mx - 1) & (J > 0) & (J < my - 1)).ravel()
+    x[interior] += rng.uniform(-amp * h, amp * h, size=(int(interior.sum()), 2))
+    dm = mesh.dofmap.astype(np.int64)
+    if mesh.etype == P2:
+        for loc, (p, q) in zip((3, 4, 5), ((1, 2), (0, 2), (0, 1))):
+            x[dm[:, loc]] = 0.5 * (x[dm[:, p]] + x[dm[:, q]])
+    else:
+        for loc, vs in ((1, (0, 2)), (3, (0, 6)), (5, (2, 8)), (7, (6, 8)), (4, (0, 2, 6, 8))):
+            x[dm[:, loc]] = np.mean([x[dm[:, v]] for v in vs], axis=0)
+    return Mesh(mesh.etype, x, mesh.xdofmap, mesh.dofmap, nx, ny, dict(mesh.meta, jitter=amp))
+
+
+def dirichlet_markers(mesh: Mesh, eps: float = 1e-10, traction: bool = True):
+    """Per-dof marker (uint8) and imposed values: x = 0 clamped, x = 1:
+    ux = +0.01 (traction) / -0.01, uy = 0 (`F.cc:627-664`, `M.cc:1403-1415`)."""
+    bc = np.zeros(mesh.ndofs, dtype=np.uint8)
+    g = np.zeros(mesh.ndofs, dtype=np.float64)
+    left = np.nonzero(np.abs(mesh.x[:, 0]) < eps)[0]
+    right = np.nonzero(np.abs(mesh.x[:, 0] - 1.0) < eps)[0]
+    for nodes in (left, right):
+        bc[2 * nodes] = 1
+        bc[2 * nodes + 1] = 1
+    g[2 * right] = 0.01 if traction else -0.01
+    return bc, g
+
+
+def body_force(mesh: Mesh) -> np.ndarray:
+    """Nodal load f = (-1e5 (x-.5)^3 (1600 (y-.5)^2 - 500), 0), interpolated at
+    the nodes (`M.cc:1431-1447`, `F.cc:564-585`).  Returns (nnodes, 2)."""
+    r = mesh.x[:, 0] - 0.5
+    y = mesh.x[:, 1] - 0.5
+    xf = 100000.0 * (-r * r * r)
+    f = np.zeros((mesh.nnodes, 2))
+    f[:, 0] = (1600.0 * y * y - 500.0) * xf
+    return f
+
+
+def damage_band(mesh: Mesh) -> np.ndarray:
+    """Synthetic nodal damage field in [0,1) for the reassembly workload
+    (SURVEY.md 8d, config 5): max(0, 1 - |y - 0.5 - 0.1 sin 6x| / 0.05),
+    capped below 1."""
+    x, y = mesh.x[:, 0], mesh.x[:, 1]
+    d = np.maximum(0.0, 1.0 - np.abs(y - 0.5 - 0.1 * np.sin(6.0 * x)) / 0.05)
+    return np.minimum(d, 0.95)
