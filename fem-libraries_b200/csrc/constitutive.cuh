@@ -1,0 +1,156 @@
+// constitutive.cuh -- tangent operator D (Voigt xx, yy, engineering xy) of the
+// asymmetric traction/compression elasto-damage law, plane strain.
+//
+// Behaviour follows damIntegrator::AssembleElementGrad of the reference
+// (MFEM/mechanic2d/asym_elasto_damage_model.cc, "M.cc"):
+//   d <= 0            Hooke                                  M.cc:873-881
+//   d > 0             d <- min(d, 1 - 1e-12)                 M.cc:739
+//     closed form     E^t P E + q M                          M.cc:766-859
+//     null strain     (1 - d) Hooke                          M.cc:861-870
+//     AD variant      Hessian of psi by nested duals         M.cc:100-155,752-765;
+//                                                            autodiff/admfem.hpp:672-699
+#pragma once
+#include "common.cuh"
+
+namespace femb {
+
+constexpr double kLimit = 1.e-12;  // M.cc:513-514
+
+__device__ __forceinline__ void hooke_scaled(double l, double m, double s, double *D)
+{
+   const double md = s * m, ld = s * l;
+   D[0] = D[4] = 2 * md + ld;
+   D[1] = D[3] = ld;
+   D[8] = md;
+   D[2] = D[5] = D[6] = D[7] = 0.;
+}
+
+// eps = [e00, e01, e10, e11], the symmetrised displacement gradient (M.cc:742-748)
+__device__ inline void tangent_closed(double l, double m, double d, const double *eps, double *D)
+{
+   const double I1 = eps[0] + eps[3];
+   const double I2 = eps[1] * eps[1] - eps[0] * eps[3];
+   if (I1 > kLimit || I2 > kLimit || I1 < -kLimit || I2 < -kLimit)
+   {
+      const double delta = I1 * I1 + 4 * I2;
+      const double r = sqrt(fmax(0., delta));
+      const double e1 = (I1 + r) / 2., e2 = (I1 - r) / 2.;
+      double cs, sn;
+      if (r < kLimit)
+      {  // singular second derivative: M.cc:784-789
+         const double sg = (2 * eps[1] / (eps[0] - eps[3])) > 0. ? 1. : -1.;
+         cs = sg * sqrt(2.) / 2.;
+         sn = cs;
+      }
+      else
+      {
+         cs = (eps[0] - eps[3]) / r;
+         sn = 2 * eps[1] / r;
+      }
+      const double a1 = (e1 >= 0) ? 1. : 0., a2 = (e2 >= 0) ? 1. : 0., a = (I1 >= 0) ? 1. : 0.;
+      const double factor = 2. * m, gamma = 0.5 * l / m;
+      const double c1 = 1. - a1 * d, c2 = 1. - a2 * d, c3 = 1. - a * d;
+      const double P00 = factor * (c1 + gamma * c3), P01 = factor * gamma * c3, P11 = factor * (c2 + gamma * c3);
+      const double de0[3] = {0.5 * (1 + cs), 0.5 * (1 - cs), 0.5 * sn};
+      const double de1[3] = {0.5 * (1 - cs), 0.5 * (1 + cs), -0.5 * sn};
+      const double cos2 = cs * cs, sin2 = sn * sn, sc = sn * cs;
+      const double M[9] = {1. - cos2, -1. + cos2, -sc, -1. + cos2, 1. - cos2, sc, -sc, sc, 1. - sin2};
+      const double q = (r >= kLimit) ? (I1 / r * (c1 - c2) + (c1 + c2)) : (c1 + c2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+         const double t0 = de0[i] * P00 + de1[i] * P01, t1 = de0[i] * P01 + de1[i] * P11;
+#pragma unroll
+         for (int j = 0; j < 3; ++j) D[3 * i + j] = (t0 * de0[j] + t1 * de1[j]) + q * (0.5 * m * M[3 * i + j]);
+      }
+   }
+   else
+      hooke_scaled(l, m, 1. - d, D);
+}
+
+// second-order forward jets == internal::dual<dual<real_t>> of admfem.hpp:619-631
+struct Jet2
+{
+   double v, a, b, ab;
+};
+__device__ __forceinline__ Jet2 jc(double c) { return Jet2{c, 0., 0., 0.}; }
+__device__ __forceinline__ Jet2 operator+(Jet2 x, Jet2 y) { return Jet2{x.v + y.v, x.a + y.a, x.b + y.b, x.ab + y.ab}; }
+__device__ __forceinline__ Jet2 operator-(Jet2 x, Jet2 y) { return Jet2{x.v - y.v, x.a - y.a, x.b - y.b, x.ab - y.ab}; }
+__device__ __forceinline__ Jet2 operator*(Jet2 x, Jet2 y)
+{
+   return Jet2{x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b,
+               x.ab * y.v + x.b * y.a + x.a * y.b + x.v * y.ab};
+}
+__device__ __forceinline__ Jet2 operator*(Jet2 x, double s) { return Jet2{x.v * s, x.a * s, x.b * s, x.ab * s}; }
+__device__ __forceinline__ Jet2 jsqrt(Jet2 x)
+{
+   const double s = sqrt(x.v), f1 = 0.5 / s, f2 = -0.25 / (s * x.v);
+   return Jet2{s, f1 * x.a, f1 * x.b, f2 * x.a * x.b + f1 * x.ab};
+}
+
+// psi(strain; l, m, d), strain = (e11, e21, e12, e22): M.cc:100-155
+__device__ inline Jet2 potential(double l, double m, double d, const Jet2 *s)
+{
+   const Jet2 I1 = s[0] + s[3];
+   const Jet2 I2 = s[1] * s[2] - s[0] * s[3];
+   if (I1.v > kLimit || I2.v > kLimit || I1.v < -kLimit || I2.v < -kLimit)
+   {
+      const Jet2 r = jsqrt(I1 * I1 + I2 * 4.);
+      const Jet2 ev1 = (I1 + r) * 0.5, ev2 = (I1 - r) * 0.5;
+      const double a1 = (ev1.v >= 0) ? 1. : 0., a2 = (ev2.v >= 0) ? 1. : 0.;
+      const double a = ((ev1.v + ev2.v) >= 0) ? 1. : 0.;
+      return (I1 * I1) * ((1. - a * d) * l / 2.) + ((ev1 * ev1) * (1 - a1 * d) + (ev2 * ev2) * (1. - a2 * d)) * m;
+   }
+   const Jet2 q = (s[0] * s[0] + s[3] * s[3]) + (s[1] * s[1] + s[2] * s[2]);
+   return ((I1 * I1) * (l / 2.) + q * m) * (1 - d);
+}
+
+__device__ inline void tangent_ad(double l, double m, double d, const double *eps, double *D)
+{
+   // column-major DenseMatrix strain -> (eps11, eps21, eps12, eps22), M.cc:96-97,681
+   const double u[4] = {eps[0], eps[2], eps[1], eps[3]};
+   double H[4][4];
+#pragma unroll
+   for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj <= ii; ++jj)
+      {  // one of the 10 functor evaluations of admfem.hpp:683-697
+         Jet2 s[4] = {jc(u[0]), jc(u[1]), jc(u[2]), jc(u[3])};
+         s[ii].a = 1.0;
+         s[jj].b = 1.0;
+         H[ii][jj] = H[jj][ii] = potential(l, m, d, s).ab;
+      }
+#pragma unroll
+   for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) D[3 * i + j] = H[i + 2 * (i % 2)][j + 2 * (j % 2)];  // M.cc:761-762
+   D[8] = 0.5 * (D[8] + H[1][2]);                                                        // M.cc:763
+}
+
+// branch structure of M.cc:732-882
+__device__ inline void tangent(int variant, double l, double m, double d, const double *eps, double *D)
+{
+   if (d > 0.)
+   {
+      d = fmin(d, 1. - kLimit);
+      if (variant == FEMB200_TANGENT_AD)
+         tangent_ad(l, m, d, eps, D);
+      else
+         tangent_closed(l, m, d, eps, D);
+   }
+   else
+      hooke_scaled(l, m, 1., D);
+}
+
+// Lame coefficients, the MFEM form (M.cc:1087-1098): lambda = E*c2, mu = E*c3
+struct LameCoef
+{
+   double c2, c3;
+};
+inline LameCoef lame_coef(double nu)
+{
+   const double c1 = 1. + nu;
+   return LameCoef{nu / (c1 * (1. - 2. * nu)), 1. / (2 * c1)};
+}
+
+}  // namespace femb

@@ -1,0 +1,416 @@
+// plan.cu -- sparsity pattern and gather maps, built on the device from the
+// cell->dof map alone.
+//
+// Role in the reference: dolfinx::fem::petsc::create_matrix(*J_form) (F.cc:688),
+// which builds the CSR structure once before the Newton loop.  The pattern is the
+// dolfinx convention: rows in dof order, columns ascending and
+// unique, structural, bs = 2.  Because every scalar row 2I+i of node I has the
+// same column set {2J, 2J+1 : J in adj(I)}, the pattern is stored once per node
+// ("block CSR": brp/bcol) and the scalar CSR is a closed-form expansion:
+//     rowptr[2I]   = 4 brp[I]
+//     rowptr[2I+1] = 4 brp[I] + 2 deg(I)
+//     colidx[rowptr[2I+i] + 2s + k] = 2 bcol[brp[I]+s] + k
+#include "plan.cuh"
+
+namespace femb {
+
+constexpr int kMaxDeg = 96;  // block degree cap of the builder (thread-local scratch)
+
+// --- node -> cell visit lists -------------------------------------------------
+__global__ void k_count_visits(int64_t nvis, const int32_t *__restrict__ dofmap, int32_t *__restrict__ cnt)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nvis) atomicAdd(&cnt[dofmap[i]], 1);
+}
+
+__global__ void k_fill_visits(int64_t nvis, int nd, const int32_t *__restrict__ dofmap,
+                              const int32_t *__restrict__ nptr, int32_t *__restrict__ cursor,
+                              uint32_t *__restrict__ tmp)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nvis) return;
+   const int32_t I = dofmap[i];
+   const int32_t p = atomicAdd(&cursor[I], 1);
+   const uint32_t e = (uint32_t)(i / nd), a = (uint32_t)(i % nd);
+   tmp[nptr[I] + p] = (e << 4) | a;
+}
+
+// atomics fill each list in arbitrary order: sort (ascending cell id) for determinism
+__global__ void k_sort_visits(int64_t nnodes, const int32_t *__restrict__ nptr, uint32_t *__restrict__ tmp)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   const int32_t lo = nptr[I], hi = nptr[I + 1];
+   for (int32_t i = lo + 1; i < hi; ++i)
+   {
+      const uint32_t v = tmp[i];
+      int32_t j = i - 1;
+      while (j >= lo && tmp[j] > v)
+      {
+         tmp[j + 1] = tmp[j];
+         --j;
+      }
+      tmp[j + 1] = v;
+   }
+}
+
+// --- neighbour sets -------------------------------------------------------------
+// sorted unique neighbour nodes of row node I into loc[]; returns the count, or
+// -1 when kMaxDeg is exceeded
+__device__ inline int gather_neighbours(int64_t I, int nd, const int32_t *__restrict__ dofmap,
+                                        const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
+                                        int32_t *loc)
+{
+   int deg = 0;
+   for (int32_t k = nptr[I]; k < nptr[I + 1]; ++k)
+   {
+      const int64_t e = vis[k] >> 4;
+      for (int b = 0; b < nd; ++b)
+      {
+         const int32_t J = dofmap[e * nd + b];
+         // sorted insert with de-duplication
+         int lo = 0, hi = deg;
+         while (lo < hi)
+         {
+            const int mid = (lo + hi) >> 1;
+            if (loc[mid] < J)
+               lo = mid + 1;
+            else
+               hi = mid;
+         }
+         if (lo < deg && loc[lo] == J) continue;
+         if (deg == kMaxDeg) return -1;
+         for (int t = deg; t > lo; --t) loc[t] = loc[t - 1];
+         loc[lo] = J;
+         ++deg;
+      }
+   }
+   return deg;
+}
+
+__global__ void k_degree(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap, const int32_t *__restrict__ nptr,
+                         const uint32_t *__restrict__ vis, int32_t *__restrict__ deg, int32_t *__restrict__ flags)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   int32_t loc[kMaxDeg];
+   const int d = gather_neighbours(I, nd, dofmap, nptr, vis, loc);
+   if (d < 0)
+   {
+      atomicOr(flags, 1);
+      deg[I] = 0;
+   }
+   else
+   {
+      deg[I] = d;
+      atomicMax(flags + 1, d);
+   }
+}
+
+__global__ void k_fill_cols(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
+                            const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
+                            const int64_t *__restrict__ brp, int32_t *__restrict__ bcol)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   int32_t loc[kMaxDeg];
+   const int d = gather_neighbours(I, nd, dofmap, nptr, vis, loc);
+   const int64_t base = brp[I];
+   for (int s = 0; s < d; ++s) bcol[base + s] = loc[s];
+}
+
+// --- slot map: position of every local dof b of visit (I, e, a) in block row I ---
+__global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
+                             const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
+                             const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+                             VisitRec *__restrict__ vrec)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   const int64_t base = brp[I];
+   const int deg = (int)(brp[I + 1] - base);
+   uint32_t touched[(kMaxDeg + 31) / 32];
+   for (int t = 0; t < (kMaxDeg + 31) / 32; ++t) touched[t] = 0u;
+   for (int32_t k = nptr[I]; k < nptr[I + 1]; ++k)
+   {
+      VisitRec r;
+      r.e = vis[k] >> 4;
+      r.a = (uint8_t)(vis[k] & 15u);
+      r.first = 0;
+      r.slot8 = 0;
+      for (int b = 0; b < 8; ++b) r.slot[b] = 0;
+      for (int b = 0; b < nd; ++b)
+      {
+         const int32_t J = dofmap[(int64_t)r.e * nd + b];
+         int lo = 0, hi = deg;
+         while (lo < hi)
+         {
+            const int mid = (lo + hi) >> 1;
+            if (bcol[base + mid] < J)
+               lo = mid + 1;
+            else
+               hi = mid;
+         }
+         if (b < 8)
+            r.slot[b] = (uint8_t)lo;
+         else
+            r.slot8 = (uint8_t)lo;
+         if (!((touched[lo >> 5] >> (lo & 31)) & 1u))
+         {
+            touched[lo >> 5] |= 1u << (lo & 31);
+            r.first |= (uint16_t)(1u << b);
+         }
+      }
+      vrec[k] = r;
+   }
+}
+
+// --- largest staging tile (in node blocks) for each candidate tile height R ------
+__global__ void k_tile_max(int64_t nnodes, const int64_t *__restrict__ brp, int32_t *__restrict__ out)
+{
+   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+   for (int r = 0; r < kNumTileR; ++r)
+   {
+      const int64_t n0 = t * tile_r(r);
+      if (n0 < nnodes)
+      {
+         const int64_t n1 = min(n0 + (int64_t)tile_r(r), nnodes);
+         atomicMax(out + r, (int32_t)(brp[n1] - brp[n0]));
+      }
+   }
+}
+
+// --- scalar CSR expansion ---------------------------------------------------------
+__global__ void k_scalar_csr(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+                             int64_t *__restrict__ rowptr, int32_t *__restrict__ colidx)
+{
+   // one warp per node row pair: coalesced colidx writes
+   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (I >= nnodes) return;
+   const int64_t b0 = brp[I];
+   const int deg = (int)(brp[I + 1] - b0);
+   if (lane == 0)
+   {
+      rowptr[2 * I] = 4 * b0;
+      rowptr[2 * I + 1] = 4 * b0 + 2 * deg;
+      if (I == nnodes - 1) rowptr[2 * nnodes] = 4 * brp[nnodes];
+   }
+   for (int t = lane; t < 4 * deg; t += 32)
+   {  // entry t of the 4*deg scalars of node I: row r = t / (2 deg), then (s, k)
+      const int r = t / (2 * deg), w = t - r * 2 * deg;
+      colidx[4 * b0 + t] = 2 * bcol[b0 + (w >> 1)] + (w & 1);
+   }
+}
+
+// --- Dirichlet list ---------------------------------------------------------------
+__global__ void k_bc_nodes(int64_t nnodes, const uint8_t *__restrict__ bc, int32_t *__restrict__ list,
+                           int32_t *__restrict__ count)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   if (bc[2 * I] | bc[2 * I + 1])
+   {
+      const int32_t p = atomicAdd(count, 1);
+      if (list) list[p] = (int32_t)I;
+   }
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n, size_t *acc)
+{
+   *p = nullptr;
+   const size_t bytes = sizeof(T) * (n ? n : 1);
+   FEMB_CUDA(cudaMalloc(p, bytes));
+   *acc += bytes;
+   return 0;
+}
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" void femb200_plan_destroy(femb200_plan *p)
+{
+   if (!p) return;
+   cudaFree(p->nptr);
+   cudaFree(p->vrec);
+   cudaFree(p->brp);
+   cudaFree(p->bcol);
+   cudaFree(p->bc);
+   cudaFree(p->bc_nodes);
+   delete p;
+}
+
+extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, const int32_t *d_dofmap,
+                                   const int32_t *d_xdofmap, void *stream, femb200_plan **out)
+{
+   FEMB_CHECK(out != nullptr, "plan_create: out is null");
+   *out = nullptr;
+   FEMB_CHECK(etype >= FEMB200_P1 && etype <= FEMB200_Q2, "plan_create: unknown element family %d", etype);
+   FEMB_CHECK(nnodes > 0 && ncells > 0, "plan_create: empty mesh (nnodes=%lld ncells=%lld)", (long long)nnodes,
+              (long long)ncells);
+   FEMB_CHECK(d_dofmap && d_xdofmap, "plan_create: null dofmap");
+   const int nd = elem_nd(etype);
+   const int64_t nvis = ncells * nd;
+   FEMB_CHECK(ncells < (int64_t(1) << 28), "plan_create: more than 2^28 cells per device is not supported");
+   FEMB_CHECK(nvis < (int64_t(1) << 31) && nnodes < (int64_t(1) << 30), "plan_create: mesh too large for int32 maps");
+   cudaStream_t st = as_stream(stream);
+
+   femb200_plan *p = new femb200_plan();
+   p->etype = etype, p->nd = nd, p->nv = elem_nv(etype);
+   p->nnodes = nnodes, p->ncells = ncells, p->nvisits = nvis;
+   p->row_lo = 0, p->row_hi = nnodes;
+   p->dofmap = d_dofmap, p->xdofmap = d_xdofmap;
+
+   int32_t *cnt = nullptr, *deg = nullptr, *flags = nullptr;
+   uint32_t *tmpvis = nullptr;
+   size_t scratch = 0;
+   int rc = 0;
+   auto fail = [&](int code) {
+      cudaFree(cnt);
+      cudaFree(deg);
+      cudaFree(flags);
+      cudaFree(tmpvis);
+      femb200_plan_destroy(p);
+      return code;
+   };
+   const int T = 256;
+   if (dev_alloc(&p->nptr, (size_t)nnodes + 1, &p->bytes) || dev_alloc(&cnt, (size_t)nnodes + 1, &scratch) ||
+       dev_alloc(&tmpvis, (size_t)nvis, &scratch) || dev_alloc(&flags, 2 + kNumTileR, &scratch))
+      return fail(1);
+   if (cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)nnodes + 1), st) != cudaSuccess ||
+       cudaMemsetAsync(flags, 0, sizeof(int32_t) * (2 + kNumTileR), st) != cudaSuccess)
+      return fail(set_error("plan_create: memset failed"));
+
+   // 1. node -> cell visit lists
+   k_count_visits<<<(unsigned)cdiv(nvis, T), T, 0, st>>>(nvis, d_dofmap, cnt);
+   if ((rc = exclusive_scan_i32_i32(cnt, p->nptr, nnodes, st))) return fail(rc);
+   cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)nnodes + 1), st);
+   k_fill_visits<<<(unsigned)cdiv(nvis, T), T, 0, st>>>(nvis, nd, d_dofmap, p->nptr, cnt, tmpvis);
+   k_sort_visits<<<(unsigned)cdiv(nnodes, T), T, 0, st>>>(nnodes, p->nptr, tmpvis);
+
+   // 2. block degrees -> brp -> bcol
+   if (dev_alloc(&deg, (size_t)nnodes + 1, &scratch) || dev_alloc(&p->brp, (size_t)nnodes + 1, &p->bytes))
+      return fail(1);
+   k_degree<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, deg, flags);
+   if ((rc = exclusive_scan_i32_i64(deg, p->brp, nnodes, st))) return fail(rc);
+   int32_t hflags[2] = {0, 0};
+   if (cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+       cudaMemcpyAsync(&p->nnzb, p->brp + nnodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+       cudaStreamSynchronize(st) != cudaSuccess)
+      return fail(set_error("plan_create: pattern build failed: %s", cudaGetErrorString(cudaGetLastError())));
+   if (hflags[0]) return fail(set_error("plan_create: a node has more than %d neighbour nodes", kMaxDeg));
+   p->max_deg = hflags[1];
+   if (dev_alloc(&p->bcol, (size_t)p->nnzb, &p->bytes) || dev_alloc(&p->vrec, (size_t)nvis, &p->bytes))
+      return fail(1);
+   k_fill_cols<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol);
+
+   // 3. slot map + staging-tile sizes
+   k_fill_slots<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
+                                                              p->vrec);
+   k_tile_max<<<(unsigned)cdiv(cdiv(nnodes, tile_r(0)), T), T, 0, st>>>(nnodes, p->brp, flags + 2);
+   if (cudaMemcpyAsync(p->tile_max_blocks, flags + 2, sizeof(int32_t) * kNumTileR, cudaMemcpyDeviceToHost, st) !=
+           cudaSuccess ||
+       cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+      return fail(set_error("plan_create: slot map build failed: %s", cudaGetErrorString(cudaGetLastError())));
+
+   cudaFree(cnt);
+   cudaFree(deg);
+   cudaFree(flags);
+   cudaFree(tmpvis);
+   *out = p;
+   return 0;
+}
+
+extern "C" int femb200_plan_sizes(const femb200_plan *p, int64_t *nnodes, int64_t *ncells, int64_t *nnz_blocks,
+                                  int64_t *nnz, int32_t *max_block_degree, int64_t *device_bytes)
+{
+   FEMB_CHECK(p != nullptr, "plan_sizes: null plan");
+   if (nnodes) *nnodes = p->nnodes;
+   if (ncells) *ncells = p->ncells;
+   if (nnz_blocks) *nnz_blocks = p->nnzb;
+   if (nnz) *nnz = 4 * p->nnzb;
+   if (max_block_degree) *max_block_degree = p->max_deg;
+   if (device_bytes) *device_bytes = (int64_t)p->bytes;
+   return 0;
+}
+
+extern "C" int femb200_plan_block_csr(const femb200_plan *p, const int64_t **d_brp, const int32_t **d_bcol)
+{
+   FEMB_CHECK(p != nullptr, "plan_block_csr: null plan");
+   if (d_brp) *d_brp = p->brp;
+   if (d_bcol) *d_bcol = p->bcol;
+   return 0;
+}
+
+extern "C" int femb200_plan_copy_block_csr(const femb200_plan *p, int64_t *d_brp, int32_t *d_bcol, void *stream)
+{
+   FEMB_CHECK(p && d_brp && d_bcol, "plan_copy_block_csr: null argument");
+   cudaStream_t st = as_stream(stream);
+   FEMB_CUDA(cudaMemcpyAsync(d_brp, p->brp, sizeof(int64_t) * (size_t)(p->nnodes + 1), cudaMemcpyDeviceToDevice, st));
+   FEMB_CUDA(cudaMemcpyAsync(d_bcol, p->bcol, sizeof(int32_t) * (size_t)p->nnzb, cudaMemcpyDeviceToDevice, st));
+   return 0;
+}
+
+extern "C" int femb200_plan_scalar_csr(const femb200_plan *p, int64_t *d_rowptr, int32_t *d_colidx, void *stream)
+{
+   FEMB_CHECK(p && d_rowptr && d_colidx, "plan_scalar_csr: null argument");
+   const int T = 256;
+   k_scalar_csr<<<(unsigned)cdiv(p->nnodes * 32, T), T, 0, as_stream(stream)>>>(p->nnodes, p->brp, p->bcol, d_rowptr,
+                                                                               d_colidx);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
+extern "C" int femb200_plan_set_dirichlet(femb200_plan *p, const uint8_t *d_bc, void *stream)
+{
+   FEMB_CHECK(p != nullptr, "plan_set_dirichlet: null plan");
+   cudaStream_t st = as_stream(stream);
+   cudaFree(p->bc_nodes);
+   p->bc_nodes = nullptr;
+   p->nbc = 0;
+   if (!d_bc)
+   {
+      cudaFree(p->bc);
+      p->bc = nullptr;
+      return 0;
+   }
+   size_t acc = 0;
+   if (!p->bc && dev_alloc(&p->bc, (size_t)(2 * p->nnodes), &acc)) return 1;
+   FEMB_CUDA(cudaMemcpyAsync(p->bc, d_bc, (size_t)(2 * p->nnodes), cudaMemcpyDeviceToDevice, st));
+   int32_t *count = nullptr;
+   if (dev_alloc(&count, 1, &acc)) return 1;
+   const int T = 256;
+   cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+   k_bc_nodes<<<(unsigned)cdiv(p->nnodes, T), T, 0, st>>>(p->nnodes, p->bc, nullptr, count);
+   int32_t n = 0;
+   cudaMemcpyAsync(&n, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+   if (cudaStreamSynchronize(st) != cudaSuccess)
+   {
+      cudaFree(count);
+      return set_error("plan_set_dirichlet: %s", cudaGetErrorString(cudaGetLastError()));
+   }
+   if (dev_alloc(&p->bc_nodes, (size_t)n, &acc))
+   {
+      cudaFree(count);
+      return 1;
+   }
+   cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+   k_bc_nodes<<<(unsigned)cdiv(p->nnodes, T), T, 0, st>>>(p->nnodes, p->bc, p->bc_nodes, count);
+   cudaStreamSynchronize(st);
+   cudaFree(count);
+   p->nbc = n;
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
+extern "C" int femb200_plan_set_row_range(femb200_plan *p, int64_t row_lo, int64_t row_hi)
+{
+   FEMB_CHECK(p != nullptr, "plan_set_row_range: null plan");
+   FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "plan_set_row_range: bad range [%lld, %lld)",
+              (long long)row_lo, (long long)row_hi);
+   p->row_lo = row_lo, p->row_hi = row_hi;
+   return 0;
+}

@@ -1,0 +1,60 @@
+// plan.cuh -- the assembly plan: node->cell visit lists, node-block CSR pattern and
+// the per-visit slot map of the write-once gather assembly.
+#pragma once
+#include "common.cuh"
+
+namespace femb {
+
+// One visit = (row node I, incident cell e, local index a of I in e).  16 bytes:
+//   word 0   cell id e
+//   word 1   a (bits 0-7) | slot of local dof 8 (bits 8-15, Q2 only) | first-touch mask (bits 16-31):
+//            bit b set when this visit is the first (in list order) to contribute to
+//            slot[b], so it stores instead of adds
+//   word 2-3 slot of local dof b = 0..7 in block row I, one byte each
+// Visits are stored grouped by row node (nptr), ascending cell id inside a group.
+struct __align__(16) VisitRec
+{
+   uint32_t e;
+   uint8_t a;
+   uint8_t slot8;
+   uint16_t first;
+   uint8_t slot[8];
+};
+// register-friendly decoded form
+struct Visit
+{
+   uint32_t e, a, first, slot8;
+   uint64_t slots;
+   __device__ __forceinline__ explicit Visit(const uint4 raw)
+       : e(raw.x), a(raw.y & 0xffu), first(raw.y >> 16), slot8((raw.y >> 8) & 0xffu),
+         slots((uint64_t)raw.z | ((uint64_t)raw.w << 32))
+   {
+   }
+   __device__ __forceinline__ int slot(int b) const { return b < 8 ? (int)((slots >> (8 * b)) & 0xffu) : (int)slot8; }
+   __device__ __forceinline__ bool is_first(int b) const { return (first >> b) & 1u; }
+};
+static_assert(sizeof(VisitRec) == 16, "VisitRec must be 16 bytes");
+
+constexpr int kNumTileR = 6;
+__host__ __device__ constexpr int tile_r(int r) { return r == 0 ? 32 : r == 1 ? 64 : r == 2 ? 96 : r == 3 ? 128 : r == 4 ? 192 : 256; }
+
+}  // namespace femb
+
+struct femb200_plan
+{
+   int etype = 0, nd = 0, nv = 0;
+   int64_t nnodes = 0, ncells = 0, nnzb = 0, nvisits = 0;
+   int32_t max_deg = 0;
+   const int32_t *dofmap = nullptr, *xdofmap = nullptr;  // borrowed
+   int32_t *nptr = nullptr;                               // [nnodes+1]
+   femb::VisitRec *vrec = nullptr;                        // [nvisits]
+   int64_t *brp = nullptr;                                // [nnodes+1]
+   int32_t *bcol = nullptr;                               // [nnzb]
+   int32_t tile_max_blocks[femb::kNumTileR] = {0, 0, 0, 0, 0, 0};
+   // Dirichlet
+   uint8_t *bc = nullptr;        // [2*nnodes] or null
+   int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
+   int32_t nbc = 0;
+   size_t bytes = 0;
+   int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
+};

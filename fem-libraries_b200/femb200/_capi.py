@@ -1,0 +1,95 @@
+"""ctypes binding of libfemb200.so (the C ABI declared in include/femb200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails, and
+every compute entry point needs a CUDA device (sm_100a).  Build the library with
+`make -C fem-libraries_b200/csrc` (or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfemb200.so")
+
+P1, P2, Q2 = 0, 1, 2
+ROWMAJOR_INTERLEAVED, COLMAJOR_BYNODES = 0, 1
+TANGENT_CLOSED, TANGENT_AD = 0, 1
+OP_CSR, OP_PA = 0, 1
+SC_FLAG, SC_ITERS, SC_FINAL, SC_RED_NOM, SC_RED_DEN, SC_RED_BETA, SC_COUNT = 4, 5, 6, 9, 10, 11, 16
+
+vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# name -> argtypes; every function returns int (0 = ok) unless listed in _SPECIAL
+SIGNATURES = {
+    "femb200_device_info": [C.POINTER(C.c_int)] * 3,
+    "femb200_tabulate_tensor_batched": [i32, i64, vp, vp, i32, vp, vp, vp, f64, vp, vp, i32, i32, vp],
+    "femb200_plan_create": [i32, i64, i64, vp, vp, vp, C.POINTER(vp)],
+    "femb200_plan_sizes": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32),
+                           C.POINTER(i64)],
+    "femb200_plan_block_csr": [vp, C.POINTER(vp), C.POINTER(vp)],
+    "femb200_plan_copy_block_csr": [vp, vp, vp, vp],
+    "femb200_plan_scalar_csr": [vp, vp, vp, vp],
+    "femb200_assemble_matrix": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp],
+    "femb200_plan_set_dirichlet": [vp, vp, vp],
+    "femb200_apply_dirichlet": [vp, vp, f64, vp],
+    "femb200_matrix_norms": [vp, vp, vp, vp],
+    "femb200_spmv": [vp, vp, vp, vp, vp],
+    "femb200_spmv_dot": [vp, vp, vp, vp, vp, vp],
+    "femb200_extract_diagonal": [vp, vp, vp, vp],
+    "femb200_jacobi_setup": [i64, vp, vp, vp],
+    "femb200_pcg": [vp, i32, vp, vp, vp, vp, i64, f64, f64, i32, vp, i32, i32, vp, C.POINTER(C.c_int),
+                    C.POINTER(C.c_double), C.POINTER(C.c_int), vp],
+    "femb200_dot": [i64, vp, vp, vp, vp],
+    "femb200_cg_set_tolerances": [vp, f64, f64, vp],
+    "femb200_cg_init": [i64, vp, vp, vp, vp, vp, vp, vp],
+    "femb200_cg_scalar_step": [vp, i32, vp],
+    "femb200_cg_apply": [vp, i32, vp, vp, vp, vp, vp, vp],
+    "femb200_cg_update_xr": [i64, vp, vp, vp, vp, vp, vp, vp],
+    "femb200_cg_update_dir": [i64, vp, vp, vp, vp, vp],
+    "femb200_pa_create": [i32, i64, i64, vp, vp, vp, i32, vp, f64, vp, C.POINTER(vp)],
+    "femb200_pa_set_dirichlet": [vp, vp, f64, vp],
+    "femb200_pa_apply": [vp, vp, vp, vp],
+    "femb200_pa_diagonal": [vp, vp, vp],
+    "femb200_gather": [i64, vp, vp, vp, vp],
+    "femb200_plan_set_row_range": [vp, i64, i64],
+}
+_SPECIAL = {
+    "femb200_version": ([], C.c_int),
+    "femb200_last_error": ([], C.c_char_p),
+    "femb200_plan_destroy": ([vp], None),
+    "femb200_pa_destroy": ([vp], None),
+}
+ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
+
+_lib = None
+
+
+class Femb200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: build it with `make -C fem-libraries_b200/csrc` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, C.c_int
+        for name, (args, res) in _SPECIAL.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, res
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Femb200Error(lib().femb200_last_error().decode(errors="replace"))
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args))

@@ -1,0 +1,418 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+The names follow the two libraries the reference drives, so that parity tests
+read like the reference's own call sequence (`F.cc` = FEniCSx driver, `M.cc` =
+MFEM driver, `manual.py` = the UFL form file; paths relative to /root/reference):
+
+  FEniCSx side (F.cc:679-688, 847-862)        here
+  -----------------------------------------   ----------------------------------
+  create_form(J) (coefficients d, E, u, nu)   ElasticityForm(mesh, E, nu, d, u)
+  fem::petsc::create_matrix(*J_form)           create_matrix(form)
+  DirichletBC bcl, bcr                         DirichletBC(marker, values)
+  MatZeroEntries + assemble_matrix(set_block_  assemble_matrix(A, form, bcs)
+    fn(A, ADD_VALUES), *J_form, {bcl, bcr})
+    + set_diagonal(..., 1.) + MatAssembly
+  ufcx tabulate_tensor(A, w, c, coord, ...)    tabulate_tensor(A, w, c, coordinate_dofs)
+                                               tabulate_tensor_batched(form)
+  MFEM side (M.cc:639, 1483-1546)
+  damIntegrator::AssembleElementGrad           element_grad_batched(form)  (col-major, byNODES)
+  BilinearFormIntegrator::AssemblePA/AddMultPA PAOperator(form).AssemblePA()/AddMultPA()/Mult()
+  CGSolver::SetRelTol/SetMaxIter/SetOperator/  CGSolver(...)
+    SetPreconditioner/Mult                       (Jacobi instead of BoomerAMG: third party, out of scope)
+
+Everything numerical runs in libfemb200.so (hand-written sm_100a CUDA) through
+the C ABI of include/femb200.h; torch only owns device buffers and streams.
+There is no CPU fallback: without a CUDA device every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from .mesh import Mesh
+
+_NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+         np.dtype(np.uint8): torch.uint8}
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("femb200 needs a CUDA device (sm_100a): there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_device(a, dtype) -> torch.Tensor | None:
+    """numpy (host) or torch (host/device) -> contiguous device tensor of `dtype`.
+    Host arrays go through pinned memory with an asynchronous copy."""
+    if a is None:
+        return None
+    dev = _require_cuda()
+    tdt = _NP2T[np.dtype(dtype)]
+    if isinstance(a, torch.Tensor):
+        t = a
+        if t.device.type != "cuda":
+            t = t.contiguous().pin_memory().to(dev, non_blocking=True)
+        return t.to(tdt).contiguous()
+    h = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+    return h.pin_memory().to(dev, non_blocking=True)
+
+
+def _p(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+@dataclass
+class DirichletBC:
+    """Constrained dofs and their imposed values (F.cc:640,664).  `marker` is a
+    per-dof uint8 array (global dof = 2 * node + component)."""
+    marker: np.ndarray
+    values: np.ndarray | None = None
+
+
+def merge_bcs(bcs, ndofs: int):
+    if bcs is None:
+        return None
+    if isinstance(bcs, DirichletBC):
+        bcs = [bcs]
+    if len(bcs) == 0:
+        return None
+    m = np.zeros(ndofs, dtype=np.uint8)
+    for bc in bcs:
+        mk = bc.marker.cpu().numpy() if isinstance(bc.marker, torch.Tensor) else np.asarray(bc.marker)
+        m |= (mk != 0).astype(np.uint8)
+    return m
+
+
+class ElasticityForm:
+    """The bilinear form J of the reference (manual.py:102) with its coefficients
+    resident on the device: geometry, cell->dof maps, Young modulus per cell (DG0,
+    manual.py:22), constant nu (manual.py:23), optional nodal damage d
+    (manual.py:19) and current iterate u (manual.py:30)."""
+
+    def __init__(self, mesh: Mesh, E, nu: float = 0.3, d=None, u=None, variant: int = capi.TANGENT_CLOSED):
+        self.mesh = mesh
+        self.etype, self.nnodes, self.ncells = mesh.etype, mesh.nnodes, mesh.ncells
+        self.nd, self.nv = mesh.nd, mesh.nv
+        self.nu = float(nu)
+        self.variant = int(variant)
+        self.x = to_device(mesh.x, np.float64)
+        self.x_stride = int(mesh.x.shape[1])
+        self.xdofmap = to_device(mesh.xdofmap, np.int32)
+        self.dofmap = to_device(mesh.dofmap, np.int32)
+        self.E = to_device(E, np.float64)
+        self.d = to_device(d, np.float64)
+        self.u = to_device(u, np.float64)
+        if self.E.numel() != self.ncells:
+            raise ValueError(f"E has {self.E.numel()} entries, expected one per cell ({self.ncells})")
+
+    # coefficient updates between Newton iterations (host or device arrays)
+    def set_u(self, u):
+        self.u = to_device(u, np.float64)
+
+    def set_damage(self, d):
+        self.d = to_device(d, np.float64)
+
+    def set_E(self, E):
+        self.E = to_device(E, np.float64)
+
+    def set_coordinates(self, x):
+        self.x = to_device(x, np.float64)
+
+
+class Matrix:
+    """CSR matrix in the dolfinx convention (rows in dof order, columns ascending,
+    structural, bs = 2 expanded): rowptr int64, colidx int32, values float64, all
+    on the device.  Owns the assembly plan (pattern + gather maps)."""
+
+    def __init__(self, form: ElasticityForm):
+        _require_cuda()
+        self.form = form
+        self._plan = C.c_void_p()
+        capi.call("femb200_plan_create", form.etype, form.nnodes, form.ncells, _p(form.dofmap), _p(form.xdofmap),
+                  _stream(), C.byref(self._plan))
+        nn, nc, nnzb, nnz, bytes_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        mdeg = C.c_int32()
+        capi.call("femb200_plan_sizes", self._plan, C.byref(nn), C.byref(nc), C.byref(nnzb), C.byref(nnz),
+                  C.byref(mdeg), C.byref(bytes_))
+        self.nnodes, self.ncells, self.nnz_blocks, self.nnz = nn.value, nc.value, nnzb.value, nnz.value
+        self.max_block_degree, self.plan_bytes = mdeg.value, bytes_.value
+        self.ndofs = 2 * self.nnodes
+        self.values = torch.empty(self.nnz, dtype=torch.float64, device="cuda")
+        self._rowptr = self._colidx = None
+        self._bc_marker = None
+        self.bc_dev = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None and self._plan.value:
+                capi.lib().femb200_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def plan(self):
+        return self._plan
+
+    def _expand(self):
+        self._rowptr = torch.empty(self.ndofs + 1, dtype=torch.int64, device="cuda")
+        self._colidx = torch.empty(self.nnz, dtype=torch.int32, device="cuda")
+        capi.call("femb200_plan_scalar_csr", self._plan, _p(self._rowptr), _p(self._colidx), _stream())
+
+    @property
+    def rowptr(self) -> torch.Tensor:
+        if self._rowptr is None:
+            self._expand()
+        return self._rowptr
+
+    @property
+    def colidx(self) -> torch.Tensor:
+        if self._colidx is None:
+            self._expand()
+        return self._colidx
+
+    def block_csr(self):
+        """(brp int64[nnodes+1], bcol int32[nnz_blocks]) device tensors (copies)."""
+        brp = torch.empty(self.nnodes + 1, dtype=torch.int64, device="cuda")
+        bcol = torch.empty(self.nnz_blocks, dtype=torch.int32, device="cuda")
+        capi.call("femb200_plan_copy_block_csr", self._plan, _p(brp), _p(bcol), _stream())
+        return brp, bcol
+
+    def set_bcs(self, bcs):
+        m = merge_bcs(bcs, self.ndofs)
+        if m is None:
+            capi.call("femb200_plan_set_dirichlet", self._plan, None, _stream())
+            self.bc_dev = None
+        else:
+            self.bc_dev = to_device(m, np.uint8)
+            capi.call("femb200_plan_set_dirichlet", self._plan, _p(self.bc_dev), _stream())
+        self._bc_marker = m
+
+    def set_row_range(self, lo: int, hi: int):
+        capi.call("femb200_plan_set_row_range", self._plan, int(lo), int(hi))
+
+    # --- operator interface (mfem::Operator::Mult / PETSc MatMult) -------------
+    def mult(self, x: torch.Tensor, y: torch.Tensor | None = None) -> torch.Tensor:
+        if y is None:
+            y = torch.empty_like(x)
+        capi.call("femb200_spmv", self._plan, _p(self.values), _p(x), _p(y), _stream())
+        return y
+
+    Mult = mult
+
+    def diagonal(self) -> torch.Tensor:
+        d = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        capi.call("femb200_extract_diagonal", self._plan, _p(self.values), _p(d), _stream())
+        return d
+
+    def norms(self):
+        """(Frobenius norm, trace), one 16-byte device->host read."""
+        out = torch.empty(2, dtype=torch.float64, device="cuda")
+        capi.call("femb200_matrix_norms", self._plan, _p(self.values), _p(out), _stream())
+        f2, tr = out.cpu().tolist()
+        return float(np.sqrt(f2)), float(tr)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.values.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.ndofs, self.ndofs))
+
+
+def create_matrix(form: ElasticityForm) -> Matrix:
+    """Role of dolfinx::fem::petsc::create_matrix(*J_form) (F.cc:688): builds the
+    sparsity pattern once, on the device, from the cell->dof map alone."""
+    return Matrix(form)
+
+
+def assemble_matrix(A: Matrix, form: ElasticityForm | None = None, bcs=None, diag: float = 1.0) -> Matrix:
+    """Role of the setJ lambda (F.cc:847-862): MatZeroEntries + assemble_matrix(
+    set_block_fn(A, ADD_VALUES), J, bcs) + set_diagonal(..., 1.) + MatAssembly.
+    One write-once gather kernel + (if any) the Dirichlet kernel."""
+    form = A.form if form is None else form
+    if bcs is not None:
+        A.set_bcs(bcs)
+    capi.call("femb200_assemble_matrix", A.plan, _p(form.x), form.x_stride, _p(form.E), form.nu, _p(form.d),
+              _p(form.u), form.variant, _p(A.values), _stream())
+    if diag != 1.0 and A.bc_dev is not None:
+        capi.call("femb200_apply_dirichlet", A.plan, _p(A.values), float(diag), _stream())
+    return A
+
+
+def tabulate_tensor_batched(form: ElasticityForm, layout: int = capi.ROWMAJOR_INTERLEAVED,
+                            out: torch.Tensor | None = None) -> torch.Tensor:
+    """All element tangents in one launch: ncells x (2 nd)^2, ufcx layout
+    (row-major, interleaved dofs) by default."""
+    _require_cuda()
+    n = 2 * form.nd
+    if out is None:
+        out = torch.empty((form.ncells, n, n), dtype=torch.float64, device="cuda")
+    capi.call("femb200_tabulate_tensor_batched", form.etype, form.ncells, _p(out), _p(form.x), form.x_stride,
+              _p(form.xdofmap), _p(form.dofmap), _p(form.E), form.nu, _p(form.d), _p(form.u), form.variant,
+              int(layout), _stream())
+    return out
+
+
+def element_grad_batched(form: ElasticityForm) -> torch.Tensor:
+    """damIntegrator::AssembleElementGrad for every element (M.cc:639-916):
+    elmat column-major, dofs byNODES.  Returned so that out[e, c, r] = elmat(r, c),
+    i.e. out[e].T is the DenseMatrix."""
+    return tabulate_tensor_batched(form, capi.COLMAJOR_BYNODES)
+
+
+def tabulate_tensor(A: np.ndarray, w: np.ndarray, c: np.ndarray, coordinate_dofs: np.ndarray,
+                    entity_local_index=None, quadrature_permutation=None) -> None:
+    """Host shim with the ufcx signature for the P1 form J (batch of one cell):
+    `A` (6x6 row-major, interleaved dofs) is caller-owned and ACCUMULATED into,
+    as ffcx kernels do.  w = [d0,d1,d2, E, u0x,u0y,u1x,u1y,u2x,u2y] (coefficient
+    order of manual.py:19,22,30), c = [nu] (manual.py:23), coordinate_dofs 3x3
+    (xyz-padded, F.cc:213)."""
+    from .mesh import P1
+    cd = np.asarray(coordinate_dofs, dtype=np.float64).reshape(3, 3)
+    w = np.asarray(w, dtype=np.float64).ravel()
+    m = Mesh(P1, cd.copy(), np.array([[0, 1, 2]], dtype=np.int32), np.array([[0, 1, 2]], dtype=np.int32))
+    d = w[0:3] if np.any(w[0:3] != 0.0) else None
+    form = ElasticityForm(m, w[3:4], float(np.asarray(c).ravel()[0]), d=d, u=w[4:10])
+    Ae = tabulate_tensor_batched(form).cpu().numpy().reshape(-1)
+    Av = np.asarray(A).reshape(-1)
+    Av += Ae
+
+
+class PAOperator:
+    """Partial-assembly (matrix-free) operator: the AssemblePA / AddMultPA /
+    AssembleDiagonalPA role of an mfem BilinearFormIntegrator."""
+
+    def __init__(self, form: ElasticityForm, bcs=None, diag: float = 1.0):
+        _require_cuda()
+        self.form = form
+        self.ndofs = 2 * form.nnodes
+        self._pa = C.c_void_p()
+        self._bcs, self._diag = bcs, float(diag)
+        self.bc_dev = None
+        self.AssemblePA()
+
+    def AssemblePA(self):
+        f = self.form
+        if self._pa.value:
+            capi.lib().femb200_pa_destroy(self._pa)
+            self._pa = C.c_void_p()
+        capi.call("femb200_pa_create", f.etype, f.nnodes, f.ncells, _p(f.dofmap), _p(f.xdofmap), _p(f.x), f.x_stride,
+                  _p(f.E), f.nu, _stream(), C.byref(self._pa))
+        m = merge_bcs(self._bcs, self.ndofs)
+        if m is not None:
+            self.bc_dev = to_device(m, np.uint8)
+            capi.call("femb200_pa_set_dirichlet", self._pa, _p(self.bc_dev), self._diag, _stream())
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pa", None) is not None and self._pa.value:
+                capi.lib().femb200_pa_destroy(self._pa)
+                self._pa = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._pa
+
+    def mult(self, x: torch.Tensor, y: torch.Tensor | None = None) -> torch.Tensor:
+        if y is None:
+            y = torch.empty_like(x)
+        capi.call("femb200_pa_apply", self._pa, _p(x), _p(y), _stream())
+        return y
+
+    Mult = mult
+
+    def AddMultPA(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        y += self.mult(x)
+
+    def diagonal(self) -> torch.Tensor:
+        d = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        capi.call("femb200_pa_diagonal", self._pa, _p(d), _stream())
+        return d
+
+    AssembleDiagonalPA = diagonal
+
+
+class CGSolver:
+    """mfem::CGSolver surface (M.cc:1502,1525-1528): SetRelTol / SetAbsTol /
+    SetMaxIter / SetOperator / SetPreconditioner / Mult, zero initial guess
+    (iterative_mode = false).  The preconditioner is Jacobi or none."""
+
+    def __init__(self, rel_tol: float = 1e-12, abs_tol: float = 0.0, max_iter: int = 2000, check_every: int = 25):
+        self.rel_tol, self.abs_tol, self.max_iter = rel_tol, abs_tol, max_iter
+        self.check_every = check_every
+        self.op = None
+        self.dinv = None
+        self._work = None
+        self.iterations, self.final_norm, self.converged = 0, 0.0, False
+
+    def SetRelTol(self, v):
+        self.rel_tol = float(v)
+
+    def SetAbsTol(self, v):
+        self.abs_tol = float(v)
+
+    def SetMaxIter(self, v):
+        self.max_iter = int(v)
+
+    def SetOperator(self, op):
+        self.op = op
+        self.dinv = None
+
+    def SetPreconditioner(self, kind: str | None = "jacobi"):
+        if kind is None or kind == "none":
+            self.dinv = None
+            return
+        if kind != "jacobi":
+            raise ValueError("only the Jacobi preconditioner is available (BoomerAMG is third party, out of scope)")
+        diag = self.op.diagonal()
+        self.dinv = torch.empty_like(diag)
+        capi.call("femb200_jacobi_setup", diag.numel(), _p(diag), _p(self.dinv), _stream())
+
+    def GetNumIterations(self):
+        return self.iterations
+
+    def GetConverged(self):
+        return self.converged
+
+    def GetFinalNorm(self):
+        return self.final_norm
+
+    def Mult(self, b: torch.Tensor, x: torch.Tensor | None = None, fixed_iters: int = 0) -> torch.Tensor:
+        if self.op is None:
+            raise RuntimeError("CGSolver.Mult: SetOperator first")
+        n = b.numel()
+        if x is None:
+            x = torch.empty_like(b)
+        if self._work is None or self._work.numel() < 3 * n + 64:
+            self._work = torch.empty(3 * n + 64, dtype=torch.float64, device="cuda")
+        it, fn, cv = C.c_int(), C.c_double(), C.c_int()
+        if isinstance(self.op, Matrix):
+            plan, kind, opp, vals = self.op.plan, capi.OP_CSR, None, _p(self.op.values)
+        else:
+            plan, kind, opp, vals = None, capi.OP_PA, self.op.handle, None
+        capi.call("femb200_pcg", plan, kind, opp, vals, _p(b), _p(x), n, self.rel_tol, self.abs_tol, self.max_iter,
+                  _p(self.dinv), self.check_every, int(fixed_iters), _p(self._work), C.byref(it), C.byref(fn),
+                  C.byref(cv), _stream())
+        self.iterations, self.final_norm, self.converged = it.value, fn.value, bool(cv.value)
+        return x
+
+
+def lifted_rhs(A_nobc_mult, g: np.ndarray, marker: np.ndarray, f: np.ndarray | None = None) -> np.ndarray:
+    """b for the linear problem K u = f with u = g on the Dirichlet dofs, in the
+    row/column-eliminated form the assembled operator uses (the apply_lifting +
+    set_bc sequence of F.cc:822-836 specialised to a linear problem):
+    b = f - K_full g on free dofs, b = g on constrained dofs."""
+    n = marker.shape[0]
+    b = np.zeros(n) if f is None else np.array(f, dtype=np.float64).reshape(n).copy()
+    b -= A_nobc_mult(g)
+    b[marker != 0] = g[marker != 0]
+    return b

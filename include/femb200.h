@@ -1,0 +1,217 @@
+/*
+ * femb200.h -- C ABI of the B200-native mechanic2d hot path.
+ *
+ * Drop-in boundary for ONE path of SalzmanA/fem-libraries: per-element tangent
+ * integration -> CSR scatter-add -> sparse operator apply (assembled SpMV and
+ * matrix-free) inside a (Jacobi-)PCG solve.  Plain pointers and sizes only: no
+ * torch types, no C++ types, no exceptions cross this boundary.
+ *
+ * Conventions
+ *  - every `d_*` pointer is DEVICE memory (sm_100a) owned by the caller unless
+ *    stated otherwise; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *    default stream); all calls are asynchronous with respect to the host unless
+ *    they return host scalars (documented per function);
+ *  - every function returns 0 on success, non-zero on error; the message of the
+ *    last error of the calling thread is femb200_last_error();
+ *  - global dof = 2 * node + component (blocked, bs = 2), as the reference's
+ *    vector P1 space (M.cc:1107 byVDIM, F.cc:691-692);
+ *  - the CSR is the dolfinx convention: rows in dof order, columns ascending and
+ *    unique, structural pattern (exact zeros kept), Dirichlet rows/columns
+ *    zeroed in-pattern with `diag` on the diagonal (F.cc:847-862);
+ *    rowptr is int64, colidx int32, values float64.
+ *
+ * File:line citations are relative to the reference tree, with
+ *   M.cc = MFEM/mechanic2d/asym_elasto_damage_model.cc
+ *   F.cc = FEniCSx/mechanic2d/asym_elasto_damage_model.cc
+ *   manual.py = FEniCSx/mechanic2d/asym_manual.py
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMB200_VERSION 100
+
+/* element families (SURVEY.md 8c conventions) */
+#define FEMB200_P1 0 /* P1 triangle, 1-point rule  (the reference: M.cc:511-512, manual.py:10,97) */
+#define FEMB200_P2 1 /* P2 triangle, 3-point rule, basix dof order                                */
+#define FEMB200_Q2 2 /* Q2 quadrilateral, 3x3 Gauss, tensor dof order                              */
+
+/* element-matrix layouts */
+#define FEMB200_ROWMAJOR_INTERLEAVED 0 /* ufcx tabulate_tensor: A[(2a+i)*n + 2b+k]              */
+#define FEMB200_COLMAJOR_BYNODES 1     /* mfem::DenseMatrix elmat(i*nd+a, k*nd+b), M.cc:647,673  */
+
+/* tangent variants for damaged points (d > 0) */
+#define FEMB200_TANGENT_CLOSED 0 /* M.cc:766-871                              */
+#define FEMB200_TANGENT_AD 1     /* M.cc:100-155,752-765; admfem.hpp:672-699 */
+
+/* operator kinds for femb200_pcg */
+#define FEMB200_OP_CSR 0 /* assembled matrix of a plan         */
+#define FEMB200_OP_PA 1  /* partial-assembly matrix-free apply  */
+
+#define FEMB200_PRECOND_NONE 0
+#define FEMB200_PRECOND_JACOBI 1
+
+typedef struct femb200_plan femb200_plan; /* sparsity pattern + gather maps, owns device memory */
+typedef struct femb200_pa femb200_pa;     /* partial-assembly operator (quadrature data)        */
+
+int femb200_version(void);
+const char *femb200_last_error(void);
+/* host scalars: SM count and compute capability of the current device */
+int femb200_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------
+ * Element kernel.
+ * Replaces: the ffcx-generated `tabulate_tensor_integral_*` of form J
+ * (manual.py:102; ufcx signature, FEniCSx/mechanic2d/addprofile:6-9) called once
+ * per cell by dolfinx, and mfem `damIntegrator::AssembleElementGrad`
+ * (M.cc:639-916) called once per element by ParNonlinearForm::GetGradient.
+ * One launch tabulates `ncells` cells; d_A is ncells x (2nd)^2, overwritten.
+ *   d_x        nnodes x x_stride coordinates (x_stride 2, or 3 for xyz-padded
+ *              dolfinx geometry, F.cc:213)
+ *   d_xdofmap  ncells x nv geometry vertices;  d_dofmap ncells x nd scalar dofs
+ *   d_E        Young modulus per cell (DG0, manual.py:22);  nu constant (manual.py:23)
+ *   d_dnod     nodal damage (P1 field on the vertices, manual.py:19) or NULL (d = 0)
+ *   d_u        dof vector (2*nnodes) of the current iterate or NULL
+ * ------------------------------------------------------------------------ */
+int femb200_tabulate_tensor_batched(int etype, int64_t ncells, double *d_A, const double *d_x, int x_stride,
+                                    const int32_t *d_xdofmap, const int32_t *d_dofmap, const double *d_E, double nu,
+                                    const double *d_dnod, const double *d_u, int variant, int layout, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Sparsity pattern + gather maps.
+ * Replaces: dolfinx::fem::petsc::create_matrix(*J_form) (F.cc:688).
+ * Builds on the device, from the cell->dof map alone: node->cell lists, the
+ * node-block CSR (brp/bcol), and the per-(cell, local row) slot map used by the
+ * write-once gather assembly.  Synchronises the stream (returns sizes).
+ * d_dofmap / d_xdofmap must stay valid for the lifetime of the plan.
+ * ------------------------------------------------------------------------ */
+int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, const int32_t *d_dofmap, const int32_t *d_xdofmap,
+                        void *stream, femb200_plan **out);
+void femb200_plan_destroy(femb200_plan *plan);
+/* host scalars: sizes of the pattern */
+int femb200_plan_sizes(const femb200_plan *plan, int64_t *nnodes, int64_t *ncells, int64_t *nnz_blocks, int64_t *nnz,
+                       int32_t *max_block_degree, int64_t *device_bytes);
+/* device pointers owned by the plan: brp[nnodes+1] int64, bcol[nnz_blocks] int32 */
+int femb200_plan_block_csr(const femb200_plan *plan, const int64_t **d_brp, const int32_t **d_bcol);
+/* the same, copied into caller-allocated device arrays */
+int femb200_plan_copy_block_csr(const femb200_plan *plan, int64_t *d_brp, int32_t *d_bcol, void *stream);
+/* expand to the scalar CSR handed back across the boundary:
+ * d_rowptr[2*nnodes+1] int64, d_colidx[nnz] int32 (caller-allocated) */
+int femb200_plan_scalar_csr(const femb200_plan *plan, int64_t *d_rowptr, int32_t *d_colidx, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Assembly.
+ * Replaces: MatZeroEntries + dolfinx::fem::assemble_matrix(set_block_fn(A,
+ * ADD_VALUES), *J_form, {bcl, bcr}) + set_diagonal(..., 1.) + MatAssembly
+ * (the setJ lambda, F.cc:847-862); on the MFEM side AddDomainIntegrator /
+ * SetEssentialTrueDofs / ParNonlinearForm::GetGradient (M.cc:1489-1490,1546).
+ * d_values[nnz] is written once (no zero-fill needed, no atomics).
+ * ------------------------------------------------------------------------ */
+int femb200_assemble_matrix(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
+                            const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream);
+/* Dirichlet dofs: d_bc is a per-dof marker (uint8, 2*nnodes).  Builds the compact
+ * list of constrained nodes once (F.cc:640,664 create the DirichletBC objects
+ * once); pass NULL to clear.  Synchronises the stream. */
+int femb200_plan_set_dirichlet(femb200_plan *plan, const uint8_t *d_bc, void *stream);
+/* zero rows and columns of the marked dofs, put `diag` on their diagonal */
+int femb200_apply_dirichlet(const femb200_plan *plan, double *d_values, double diag, void *stream);
+/* Frobenius norm^2 and trace of the assembled matrix into d_out[2] (device) */
+int femb200_matrix_norms(const femb200_plan *plan, const double *d_values, double *d_out, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Assembled operator apply.
+ * Replaces: HypreParMatrix::Mult inside mfem::CGSolver (M.cc:1502,1525-1528) /
+ * PETSc MatMult inside KSP cg (F.cc:718-722).  d_values is the scalar-CSR value
+ * array of femb200_assemble_matrix; the kernel walks the node-block pattern.
+ * ------------------------------------------------------------------------ */
+int femb200_spmv(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, void *stream);
+/* y = A x and d_dot[0] = <x, y> in the same pass (deterministic reduction) */
+int femb200_spmv_dot(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, double *d_dot,
+                     void *stream);
+int femb200_extract_diagonal(const femb200_plan *plan, const double *d_values, double *d_diag, void *stream);
+/* d_dinv[i] = 1 / d_diag[i] (Jacobi preconditioner) */
+int femb200_jacobi_setup(int64_t n, const double *d_diag, double *d_dinv, void *stream);
+
+/* ------------------------------------------------------------------------
+ * (Jacobi-)PCG with mfem::CGSolver semantics (M.cc:1502,1525-1528; the PETSc
+ * side is KSP cg with the same tolerances, F.cc:718-722): zero initial guess,
+ * stop when <B r, r> <= max(rtol^2 <B r0, r0>, atol^2), at most maxit
+ * iterations.  The reference's preconditioner B is HYPRE BoomerAMG (third
+ * party, out of scope); here B = diag(A)^-1 (d_dinv) or the identity (NULL).
+ *   op_kind FEMB200_OP_CSR: plan + d_values;  FEMB200_OP_PA: op = femb200_pa*
+ *   n       number of dofs (2 * nnodes)
+ *   d_work  3*n + 64 doubles of scratch
+ * Device-resident scalars: the host polls convergence every `check_every`
+ * iterations only.  `fixed_iters` > 0 runs exactly that many iterations without
+ * any poll (benchmark mode).  Host scalars out: iterations, <B r, r>^(1/2),
+ * converged flag.  Synchronises the stream before returning.
+ * ------------------------------------------------------------------------ */
+int femb200_pcg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const double *d_b,
+                double *d_x, int64_t n, double rtol, double atol, int maxit, const double *d_dinv, int check_every,
+                int fixed_iters, double *d_work, int *iters, double *final_norm, int *converged, void *stream);
+
+/* CG building blocks, used one by one by the multi-GPU driver, which all-reduces
+ * the partial sums between a vector kernel and its scalar step (the analogue of
+ * the MPI_Allreduce inside CGSolver / KSP).  d_scal: 16 device doubles,
+ *   [0] nom [1] den [2] betanom [3] r0 [4] flag (0 run, 1 converged, 2 breakdown)
+ *   [5] iterations [6] last <B r, r> [7] rtol^2 [8] atol^2
+ *   [9] local <B r0, r0> [10] local <d, A d> [11] local <B r, r> [12] beta
+ * Every kernel is a no-op once the flag is set. */
+#define FEMB200_SC_FLAG 4
+#define FEMB200_SC_ITERS 5
+#define FEMB200_SC_FINAL 6
+#define FEMB200_SC_RED_NOM 9
+#define FEMB200_SC_RED_DEN 10
+#define FEMB200_SC_RED_BETA 11
+#define FEMB200_SC_COUNT 16
+int femb200_dot(int64_t n, const double *d_a, const double *d_b, double *d_out, void *stream);
+int femb200_cg_set_tolerances(double *d_scal, double rtol, double atol, void *stream);
+/* x = 0, r = b, d = B b, scal[9] = local <d, r> */
+int femb200_cg_init(int64_t n, const double *d_b, const double *d_dinv, double *d_x, double *d_r, double *d_dir,
+                    double *d_scal, void *stream);
+/* phase 0: after cg_init; 1: after cg_apply; 2: after cg_update_xr */
+int femb200_cg_scalar_step(double *d_scal, int phase, void *stream);
+/* Ad = A d, scal[10] = local <d, A d> */
+int femb200_cg_apply(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const double *d_dir,
+                     double *d_Ad, double *d_scal, void *stream);
+/* x += alpha d, r -= alpha Ad, scal[11] = local <B r, r> */
+int femb200_cg_update_xr(int64_t n, double *d_scal, const double *d_dir, const double *d_Ad, const double *d_dinv,
+                         double *d_x, double *d_r, void *stream);
+/* d = B r + beta d */
+int femb200_cg_update_dir(int64_t n, const double *d_scal, const double *d_r, const double *d_dinv, double *d_dir,
+                          void *stream);
+
+/* d_dst[k] = d_src[d_node_idx[k]] over nodes (2 doubles each): packs the interface
+ * dofs of a halo message before ncclSend (role of the dolfinx Scatterer behind
+ * VecGhostUpdate(INSERT, FORWARD), F.cc:865-866) */
+int femb200_gather(int64_t nnodes_out, const int32_t *d_node_idx, const double *d_src, double *d_dst, void *stream);
+/* restrict femb200_spmv / femb200_cg_apply to the node rows [row_lo, row_hi)
+ * (the rows this rank owns); rows outside are left untouched */
+int femb200_plan_set_row_range(femb200_plan *plan, int64_t row_lo, int64_t row_hi);
+
+/* ------------------------------------------------------------------------
+ * Partial assembly (matrix-free).
+ * Role of mfem BilinearFormIntegrator::AssemblePA / AddMultPA (not exercised by
+ * the reference, discussed at doc.tex:1445-1449): per-cell data once
+ * (pa_create = AssemblePA), then y = A x by element-local sum-factorised
+ * contractions (pa_apply = AddMultPA into a zeroed y).
+ * d_dofmap must stay valid for the lifetime of the operator.
+ * ------------------------------------------------------------------------ */
+int femb200_pa_create(int etype, int64_t nnodes, int64_t ncells, const int32_t *d_dofmap, const int32_t *d_xdofmap,
+                      const double *d_x, int x_stride, const double *d_E, double nu, void *stream, femb200_pa **out);
+void femb200_pa_destroy(femb200_pa *pa);
+/* per-dof marker (uint8, 2*nnodes) or NULL to clear; synchronises the stream */
+int femb200_pa_set_dirichlet(femb200_pa *pa, const uint8_t *d_bc, double diag, void *stream);
+/* y = A x (overwrites y) */
+int femb200_pa_apply(const femb200_pa *pa, const double *d_x, double *d_y, void *stream);
+int femb200_pa_diagonal(const femb200_pa *pa, double *d_diag, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB200_H */

@@ -1,0 +1,407 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the femb200 host layer)
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CSR row pointers / column indices bit-exact;
+matrix values <= 1e-12 relative Frobenius; CG solutions <= 1e-10 relative L2.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle  # noqa: E402
+from femb200 import mesh as fm  # noqa: E402
+
+TOL_VALUES = 1e-12  # relative Frobenius norm, FP64
+TOL_CG = 1e-10      # relative L2 of CG solutions at identical tolerance
+
+
+def fem():
+    from femb200 import fem as f
+    return f
+
+
+def relfro(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def make_mesh(kind, n, jit=0.2, seed=3, ny=None):
+    if kind == "P1":
+        m = fm.structured_triangles(n, ny, order=1)
+    elif kind == "P2":
+        m = fm.structured_triangles(n, ny, order=2)
+    else:
+        m = fm.structured_quads_q2(n, ny)
+    return fm.jitter(m, jit, seed=seed) if jit else m
+
+
+def square_mesh(square):
+    return fm.Mesh(fm.P1, square["x"], square["tri"], square["tri"])
+
+
+# ---------------------------------------------------------------------------
+# sparsity pattern: bit-exact
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [("P1", 7), ("P2", 9), ("Q2", 6), ("P2", 64)])
+def test_pattern_bit_exact(kind, n):
+    m = make_mesh(kind, n, ny=n + 2)
+    A = fem().create_matrix(fem().ElasticityForm(m, fm.young_per_cell(m.ncells)))
+    rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+    assert A.nnz == rowptr[-1]
+    assert A.rowptr.dtype.is_floating_point is False and A.rowptr.element_size() == 8
+    assert A.colidx.element_size() == 4
+    np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
+
+
+def test_pattern_square_msh_kat(square, kat):
+    m = square_mesh(square)
+    A = fem().create_matrix(fem().ElasticityForm(m, oracle.E_table()[square["tag"] % 200]))
+    assert A.nnz == kat["survey_values"]["nnz"] == 1520 and A.nnz_blocks == 380 and A.ndofs == 124
+    rowptr, colidx = oracle.build_pattern(62, square["tri"])
+    np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
+
+
+def test_pattern_single_cell_and_shuffled_cells():
+    # smallest mesh: one triangle
+    m = fm.Mesh(fm.P1, np.array([[0., 0.], [1., 0.], [0., 1.]]), np.array([[0, 1, 2]], dtype=np.int32),
+                np.array([[0, 1, 2]], dtype=np.int32))
+    A = fem().create_matrix(fem().ElasticityForm(m, np.array([1e7])))
+    rowptr, colidx = oracle.build_pattern(3, m.dofmap)
+    np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
+    # cell order must not matter for the structure
+    m2 = make_mesh("P2", 8)
+    perm = np.random.default_rng(0).permutation(m2.ncells)
+    ms = fm.Mesh(m2.etype, m2.x, m2.xdofmap[perm].copy(), m2.dofmap[perm].copy(), m2.nx, m2.ny)
+    A2 = fem().create_matrix(fem().ElasticityForm(ms, fm.young_per_cell(ms.ncells)))
+    rowptr, colidx = oracle.build_pattern(m2.nnodes, m2.dofmap)
+    np.testing.assert_array_equal(A2.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(A2.colidx.cpu().numpy(), colidx)
+
+
+# ---------------------------------------------------------------------------
+# element kernel (ufcx tabulate_tensor / mfem AssembleElementGrad)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["P1", "P2", "Q2"])
+@pytest.mark.parametrize("damage", [None, "closed", "ad"])
+def test_tabulate_batched(kind, damage):
+    m = make_mesh(kind, 9)
+    E = fm.young_per_cell(m.ncells)
+    rng = np.random.default_rng(2)
+    d = u = None
+    variant = oracle.TANGENT_CLOSED
+    if damage:
+        d = fm.damage_band(m)
+        u = 1e-3 * rng.standard_normal(m.ndofs)
+        variant = oracle.TANGENT_AD if damage == "ad" else oracle.TANGENT_CLOSED
+    form = fem().ElasticityForm(m, E, 0.3, d=d, u=u, variant=variant)
+    for layout in (oracle.LAYOUT_ROWMAJOR_INTERLEAVED, oracle.LAYOUT_COLMAJOR_BYNODES):
+        got = fem().tabulate_tensor_batched(form, layout).cpu().numpy()
+        want = oracle.tabulate_batch(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, d, u, variant, layout)
+        assert relfro(got, want) < TOL_VALUES
+        worst = max(relfro(got[e], want[e]) for e in range(m.ncells))
+        assert worst < 1e-11
+    if damage:
+        assert (d[m.xdofmap].mean(axis=1) > 0).sum() > 0  # the damaged branch is really exercised
+
+
+def test_tabulate_tensor_ufcx_shim(square):
+    """Per-cell call with the ufcx signature: A is caller-owned and accumulated into."""
+    x, tri = square["x"], square["tri"]
+    rng = np.random.default_rng(4)
+    for e in (0, 17, 97):
+        cd = np.zeros((3, 3))
+        cd[:, :2] = x[tri[e]]
+        w = np.concatenate([[0.0, 0.3, 0.6] if e == 17 else np.zeros(3), [6.1e7], 1e-3 * rng.standard_normal(6)])
+        A = np.full((6, 6), 2.5)
+        fem().tabulate_tensor(A, w, np.array([0.3]), cd)
+        want = np.full(36, 2.5)
+        oracle.tabulate_tensor_J_p1(w, np.array([0.3]), cd, A=want)
+        assert relfro(A.ravel(), want) < TOL_VALUES
+
+
+def test_element_grad_mfem_layout(square):
+    """elmat column-major, byNODES (M.cc:647,673) against the two MFEM-style oracle paths."""
+    m = square_mesh(square)
+    E = oracle.E_table()[square["tag"] % 200]
+    got = fem().element_grad_batched(fem().ElasticityForm(m, E)).cpu().numpy()
+    for e in range(0, 98, 9):
+        lam, mu = oracle.lame(E[e], 0.3)
+        want = oracle.p1_grad_mfem(square["x"][square["tri"][e]], lam, mu, blocks=(e % 2 == 1))
+        assert relfro(got[e].T, want) < TOL_VALUES
+
+
+# ---------------------------------------------------------------------------
+# assembly
+# ---------------------------------------------------------------------------
+def oracle_assemble(m, E, d=None, u=None, variant=0, bc=None):
+    rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+    vals = oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rowptr, colidx, dnod=d, u=u,
+                                  variant=variant, bc=bc)
+    return rowptr, colidx, vals
+
+
+def test_assembly_square_msh_known_answers(square, kat):
+    m = square_mesh(square)
+    E = oracle.E_table()[square["tag"] % 200]
+    f = fem()
+    A = f.assemble_matrix(f.create_matrix(f.ElasticityForm(m, E)))
+    sv = kat["survey_values"]
+    fro, tr = A.norms()
+    assert abs(fro - sv["fro_norm"]) / sv["fro_norm"] < 1e-13
+    assert abs(tr - sv["trace"]) / sv["trace"] < 1e-13
+    K = A.to_scipy()
+    u = np.zeros(124)
+    u[0::2], u[1::2] = 0.01 * square["x"][:, 0], -0.003 * square["x"][:, 1]
+    assert abs(u @ (K @ u) - sv["energy_closed_form"]) / sv["energy_closed_form"] < 1e-12
+    _, _, want = oracle_assemble(m, E)
+    assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
+@pytest.mark.parametrize("kind,n", [("P1", 11), ("P2", 10), ("Q2", 8), ("P2", 48)])
+@pytest.mark.parametrize("with_bc", [False, True])
+def test_assembly_linear(kind, n, with_bc, monkeypatch):
+    m = make_mesh(kind, n, ny=n + 3)
+    E = fm.young_per_cell(m.ncells)
+    f = fem()
+    bc = fm.dirichlet_markers(m)[0] if with_bc else None
+    _, _, want = oracle_assemble(m, E, bc=bc)
+    form = f.ElasticityForm(m, E)
+    A = f.create_matrix(form)
+    f.assemble_matrix(A, form, bcs=[f.DirichletBC(bc)] if with_bc else None)
+    got = A.values.cpu().numpy()
+    assert relfro(got, want) < TOL_VALUES
+    if with_bc:  # zeros and the unit diagonal must be exact, not approximate
+        np.testing.assert_array_equal(got[want == 0.0], 0.0)
+        np.testing.assert_array_equal(got[want == 1.0], 1.0)
+    if kind in ("P1", "P2"):  # the generic per-quadrature-point path must give the same matrix
+        monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
+        f.assemble_matrix(A, form)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
+@pytest.mark.parametrize("kind", ["P1", "P2", "Q2"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_assembly_damaged_tangent(kind, variant):
+    """Config 5: damaged tangent (closed form M.cc:736-872, AD M.cc:752-765), values-only
+    reassembly on a frozen pattern."""
+    m = make_mesh(kind, 12)
+    E = fm.young_per_cell(m.ncells)
+    d = fm.damage_band(m)
+    rng = np.random.default_rng(9)
+    f = fem()
+    form = f.ElasticityForm(m, E, 0.3, d=d, variant=variant)
+    A = f.create_matrix(form)
+    bc = fm.dirichlet_markers(m)[0]
+    A.set_bcs([f.DirichletBC(bc)])
+    for it in range(3):  # repeated reassembly with a new iterate
+        u = 1e-3 * rng.standard_normal(m.ndofs) * (it + 1)
+        form.set_u(u)
+        f.assemble_matrix(A, form)
+        _, _, want = oracle_assemble(m, E, d=d, u=u, variant=variant, bc=bc)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
+def test_assembly_tile_sizes(monkeypatch):
+    """Every staging-tile height must produce the same matrix (ragged last tile included)."""
+    m = make_mesh("P2", 13, ny=7)
+    E = fm.young_per_cell(m.ncells)
+    _, _, want = oracle_assemble(m, E)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.create_matrix(form)
+    for R in (32, 64, 96, 128, 192, 256):
+        monkeypatch.setenv("FEMB200_TILE_R", str(R))
+        A.values.fill_(float("nan"))
+        f.assemble_matrix(A, form)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
+# ---------------------------------------------------------------------------
+# operator apply: assembled SpMV and matrix-free
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [("P1", 9), ("P2", 17), ("Q2", 11)])
+def test_spmv_and_pa_apply(kind, n):
+    import torch
+    m = make_mesh(kind, n, ny=n + 1)
+    E = fm.young_per_cell(m.ncells)
+    f = fem()
+    bc = fm.dirichlet_markers(m)[0]
+    rng = np.random.default_rng(12)
+    v = rng.standard_normal(m.ndofs)
+    vd = f.to_device(v, np.float64)
+    for marker in (None, bc):
+        rowptr, colidx, vals = oracle_assemble(m, E, bc=marker)
+        want = oracle.spmv(rowptr, colidx, vals, v)
+        bcs = None if marker is None else [f.DirichletBC(marker)]
+        form = f.ElasticityForm(m, E)
+        A = f.assemble_matrix(f.create_matrix(form), form, bcs=bcs)
+        y = A.mult(vd).cpu().numpy()
+        assert relfro(y, want) < 1e-13
+        # fused <x, y>
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        y2 = torch.empty_like(vd)
+        f.capi.call("femb200_spmv_dot", A.plan, f._p(A.values), f._p(vd), f._p(y2), f._p(out), f._stream())
+        assert abs(out.item() - v @ want) <= 1e-12 * np.abs(v * want).sum()
+        np.testing.assert_array_equal(y2.cpu().numpy(), y)
+        # diagonal
+        K = sp.csr_matrix((vals, colidx, rowptr), shape=(m.ndofs, m.ndofs))
+        np.testing.assert_allclose(A.diagonal().cpu().numpy(), K.diagonal(), rtol=1e-12)
+        # matrix-free
+        pa = f.PAOperator(form, bcs=bcs)
+        ypa = pa.mult(vd).cpu().numpy()
+        want_mf = oracle.apply_matrix_free(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, v, bc=marker)
+        assert relfro(ypa, want_mf) < 1e-13
+        assert relfro(ypa, y) < TOL_VALUES  # assembled SpMV == matrix-free apply
+        np.testing.assert_allclose(pa.diagonal().cpu().numpy(), K.diagonal(), rtol=1e-11)
+
+
+# ---------------------------------------------------------------------------
+# CG
+# ---------------------------------------------------------------------------
+def linear_problem(m, E):
+    bc, g = fm.dirichlet_markers(m)
+    rowptr, colidx, full = oracle_assemble(m, E)
+    _, _, vals = oracle_assemble(m, E, bc=bc)
+    b = -oracle.spmv(rowptr, colidx, full, g)
+    b[bc != 0] = g[bc != 0]
+    return bc, g, rowptr, colidx, vals, b
+
+
+@pytest.mark.parametrize("kind,n", [("P1", 12), ("P2", 16), ("Q2", 10)])
+@pytest.mark.parametrize("precond", ["jacobi", None])
+def test_pcg_against_oracle(kind, n, precond):
+    m = make_mesh(kind, n)
+    E = fm.young_per_cell(m.ncells)
+    bc, g, rowptr, colidx, vals, b = linear_problem(m, E)
+    want, it_o, fn_o, conv_o = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=4000, jacobi=precond == "jacobi")
+    assert conv_o
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form, bcs=[f.DirichletBC(bc)])
+    for op in (A, f.PAOperator(form, bcs=[f.DirichletBC(bc)])):
+        cg = f.CGSolver()
+        cg.SetRelTol(1e-12)
+        cg.SetMaxIter(4000)
+        cg.SetOperator(op)
+        cg.SetPreconditioner(precond)
+        x = cg.Mult(f.to_device(b, np.float64)).cpu().numpy()
+        assert cg.GetConverged()
+        assert relfro(x, want) < TOL_CG
+        assert abs(cg.GetNumIterations() - it_o) <= max(3, it_o // 50)
+        K = sp.csr_matrix((vals, colidx, rowptr), shape=(m.ndofs, m.ndofs))
+        ref = sp.linalg.spsolve(K.tocsc(), b)
+        assert relfro(x, ref) < 1e-8
+
+
+def test_pcg_edge_cases():
+    m = make_mesh("P2", 6)
+    E = fm.young_per_cell(m.ncells)
+    bc, g, rowptr, colidx, vals, b = linear_problem(m, E)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form, bcs=[f.DirichletBC(bc)])
+    cg = f.CGSolver(rel_tol=1e-12, max_iter=5)
+    cg.SetOperator(A)
+    cg.SetPreconditioner("jacobi")
+    bd = f.to_device(b, np.float64)
+    x5 = cg.Mult(bd).cpu().numpy()
+    want5, it5, fn5, conv5 = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=5, jacobi=True)
+    assert (not cg.GetConverged()) and (not conv5) and cg.GetNumIterations() == it5 == 5
+    assert relfro(x5, want5) < 1e-12
+    assert abs(cg.GetFinalNorm() - fn5) < 1e-10 * fn5
+    # zero right-hand side: converged at iteration 0, x = 0
+    cg.SetMaxIter(100)
+    x0 = cg.Mult(f.to_device(np.zeros_like(b), np.float64)).cpu().numpy()
+    assert cg.GetConverged() and cg.GetNumIterations() == 0 and not x0.any()
+    # fixed-iteration (benchmark) mode runs exactly that many iterations
+    x7 = cg.Mult(bd, fixed_iters=7).cpu().numpy()
+    want7, _, _, _ = oracle.pcg(rowptr, colidx, vals, b, rtol=0.0, maxit=7, jacobi=True)
+    assert cg.GetNumIterations() == 7 and relfro(x7, want7) < 1e-12
+    # convergence poll interval must not change the answer
+    cg2 = f.CGSolver(rel_tol=1e-12, max_iter=2000, check_every=1)
+    cg2.SetOperator(A)
+    cg2.SetPreconditioner("jacobi")
+    cg3 = f.CGSolver(rel_tol=1e-12, max_iter=2000, check_every=1000)
+    cg3.SetOperator(A)
+    cg3.SetPreconditioner("jacobi")
+    xa, xb = cg2.Mult(bd).cpu().numpy(), cg3.Mult(bd).cpu().numpy()
+    np.testing.assert_array_equal(xa, xb)  # deterministic reductions: bit-identical
+    assert cg2.GetNumIterations() == cg3.GetNumIterations()
+
+
+def test_error_behaviour():
+    """No exceptions cross the C ABI: status + femb200_last_error, raised here as Femb200Error."""
+    import ctypes as C
+    f = fem()
+    m = make_mesh("P2", 4)
+    form = f.ElasticityForm(m, fm.young_per_cell(m.ncells))
+    plan = C.c_void_p()
+    with pytest.raises(f.capi.Femb200Error, match="unknown element family"):
+        f.capi.call("femb200_plan_create", 7, m.nnodes, m.ncells, f._p(form.dofmap), f._p(form.xdofmap), f._stream(),
+                    C.byref(plan))
+    with pytest.raises(f.capi.Femb200Error, match="empty mesh"):
+        f.capi.call("femb200_plan_create", 1, 0, 0, f._p(form.dofmap), f._p(form.xdofmap), f._stream(), C.byref(plan))
+    A = f.create_matrix(form)
+    with pytest.raises(f.capi.Femb200Error, match="x_stride"):
+        f.capi.call("femb200_assemble_matrix", A.plan, f._p(form.x), 5, f._p(form.E), 0.3, None, None, 0,
+                    f._p(A.values), f._stream())
+    with pytest.raises(f.capi.Femb200Error, match="alias"):
+        v = f.to_device(np.ones(m.ndofs), np.float64)
+        f.capi.call("femb200_spmv", A.plan, f._p(A.values), f._p(v), f._p(v), f._stream())
+    with pytest.raises(ValueError):
+        f.ElasticityForm(m, np.ones(3))
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (BASELINE config 2: P2, n = 1448, 4.19 M elements)
+# ---------------------------------------------------------------------------
+@pytest.mark.skipif(os.environ.get("FEMB200_SKIP_LARGE") == "1", reason="large case disabled")
+def test_full_size_properties():
+    import torch
+    n = 1448
+    m = fm.jitter(fm.structured_triangles(n, order=2), 0.2, seed=1234)
+    assert m.ncells == 4193408 and m.ndofs == 16785218
+    E = fm.young_per_cell(m.ncells)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.create_matrix(form)
+    assert A.nnz == 385886212  # 4 (46 n^2 + 16 n + 1)
+    f.assemble_matrix(A, form)
+    fro, tr = A.norms()
+    # rigid-body null space
+    x = m.x
+    for t in (np.tile([1., 0.], m.nnodes), np.tile([0., 1.], m.nnodes),
+              np.stack([-x[:, 1], x[:, 0]], axis=1).ravel()):
+        y = A.mult(f.to_device(t, np.float64))
+        assert y.abs().max().item() < 1e-12 * fro
+    # symmetry through two random vectors, and SpMV == matrix-free apply
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(m.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(m.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    Aa, Ab = A.mult(a), A.mult(b)
+    assert abs((b @ Aa - a @ Ab).item()) < 1e-11 * abs((b @ Aa).item()) + 1e-6 * fro * 1e-12
+    pa = f.PAOperator(form)
+    ya = pa.mult(a)
+    assert ((ya - Aa).norm() / Aa.norm()).item() < TOL_VALUES
+    # trace == sum of the diagonal, linearity of assembly in E
+    assert abs(A.diagonal().sum().item() - tr) < 1e-12 * abs(tr)
+    v1 = A.values.clone()
+    form.set_E(2.0 * E)
+    f.assemble_matrix(A, form)
+    assert ((A.values - 2.0 * v1).norm() / v1.norm()).item() < 1e-14
+    # a window of rows against the oracle (cells of the first 6 cell rows)
+    nrows_nodes = 5 * (2 * n + 1)
+    sub_cells = 2 * n * 6
+    sub = fm.Mesh(m.etype, m.x[:13 * (2 * n + 1)], m.xdofmap[:sub_cells], m.dofmap[:sub_cells])
+    rowptr, colidx, want = oracle_assemble(sub, E[:sub_cells])
+    hi = int(rowptr[2 * nrows_nodes])
+    got = (0.5 * A.values[:hi]).cpu().numpy()
+    np.testing.assert_array_equal(A.rowptr[:2 * nrows_nodes + 1].cpu().numpy(), rowptr[:2 * nrows_nodes + 1])
+    np.testing.assert_array_equal(A.colidx[:hi].cpu().numpy(), colidx[:hi])
+    assert relfro(got, want[:hi]) < TOL_VALUES
