@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of the mechanic2d elasticity examples on N B200s.
+
+Workload (BASELINE.json configs[1]): P2 triangles, structured n x n cells split
+by the right diagonal (n = 1448 -> 4 193 408 elements, 16 785 218 dofs, 385 886 212
+CSR non-zeros per GPU), jittered vertices, the reference's 200-value Young-modulus
+table, nu = 0.3, Dirichlet x = 0 / x = 1.  At N > 1 every rank owns an n x n strip of
+a [0,1] x [0,N] domain (weak scaling), assembles it without communication (one
+ghost row of cells) and runs CG with NCCL halo exchange + all-reduce.
+
+One timed STEP = one full matrix assembly (element integration + scatter into
+the CSR + Dirichlet rows/cols), the setJ lambda of the reference (F.cc:847-862).
+`value` = dofs assembled per second over all ranks (GDOF/s).  The same run also
+times the operator apply inside CG (SpMV alone and whole PCG iterations) and
+reports them, with their own roofline, under "cg".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "fem-libraries_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "assembly GDOF/s (P2 elasticity, CSR) with CG SpMV GB/s alongside"
+UNIT = "GDOF/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# algorithmic bytes
+# ---------------------------------------------------------------------------
+def assembly_bytes(nnz: int, ncells: int, nnodes: int) -> int:
+    """write nnz values once + read connectivity (6 x int32), E (8 B) per cell and
+    coordinates (16 B) per node: ~808 B per P2 element."""
+    return 8 * nnz + ncells * (6 * 4 + 8) + nnodes * 16
+
+
+def spmv_bytes(nnz_blocks: int, nnodes: int) -> int:
+    """block pattern: 32 B of values + 4 B column index per 2x2 block; per node 8 B of
+    row pointer, 16 B of x read, 16 B of y written."""
+    return 36 * nnz_blocks + nnodes * (8 + 16 + 16)
+
+
+def cg_iter_bytes(nnz_blocks: int, nnodes: int, jacobi: bool = True) -> int:
+    """SpMV + update_xr (read d, Ad, x, r, dinv; write x, r) + update_dir (read r, dinv,
+    d; write d), 16 B per node per vector pass."""
+    passes = (7 if jacobi else 6) + (4 if jacobi else 3)
+    return spmv_bytes(nnz_blocks, nnodes) + passes * 16 * nnodes
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(n: int, rank: int, world: int):
+    """Rank-local mesh (with its ghost layers at N > 1), materials and Dirichlet data."""
+    from femb200 import mesh as fm
+    if world == 1:
+        m = fm.jitter(fm.structured_triangles(n, order=2), 0.2, seed=1234)
+        E = fm.young_per_cell(m.ncells)
+        bc, g = fm.dirichlet_markers(m)
+        return m, E, bc, g, None
+    from femb200 import dist
+    part = dist.strip_partition(n, n * world, order=2, rank=rank, world=world, jitter_amp=0.2, seed=1234)
+    return part.mesh, part.E, part.bc, part.g, part
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference (oracle) on the host cores
+# ---------------------------------------------------------------------------
+def cpu_reference(n_sample: int, steps: int, warmup: int, spmv_reps: int = 5):
+    from oracle import oracle
+    from femb200 import mesh as fm
+    m = fm.jitter(fm.structured_triangles(n_sample, order=2), 0.2, seed=1234)
+    E = fm.young_per_cell(m.ncells)
+    bc, _ = fm.dirichlet_markers(m)
+    rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+    vals = np.empty(int(rowptr[-1]))
+    nt_all = oracle.num_threads()
+    best = None
+    for nt in sorted({1, nt_all}):
+        ts = []
+        for i in range(warmup + steps):
+            t = time.perf_counter()
+            oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rowptr, colidx, bc=bc, nthreads=nt,
+                                   values=vals)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t)
+        t_asm = float(np.mean(ts))
+        v = np.random.default_rng(0).standard_normal(m.ndofs)
+        y = np.empty(m.ndofs)
+        oracle.spmv(rowptr, colidx, vals, v, nthreads=nt, y=y)
+        t = time.perf_counter()
+        for _ in range(spmv_reps):
+            oracle.spmv(rowptr, colidx, vals, v, nthreads=nt, y=y)
+        t_spmv = (time.perf_counter() - t) / spmv_reps
+        rec = {"threads": nt, "assembly_s": t_asm, "assembly_gdofs": m.ndofs / t_asm / 1e9, "spmv_s": t_spmv,
+               "spmv_gbs": (12 * int(rowptr[-1]) + 24 * m.ndofs + 8) / t_spmv / 1e9,
+               "spmv_gdofs": m.ndofs / t_spmv / 1e9}
+        if best is None or rec["assembly_gdofs"] > best["assembly_gdofs"]:
+            best = rec
+    best["sample"] = (f"P2 n={n_sample} ({m.ncells} elements, {m.ndofs} dofs) of the n=1448 workload, "
+                      f"{steps} assemblies after {warmup} warm-ups, oracle/fem_oracle.c -O3 OpenMP")
+    best["ms_per_step"] = 1e3 * best["assembly_s"]
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.cpu_n, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["assembly_gdofs"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "P2 triangles, structured n=1448 (4 193 408 elements), assembly + CG SpMV",
+                       "timed_on": r["sample"]},
+            "cpu_baseline": {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                             "sample": r["sample"]},
+            "cg": {"spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"]},
+            "e2e": {"value": r["assembly_gdofs"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from femb200 import fem
+    K, W, n = args.steps, max(args.warmup, 0), args.n
+
+    m, E, bc, g, part = build_problem(n, rank, world)
+    form = fem.ElasticityForm(m, E, 0.3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    A = fem.create_matrix(form)
+    A.set_bcs([fem.DirichletBC(bc, g)])
+    torch.cuda.synchronize()
+    pattern_ms = 1e3 * (time.perf_counter() - t0)
+    owned_nodes = m.nnodes if part is None else part.n_owned
+    owned_dofs = 2 * owned_nodes
+    owned_cells = m.ncells if part is None else part.n_owned_cells
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def maxtime(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumint(v: int) -> int:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device="cuda")
+        td.all_reduce(t)
+        return int(t.item())
+
+    def timed(fn, k):
+        """k calls bracketed by barrier + synchronize; device time by CUDA events on the
+        launching stream; returns (total ms max over ranks, per-call ms list of this rank)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        e.record()
+        barrier()
+        return maxtime(s.elapsed_time(e)), [a.elapsed_time(b) for a, b in evs]
+
+    # ---- assembly: the timed step -----------------------------------------
+    def step():
+        fem.assemble_matrix(A, form)
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, per_call = timed(step, K)
+    asm_ms = total_ms / K
+    kernel_ms = float(np.mean(per_call))
+    total_dofs = sumint(owned_dofs)
+    total_cells = sumint(owned_cells)
+    value = total_dofs / (asm_ms * 1e-3) / 1e9
+
+    # ---- operator apply inside CG ------------------------------------------
+    if part is None:
+        bvec = fem.to_device(np.where(bc != 0, g, 1.0), np.float64)
+        cg = fem.CGSolver(rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters)
+        cg.SetOperator(A)
+        cg.SetPreconditioner("jacobi")
+        xsol = torch.empty_like(bvec)
+        ytmp = torch.empty_like(bvec)
+
+        def cg_run():
+            cg.Mult(bvec, xsol, fixed_iters=args.cg_iters)
+
+        def spmv_run():
+            A.mult(bvec, ytmp)
+    else:
+        from femb200 import dist
+        dcg = dist.DistCG(A, part, rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters)
+        bvec = fem.to_device(np.where(bc != 0, g, 1.0), np.float64)
+        xsol = torch.zeros_like(bvec)
+        ytmp = torch.empty_like(bvec)
+
+        def cg_run():
+            dcg.solve(bvec, xsol, fixed_iters=args.cg_iters)
+
+        def spmv_run():
+            dcg.halo.forward(bvec)
+            A.mult(bvec, ytmp)
+
+    for _ in range(max(1, min(W, 2))):
+        cg_run()
+        spmv_run()
+    kc = max(1, min(K, 5))
+    cg_total, _ = timed(cg_run, kc)
+    # one PCG call = setup (init + first apply) + cg_iters iterations: count cg_iters + 1 applies
+    cg_iter_ms = cg_total / kc / (args.cg_iters + 1)
+    ks = max(K, 10)
+    spmv_total, spmv_calls = timed(spmv_run, ks)
+    spmv_ms = spmv_total / ks
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: host buffers through the public API -------------------
+    hx = torch.from_numpy(np.ascontiguousarray(m.x)).pin_memory()
+    hE = torch.from_numpy(np.ascontiguousarray(E)).pin_memory()
+    hout = torch.empty(2, dtype=torch.float64).pin_memory()
+    dout = torch.empty(2, dtype=torch.float64, device="cuda")
+
+    def e2e_step():
+        form.x.copy_(hx, non_blocking=True)            # H2D: coordinates of this step
+        form.E.copy_(hE, non_blocking=True)            # H2D: material field of this step
+        fem.assemble_matrix(A, form)
+        fem.capi.call("femb200_matrix_norms", A.plan, fem._p(A.values), fem._p(dout), fem._stream())
+        hout.copy_(dout, non_blocking=True)            # D2H: (|K|_F^2, trace K)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(1, min(W, 2))):
+        e2e_step()
+    e2e_total, _ = timed(e2e_step, K)
+    e2e_ms = e2e_total / K
+    e2e_value = total_dofs / (e2e_ms * 1e-3) / 1e9
+    h2d = hx.numel() * 8 + hE.numel() * 8
+    fro, tr = float(np.sqrt(hout[0].item())), float(hout[1].item())
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)
+    s_bytes = spmv_bytes(A.nnz_blocks if part is None else part.owned_nnz_blocks(A), owned_nodes)
+    c_bytes = cg_iter_bytes(A.nnz_blocks if part is None else part.owned_nnz_blocks(A), owned_nodes)
+    a_gbs = a_bytes / (kernel_ms * 1e-3) / 1e9
+    s_gbs = s_bytes / (float(np.mean(spmv_calls)) * 1e-3) / 1e9
+    c_gbs = c_bytes / (cg_iter_ms * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": asm_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"P2 triangles, structured n={n} per GPU ({m.ncells} local elements incl. ghost row), "
+                               "jittered, E = reference 200-value table, nu = 0.3; step = full CSR assembly + Dirichlet",
+                   "elements": total_cells, "dofs": total_dofs, "nnz_per_gpu": A.nnz,
+                   "l2": "inputs + outputs per step (3.5 GB) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"strips x{world}" if world > 1 else "single GPU", "cg_iters": args.cg_iters,
+                   "pattern_build_ms": pattern_ms},
+        "roofline": {"kernel": "assemble_kernel<P2,fast> (+ dirichlet_kernel)", "bound": "hbm", "achieved": a_gbs,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a_gbs / peak,
+                     "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": kernel_ms,
+                     "traffic": traffic_from_profile("assemble")},
+        "cg": {"spmv_ms": spmv_ms, "spmv_gbs": s_gbs, "spmv_frac": s_gbs / peak, "spmv_gdofs": owned_dofs * world / (spmv_ms * 1e-3) / 1e9,
+               "spmv_algorithmic_bytes": s_bytes, "spmv_traffic": traffic_from_profile("spmv"),
+               "cg_iter_ms": cg_iter_ms, "cg_iter_gbs": c_gbs, "cg_iter_frac": c_gbs / peak,
+               "cg_iter_gdofs": total_dofs / (cg_iter_ms * 1e-3) / 1e9, "precond": "jacobi", "iters": args.cg_iters},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 16, "what": "pinned host x,E -> device, assemble_matrix(A, form, bcs), "
+                                                  "matrix_norms, 16-byte read back", "fro": fro, "trace": tr},
+        "gpu_launches": 2 * K,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(args.cpu_n, 3, 1)
+        line["cpu_baseline"] = {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                "sample": r["sample"], "spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def traffic_from_profile(which: str):
+    """dram bytes per launch from the committed ncu --set full summary, if present."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(which)
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1448, help="cells per side per GPU (1448 -> 4.19 M P2 triangles)")
+    ap.add_argument("--cg-iters", type=int, default=25)
+    ap.add_argument("--cpu-n", type=int, default=512, help="cells per side of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

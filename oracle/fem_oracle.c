@@ -760,7 +760,7 @@ int64_t orc_build_pattern(int64_t nnodes, int64_t ncells, int nd, const int32_t 
 /* x: nnodes x 2; xdofmap: ncells x nv; dofmap: ncells x nd; E: ncells;      */
 /* dnod: damage per node (P1 field on the geometry vertices) or NULL;        */
 /* u: 2*nnodes dof vector or NULL; bc: per-dof marker or NULL.               */
-/* nthreads > 1 uses OpenMP over cells with atomic adds.                     */
+/* nthreads > 1: row-block ownership per thread (domain decomposition).       */
 /* ------------------------------------------------------------------------ */
 static inline int64_t find_col(const int32_t *colidx, int64_t lo, int64_t hi, int32_t c)
 {
@@ -784,59 +784,72 @@ void orc_assemble_matrix(int etype, int64_t ncells, int64_t nnodes, const double
    const int64_t nnz = rowptr[2 * nnodes];
    memset(values, 0, (size_t)nnz * sizeof(double)); /* MatZeroEntries, F.cc:850 */
    if (nthreads < 1) nthreads = 1;
-#pragma omp parallel for schedule(static) num_threads(nthreads)
-   for (int64_t e = 0; e < ncells; ++e)
+   /* nthreads > 1: the reference parallelises by domain decomposition (one MPI rank
+    * per mesh partition, doc.tex:393-464): thread t owns a contiguous block of
+    * node rows and integrates every cell touching them (interface cells are
+    * integrated by both neighbours, as ghost cells would be); no atomics. */
+#pragma omp parallel num_threads(nthreads)
    {
-      double xv[8], dv[4], ue[18], A[18 * 18];
-      for (int v = 0; v < nv; ++v)
+#ifdef _OPENMP
+      const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+      const int tid = 0, nt = 1;
+#endif
+      const int64_t node_lo = nnodes * tid / nt, node_hi = nnodes * (tid + 1) / nt;
+      for (int64_t e = 0; e < ncells; ++e)
       {
-         const int32_t g = xdofmap[e * nv + v];
-         xv[2 * v] = x[2 * (int64_t)g];
-         xv[2 * v + 1] = x[2 * (int64_t)g + 1];
-         if (dnod) dv[v] = dnod[g];
-      }
-      if (u)
+         int mine = 0;
          for (int a = 0; a < nd; ++a)
          {
             const int64_t g = dofmap[e * nd + a];
-            ue[2 * a] = u[2 * g];
-            ue[2 * a + 1] = u[2 * g + 1];
+            if (g >= node_lo && g < node_hi) mine = 1;
          }
-      double lam, mu;
-      orc_lame(E[e], nu, &lam, &mu);
-      for (int i = 0; i < n * n; ++i) A[i] = 0.;
-      orc_element_grad(etype, xv, lam, mu, dnod ? dv : NULL, u ? ue : NULL, variant, ORC_LAYOUT_ROWMAJOR_INTERLEAVED,
-                       A);
-      if (bc) /* dolfinx assemble_matrix zeroes BC rows and columns of A_e, F.cc:852 */
-         for (int a = 0; a < nd; ++a)
-            for (int i = 0; i < 2; ++i)
-               if (bc[2 * (int64_t)dofmap[e * nd + a] + i])
-               {
-                  const int r = 2 * a + i;
-                  for (int c = 0; c < n; ++c) A[r * n + c] = A[c * n + r] = 0.;
-               }
-      for (int a = 0; a < nd; ++a)
-         for (int i = 0; i < 2; ++i)
+         if (!mine) continue;
+         double xv[8], dv[4], ue[18], A[18 * 18];
+         for (int v = 0; v < nv; ++v)
          {
-            const int64_t row = 2 * (int64_t)dofmap[e * nd + a] + i;
-            const int64_t lo = rowptr[row], hi = rowptr[row + 1];
-            for (int b = 0; b < nd; ++b)
+            const int32_t g = xdofmap[e * nv + v];
+            xv[2 * v] = x[2 * (int64_t)g];
+            xv[2 * v + 1] = x[2 * (int64_t)g + 1];
+            if (dnod) dv[v] = dnod[g];
+         }
+         if (u)
+            for (int a = 0; a < nd; ++a)
             {
-               const int64_t p = find_col(colidx, lo, hi, 2 * dofmap[e * nd + b]);
-               if (nthreads > 1)
+               const int64_t g = dofmap[e * nd + a];
+               ue[2 * a] = u[2 * g];
+               ue[2 * a + 1] = u[2 * g + 1];
+            }
+         double lam, mu;
+         orc_lame(E[e], nu, &lam, &mu);
+         for (int i = 0; i < n * n; ++i) A[i] = 0.;
+         orc_element_grad(etype, xv, lam, mu, dnod ? dv : NULL, u ? ue : NULL, variant,
+                          ORC_LAYOUT_ROWMAJOR_INTERLEAVED, A);
+         if (bc) /* dolfinx assemble_matrix zeroes BC rows and columns of A_e, F.cc:852 */
+            for (int a = 0; a < nd; ++a)
+               for (int i = 0; i < 2; ++i)
+                  if (bc[2 * (int64_t)dofmap[e * nd + a] + i])
+                  {
+                     const int r = 2 * a + i;
+                     for (int c = 0; c < n; ++c) A[r * n + c] = A[c * n + r] = 0.;
+                  }
+         for (int a = 0; a < nd; ++a)
+         {
+            const int64_t ga = dofmap[e * nd + a];
+            if (ga < node_lo || ga >= node_hi) continue;
+            for (int i = 0; i < 2; ++i)
+            {
+               const int64_t row = 2 * ga + i;
+               const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+               for (int b = 0; b < nd; ++b)
                {
-#pragma omp atomic
-                  values[p] += A[(2 * a + i) * n + 2 * b];
-#pragma omp atomic
-                  values[p + 1] += A[(2 * a + i) * n + 2 * b + 1];
-               }
-               else
-               {
+                  const int64_t p = find_col(colidx, lo, hi, 2 * dofmap[e * nd + b]);
                   values[p] += A[(2 * a + i) * n + 2 * b];
                   values[p + 1] += A[(2 * a + i) * n + 2 * b + 1];
                }
             }
          }
+      }
    }
    if (bc) /* set_diagonal(..., 1.) with INSERT_VALUES, F.cc:857 */
       for (int64_t row = 0; row < 2 * nnodes; ++row)
