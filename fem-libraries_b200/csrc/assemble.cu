@@ -33,6 +33,7 @@
 #include "constitutive.cuh"
 #include "element.cuh"
 #include "plan.cuh"
+#include "reduce.cuh"
 
 namespace femb {
 
@@ -86,18 +87,33 @@ struct AsmArgs
    const double *dnod, *u;
    int variant;
    double *values;
+   int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
 };
 
 // ---- fast path: straight-sided P1 / P2 triangle, linear elasticity --------------
+// kr[t] = 2x2 block (row node = local dof a of the visit, column = ROTATED local dof t:
+// vertices (m, m1, m2) then edges (3+m, 3+m1, 3+m2), see rotated_index)
+__device__ __forceinline__ int rotated_index(int t, int a)
+{
+   const int m = (a >= 3) ? a - 3 : a;
+   const int tt = (t >= 3) ? t - 3 : t;
+   int b = m + tt;
+   b = (b >= 3) ? b - 3 : b;
+   return (t >= 3) ? b + 3 : b;
+}
+
 template <int ET>
-__device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, double2 *sv, int r0, int r1)
+__device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, double (*kr)[4])
 {
    const int a = r.a;
    const int m = (a >= 3) ? a - 3 : a;  // rotation: own vertex / own edge becomes number 0
    const int64_t e = r.e;
    const int32_t *xd = A.xdofmap + e * 3;
    const int m1 = (m + 1 >= 3) ? m - 2 : m + 1, m2 = (m + 2 >= 3) ? m - 1 : m + 2;
-   const int64_t v0 = xd[m], v1 = xd[m1], v2 = xd[m2];
+   const int32_t xd0 = xd[0], xd1 = xd[1], xd2 = xd[2];
+   const int64_t v0 = (m == 0) ? xd0 : (m == 1 ? xd1 : xd2);
+   const int64_t v1 = (m1 == 0) ? xd0 : (m1 == 1 ? xd1 : xd2);
+   const int64_t v2 = (m2 == 0) ? xd0 : (m2 == 1 ? xd1 : xd2);
    const double x0 = A.x[v0 * A.xs], y0 = A.x[v0 * A.xs + 1];
    const double x1 = A.x[v1 * A.xs], y1 = A.x[v1 * A.xs + 1];
    const double x2 = A.x[v2 * A.xs], y2 = A.x[v2 * A.xs + 1];
@@ -108,7 +124,6 @@ __device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, dou
    const double g2[2] = {-(y1 - y0) * id, (x1 - x0) * id};
    const double T = 0.5 * fabs(det);
    const double tl = T * Ee * A.lc.c2, tm = T * Ee * A.lc.c3;
-   double k[4];
    if (a < 3)
    {  // row = (rotated) vertex 0
       const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
@@ -118,29 +133,22 @@ __device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, dou
       w_block(g0, g2, tl, tm, w02);
       if (ET == FEMB200_P1)
       {  // P1: K_ab = W^{ab}  (M.cc:885-887)
-         stage_block(sv, r0, r1, r.slot(m), w00, r.is_first(m));
-         stage_block(sv, r0, r1, r.slot(m1), w01, r.is_first(m1));
-         stage_block(sv, r0, r1, r.slot(m2), w02, r.is_first(m2));
+#pragma unroll
+         for (int i = 0; i < 4; ++i) kr[0][i] = w00[i], kr[1][i] = w01[i], kr[2][i] = w02[i];
       }
       else
       {
          const double c3 = -1. / 3., c43 = 4. / 3.;
-         stage_block(sv, r0, r1, r.slot(m), w00, r.is_first(m));
 #pragma unroll
-         for (int i = 0; i < 4; ++i) k[i] = c3 * w01[i];
-         stage_block(sv, r0, r1, r.slot(m1), k, r.is_first(m1));
-#pragma unroll
-         for (int i = 0; i < 4; ++i) k[i] = c3 * w02[i];
-         stage_block(sv, r0, r1, r.slot(m2), k, r.is_first(m2));
-         // rotated edges: 0' = (1,2) opposite (structural zero), 1' = (2,0), 2' = (0,1)
-         k[0] = k[1] = k[2] = k[3] = 0.;
-         stage_block(sv, r0, r1, r.slot(3 + m), k, r.is_first(3 + m));
-#pragma unroll
-         for (int i = 0; i < 4; ++i) k[i] = c43 * w02[i];
-         stage_block(sv, r0, r1, r.slot(3 + m1), k, r.is_first(3 + m1));
-#pragma unroll
-         for (int i = 0; i < 4; ++i) k[i] = c43 * w01[i];
-         stage_block(sv, r0, r1, r.slot(3 + m2), k, r.is_first(3 + m2));
+         for (int i = 0; i < 4; ++i)
+         {
+            kr[0][i] = w00[i];
+            kr[1][i] = c3 * w01[i];
+            kr[2][i] = c3 * w02[i];
+            kr[3][i] = 0.;  // rotated edges: 0' = (1,2) opposite (structural zero), 1' = (2,0), 2' = (0,1)
+            kr[4][i] = c43 * w02[i];
+            kr[5][i] = c43 * w01[i];
+         }
       }
    }
    else
@@ -151,30 +159,24 @@ __device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, dou
       w_block(g2, g2, tl, tm, w22);
       const double c43 = 4. / 3.;
       // vertices: opposite 0' -> 0; 1' (= p) -> 4/3 W^{21} = 4/3 (W^{12})^t; 2' (= q) -> 4/3 W^{12}
-      k[0] = k[1] = k[2] = k[3] = 0.;
-      stage_block(sv, r0, r1, r.slot(m), k, r.is_first(m));
-      k[0] = c43 * w12[0], k[1] = c43 * w12[2], k[2] = c43 * w12[1], k[3] = c43 * w12[3];
-      stage_block(sv, r0, r1, r.slot(m1), k, r.is_first(m1));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) k[i] = c43 * w12[i];
-      stage_block(sv, r0, r1, r.slot(m2), k, r.is_first(m2));
+      kr[0][0] = kr[0][1] = kr[0][2] = kr[0][3] = 0.;
+      kr[1][0] = c43 * w12[0], kr[1][1] = c43 * w12[2], kr[1][2] = c43 * w12[1], kr[1][3] = c43 * w12[3];
       // S = W12 + W21 (symmetric)
-      const double s[4] = {2. * w12[0], w12[1] + w12[2], w12[1] + w12[2], 2. * w12[3]};
+      const double sy[4] = {2. * w12[0], w12[1] + w12[2], w12[1] + w12[2], 2. * w12[3]};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) k[i] = c43 * (2. * w11[i] + s[i] + 2. * w22[i]);
-      stage_block(sv, r0, r1, r.slot(3 + m), k, r.is_first(3 + m));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) k[i] = -c43 * (2. * w11[i] + s[i]);
-      stage_block(sv, r0, r1, r.slot(3 + m1), k, r.is_first(3 + m1));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) k[i] = -c43 * (s[i] + 2. * w22[i]);
-      stage_block(sv, r0, r1, r.slot(3 + m2), k, r.is_first(3 + m2));
+      for (int i = 0; i < 4; ++i)
+      {
+         kr[2][i] = c43 * w12[i];
+         kr[3][i] = c43 * (2. * w11[i] + sy[i] + 2. * w22[i]);
+         kr[4][i] = -c43 * (2. * w11[i] + sy[i]);
+         kr[5][i] = -c43 * (sy[i] + 2. * w22[i]);
+      }
    }
 }
 
 // ---- generic path: per-quadrature-point loop, damaged tangent, any family -------
 template <int ET>
-__device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double2 *sv, int r0, int r1)
+__device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double (*kb)[4])
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq;
    const int a = r.a;
@@ -190,7 +192,6 @@ __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double2 *
    }
    const double Ee = A.E[e];
    const double lam = Ee * A.lc.c2, mu = Ee * A.lc.c3;
-   double kb[nd][4];
 #pragma unroll
    for (int b = 0; b < nd; ++b) kb[b][0] = kb[b][1] = kb[b][2] = kb[b][3] = 0.;
 #pragma unroll 1
@@ -228,40 +229,89 @@ __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double2 *
 #pragma unroll
       for (int b = 0; b < nd; ++b) bdb_block(ga, G[b], D, w, kb[b]);
    }
-#pragma unroll
-   for (int b = 0; b < nd; ++b) stage_block(sv, r0, r1, r.slot(b), kb[b], r.is_first(b));
 }
 
-template <int ET, bool FAST>
-__global__ void assemble_kernel(AsmArgs A)
+// One thread per VISIT (row node I, incident cell e): all visits of a tile of R
+// consecutive node rows are computed concurrently, then merged into the staging
+// image in `maxcnt` rounds: round q stages the q-th visit of every node, so a
+// slot is never touched by two threads at once and every sum runs in ascending
+// cell order (the order of the reference's serial cell loop).
+template <int ET, bool FAST, int THREADS>
+__global__ void __launch_bounds__(THREADS) assemble_kernel(AsmArgs A, int R)
 {
+   constexpr int nd = Elem<ET>::nd;
    extern __shared__ double2 sv[];
-   const int R = blockDim.x, tid = threadIdx.x;
+   __shared__ int s_maxcnt;
+   const int tid = threadIdx.x;
    const int64_t n0 = (int64_t)blockIdx.x * R;
-   const int64_t n1 = min(n0 + (int64_t)R, A.nnodes);
+   const int nloc = (int)min((int64_t)R, A.nnodes - n0);
    const int64_t b0 = A.brp[n0];
-   const int units = 2 * (int)(A.brp[n1] - b0);  // 16-byte units of this tile
-   const int64_t I = n0 + tid;
-   if (I < n1)
+   const int units = 2 * (int)(A.brp[n0 + nloc] - b0);  // 16-byte units of this tile
+   // tile metadata behind the staging area: visit offsets and row unit offsets
+   int32_t *s_nptr = reinterpret_cast<int32_t *>(sv + A.stage_units);
+   int32_t *s_roff = s_nptr + (R + 1);
+   if (tid == 0) s_maxcnt = 0;
+   for (int i = tid; i <= nloc; i += THREADS)
    {
-      const int64_t bi = A.brp[I];
-      const int deg = (int)(A.brp[I + 1] - bi);
-      const int r0 = 2 * (int)(bi - b0), r1 = r0 + deg;
-      const int32_t k1 = A.nptr[I + 1];
-      for (int32_t k = A.nptr[I]; k < k1; ++k)
-      {
-         const Visit r(*reinterpret_cast<const uint4 *>(A.vrec + k));
-         if (FAST)
-            visit_fast<ET>(A, r, sv, r0, r1);
-         else
-            visit_generic<ET>(A, r, sv, r0, r1);
-      }
+      s_nptr[i] = A.nptr[n0 + i];
+      s_roff[i] = 2 * (int)(A.brp[n0 + i] - b0);
    }
    __syncthreads();
+   for (int i = tid; i < nloc; i += THREADS) atomicMax(&s_maxcnt, s_nptr[i + 1] - s_nptr[i]);
+   const int32_t k0 = s_nptr[0];
+   const int nvis = s_nptr[nloc] - k0;
+   __syncthreads();
+   const int maxcnt = s_maxcnt;
+   for (int base = 0; base < nvis; base += THREADS)
+   {
+      const int v = base + tid;
+      const bool active = v < nvis;
+      double kb[nd][4];
+      int rank = -1, r0 = 0, r1 = 0;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (active)
+      {
+         const int32_t k = k0 + v;
+         raw = *reinterpret_cast<const uint4 *>(A.vrec + k);
+         int lo = 0, hi = nloc;  // largest i with s_nptr[i] <= k
+         while (hi - lo > 1)
+         {
+            const int mid = (lo + hi) >> 1;
+            if (s_nptr[mid] <= k)
+               lo = mid;
+            else
+               hi = mid;
+         }
+         rank = k - s_nptr[lo];
+         r0 = s_roff[lo];
+         r1 = r0 + ((s_roff[lo + 1] - r0) >> 1);
+      }
+      const Visit r(raw);
+      if (active)
+      {
+         if (FAST)
+            visit_fast<ET>(A, r, kb);
+         else
+            visit_generic<ET>(A, r, kb);
+      }
+      for (int q = 0; q < maxcnt; ++q)
+      {
+         if (rank == q)
+         {
+#pragma unroll
+            for (int t = 0; t < nd; ++t)
+            {
+               const int b = FAST ? rotated_index(t, (int)r.a) : t;
+               stage_block(sv, r0, r1, r.slot(b), kb[t], r.is_first(b));
+            }
+         }
+         __syncthreads();
+      }
+   }
    // stream the finished tile out: one contiguous byte range of the CSR values
    double *dst = A.values + 4 * b0;
    const int padded = (units + 7) & ~7;
-   for (int i = tid; i < padded; i += R)
+   for (int i = tid; i < padded; i += THREADS)
    {
       const int u = swz(i);
       if (u < units) st_stream_d2(dst + 2 * (int64_t)u, sv[i]);
@@ -318,51 +368,54 @@ __global__ void dirichlet_kernel(int nbc, const int32_t *__restrict__ bc_nodes, 
 }
 
 // ---- Frobenius norm^2 and trace --------------------------------------------------
-__global__ void norms_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
-                             const double *__restrict__ values, double *__restrict__ out)
+__global__ void __launch_bounds__(256)
+norms_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+             const double *__restrict__ values, ReduceScratch red, double *__restrict__ out)
 {
-   double fro = 0., tr = 0.;
+   double acc[2] = {0., 0.};  // fro^2, trace
    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
    const int lane = threadIdx.x & 31;
    for (int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < nnodes; I += nw)
    {
       const int64_t bi = brp[I];
       const int deg = (int)(brp[I + 1] - bi);
-      const double *row = values + 4 * bi;
-      for (int t = lane; t < 4 * deg; t += 32) fro += row[t] * row[t];
+      const double2 *row = reinterpret_cast<const double2 *>(values + 4 * bi);
+      for (int t = lane; t < 2 * deg; t += 32)
+      {
+         const double2 v = row[t];
+         acc[0] += v.x * v.x + v.y * v.y;
+      }
       for (int s = lane; s < deg; s += 32)
-         if (bcol[bi + s] == I) tr += row[2 * s] + row[2 * deg + 2 * s + 1];
+         if (bcol[bi + s] == I) acc[1] += values[4 * bi + 2 * s] + values[4 * bi + 2 * deg + 2 * s + 1];
    }
-   fro = warp_sum(fro);
-   tr = warp_sum(tr);
-   if (lane == 0)
-   {
-      atomicAdd(out, fro);
-      atomicAdd(out + 1, tr);
-   }
+   block_reduce_finish_n<256, 2>(acc, red, out);
 }
 
 template <int ET, bool FAST>
-static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
+static int launch_assemble(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
-   // tile height: the largest candidate whose staging fits 3 CTAs per SM
+   constexpr int THREADS = FAST ? 256 : 128;
+   // tile height R (node rows per CTA): about one visit per thread
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
+   const double vis_per_node = (double)p->nvisits / (double)p->nnodes;
    int best = 0;
    for (int r = 0; r < kNumTileR; ++r)
    {
-      const size_t bytes = 32 * (size_t)p->tile_max_blocks[r] + 128;
-      if (bytes <= budget / 3 - 1024 && tile_r(r) <= 128) best = r;
+      const size_t bytes = 32 * (size_t)p->tile_max_blocks[r] + 8 * (tile_r(r) + 1) + 128;
+      if (bytes <= budget / 3 && tile_r(r) * vis_per_node <= 1.25 * THREADS) best = r;
    }
    const char *env = getenv("FEMB200_TILE_R");
    if (env)
       for (int r = 0; r < kNumTileR; ++r)
          if (atoi(env) == tile_r(r)) best = r;
    const int R = tile_r(best);
-   const size_t smem = 32 * (size_t)p->tile_max_blocks[best] + 128;
+   A.stage_units = (2 * p->tile_max_blocks[best] + 7) & ~7;
+   const size_t smem = 16 * (size_t)A.stage_units + 8 * (size_t)(R + 1) + 16;
    FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", R, smem, budget);
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
    const unsigned grid = (unsigned)cdiv(p->nnodes, R);
-   assemble_kernel<ET, FAST><<<grid, R, smem, st>>>(A);
+   assemble_kernel<ET, FAST, THREADS><<<grid, THREADS, smem, st>>>(A, R);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -415,10 +468,11 @@ extern "C" int femb200_matrix_norms(const femb200_plan *p, const double *d_value
 {
    FEMB_CHECK(p && d_values && d_out, "matrix_norms: null argument");
    cudaStream_t st = as_stream(stream);
-   FEMB_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(double), st));
    const int T = 256;
-   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(p->nnodes * 32, T), (int64_t)devinfo().sm_count * 16);
-   norms_kernel<<<grid, T, 0, st>>>(p->nnodes, p->brp, p->bcol, d_values, d_out);
+   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(p->nnodes * 32, T), (int64_t)devinfo().sm_count * 8);
+   ReduceScratch red;
+   if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
+   norms_kernel<<<grid, T, 0, st>>>(p->nnodes, p->brp, p->bcol, d_values, red, d_out);
    FEMB_LAUNCH_CHECK();
    return 0;
 }

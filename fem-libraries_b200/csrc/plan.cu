@@ -292,7 +292,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
    k_sort_visits<<<(unsigned)cdiv(nnodes, T), T, 0, st>>>(nnodes, p->nptr, tmpvis);
 
    // 2. block degrees -> brp -> bcol
-   if (dev_alloc(&deg, (size_t)nnodes + 1, &scratch) || dev_alloc(&p->brp, (size_t)nnodes + 1, &p->bytes))
+   if (dev_alloc(&deg, (size_t)nnodes + 1, &scratch) || dev_alloc(&p->brp, (size_t)nnodes + 4, &p->bytes))
       return fail(1);
    k_degree<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, deg, flags);
    if ((rc = exclusive_scan_i32_i64(deg, p->brp, nnodes, st))) return fail(rc);
@@ -303,7 +303,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       return fail(set_error("plan_create: pattern build failed: %s", cudaGetErrorString(cudaGetLastError())));
    if (hflags[0]) return fail(set_error("plan_create: a node has more than %d neighbour nodes", kMaxDeg));
    p->max_deg = hflags[1];
-   if (dev_alloc(&p->bcol, (size_t)p->nnzb, &p->bytes) || dev_alloc(&p->vrec, (size_t)nvis, &p->bytes))
+   if (dev_alloc(&p->bcol, (size_t)p->nnzb + 8, &p->bytes) || dev_alloc(&p->vrec, (size_t)nvis, &p->bytes))
       return fail(1);
    k_fill_cols<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol);
 

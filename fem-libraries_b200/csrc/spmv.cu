@@ -11,6 +11,8 @@
 // scalar rows and of x[2J..2J+1], shuffle reduction over the eight lanes.
 // <x, y> is optionally fused (CG needs <d, A d>): deterministic two-stage
 // reduction (block partials, last block sums them in a fixed order).
+#include <algorithm>
+
 #include "plan.cuh"
 #include "reduce.cuh"
 
@@ -75,6 +77,181 @@ spmv_kernel(int64_t row_lo, int64_t nnodes, const int64_t *__restrict__ brp, con
    if (DOT) block_reduce_finish<kSpmvThreads>(part, red, out);
 }
 
+// ---------------------------------------------------------------------------
+// TMA-staged persistent variant (default).  The node rows [n0, n0 + R) of a tile
+// own one contiguous byte range of the value array, of bcol and of brp: a producer
+// warp streams those three ranges into shared memory with 1-D bulk copies
+// (cp.async.bulk -> UBLKCP) completing on an mbarrier, S stages deep, while eight
+// consumer warps reduce the previous tiles out of shared memory; the only
+// per-thread global loads left are the gathers of x (L1/L2 hits: the lattice
+// numbering keeps the reuse window at a few node rows).  Grid = resident CTAs only,
+// so the fused <x, y> needs ~300 tickets instead of one per 32 rows.
+// ---------------------------------------------------------------------------
+constexpr int kTmaStages = 3;
+constexpr int kTmaConsumers = 256;
+constexpr int kTmaThreads = kTmaConsumers + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+   asm volatile(
+       "{\n"
+       ".reg .pred P1;\n"
+       "LAB_WAIT:\n"
+       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+       "@P1 bra DONE;\n"
+       "bra LAB_WAIT;\n"
+       "DONE:\n"
+       "}" ::"r"(smem_u32(bar)),
+       "r"(parity)
+       : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(dst)),
+                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+}
+
+struct SpmvTile
+{
+   int vbytes, cbytes, pbytes;  // stage capacities: values, column indices, row pointers
+};
+
+template <bool DOT, int R>
+__global__ void __launch_bounds__(kTmaThreads)
+spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+                const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
+                const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out, SpmvTile cap, int ntiles)
+{
+   extern __shared__ __align__(128) unsigned char smem[];
+   __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
+   if (flag && *flag != 0.) return;  // converged CG: become a no-op (uniform over the grid)
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const int stage_bytes = cap.vbytes + cap.cbytes + cap.pbytes;
+   if (tid == 0)
+   {
+#pragma unroll
+      for (int s = 0; s < kTmaStages; ++s)
+      {
+         mbar_init(&full[s], 1);
+         mbar_init(&empty[s], kTmaConsumers / 32);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   const int first = blockIdx.x, stride = gridDim.x;
+   const int nmine = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+   double part = 0.;
+   if (warp == kTmaConsumers / 32)
+   {  // ---- producer warp: one lane issues the bulk copies ----
+      if (lane == 0)
+         for (int it = 0; it < nmine; ++it)
+         {
+            const int s = it % kTmaStages;
+            if (it >= kTmaStages) mbar_wait(&empty[s], ((it / kTmaStages) - 1) & 1);
+            const int64_t n0 = row_lo + (int64_t)(first + it * stride) * R;
+            const int nloc = (int)min((int64_t)R, row_hi - n0);
+            const int64_t b0 = brp[n0], b1 = brp[n0 + nloc];
+            const int64_t c0 = b0 & ~(int64_t)3, p0 = n0 & ~(int64_t)1;
+            const uint32_t vb = (uint32_t)(32 * (b1 - b0));
+            const uint32_t cb = (uint32_t)((4 * (b1 - c0) + 15) & ~(int64_t)15);
+            const uint32_t pb = (uint32_t)((8 * (n0 + nloc + 1 - p0) + 15) & ~(int64_t)15);
+            unsigned char *st = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], vb + cb + pb);
+            if (vb) bulk_g2s(st, values + 4 * b0, vb, &full[s]);
+            if (cb) bulk_g2s(st + cap.vbytes, bcol + c0, cb, &full[s]);
+            bulk_g2s(st + cap.vbytes + cap.cbytes, brp + p0, pb, &full[s]);
+         }
+   }
+   else
+   {  // ---- consumer warps: 8 lanes per node row pair ----
+      const int sub = lane & (kSpmvLanes - 1);
+      const double2 *x2 = reinterpret_cast<const double2 *>(x);
+      for (int it = 0; it < nmine; ++it)
+      {
+         const int s = it % kTmaStages;
+         const int64_t n0 = row_lo + (int64_t)(first + it * stride) * R;
+         const int nloc = (int)min((int64_t)R, row_hi - n0);
+         const unsigned char *st = smem + (size_t)s * stage_bytes;
+         const double2 *sval = reinterpret_cast<const double2 *>(st);
+         const int32_t *scol = reinterpret_cast<const int32_t *>(st + cap.vbytes);
+         const int64_t *sbrp = reinterpret_cast<const int64_t *>(st + cap.vbytes + cap.cbytes) + (n0 & 1);
+         mbar_wait(&full[s], (it / kTmaStages) & 1);
+         const int64_t b0 = sbrp[0];
+         const int coff = (int)(b0 & 3);
+#pragma unroll
+         for (int pass = 0; pass < R * kSpmvLanes / kTmaConsumers; ++pass)
+         {
+            const int i = pass * (kTmaConsumers / kSpmvLanes) + tid / kSpmvLanes;
+            double y0 = 0., y1 = 0.;
+            if (i < nloc)
+            {
+               const int pb = (int)(sbrp[i] - b0);
+               const int deg = (int)(sbrp[i + 1] - b0) - pb;
+               const double2 *row0 = sval + 2 * pb, *row1 = row0 + deg;
+               const int32_t *cols = scol + coff + pb;
+               int t = sub;
+               for (; t + 2 * kSpmvLanes < deg; t += 3 * kSpmvLanes)
+               {
+                  const double2 v0 = x2[cols[t]], v1 = x2[cols[t + kSpmvLanes]], v2 = x2[cols[t + 2 * kSpmvLanes]];
+                  const double2 a0 = row0[t], a1 = row0[t + kSpmvLanes], a2 = row0[t + 2 * kSpmvLanes];
+                  const double2 c0 = row1[t], c1 = row1[t + kSpmvLanes], c2 = row1[t + 2 * kSpmvLanes];
+                  y0 += a0.x * v0.x + a0.y * v0.y + a1.x * v1.x + a1.y * v1.y + a2.x * v2.x + a2.y * v2.y;
+                  y1 += c0.x * v0.x + c0.y * v0.y + c1.x * v1.x + c1.y * v1.y + c2.x * v2.x + c2.y * v2.y;
+               }
+               if (t + kSpmvLanes < deg)
+               {
+                  const double2 v0 = x2[cols[t]], v1 = x2[cols[t + kSpmvLanes]];
+                  const double2 a0 = row0[t], a1 = row0[t + kSpmvLanes];
+                  const double2 c0 = row1[t], c1 = row1[t + kSpmvLanes];
+                  y0 += a0.x * v0.x + a0.y * v0.y + a1.x * v1.x + a1.y * v1.y;
+                  y1 += c0.x * v0.x + c0.y * v0.y + c1.x * v1.x + c1.y * v1.y;
+               }
+               else if (t < deg)
+               {
+                  const double2 v0 = x2[cols[t]];
+                  const double2 a0 = row0[t], c0 = row1[t];
+                  y0 += a0.x * v0.x + a0.y * v0.y;
+                  y1 += c0.x * v0.x + c0.y * v0.y;
+               }
+            }
+#pragma unroll
+            for (int o = kSpmvLanes / 2; o > 0; o >>= 1)
+            {
+               y0 += __shfl_xor_sync(0xffffffffu, y0, o);
+               y1 += __shfl_xor_sync(0xffffffffu, y1, o);
+            }
+            if (i < nloc && sub == 0)
+            {
+               reinterpret_cast<double2 *>(y)[n0 + i] = make_double2(y0, y1);
+               if (DOT)
+               {
+                  const double2 xi = x2[n0 + i];
+                  part += xi.x * y0 + xi.y * y1;
+               }
+            }
+         }
+         __syncwarp();
+         if (lane == 0) mbar_arrive(&empty[s]);
+      }
+   }
+   if (DOT) block_reduce_finish<kTmaThreads>(part, red, out);
+}
+
 __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
                             const double *__restrict__ values, double *__restrict__ diag)
 {
@@ -101,22 +278,61 @@ __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, con
    diag[2 * I + 1] = d1;
 }
 
+template <bool DOT, int R>
+static int spmv_tma_launch(const femb200_plan *p, int tile_idx, const double *d_values, const double *d_x, double *d_y,
+                           const double *d_flag, double *d_dot_out, cudaStream_t st)
+{
+   const int64_t nrows = p->row_hi - p->row_lo;
+   const int ntiles = (int)cdiv(nrows, R);
+   SpmvTile cap;
+   cap.vbytes = 32 * p->tile_max_blocks[tile_idx];
+   cap.cbytes = ((4 * (p->tile_max_blocks[tile_idx] + 4) + 15) & ~15);
+   cap.pbytes = ((8 * (R + 3) + 15) & ~15);
+   // tiles of a row range that does not start on a multiple of R straddle two plan tiles
+   if (p->row_lo % R) cap.vbytes *= 2, cap.cbytes *= 2;
+   const size_t smem = (size_t)kTmaStages * (cap.vbytes + cap.cbytes + cap.pbytes);
+   const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
+   if (smem > budget) return -1;  // caller falls back to the direct kernel
+   FEMB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<DOT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (smem + 1024)));
+   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)devinfo().sm_count * per_sm);
+   ReduceScratch red{nullptr, nullptr};
+   if (DOT)
+      if (int rc = reduce_scratch(grid, st, &red)) return rc;
+   spmv_tma_kernel<DOT, R><<<grid, kTmaThreads, smem, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
+                                                            d_flag, red, d_dot_out, cap, ntiles);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
 int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
                 double *d_dot_out, cudaStream_t st)
 {
    const int64_t nrows = p->row_hi - p->row_lo;
-   if (nrows <= 0) return 0;
+   if (nrows <= 0)
+   {
+      if (d_dot_out) FEMB_CUDA(cudaMemsetAsync(d_dot_out, 0, sizeof(double), st));
+      return 0;
+   }
+   const bool direct = getenv("FEMB200_SPMV_DIRECT") != nullptr;
+   if (!direct)
+   {
+      // tile_r(1) == 64 node rows per tile
+      const int rc = d_dot_out ? spmv_tma_launch<true, 64>(p, 1, d_values, d_x, d_y, d_flag, d_dot_out, st)
+                               : spmv_tma_launch<false, 64>(p, 1, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      if (rc >= 0) return rc;
+   }
    const unsigned grid = (unsigned)cdiv(nrows * kSpmvLanes, kSpmvThreads);
    if (d_dot_out)
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red)) return rc;
-      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag, red,
-                                                        d_dot_out);
+      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
+                                                        d_flag, red, d_dot_out);
    }
    else
-      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag,
-                                                         ReduceScratch{nullptr, nullptr}, nullptr);
+      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
+                                                         d_flag, ReduceScratch{nullptr, nullptr}, nullptr);
    FEMB_LAUNCH_CHECK();
    return 0;
 }

@@ -261,6 +261,36 @@ def test_spmv_and_pa_apply(kind, n):
         np.testing.assert_allclose(pa.diagonal().cpu().numpy(), K.diagonal(), rtol=1e-11)
 
 
+@pytest.mark.parametrize("direct", [False, True])
+def test_spmv_variants_and_row_ranges(direct, monkeypatch):
+    """TMA-staged and direct kernels; owned-row ranges (multi-GPU) incl. odd and ragged bounds."""
+    import torch
+    if direct:
+        monkeypatch.setenv("FEMB200_SPMV_DIRECT", "1")
+    m = make_mesh("P2", 40, ny=23)
+    E = fm.young_per_cell(m.ncells)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form)
+    rowptr, colidx, vals = oracle_assemble(m, E)
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(m.ndofs)
+    want = oracle.spmv(rowptr, colidx, vals, v)
+    vd = f.to_device(v, np.float64)
+    for lo, hi in ((0, m.nnodes), (1, m.nnodes - 1), (81, 81 + 64), (163, 1000), (m.nnodes - 5, m.nnodes), (7, 7)):
+        A.set_row_range(lo, hi)
+        y = torch.full((m.ndofs,), -7.0, dtype=torch.float64, device="cuda")
+        out = torch.full((1,), -1.0, dtype=torch.float64, device="cuda")
+        f.capi.call("femb200_spmv_dot", A.plan, f._p(A.values), f._p(vd), f._p(y), f._p(out), f._stream())
+        yh = y.cpu().numpy()
+        assert relfro(yh[2 * lo:2 * hi], want[2 * lo:2 * hi]) < 1e-13 if hi > lo else True
+        np.testing.assert_array_equal(yh[:2 * lo], -7.0)
+        np.testing.assert_array_equal(yh[2 * hi:], -7.0)
+        ref = v[2 * lo:2 * hi] @ want[2 * lo:2 * hi]
+        assert abs(out.item() - ref) <= 1e-12 * max(1.0, np.abs(v[2 * lo:2 * hi] * want[2 * lo:2 * hi]).sum())
+    A.set_row_range(0, m.nnodes)
+
+
 # ---------------------------------------------------------------------------
 # CG
 # ---------------------------------------------------------------------------
