@@ -85,14 +85,53 @@ struct AsmArgs
    const double *E;
    LameCoef lc;
    const double *dnod, *u;
+   const double *cellrec;
    int variant;
    double *values;
+   int debug;        // developer switch: 1 = skip the visits, 2 = skip the stream-out
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
 };
 
 // ---- fast path: straight-sided P1 / P2 triangle, linear elasticity --------------
-// kr[t] = 2x2 block (row node = local dof a of the visit, column = ROTATED local dof t:
-// vertices (m, m1, m2) then edges (3+m, 3+m1, 3+m2), see rotated_index)
+// The three dependent load levels of a visit (visit record -> cell vertices ->
+// coordinates) are split into separate functions so that the kernel can issue each
+// level for a batch of visits before consuming any of them.
+struct FastGeo
+{
+   double g1x, g1y, g2x, g2y, tl, tm;  // grad lambda_1, grad lambda_2 (original vertex order), |T| lambda, |T| mu
+};
+
+// per-cell pre-pass (coalesced over cells): everything a visit needs from its cell in
+// one 48-byte record, so that a visit costs three 16-byte loads of one line instead
+// of ten scattered 4/8-byte loads (the L1 tag stage, one line per cycle, was the
+// throughput limit of the gather: profiles/r1_assemble_v3.md)
+__global__ void cell_setup_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, const double *__restrict__ x,
+                                  int xs, const double *__restrict__ E, LameCoef lc, double *__restrict__ rec)
+{
+   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= ncells) return;
+   const int64_t v0 = xdofmap[3 * e], v1 = xdofmap[3 * e + 1], v2 = xdofmap[3 * e + 2];
+   const double x0 = x[v0 * xs], y0 = x[v0 * xs + 1];
+   const double x1 = x[v1 * xs], y1 = x[v1 * xs + 1];
+   const double x2 = x[v2 * xs], y2 = x[v2 * xs + 1];
+   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+   const double id = 1. / det;
+   const double T = 0.5 * fabs(det), Ee = E[e];
+   double2 *r = reinterpret_cast<double2 *>(rec + 6 * e);
+   r[0] = make_double2((y2 - y0) * id, -(x2 - x0) * id);
+   r[1] = make_double2(-(y1 - y0) * id, (x1 - x0) * id);
+   r[2] = make_double2(T * Ee * lc.c2, T * Ee * lc.c3);
+}
+
+__device__ __forceinline__ FastGeo fast_geo(const AsmArgs &A, const Visit &r)
+{
+   const double2 *p = reinterpret_cast<const double2 *>(A.cellrec + 6 * (int64_t)r.e);
+   const double2 a = p[0], b = p[1], c = p[2];
+   return FastGeo{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+
+// column order of the blocks produced below: ROTATED local dofs, vertices (m, m1, m2)
+// then edges (3+m, 3+m1, 3+m2)
 __device__ __forceinline__ int rotated_index(int t, int a)
 {
    const int m = (a >= 3) ? a - 3 : a;
@@ -102,75 +141,87 @@ __device__ __forceinline__ int rotated_index(int t, int a)
    return (t >= 3) ? b + 3 : b;
 }
 
+// row 0 of W^{cd} = |T| (lam g_c (x) g_d + mu g_d (x) g_c + mu (g_c . g_d) I)
+__device__ __forceinline__ void w_row(const double *gc, const double *gd, double tl, double tm, double *w)
+{
+   w[0] = (tl + 2. * tm) * (gc[0] * gd[0]) + tm * (gc[1] * gd[1]);
+   w[1] = tl * (gc[0] * gd[1]) + tm * (gc[1] * gd[0]);
+}
+
+// Computes ONE scalar row (h = 0: x-row, h = 1: y-row) of the row slice of the element
+// matrix owned by the visit and stages it: two threads share a node, which doubles
+// the resident warps for the same staging footprint.  Row 1 is row 0 with the x and y
+// components of every gradient exchanged and the two outputs swapped.
 template <int ET>
-__device__ __forceinline__ void visit_fast(const AsmArgs &A, const Visit &r, double (*kr)[4])
+__device__ __forceinline__ void fast_compute_stage(const AsmArgs &A, const Visit &r, const FastGeo &g, double2 *sv,
+                                                   int rbase, int h)
 {
    const int a = r.a;
    const int m = (a >= 3) ? a - 3 : a;  // rotation: own vertex / own edge becomes number 0
-   const int64_t e = r.e;
-   const int32_t *xd = A.xdofmap + e * 3;
-   const int m1 = (m + 1 >= 3) ? m - 2 : m + 1, m2 = (m + 2 >= 3) ? m - 1 : m + 2;
-   const int32_t xd0 = xd[0], xd1 = xd[1], xd2 = xd[2];
-   const int64_t v0 = (m == 0) ? xd0 : (m == 1 ? xd1 : xd2);
-   const int64_t v1 = (m1 == 0) ? xd0 : (m1 == 1 ? xd1 : xd2);
-   const int64_t v2 = (m2 == 0) ? xd0 : (m2 == 1 ? xd1 : xd2);
-   const double x0 = A.x[v0 * A.xs], y0 = A.x[v0 * A.xs + 1];
-   const double x1 = A.x[v1 * A.xs], y1 = A.x[v1 * A.xs + 1];
-   const double x2 = A.x[v2 * A.xs], y2 = A.x[v2 * A.xs + 1];
-   const double Ee = A.E[e];
-   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
-   const double id = 1. / det;
-   const double g1[2] = {(y2 - y0) * id, -(x2 - x0) * id};
-   const double g2[2] = {-(y1 - y0) * id, (x1 - x0) * id};
-   const double T = 0.5 * fabs(det);
-   const double tl = T * Ee * A.lc.c2, tm = T * Ee * A.lc.c3;
+   // gradients of the rotated barycentric coordinates 1' = m + 1, 2' = m + 2 (mod 3)
+   const double h0x = -g.g1x - g.g2x, h0y = -g.g1y - g.g2y;
+   const double a1x = m == 0 ? g.g1x : (m == 1 ? g.g2x : h0x), a1y = m == 0 ? g.g1y : (m == 1 ? g.g2y : h0y);
+   const double a2x = m == 0 ? g.g2x : (m == 1 ? h0x : g.g1x), a2y = m == 0 ? g.g2y : (m == 1 ? h0y : g.g1y);
+   const double g1[2] = {h ? a1y : a1x, h ? a1x : a1y};
+   const double g2[2] = {h ? a2y : a2x, h ? a2x : a2y};
+   const double tl = g.tl, tm = g.tm;
+   double k[2];
+   auto put = [&](int t, const double *kk) {
+      const int b = rotated_index(t, a);
+      stage_put(sv, rbase + r.slot(b), h ? kk[1] : kk[0], h ? kk[0] : kk[1], r.is_first(b));
+   };
    if (a < 3)
    {  // row = (rotated) vertex 0
       const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
-      double w00[4], w01[4], w02[4];
-      w_block(g0, g0, tl, tm, w00);
-      w_block(g0, g1, tl, tm, w01);
-      w_block(g0, g2, tl, tm, w02);
+      double w00[2], w01[2], w02[2];
+      w_row(g0, g0, tl, tm, w00);
+      w_row(g0, g1, tl, tm, w01);
+      w_row(g0, g2, tl, tm, w02);
       if (ET == FEMB200_P1)
       {  // P1: K_ab = W^{ab}  (M.cc:885-887)
-#pragma unroll
-         for (int i = 0; i < 4; ++i) kr[0][i] = w00[i], kr[1][i] = w01[i], kr[2][i] = w02[i];
+         put(0, w00);
+         put(1, w01);
+         put(2, w02);
       }
       else
       {
          const double c3 = -1. / 3., c43 = 4. / 3.;
-#pragma unroll
-         for (int i = 0; i < 4; ++i)
-         {
-            kr[0][i] = w00[i];
-            kr[1][i] = c3 * w01[i];
-            kr[2][i] = c3 * w02[i];
-            kr[3][i] = 0.;  // rotated edges: 0' = (1,2) opposite (structural zero), 1' = (2,0), 2' = (0,1)
-            kr[4][i] = c43 * w02[i];
-            kr[5][i] = c43 * w01[i];
-         }
+         put(0, w00);
+         k[0] = c3 * w01[0], k[1] = c3 * w01[1];
+         put(1, k);
+         k[0] = c3 * w02[0], k[1] = c3 * w02[1];
+         put(2, k);
+         // rotated edges: 0' = (1,2) opposite (structural zero), 1' = (2,0), 2' = (0,1)
+         k[0] = k[1] = 0.;
+         put(3, k);
+         k[0] = c43 * w02[0], k[1] = c43 * w02[1];
+         put(4, k);
+         k[0] = c43 * w01[0], k[1] = c43 * w01[1];
+         put(5, k);
       }
    }
    else
-   {  // row = (rotated) edge 0 = (1,2); uses sum_d W^{cd} = 0 to stay within W11, W12, W22
-      double w11[4], w12[4], w22[4];
-      w_block(g1, g1, tl, tm, w11);
-      w_block(g1, g2, tl, tm, w12);
-      w_block(g2, g2, tl, tm, w22);
+   {  // row = (rotated) edge 0 = (1,2); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
+      double w11[2], w12[2], w21[2], w22[2];
+      w_row(g1, g1, tl, tm, w11);
+      w_row(g1, g2, tl, tm, w12);
+      w_row(g2, g1, tl, tm, w21);  // = row of (W^{12})^t
+      w_row(g2, g2, tl, tm, w22);
       const double c43 = 4. / 3.;
-      // vertices: opposite 0' -> 0; 1' (= p) -> 4/3 W^{21} = 4/3 (W^{12})^t; 2' (= q) -> 4/3 W^{12}
-      kr[0][0] = kr[0][1] = kr[0][2] = kr[0][3] = 0.;
-      kr[1][0] = c43 * w12[0], kr[1][1] = c43 * w12[2], kr[1][2] = c43 * w12[1], kr[1][3] = c43 * w12[3];
-      // S = W12 + W21 (symmetric)
-      const double sy[4] = {2. * w12[0], w12[1] + w12[2], w12[1] + w12[2], 2. * w12[3]};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-      {
-         kr[2][i] = c43 * w12[i];
-         kr[3][i] = c43 * (2. * w11[i] + sy[i] + 2. * w22[i]);
-         kr[4][i] = -c43 * (2. * w11[i] + sy[i]);
-         kr[5][i] = -c43 * (sy[i] + 2. * w22[i]);
-      }
+      // vertices: opposite 0' -> 0; 1' (= p) -> 4/3 W^{21}; 2' (= q) -> 4/3 W^{12}
+      k[0] = k[1] = 0.;
+      put(0, k);
+      k[0] = c43 * w21[0], k[1] = c43 * w21[1];
+      put(1, k);
+      k[0] = c43 * w12[0], k[1] = c43 * w12[1];
+      put(2, k);
+      const double sy[2] = {w12[0] + w21[0], w12[1] + w21[1]};  // S = W12 + W21
+      k[0] = c43 * (2. * w11[0] + sy[0] + 2. * w22[0]), k[1] = c43 * (2. * w11[1] + sy[1] + 2. * w22[1]);
+      put(3, k);
+      k[0] = -c43 * (2. * w11[0] + sy[0]), k[1] = -c43 * (2. * w11[1] + sy[1]);
+      put(4, k);
+      k[0] = -c43 * (sy[0] + 2. * w22[0]), k[1] = -c43 * (sy[1] + 2. * w22[1]);
+      put(5, k);
    }
 }
 
@@ -231,87 +282,101 @@ __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double (*
    }
 }
 
-// One thread per VISIT (row node I, incident cell e): all visits of a tile of R
-// consecutive node rows are computed concurrently, then merged into the staging
-// image in `maxcnt` rounds: round q stages the q-th visit of every node, so a
-// slot is never touched by two threads at once and every sum runs in ascending
-// cell order (the order of the reference's serial cell loop).
-template <int ET, bool FAST, int THREADS>
-__global__ void __launch_bounds__(THREADS) assemble_kernel(AsmArgs A, int R)
+// One thread owns one block row (node I) of a tile of R consecutive node rows and
+// walks the cells incident to I.  Threads are assigned to nodes in order of
+// DECREASING visit count (P2: vertex nodes have 6 incident cells, edge nodes 2), so
+// the lanes of a warp run the same number of visits; on the fast path the three
+// dependent load levels are issued for CH visits at a time.
+template <int ET, bool FAST, int CH, int TPN>
+__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs A)
 {
    constexpr int nd = Elem<ET>::nd;
    extern __shared__ double2 sv[];
-   __shared__ int s_maxcnt;
-   const int tid = threadIdx.x;
+   __shared__ int s_hist[8], s_base[8];
+   // fast path: two threads per node (one per scalar row); generic path: one
+   const int R = blockDim.x / TPN, tid = threadIdx.x;
    const int64_t n0 = (int64_t)blockIdx.x * R;
    const int nloc = (int)min((int64_t)R, A.nnodes - n0);
    const int64_t b0 = A.brp[n0];
    const int units = 2 * (int)(A.brp[n0 + nloc] - b0);  // 16-byte units of this tile
-   // tile metadata behind the staging area: visit offsets and row unit offsets
-   int32_t *s_nptr = reinterpret_cast<int32_t *>(sv + A.stage_units);
-   int32_t *s_roff = s_nptr + (R + 1);
-   if (tid == 0) s_maxcnt = 0;
-   for (int i = tid; i <= nloc; i += THREADS)
+   // tile metadata behind the staging area
+   int32_t *s_k0 = reinterpret_cast<int32_t *>(sv + A.stage_units);  // first visit of node i
+   int32_t *s_cnt = s_k0 + R;                                         // number of visits
+   int32_t *s_roff = s_cnt + R;                                       // unit offset of row 0, [R + 1]
+   uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_roff + R + 1);
+   if (tid < 8) s_hist[tid] = 0;
+   __syncthreads();
+   int my_off = 0, key = 0;
+   if (tid < nloc)
    {
-      s_nptr[i] = A.nptr[n0 + i];
-      s_roff[i] = 2 * (int)(A.brp[n0 + i] - b0);
+      const int32_t k0 = A.nptr[n0 + tid], k1 = A.nptr[n0 + tid + 1];
+      s_k0[tid] = k0;
+      s_cnt[tid] = k1 - k0;
+      s_roff[tid] = 2 * (int)(A.brp[n0 + tid] - b0);
+      key = min(k1 - k0, 7);
+      my_off = atomicAdd(&s_hist[key], 1);
+   }
+   if (tid == 0) s_roff[nloc] = units;
+   __syncthreads();
+   if (tid < 8)
+   {
+      int base = 0;
+      for (int kk = 7; kk > tid; --kk) base += s_hist[kk];
+      s_base[tid] = base;
    }
    __syncthreads();
-   for (int i = tid; i < nloc; i += THREADS) atomicMax(&s_maxcnt, s_nptr[i + 1] - s_nptr[i]);
-   const int32_t k0 = s_nptr[0];
-   const int nvis = s_nptr[nloc] - k0;
+   if (tid < nloc) s_perm[s_base[key] + my_off] = (uint16_t)tid;
    __syncthreads();
-   const int maxcnt = s_maxcnt;
-   for (int base = 0; base < nvis; base += THREADS)
+   if (tid / TPN < nloc && A.debug != 1)
    {
-      const int v = base + tid;
-      const bool active = v < nvis;
-      double kb[nd][4];
-      int rank = -1, r0 = 0, r1 = 0;
-      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-      if (active)
+      const int i = s_perm[tid / TPN];
+      const int32_t k0 = s_k0[i];
+      const int cnt = s_cnt[i];
+      const int r0 = s_roff[i];
+      const int r1 = r0 + ((s_roff[i + 1] - r0) >> 1);
+      if (FAST)
       {
-         const int32_t k = k0 + v;
-         raw = *reinterpret_cast<const uint4 *>(A.vrec + k);
-         int lo = 0, hi = nloc;  // largest i with s_nptr[i] <= k
-         while (hi - lo > 1)
+         for (int c = 0; c < cnt; c += CH)
          {
-            const int mid = (lo + hi) >> 1;
-            if (s_nptr[mid] <= k)
-               lo = mid;
-            else
-               hi = mid;
-         }
-         rank = k - s_nptr[lo];
-         r0 = s_roff[lo];
-         r1 = r0 + ((s_roff[lo + 1] - r0) >> 1);
-      }
-      const Visit r(raw);
-      if (active)
-      {
-         if (FAST)
-            visit_fast<ET>(A, r, kb);
-         else
-            visit_generic<ET>(A, r, kb);
-      }
-      for (int q = 0; q < maxcnt; ++q)
-      {
-         if (rank == q)
-         {
+            uint4 raw[CH];
+            FastGeo geo[CH];
 #pragma unroll
-            for (int t = 0; t < nd; ++t)
-            {
-               const int b = FAST ? rotated_index(t, (int)r.a) : t;
-               stage_block(sv, r0, r1, r.slot(b), kb[t], r.is_first(b));
-            }
+            for (int j = 0; j < CH; ++j)
+               raw[j] = (c + j < cnt) ? *reinterpret_cast<const uint4 *>(A.vrec + k0 + c + j) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+               if (c + j < cnt) geo[j] = fast_geo(A, Visit(raw[j]));
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+               if (c + j < cnt)
+               {
+                  if (TPN == 2)
+                     fast_compute_stage<ET>(A, Visit(raw[j]), geo[j], sv, (tid & 1) ? r1 : r0, tid & 1);
+                  else
+                  {
+                     fast_compute_stage<ET>(A, Visit(raw[j]), geo[j], sv, r0, 0);
+                     fast_compute_stage<ET>(A, Visit(raw[j]), geo[j], sv, r1, 1);
+                  }
+               }
          }
-         __syncthreads();
+      }
+      else
+      {
+         for (int c = 0; c < cnt; ++c)
+         {
+            const Visit r(*reinterpret_cast<const uint4 *>(A.vrec + k0 + c));
+            double kb[nd][4];
+            visit_generic<ET>(A, r, kb);
+#pragma unroll
+            for (int b = 0; b < nd; ++b) stage_block(sv, r0, r1, r.slot(b), kb[b], r.is_first(b));
+         }
       }
    }
+   __syncthreads();
    // stream the finished tile out: one contiguous byte range of the CSR values
    double *dst = A.values + 4 * b0;
    const int padded = (units + 7) & ~7;
-   for (int i = tid; i < padded; i += THREADS)
+   for (int i = tid; i < padded && A.debug != 2; i += blockDim.x)
    {
       const int u = swz(i);
       if (u < units) st_stream_d2(dst + 2 * (int64_t)u, sv[i]);
@@ -391,33 +456,54 @@ norms_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__r
    block_reduce_finish_n<256, 2>(acc, red, out);
 }
 
-template <int ET, bool FAST>
-static int launch_assemble(const femb200_plan *p, AsmArgs A, cudaStream_t st)
+template <int ET, bool FAST, int CH, int TPN>
+static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
-   constexpr int THREADS = FAST ? 256 : 128;
-   // tile height R (node rows per CTA): about one visit per thread
+   // tile height R = threads per CTA: the largest candidate that keeps >= 4 CTAs per SM
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
-   const double vis_per_node = (double)p->nvisits / (double)p->nnodes;
+   auto tile_smem = [&](int r) {
+      const size_t units = (2 * (size_t)p->tile_max_blocks[r] + 7) & ~(size_t)7;
+      return 16 * units + 4 * (3 * (size_t)tile_r(r) + 1) + 2 * (size_t)tile_r(r) + 16;
+   };
    int best = 0;
    for (int r = 0; r < kNumTileR; ++r)
-   {
-      const size_t bytes = 32 * (size_t)p->tile_max_blocks[r] + 8 * (tile_r(r) + 1) + 128;
-      if (bytes <= budget / 3 && tile_r(r) * vis_per_node <= 1.25 * THREADS) best = r;
-   }
+      if (tile_smem(r) + 1024 <= budget / 4 && tile_r(r) <= 128) best = r;
+   const int maxR = 256 / TPN;
    const char *env = getenv("FEMB200_TILE_R");
    if (env)
       for (int r = 0; r < kNumTileR; ++r)
-         if (atoi(env) == tile_r(r)) best = r;
+         if (atoi(env) == tile_r(r) && tile_r(r) <= maxR) best = r;
    const int R = tile_r(best);
    A.stage_units = (2 * p->tile_max_blocks[best] + 7) & ~7;
-   const size_t smem = 16 * (size_t)A.stage_units + 8 * (size_t)(R + 1) + 16;
+   const size_t smem = tile_smem(best);
    FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", R, smem, budget);
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
    const unsigned grid = (unsigned)cdiv(p->nnodes, R);
-   assemble_kernel<ET, FAST, THREADS><<<grid, THREADS, smem, st>>>(A, R);
+   assemble_kernel<ET, FAST, CH, TPN><<<grid, TPN * R, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
    return 0;
+}
+
+template <int ET, bool FAST>
+static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
+{
+   if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
+   // developer switches: visits batched per load level (CH), threads per node (TPN)
+   const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
+   const int ch = env ? atoi(env) : 2, tpn = env2 ? atoi(env2) : 1;
+   if (tpn == 2)
+      switch (ch)
+      {
+         case 1: return launch_assemble_ch<ET, FAST, 1, 2>(p, A, st);
+         case 3: return launch_assemble_ch<ET, FAST, 3, 2>(p, A, st);
+         default: return launch_assemble_ch<ET, FAST, 2, 2>(p, A, st);
+      }
+   switch (ch)
+   {
+      case 1: return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
+      case 3: return launch_assemble_ch<ET, FAST, 3, 1>(p, A, st);
+      default: return launch_assemble_ch<ET, FAST, 2, 1>(p, A, st);
+   }
 }
 
 }  // namespace femb
@@ -436,6 +522,21 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);
    const bool linear = (d_dnod == nullptr) && !getenv("FEMB200_FORCE_GENERIC");
+   A.cellrec = nullptr;
+   A.debug = getenv("FEMB200_ASM_DEBUG") ? atoi(getenv("FEMB200_ASM_DEBUG")) : 0;
+   if (linear && p->etype != FEMB200_Q2)
+   {
+      femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan
+      if (!pm->cellrec)
+      {
+         FEMB_CUDA(cudaMalloc(&pm->cellrec, sizeof(double) * 6 * (size_t)p->ncells));
+         pm->bytes += sizeof(double) * 6 * (size_t)p->ncells;
+      }
+      cell_setup_kernel<<<(unsigned)cdiv(p->ncells, 256), 256, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, A.lc,
+                                                                        pm->cellrec);
+      FEMB_LAUNCH_CHECK();
+      A.cellrec = pm->cellrec;
+   }
    int rc;
    switch (p->etype)
    {

@@ -240,6 +240,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->bcol);
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
+   cudaFree(p->cellrec);
    delete p;
 }
 

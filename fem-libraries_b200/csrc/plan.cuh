@@ -56,5 +56,6 @@ struct femb200_plan
    int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
    int32_t nbc = 0;
    size_t bytes = 0;
+   double *cellrec = nullptr;  // [ncells][6] per-cell (grad l1, grad l2, |T| lambda, |T| mu), fast path, lazily allocated
    int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
 };
