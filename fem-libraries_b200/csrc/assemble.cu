@@ -467,7 +467,7 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    };
    int best = 0;
    for (int r = 0; r < kNumTileR; ++r)
-      if (tile_smem(r) + 1024 <= budget / 4 && tile_r(r) <= 128) best = r;
+      if (tile_smem(r) + 1024 <= budget / 4 && tile_r(r) <= 64) best = r;
    const int maxR = 256 / TPN;
    const char *env = getenv("FEMB200_TILE_R");
    if (env)
@@ -490,7 +490,7 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
-   const int ch = env ? atoi(env) : 2, tpn = env2 ? atoi(env2) : 1;
+   const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
    if (tpn == 2)
       switch (ch)
       {

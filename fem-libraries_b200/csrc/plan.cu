@@ -181,6 +181,14 @@ __global__ void k_tile_max(int64_t nnodes, const int64_t *__restrict__ brp, int3
    }
 }
 
+// largest tile of the tiling [lo + t R, lo + (t + 1) R) of the row range [lo, hi)
+__global__ void k_range_tile_max(int64_t lo, int64_t hi, int R, const int64_t *__restrict__ brp, int32_t *__restrict__ out)
+{
+   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t n0 = lo + t * R;
+   if (n0 < hi) atomicMax(out, (int32_t)(brp[min(n0 + (int64_t)R, hi)] - brp[n0]));
+}
+
 // --- scalar CSR expansion ---------------------------------------------------------
 __global__ void k_scalar_csr(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
                              int64_t *__restrict__ rowptr, int32_t *__restrict__ colidx)
@@ -317,6 +325,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
       return fail(set_error("plan_create: slot map build failed: %s", cudaGetErrorString(cudaGetLastError())));
 
+   p->row_tile_max_blocks = p->tile_max_blocks[1];
    cudaFree(cnt);
    cudaFree(deg);
    cudaFree(flags);
@@ -413,5 +422,18 @@ extern "C" int femb200_plan_set_row_range(femb200_plan *p, int64_t row_lo, int64
    FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "plan_set_row_range: bad range [%lld, %lld)",
               (long long)row_lo, (long long)row_hi);
    p->row_lo = row_lo, p->row_hi = row_hi;
+   p->row_tile_max_blocks = p->tile_max_blocks[1];
+   if (row_lo % 64 != 0 && row_hi > row_lo)
+   {  // the SpMV tiles no longer coincide with the plan's aligned tiles: measure them
+      int32_t *d = nullptr, h = 0;
+      FEMB_CUDA(cudaMalloc(&d, sizeof(int32_t)));
+      FEMB_CUDA(cudaMemset(d, 0, sizeof(int32_t)));
+      const int64_t nt = cdiv(row_hi - row_lo, 64);
+      k_range_tile_max<<<(unsigned)cdiv(nt, 256), 256>>>(row_lo, row_hi, 64, p->brp, d);
+      const cudaError_t e = cudaMemcpy(&h, d, sizeof(int32_t), cudaMemcpyDeviceToHost);
+      cudaFree(d);
+      FEMB_CHECK(e == cudaSuccess, "plan_set_row_range: %s", cudaGetErrorString(e));
+      p->row_tile_max_blocks = h;
+   }
    return 0;
 }

@@ -279,17 +279,16 @@ __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, con
 }
 
 template <bool DOT, int R>
-static int spmv_tma_launch(const femb200_plan *p, int tile_idx, const double *d_values, const double *d_x, double *d_y,
+static int spmv_tma_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
                            const double *d_flag, double *d_dot_out, cudaStream_t st)
 {
    const int64_t nrows = p->row_hi - p->row_lo;
    const int ntiles = (int)cdiv(nrows, R);
    SpmvTile cap;
-   cap.vbytes = 32 * p->tile_max_blocks[tile_idx];
-   cap.cbytes = ((4 * (p->tile_max_blocks[tile_idx] + 4) + 15) & ~15);
+   static_assert(R == 64, "plan->row_tile_max_blocks is measured for 64-row tiles");
+   cap.vbytes = 32 * p->row_tile_max_blocks;
+   cap.cbytes = ((4 * (p->row_tile_max_blocks + 4) + 15) & ~15);
    cap.pbytes = ((8 * (R + 3) + 15) & ~15);
-   // tiles of a row range that does not start on a multiple of R straddle two plan tiles
-   if (p->row_lo % R) cap.vbytes *= 2, cap.cbytes *= 2;
    const size_t smem = (size_t)kTmaStages * (cap.vbytes + cap.cbytes + cap.pbytes);
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
    if (smem > budget) return -1;  // caller falls back to the direct kernel
@@ -318,8 +317,8 @@ int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x
    if (!direct)
    {
       // tile_r(1) == 64 node rows per tile
-      const int rc = d_dot_out ? spmv_tma_launch<true, 64>(p, 1, d_values, d_x, d_y, d_flag, d_dot_out, st)
-                               : spmv_tma_launch<false, 64>(p, 1, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      const int rc = d_dot_out ? spmv_tma_launch<true, 64>(p, d_values, d_x, d_y, d_flag, d_dot_out, st)
+                               : spmv_tma_launch<false, 64>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
       if (rc >= 0) return rc;
    }
    const unsigned grid = (unsigned)cdiv(nrows * kSpmvLanes, kSpmvThreads);

@@ -105,6 +105,9 @@ def strip_partition(nx: int, ny_total: int, order: int, rank: int, world: int, j
     mx = 2 * nx + 1
     h = 1.0 / nx
     m = fm.structured_triangles(nx, r1g - r0, order=2, ly=(r1g - r0) * h, y0=r0 * h)
+    # coordinates bit-identical to the single-process mesh: take the y of the GLOBAL lattice rows
+    yg = np.linspace(0.0, ny_total / nx, 2 * ny_total + 1)[2 * r0:2 * r1g + 1]
+    m.x[:, 1] = np.repeat(yg, mx)
     m = jitter_rows(m, jitter_amp, seed, 2 * r0, 2 * ny_total + 1)
     cell_offset = 2 * nx * r0
     E = fm.young_per_cell(m.ncells, first_cell=cell_offset)
