@@ -8,20 +8,26 @@
  * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference
  * legs, never the product.
  *
- * PARITY UNPINNED at the library boundary: the reference ships no golden
- * vectors, no tests and no fixtures for this path, and MFEM /
- * dolfinx / ffcx are absent from this image, so the reference binaries cannot
- * be run.  What pins this file instead:
+ * PARITY STATUS.  The reference ships no golden vectors, no tests and no fixtures
+ * for this path, and MFEM / dolfinx / ffcx are absent from this
+ * image, so the reference binaries cannot be run.  What pins this file:
+ *   - PINNED (P1 element kernel, the only element the reference has): oracle/_ref
+ *     = the reference's own damIntegrator + asym_stress (M.cc:207-329, 490-953)
+ *     compiled in place from /root/reference against a minimal MFEM stand-in
+ *     (oracle/ref_shim/); tests/golden/ref_p1_vectors.json holds its outputs on
+ *     every triangle of common/data/square.msh (d = 0, both reference code paths)
+ *     and on 40 damaged cases (tangent, residual, load; special branches);
+ *     tests/test_reference_goldens.py checks this file against them (<= 1e-14
+ *     linear, <= 1e-12 damaged);
  *   - the known answers derived from the reference formulas on the reference's
- *     only mesh (common/data/square.msh): see tests/golden/square_kat.json;
- *   - three independent code paths for the P1 tangent that must agree
- *     (B.D.B^t as M.cc:699-704,886-887; tensor-product blocks as
- *     M.cc:705-717,893-911; generic quadrature loop);
- *   - closed-form damaged tangent (M.cc:736-872) against the dual-number
- *     Hessian of the potential (M.cc:100-155,752-765; admfem.hpp:672-699);
- *   - oracle/_ref: the reference's own damIntegrator compiled in place from
- *     /root/reference against a minimal dense-algebra shim (see
- *     oracle/ref_shim/), when that build is available.
+ *     only mesh (common/data/square.msh): tests/golden/square_kat.json;
+ *   - three independent code paths for the P1 tangent that must agree, and the
+ *     closed-form damaged tangent against the dual-number Hessian of the potential.
+ *   - UNPINNED (no reference code or vectors exist): P2 / Q2 elements, the CSR
+ *     ordering convention (dolfinx: un-vendored), the Jacobi-PCG iteration (the
+ *     reference preconditions with HYPRE BoomerAMG).  These follow SURVEY.md 8c /
+ *     A.9 and are checked by properties only (patch test, rigid-body null space,
+ *     symmetry, assembled == matrix-free, direct solve).
  *
  * All file:line citations are relative to /root/reference/, with
  *   M.cc  = MFEM/mechanic2d/asym_elasto_damage_model.cc

@@ -4,8 +4,10 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  The product package
 (fem-libraries_b200/femb200) never imports this module.
 
-PARITY UNPINNED at the library boundary (the reference ships no golden vectors;
-see the header of fem_oracle.c and DESIGN.md).
+Parity status: the P1 element kernel is pinned against the reference's own compiled
+code (oracle/_ref, tests/golden/ref_p1_vectors.json); P2/Q2, the CSR convention and
+the Jacobi-PCG have no reference code or vectors ("parity unpinned" for those; see
+the header of fem_oracle.c and DESIGN.md).
 """
 from __future__ import annotations
 
