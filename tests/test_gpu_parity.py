@@ -146,6 +146,34 @@ def oracle_assemble(m, E, d=None, u=None, variant=0, bc=None):
     return rowptr, colidx, vals
 
 
+def test_assembly_unstructured_and_ragged():
+    """square.msh (unstructured, up to 8 cells per node), a one-cell mesh, a mesh with an unused
+    node and a shuffled cell order: pull kernel and staged kernel against the oracle."""
+    f = fem()
+    rng = np.random.default_rng(5)
+    m1 = fm.Mesh(fm.P1, np.array([[0., 0.], [1., 0.], [0., 1.]]), np.array([[0, 1, 2]], dtype=np.int32),
+                 np.array([[0, 1, 2]], dtype=np.int32))
+    m2 = make_mesh("P2", 9, ny=5)
+    perm = rng.permutation(m2.ncells)
+    m2s = fm.Mesh(m2.etype, m2.x, m2.xdofmap[perm].copy(), m2.dofmap[perm].copy(), m2.nx, m2.ny)
+    m3 = make_mesh("P1", 5)
+    m3u = fm.Mesh(fm.P1, np.vstack([m3.x, [[5., 5.]]]), m3.xdofmap, m3.dofmap)  # last node belongs to no cell
+    for m in (m1, m2s, m3u):
+        E = 1e7 * (1 + rng.random(m.ncells))
+        _, _, want = oracle_assemble(m, E)
+        form = f.ElasticityForm(m, E)
+        A = f.create_matrix(form)
+        for pull in (False, True):
+            if pull:
+                os.environ["FEMB200_ASM_PULL"] = "1"
+            try:
+                A.values.fill_(float("nan"))
+                f.assemble_matrix(A, form)
+            finally:
+                os.environ.pop("FEMB200_ASM_PULL", None)
+            assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
 def test_assembly_square_msh_known_answers(square, kat):
     m = square_mesh(square)
     E = oracle.E_table()[square["tag"] % 200]
@@ -176,11 +204,22 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
     f.assemble_matrix(A, form, bcs=[f.DirichletBC(bc)] if with_bc else None)
     got = A.values.cpu().numpy()
     assert relfro(got, want) < TOL_VALUES
-    if with_bc:  # zeros and the unit diagonal must be exact, not approximate
-        np.testing.assert_array_equal(got[want == 0.0], 0.0)
-        np.testing.assert_array_equal(got[want == 1.0], 1.0)
-    if kind in ("P1", "P2"):  # the generic per-quadrature-point path must give the same matrix
+    if with_bc:  # Dirichlet rows / columns and the unit diagonal must be exact, not approximate
+        rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+        rows = np.repeat(np.arange(m.ndofs), np.diff(rowptr))
+        touched = (bc[rows] != 0) | (bc[colidx] != 0)
+        np.testing.assert_array_equal(got[touched], want[touched])
+        assert set(np.unique(want[touched])) == {0.0, 1.0}
+    if kind in ("P1", "P2"):
+        # the output-centric (pull) variant and the generic per-quadrature-point path must give
+        # the same matrix
+        monkeypatch.setenv("FEMB200_ASM_PULL", "1")
+        A.values.fill_(float("nan"))
+        f.assemble_matrix(A, form)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+        monkeypatch.delenv("FEMB200_ASM_PULL")
         monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
+        A.values.fill_(float("nan"))
         f.assemble_matrix(A, form)
         assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
 
