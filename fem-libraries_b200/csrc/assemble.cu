@@ -231,171 +231,6 @@ __device__ __forceinline__ void fast_compute_stage(const AsmArgs &A, const Visit
    }
 }
 
-// ---- fast path, precomputed staging offsets --------------------------------------------
-// Same arithmetic as fast_compute_stage, but the six targets of a visit come straight out of
-// the plan record (csrc/plan.cuh: rotated column order, swizzled tile-relative block index,
-// first-touch bit), so a staged unit costs a shift, a mask and an add instead of ~20 integer
-// instructions.  Staging layout: unit 2 * sblk + h (both scalar rows of a block adjacent),
-// sblk = blk ^ ((blk >> 2) & 3); lanes (2i, 2i+1) hold the two rows of node i.
-template <int ET>
-__device__ __forceinline__ void fast2_compute_stage(const AsmArgs &A, uint4 raw, const FastGeo &g, double2 *sv, int h)
-{
-   const int a = (int)(raw.x >> 28);
-   const int m = (a >= 3) ? a - 3 : a;  // rotation: own vertex / own edge becomes number 0
-   const double h0x = -g.g1x - g.g2x, h0y = -g.g1y - g.g2y;
-   const double a1x = m == 0 ? g.g1x : (m == 1 ? g.g2x : h0x), a1y = m == 0 ? g.g1y : (m == 1 ? g.g2y : h0y);
-   const double a2x = m == 0 ? g.g2x : (m == 1 ? h0x : g.g1x), a2y = m == 0 ? g.g2y : (m == 1 ? h0y : g.g1y);
-   const double g1[2] = {h ? a1y : a1x, h ? a1x : a1y};
-   const double g2[2] = {h ? a2y : a2x, h ? a2x : a2y};
-   const double tl = A.lc.c2, tm = A.lc.c3;
-   auto put = [&](int t, double k0, double k1) {
-      const uint32_t w = t < 2 ? raw.y : (t < 4 ? raw.z : raw.w);
-      const uint32_t f = (t & 1) ? (w >> 16) : (w & 0xffffu);
-      double2 *p = sv + 2 * (f & 0x7fffu) + h;
-      const double v0 = h ? k1 : k0, v1 = h ? k0 : k1;
-      if (f & 0x8000u)
-         *p = make_double2(v0, v1);
-      else
-      {
-         double2 v = *p;
-         v.x += v0, v.y += v1;
-         *p = v;
-      }
-   };
-   if (a < 3)
-   {  // row = (rotated) vertex 0
-      const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
-      double w00[2], w01[2], w02[2];
-      w_row(g0, g0, tl, tm, w00);
-      w_row(g0, g1, tl, tm, w01);
-      w_row(g0, g2, tl, tm, w02);
-      if (ET == FEMB200_P1)
-      {  // P1: K_ab = W^{ab}  (M.cc:885-887)
-         put(0, w00[0], w00[1]);
-         put(1, w01[0], w01[1]);
-         put(2, w02[0], w02[1]);
-      }
-      else
-      {
-         const double c3 = -1. / 3., c43 = 4. / 3.;
-         put(0, w00[0], w00[1]);
-         put(1, c3 * w01[0], c3 * w01[1]);
-         put(2, c3 * w02[0], c3 * w02[1]);
-         put(3, 0., 0.);  // rotated edges: 0' = (1,2) opposite (structural zero), 1' = (2,0), 2' = (0,1)
-         put(4, c43 * w02[0], c43 * w02[1]);
-         put(5, c43 * w01[0], c43 * w01[1]);
-      }
-   }
-   else
-   {  // row = (rotated) edge 0 = (1,2); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
-      double w11[2], w12[2], w21[2], w22[2];
-      w_row(g1, g1, tl, tm, w11);
-      w_row(g1, g2, tl, tm, w12);
-      w_row(g2, g1, tl, tm, w21);
-      w_row(g2, g2, tl, tm, w22);
-      const double c43 = 4. / 3.;
-      const double s0 = w12[0] + w21[0], s1 = w12[1] + w21[1];  // S = W12 + W21
-      put(0, 0., 0.);
-      put(1, c43 * w21[0], c43 * w21[1]);
-      put(2, c43 * w12[0], c43 * w12[1]);
-      put(3, c43 * (2. * w11[0] + s0 + 2. * w22[0]), c43 * (2. * w11[1] + s1 + 2. * w22[1]));
-      put(4, -c43 * (2. * w11[0] + s0), -c43 * (2. * w11[1] + s1));
-      put(5, -c43 * (s0 + 2. * w22[0]), -c43 * (s1 + 2. * w22[1]));
-   }
-}
-
-struct FastArgs
-{
-   int64_t nnodes;
-   const int32_t *nptr;
-   const int64_t *brp;
-   const uint4 *vfast;
-   const uint8_t *ilb;
-   int nb_pad;  // capacity of the staging image in blocks (multiple of 4)
-   int nv_pad;  // capacity of the visit tables (multiple of 8)
-};
-
-// One CTA = kFastR node rows.  Everything a tile reads from global memory is brought in by the
-// whole CTA in three coalesced load levels before any visit is processed (tile extents -> visit
-// records and block owners -> cell records), so the visit loop itself is shared memory and
-// arithmetic only; the tile then leaves through coalesced 16-byte streaming stores.
-template <int ET>
-__global__ void __launch_bounds__(2 * kFastR) assemble_fast_kernel(AsmArgs A, FastArgs F)
-{
-   constexpr int R = kFastR, THREADS = 2 * kFastR;
-   extern __shared__ double2 sv[];  // [2 * nb_pad] staging image, then the tile tables
-   __shared__ int s_hist[8], s_base[8];
-   double2 *s_geo = sv + 2 * F.nb_pad;                                  // [2 * nv_pad] cell record of every visit
-   uint4 *s_vrec = reinterpret_cast<uint4 *>(s_geo + 2 * F.nv_pad);     // [nv_pad]
-   int32_t *s_k0 = reinterpret_cast<int32_t *>(s_vrec + F.nv_pad);      // first visit of node i (tile-relative)
-   int32_t *s_cnt = s_k0 + R;                                            // number of visits
-   int32_t *s_rb = s_cnt + R;                                            // [R + 1] first block of row i in the tile
-   uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_rb + R + 1);       // [R]
-   uint8_t *s_il = reinterpret_cast<uint8_t *>(s_perm + R);              // [nb_pad] owner row of every block
-   const int tid = threadIdx.x;
-   const int64_t n0 = (int64_t)blockIdx.x * R;
-   const int nloc = (int)min((int64_t)R, F.nnodes - n0);
-   // level 1: tile extents
-   const int64_t b0 = F.brp[n0];
-   const int32_t k0t = F.nptr[n0];
-   const int nb = (int)(F.brp[n0 + nloc] - b0);
-   const int nv = F.nptr[n0 + nloc] - k0t;
-   if (tid < 8) s_hist[tid] = 0;
-   // level 2: visit records, block owners, per-node offsets
-   for (int i = tid; i < nv; i += THREADS) s_vrec[i] = F.vfast[k0t + i];
-   for (int i = tid; i < nb; i += THREADS) s_il[i] = F.ilb[b0 + i];
-   __syncthreads();
-   int my_off = 0, key = 0;
-   if (tid < nloc)
-   {
-      const int32_t k0 = F.nptr[n0 + tid], k1 = F.nptr[n0 + tid + 1];
-      s_k0[tid] = k0 - k0t;
-      s_cnt[tid] = k1 - k0;
-      s_rb[tid] = (int32_t)(F.brp[n0 + tid] - b0);
-      key = min(k1 - k0, 7);
-      my_off = atomicAdd(&s_hist[key], 1);
-   }
-   if (tid == nloc) s_rb[nloc] = nb;
-   // level 3: the 32-byte cell record of every visit
-   for (int i = tid; i < nv; i += THREADS)
-   {
-      const double2 *p = reinterpret_cast<const double2 *>(A.cellrec + 4 * (int64_t)(s_vrec[i].x & 0x0fffffffu));
-      const double2 q0 = p[0], q1 = p[1];
-      s_geo[2 * i] = q0, s_geo[2 * i + 1] = q1;
-   }
-   __syncthreads();
-   if (tid < 8)
-   {
-      int base = 0;
-      for (int kk = 7; kk > tid; --kk) base += s_hist[kk];
-      s_base[tid] = base;
-   }
-   __syncthreads();
-   if (tid < nloc) s_perm[s_base[key] + my_off] = (uint16_t)tid;  // nodes in order of decreasing visit count
-   __syncthreads();
-   if ((tid >> 1) < nloc)
-   {
-      const int i = s_perm[tid >> 1];
-      const int h = tid & 1;
-      const int k0 = s_k0[i], k1 = k0 + s_cnt[i];
-      for (int k = k0; k < k1; ++k)
-      {
-         const double2 q0 = s_geo[2 * k], q1 = s_geo[2 * k + 1];
-         fast2_compute_stage<ET>(A, s_vrec[k], FastGeo{q0.x, q0.y, q1.x, q1.y}, sv, h);
-      }
-   }
-   __syncthreads();
-   // stream-out: staging unit p = 2 sblk + h  ->  scalar row h of block blk = sblk ^ ((sblk >> 2) & 3)
-   double *dst = A.values + 4 * b0;
-   const int nunits = 2 * ((nb + 3) & ~3);
-   for (int p = tid; p < nunits; p += THREADS)
-   {
-      const int sblk = p >> 1, h = p & 1;
-      const int blk = sblk ^ ((sblk >> 2) & 3);
-      if (blk < nb) st_stream_d2(dst + 2 * (int64_t)(s_rb[s_il[blk] + h] + blk), sv[p]);
-   }
-}
-
 // ---- generic path: per-quadrature-point loop, damaged tangent, any family -------
 template <int ET>
 __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double (*kb)[4])
@@ -659,39 +494,13 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    return 0;
 }
 
-int launch_assemble_pull(const femb200_plan *p, const double *cellrec, LameCoef lc, double *d_values, cudaStream_t st);
-
-template <int ET>
-static int launch_assemble_fast(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
-{
-   FastArgs F;
-   F.nnodes = p->nnodes, F.nptr = p->nptr, F.brp = p->brp, F.vfast = p->vfast, F.ilb = p->ilb;
-   F.nb_pad = (p->tile_max_blocks[1] + 15) & ~15;  // tile_r(1) == kFastR
-   F.nv_pad = (p->fast_max_visits + 7) & ~7;
-   const size_t smem = 32 * (size_t)F.nb_pad + 48 * (size_t)F.nv_pad + 4 * (size_t)(3 * kFastR + 1) + 2 * (size_t)kFastR +
-                       (size_t)F.nb_pad + 32;
-   const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
-   if (smem > budget / 2) return -1;  // unusually dense tiles: the generic staged kernel handles them
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   assemble_fast_kernel<ET><<<(unsigned)cdiv(p->nnodes, kFastR), 2 * kFastR, smem, st>>>(A, F);
-   FEMB_LAUNCH_CHECK();
-   return 0;
-}
-
 template <int ET, bool FAST>
 static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
 {
-   static_assert(tile_r(1) == kFastR, "tile_max_blocks[1] must describe kFastR-row tiles");
-   if constexpr (FAST)
-      if (p->fast_ok && !getenv("FEMB200_ASM_OLD"))
-      {
-         const int rc = launch_assemble_fast<ET>(p, A, st);
-         if (rc >= 0) return rc;
-      }
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
-   const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
+   const int ch = env ? atoi(env) : 2, tpn = env2 ? atoi(env2) : 2;
    if (tpn == 2)
       switch (ch)
       {
@@ -738,10 +547,8 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
       FEMB_LAUNCH_CHECK();
       A.cellrec = pm->cellrec;
    }
-   int rc = -1;
-   if (A.cellrec && getenv("FEMB200_ASM_PULL")) rc = launch_assemble_pull(p, A.cellrec, A.lc, d_values, st);
-   if (rc > 0) return rc;
-   if (rc < 0) switch (p->etype)
+   int rc;
+   switch (p->etype)
    {
       case FEMB200_P1:
          rc = linear ? launch_assemble<FEMB200_P1, true>(p, A, st) : launch_assemble<FEMB200_P1, false>(p, A, st);

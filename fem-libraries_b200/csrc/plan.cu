@@ -165,179 +165,6 @@ __global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__
    }
 }
 
-// --- fast-path visit records: rotated column order, tile-relative swizzled block offsets -----
-__device__ __forceinline__ int rotated_local(int t, int a)
-{  // local dof of ROTATED column t for a row with local index a (vertices then edges)
-   const int m = (a >= 3) ? a - 3 : a;
-   const int tt = (t >= 3) ? t - 3 : t;
-   int b = m + tt;
-   b = (b >= 3) ? b - 3 : b;
-   return (t >= 3) ? b + 3 : b;
-}
-
-__global__ void k_fill_fast(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
-                            const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
-                            const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
-                            uint4 *__restrict__ vfast, uint8_t *__restrict__ ilb, int32_t *__restrict__ flags)
-{
-   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (I >= nnodes) return;
-   const int64_t base = brp[I];
-   const int deg = (int)(brp[I + 1] - base);
-   const int64_t tile0 = (I / kFastR) * kFastR;
-   const int rel = (int)(base - brp[tile0]);  // first block of row I in its tile
-   if (rel + deg > 32767) atomicOr(flags, 1);
-   for (int s = 0; s < deg; ++s) ilb[base + s] = (uint8_t)(I - tile0);
-   uint32_t touched[(kMaxDeg + 31) / 32];
-   for (int t = 0; t < (kMaxDeg + 31) / 32; ++t) touched[t] = 0u;
-   for (int32_t k = nptr[I]; k < nptr[I + 1]; ++k)
-   {
-      const uint32_t e = vis[k] >> 4, a = vis[k] & 15u;
-      uint32_t w[3] = {0u, 0u, 0u};
-      for (int t = 0; t < nd; ++t)
-      {
-         const int32_t J = dofmap[(int64_t)e * nd + rotated_local(t, (int)a)];
-         int lo = 0, hi = deg;
-         while (lo < hi)
-         {
-            const int mid = (lo + hi) >> 1;
-            if (bcol[base + mid] < J)
-               lo = mid + 1;
-            else
-               hi = mid;
-         }
-         const uint32_t blk = (uint32_t)(rel + lo);
-         uint32_t f = blk ^ ((blk >> 2) & 3u);
-         if (!((touched[lo >> 5] >> (lo & 31)) & 1u))
-         {
-            touched[lo >> 5] |= 1u << (lo & 31);
-            f |= 0x8000u;
-         }
-         w[t >> 1] |= f << (16 * (t & 1));
-      }
-      if (e >> 28) atomicOr(flags, 1);
-      vfast[k] = make_uint4(e | (a << 28), w[0], w[1], w[2]);
-   }
-}
-
-__global__ void k_fast_tile_visits(int64_t nnodes, const int32_t *__restrict__ nptr, int32_t *__restrict__ out)
-{
-   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   const int64_t n0 = t * kFastR;
-   if (n0 < nnodes) atomicMax(out, nptr[min(n0 + (int64_t)kFastR, nnodes)] - nptr[n0]);
-}
-
-// --- pull plan --------------------------------------------------------------------------
-// one CTA per tile: unique sorted incident cells of the tile (rank sort in shared memory)
-constexpr int kPullMaxVis = 2048;  // visits per tile handled by the builder
-
-__global__ void __launch_bounds__(256)
-k_pull_tile_cells(int64_t nnodes, const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
-                  const int32_t *__restrict__ tile_cptr, int32_t *__restrict__ tile_count,
-                  int32_t *__restrict__ tile_cells, uint16_t *__restrict__ vis16, int32_t *__restrict__ flags)
-{
-   __shared__ uint32_t sc[kPullMaxVis];
-   __shared__ uint16_t srank[kPullMaxVis];
-   __shared__ int s_nuniq;
-   const int64_t n0 = (int64_t)blockIdx.x * kPullR;
-   const int64_t n1 = min(n0 + (int64_t)kPullR, nnodes);
-   const int32_t k0 = nptr[n0], k1 = nptr[n1];
-   const int nv = k1 - k0;
-   if (nv > kPullMaxVis)
-   {
-      if (threadIdx.x == 0) atomicOr(flags, 1);
-      return;
-   }
-   if (threadIdx.x == 0) s_nuniq = 0;
-   for (int i = threadIdx.x; i < nv; i += 256) sc[i] = vis[k0 + i] >> 4;
-   __syncthreads();
-   // first occurrences, then the rank of every visit's cell among the distinct cells of the tile
-   __shared__ uint8_t sfirst[kPullMaxVis];
-   for (int i = threadIdx.x; i < nv; i += 256)
-   {
-      const uint32_t c = sc[i];
-      bool first = true;
-      for (int j = 0; j < i; ++j) first = first && (sc[j] != c);
-      sfirst[i] = first;
-      if (first) atomicAdd(&s_nuniq, 1);
-   }
-   __syncthreads();
-   for (int i = threadIdx.x; i < nv; i += 256)
-   {
-      const uint32_t c = sc[i];
-      int rank = 0;
-      for (int j = 0; j < nv; ++j) rank += (sfirst[j] && sc[j] < c);
-      srank[i] = (uint16_t)rank;
-   }
-   __syncthreads();
-   if (tile_count)
-   {  // pass 1: sizes only
-      if (threadIdx.x == 0)
-      {
-         tile_count[blockIdx.x] = s_nuniq;
-         atomicMax(flags + 1, s_nuniq);
-         atomicMax(flags + 2, nv);
-         if (s_nuniq > 4095) atomicOr(flags, 2);
-      }
-      return;
-   }
-   const int32_t base = tile_cptr[blockIdx.x];
-   for (int i = threadIdx.x; i < nv; i += 256)
-   {
-      tile_cells[base + srank[i]] = (int32_t)sc[i];  // duplicates write the same value
-      vis16[k0 + i] = (uint16_t)((srank[i] << 4) | (vis[k0 + i] & 15u));
-   }
-}
-
-// per node: the pull records of its block row
-__global__ void k_pull_records(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
-                               const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
-                               const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
-                               uint32_t *__restrict__ pull, int32_t *__restrict__ flags)
-{
-   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (I >= nnodes) return;
-   const int64_t base = brp[I];
-   const int deg = (int)(brp[I + 1] - base);
-   const uint32_t il = (uint32_t)(I % kPullR);
-   for (int s = 0; s < deg; ++s) pull[base + s] = il | 0xffff00u;
-   const int32_t k0 = nptr[I], k1 = nptr[I + 1];
-   if (k1 - k0 > 15)
-   {
-      atomicOr(flags, 4);
-      return;
-   }
-   for (int32_t k = k0; k < k1; ++k)
-   {
-      const int64_t e = vis[k] >> 4;
-      const uint32_t vi = (uint32_t)(k - k0);
-      for (int b = 0; b < nd; ++b)
-      {
-         const int32_t J = dofmap[e * nd + b];
-         int lo = 0, hi = deg;
-         while (lo < hi)
-         {
-            const int mid = (lo + hi) >> 1;
-            if (bcol[base + mid] < J)
-               lo = mid + 1;
-            else
-               hi = mid;
-         }
-         uint32_t rec = pull[base + lo];
-         const uint32_t c = (vi << 4) | (uint32_t)b;
-         if (J == I)
-            rec = (rec & ~0xff00u) | 0xfe00u;  // diagonal: all visits of the node contribute
-         else if (((rec >> 8) & 0xffu) == 0xffu)
-            rec = (rec & ~0xff00u) | (c << 8);
-         else if (((rec >> 16) & 0xffu) == 0xffu)
-            rec = (rec & ~0xff0000u) | (c << 16);
-         else
-            atomicOr(flags, 8);  // more than two cells share a node pair: not a conforming 2-D mesh
-         pull[base + lo] = rec;
-      }
-   }
-}
-
 // --- largest staging tile (in node blocks) for each candidate tile height R ------
 __global__ void k_tile_max(int64_t nnodes, const int64_t *__restrict__ brp, int32_t *__restrict__ out)
 {
@@ -422,12 +249,6 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
    cudaFree(p->cellrec);
-   cudaFree(p->tile_cptr);
-   cudaFree(p->tile_cells);
-   cudaFree(p->vis16);
-   cudaFree(p->pull);
-   cudaFree(p->vfast);
-   cudaFree(p->ilb);
    delete p;
 }
 
@@ -506,66 +327,6 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
 
    p->row_tile_max_blocks = p->tile_max_blocks[1];
 
-   // 3b. fast-path records (straight-sided triangles)
-   if (etype != FEMB200_Q2)
-   {
-      int32_t *ff = nullptr, hff[2] = {0, 0};
-      size_t scr = 0;
-      bool ok = !dev_alloc(&ff, 2, &scr) && !dev_alloc(&p->vfast, (size_t)nvis, &p->bytes) &&
-                !dev_alloc(&p->ilb, (size_t)p->nnzb + 16, &p->bytes);
-      if (ok)
-      {
-         cudaMemsetAsync(ff, 0, 2 * sizeof(int32_t), st);
-         k_fast_tile_visits<<<(unsigned)cdiv(cdiv(nnodes, kFastR), 256), 256, 0, st>>>(nnodes, p->nptr, ff + 1);
-         k_fill_fast<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
-                                                                  p->vfast, p->ilb, ff);
-         ok = cudaMemcpyAsync(hff, ff, sizeof(hff), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-              cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess && hff[0] == 0;
-         p->fast_max_visits = hff[1];
-      }
-      p->fast_ok = ok;
-      cudaFree(ff);
-      cudaGetLastError();
-   }
-
-   // 4. pull plan (optional: any limit exceeded -> the staged kernel is used instead)
-   if (etype != FEMB200_Q2 && getenv("FEMB200_ASM_PULL"))
-   {
-      p->ntiles = cdiv(nnodes, kPullR);
-      int32_t *pf = nullptr, *tcount = nullptr;
-      size_t scr = 0;
-      bool ok = !dev_alloc(&pf, 4, &scr) && !dev_alloc(&tcount, (size_t)p->ntiles + 1, &scr) &&
-                !dev_alloc(&p->tile_cptr, (size_t)p->ntiles + 1, &p->bytes) &&
-                !dev_alloc(&p->vis16, (size_t)nvis, &p->bytes) && !dev_alloc(&p->pull, (size_t)p->nnzb, &p->bytes);
-      int32_t hf[4] = {0, 0, 0, 0}, ncell_total = 0;
-      if (ok)
-      {
-         cudaMemsetAsync(pf, 0, 4 * sizeof(int32_t), st);
-         cudaMemsetAsync(tcount, 0, sizeof(int32_t) * ((size_t)p->ntiles + 1), st);
-         k_pull_tile_cells<<<(unsigned)p->ntiles, 256, 0, st>>>(nnodes, p->nptr, tmpvis, nullptr, tcount, nullptr, nullptr, pf);
-         ok = exclusive_scan_i32_i32(tcount, p->tile_cptr, p->ntiles, st) == 0;
-         ok = ok && cudaMemcpyAsync(hf, pf, sizeof(hf), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-              cudaMemcpyAsync(&ncell_total, p->tile_cptr + p->ntiles, sizeof(int32_t), cudaMemcpyDeviceToHost, st) ==
-                  cudaSuccess &&
-              cudaStreamSynchronize(st) == cudaSuccess && hf[0] == 0;
-      }
-      if (ok) ok = !dev_alloc(&p->tile_cells, (size_t)ncell_total, &p->bytes);
-      if (ok)
-      {
-         k_pull_tile_cells<<<(unsigned)p->ntiles, 256, 0, st>>>(nnodes, p->nptr, tmpvis, p->tile_cptr, nullptr, p->tile_cells,
-                                                               p->vis16, pf);
-         k_pull_records<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
-                                                                     p->pull, pf);
-         int32_t hf2[4] = {0, 0, 0, 0};
-         ok = cudaMemcpyAsync(hf2, pf, sizeof(hf2), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-              cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess && hf2[0] == 0;
-         p->pull_max_cells = hf[1], p->pull_max_visits = hf[2];
-      }
-      p->pull_ok = ok;
-      cudaFree(pf);
-      cudaFree(tcount);
-      cudaGetLastError();
-   }
    cudaFree(cnt);
    cudaFree(deg);
    cudaFree(flags);

@@ -35,8 +35,6 @@ struct Visit
 };
 static_assert(sizeof(VisitRec) == 16, "VisitRec must be 16 bytes");
 
-constexpr int kFastR = 64;  // node rows per tile of the fast staged assembly
-constexpr int kPullR = 64;  // node rows per tile of the pull assembly
 constexpr int kNumTileR = 6;
 __host__ __device__ constexpr int tile_r(int r) { return r == 0 ? 32 : r == 1 ? 64 : r == 2 ? 96 : r == 3 ? 128 : r == 4 ? 192 : 256; }
 
@@ -58,29 +56,6 @@ struct femb200_plan
    int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
    int32_t nbc = 0;
    size_t bytes = 0;
-   // --- output-centric ("pull") assembly plan, fast path (csrc/assemble_pull.cu) ---------------
-   // tiles of kPullR consecutive node rows; per tile the sorted unique incident cells, per visit a
-   // 16-bit (tile-local cell << 4 | local row a), per node block a 32-bit pull record
-   //   byte 0: tile-local node   byte 1, 2: contributions (visit-in-node << 4 | local col b), 0xff = none,
-   //   0xfe in byte 1 = diagonal block (summed over all visits of the node)
-   // --- fast-path staging plan (csrc/assemble.cu, assemble_fast_kernel) -----------------------
-   // tiles of kFastR node rows; per visit one uint4:
-   //   word 0   cell id (bits 0-27) | local row a (bits 28-31)
-   //   word 1-3 six 16-bit fields, one per ROTATED local column t (vertices m, m+1, m+2 then the
-   //            edges 3+m, ...; P1 uses three): bits 0-14 = swizzled tile-relative block index
-   //            sblk = blk ^ ((blk >> 2) & 3) of the target block, bit 15 = first touch (store, do not add)
-   // per node block one byte = tile-local node (stream-out: which row pair the block belongs to)
-   uint4 *vfast = nullptr;    // [nvisits]
-   uint8_t *ilb = nullptr;    // [nnzb]
-   bool fast_ok = false;
-   int32_t fast_max_visits = 0;  // visits of the largest kFastR-row tile
-   bool pull_ok = false;
-   int64_t ntiles = 0;
-   int32_t *tile_cptr = nullptr;   // [ntiles + 1] offsets into tile_cells
-   int32_t *tile_cells = nullptr;  // global cell ids
-   uint16_t *vis16 = nullptr;      // [nvisits]
-   uint32_t *pull = nullptr;       // [nnzb]
-   int32_t pull_max_cells = 0, pull_max_visits = 0;
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
    int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
    int32_t row_tile_max_blocks = 0;  // largest 64-row tile (in node blocks) of the tiling that starts at row_lo

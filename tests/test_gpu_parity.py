@@ -163,15 +163,9 @@ def test_assembly_unstructured_and_ragged():
         _, _, want = oracle_assemble(m, E)
         form = f.ElasticityForm(m, E)
         A = f.create_matrix(form)
-        for pull in (False, True):
-            if pull:
-                os.environ["FEMB200_ASM_PULL"] = "1"
-            try:
-                A.values.fill_(float("nan"))
-                f.assemble_matrix(A, form)
-            finally:
-                os.environ.pop("FEMB200_ASM_PULL", None)
-            assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+        A.values.fill_(float("nan"))
+        f.assemble_matrix(A, form)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
 
 
 def test_assembly_square_msh_known_answers(square, kat):
@@ -211,13 +205,16 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
         np.testing.assert_array_equal(got[touched], want[touched])
         assert set(np.unique(want[touched])) == {0.0, 1.0}
     if kind in ("P1", "P2"):
-        # the output-centric (pull) variant and the generic per-quadrature-point path must give
-        # the same matrix
-        monkeypatch.setenv("FEMB200_ASM_PULL", "1")
-        A.values.fill_(float("nan"))
-        f.assemble_matrix(A, form)
-        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
-        monkeypatch.delenv("FEMB200_ASM_PULL")
+        # the developer variants of the fast kernel and the generic per-quadrature-point path
+        # must give the same matrix
+        for tpn, ch in (("1", "1"), ("1", "3"), ("2", "1"), ("2", "3")):
+            monkeypatch.setenv("FEMB200_ASM_TPN", tpn)
+            monkeypatch.setenv("FEMB200_ASM_CH", ch)
+            A.values.fill_(float("nan"))
+            f.assemble_matrix(A, form)
+            assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+        monkeypatch.delenv("FEMB200_ASM_TPN")
+        monkeypatch.delenv("FEMB200_ASM_CH")
         monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
         A.values.fill_(float("nan"))
         f.assemble_matrix(A, form)

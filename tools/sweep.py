@@ -33,7 +33,6 @@ def timeit(fn, k=10, w=3):
     return s.elapsed_time(e) / k
 
 
-os.environ["FEMB200_ASM_OLD"] = "1"
 ref = None
 for tpn, ch, R in itertools.product(os.environ.get("TPNS", "1,2").split(","), os.environ.get("CHS", "1,2,3").split(","), os.environ.get("RS", "64,96,128").split(",")):
     os.environ["FEMB200_ASM_CH"], os.environ["FEMB200_TILE_R"], os.environ["FEMB200_ASM_TPN"] = ch, R, tpn
@@ -50,9 +49,3 @@ v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
 y = torch.empty_like(v)
 t = timeit(lambda: A.mult(v, y), 20)
 print(f"spmv: {t:.3f} ms frac {(36*A.nnz_blocks + 40*m.nnodes)/t/1e6/6451.2:.3f}")
-for ch in ("1",):
-    os.environ["FEMB200_ASM_CH"] = ch
-    os.environ.pop("FEMB200_ASM_OLD", None)
-    t = timeit(lambda: fem.assemble_matrix(A, form))
-    chk = A.values.double().square().sum().item()
-    print(f"assembly FAST2 CH={ch}: {t:.3f} ms  {m.ndofs / t / 1e6:.2f} GDOF/s  frac {(8*A.nnz + 32*m.ncells + 16*m.nnodes)/t/1e6/6451.2:.3f} chk {abs(chk-ref)/abs(ref):.1e} plan {A.plan_bytes/1e6:.0f} MB", flush=True)
