@@ -325,7 +325,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
       return fail(set_error("plan_create: slot map build failed: %s", cudaGetErrorString(cudaGetLastError())));
 
-   p->row_tile_max_blocks = p->tile_max_blocks[1];
+   p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
 
    cudaFree(cnt);
    cudaFree(deg);
@@ -423,18 +423,22 @@ extern "C" int femb200_plan_set_row_range(femb200_plan *p, int64_t row_lo, int64
    FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "plan_set_row_range: bad range [%lld, %lld)",
               (long long)row_lo, (long long)row_hi);
    p->row_lo = row_lo, p->row_hi = row_hi;
-   p->row_tile_max_blocks = p->tile_max_blocks[1];
+   p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
    if (row_lo % 64 != 0 && row_hi > row_lo)
    {  // the SpMV tiles no longer coincide with the plan's aligned tiles: measure them
-      int32_t *d = nullptr, h = 0;
-      FEMB_CUDA(cudaMalloc(&d, sizeof(int32_t)));
-      FEMB_CUDA(cudaMemset(d, 0, sizeof(int32_t)));
-      const int64_t nt = cdiv(row_hi - row_lo, 64);
-      k_range_tile_max<<<(unsigned)cdiv(nt, 256), 256>>>(row_lo, row_hi, 64, p->brp, d);
-      const cudaError_t e = cudaMemcpy(&h, d, sizeof(int32_t), cudaMemcpyDeviceToHost);
+      int32_t *d = nullptr, h[2] = {0, 0};
+      FEMB_CUDA(cudaMalloc(&d, 2 * sizeof(int32_t)));
+      FEMB_CUDA(cudaMemset(d, 0, 2 * sizeof(int32_t)));
+      for (int k = 0; k < 2; ++k)
+      {
+         const int R = 32 << k;
+         const int64_t nt = cdiv(row_hi - row_lo, R);
+         k_range_tile_max<<<(unsigned)cdiv(nt, 256), 256>>>(row_lo, row_hi, R, p->brp, d + k);
+      }
+      const cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
       cudaFree(d);
       FEMB_CHECK(e == cudaSuccess, "plan_set_row_range: %s", cudaGetErrorString(e));
-      p->row_tile_max_blocks = h;
+      p->row_tile_max[0] = h[0], p->row_tile_max[1] = h[1];
    }
    return 0;
 }

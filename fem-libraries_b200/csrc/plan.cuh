@@ -58,5 +58,5 @@ struct femb200_plan
    size_t bytes = 0;
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
    int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
-   int32_t row_tile_max_blocks = 0;  // largest 64-row tile (in node blocks) of the tiling that starts at row_lo
+   int32_t row_tile_max[2] = {0, 0};  // largest 32- / 64-row tile (in node blocks) of the tiling that starts at row_lo
 };

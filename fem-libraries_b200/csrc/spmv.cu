@@ -82,12 +82,11 @@ spmv_kernel(int64_t row_lo, int64_t nnodes, const int64_t *__restrict__ brp, con
 // own one contiguous byte range of the value array, of bcol and of brp: a producer
 // warp streams those three ranges into shared memory with 1-D bulk copies
 // (cp.async.bulk -> UBLKCP) completing on an mbarrier, S stages deep, while eight
-// consumer warps reduce the previous tiles out of shared memory; the only
+// consumer warps (L lanes per node row pair) reduce the previous tiles out of shared memory; the only
 // per-thread global loads left are the gathers of x (L1/L2 hits: the lattice
 // numbering keeps the reuse window at a few node rows).  Grid = resident CTAs only,
 // so the fused <x, y> needs ~300 tickets instead of one per 32 rows.
 // ---------------------------------------------------------------------------
-constexpr int kTmaStages = 3;
 constexpr int kTmaConsumers = 256;
 constexpr int kTmaThreads = kTmaConsumers + 32;
 
@@ -131,7 +130,7 @@ struct SpmvTile
    int vbytes, cbytes, pbytes;  // stage capacities: values, column indices, row pointers
 };
 
-template <bool DOT, int R>
+template <bool DOT, int R, int kTmaStages, int L>
 __global__ void __launch_bounds__(kTmaThreads)
 spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
                 const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
@@ -178,7 +177,8 @@ spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp,
          }
    }
    else
-   {  // ---- consumer warps: 8 lanes per node row pair ----
+   {  // ---- consumer warps: L lanes per node row pair ----
+      constexpr int kSpmvLanes = L;
       const int sub = lane & (kSpmvLanes - 1);
       const double2 *x2 = reinterpret_cast<const double2 *>(x);
       for (int it = 0; it < nmine; ++it)
@@ -278,30 +278,54 @@ __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, con
    diag[2 * I + 1] = d1;
 }
 
-template <bool DOT, int R>
+template <bool DOT, int R, int S, int L>
 static int spmv_tma_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
                            const double *d_flag, double *d_dot_out, cudaStream_t st)
 {
+   static_assert(R == 32 || R == 64, "plan->row_tile_max is measured for 32- and 64-row tiles");
+   static_assert(R * L % kTmaConsumers == 0, "a tile must be a whole number of consumer passes");
    const int64_t nrows = p->row_hi - p->row_lo;
    const int ntiles = (int)cdiv(nrows, R);
+   const int maxb = p->row_tile_max[R == 32 ? 0 : 1];
    SpmvTile cap;
-   static_assert(R == 64, "plan->row_tile_max_blocks is measured for 64-row tiles");
-   cap.vbytes = 32 * p->row_tile_max_blocks;
-   cap.cbytes = ((4 * (p->row_tile_max_blocks + 4) + 15) & ~15);
+   cap.vbytes = 32 * maxb;
+   cap.cbytes = ((4 * (maxb + 4) + 15) & ~15);
    cap.pbytes = ((8 * (R + 3) + 15) & ~15);
-   const size_t smem = (size_t)kTmaStages * (cap.vbytes + cap.cbytes + cap.pbytes);
+   const size_t smem = (size_t)S * (cap.vbytes + cap.cbytes + cap.pbytes);
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
    if (smem > budget) return -1;  // caller falls back to the direct kernel
-   FEMB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<DOT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (smem + 1024)));
+   FEMB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<DOT, R, S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(7, (budget + 1024) / (smem + 1024)));
    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)devinfo().sm_count * per_sm);
    ReduceScratch red{nullptr, nullptr};
    if (DOT)
       if (int rc = reduce_scratch(grid, st, &red)) return rc;
-   spmv_tma_kernel<DOT, R><<<grid, kTmaThreads, smem, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
-                                                            d_flag, red, d_dot_out, cap, ntiles);
+   spmv_tma_kernel<DOT, R, S, L><<<grid, kTmaThreads, smem, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x,
+                                                                  d_y, d_flag, red, d_dot_out, cap, ntiles);
    FEMB_LAUNCH_CHECK();
    return 0;
+}
+
+template <bool DOT>
+static int spmv_tma_dispatch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
+                             const double *d_flag, double *d_dot_out, cudaStream_t st)
+{
+   // developer switch FEMB200_SPMV_CFG = <R><S><L>; default 6424 = 64-row tiles, 2 stages (3 CTAs per SM), 4 lanes
+   // per row: 0.59 ms on the n = 1448 P2 matrix against 0.99 ms for 6438 (profiles/r1_summary.md)
+   const char *env = getenv("FEMB200_SPMV_CFG");
+   const int cfg = env ? atoi(env) : 6424;
+   switch (cfg)
+   {
+      case 3228: return spmv_tma_launch<DOT, 32, 2, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 3238: return spmv_tma_launch<DOT, 32, 3, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 3248: return spmv_tma_launch<DOT, 32, 4, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 6434: return spmv_tma_launch<DOT, 64, 3, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 6444: return spmv_tma_launch<DOT, 64, 4, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 6428: return spmv_tma_launch<DOT, 64, 2, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 6448: return spmv_tma_launch<DOT, 64, 4, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      case 6438: return spmv_tma_launch<DOT, 64, 3, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      default: return spmv_tma_launch<DOT, 64, 2, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+   }
 }
 
 int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
@@ -316,9 +340,8 @@ int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x
    const bool direct = getenv("FEMB200_SPMV_DIRECT") != nullptr;
    if (!direct)
    {
-      // tile_r(1) == 64 node rows per tile
-      const int rc = d_dot_out ? spmv_tma_launch<true, 64>(p, d_values, d_x, d_y, d_flag, d_dot_out, st)
-                               : spmv_tma_launch<false, 64>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      const int rc = d_dot_out ? spmv_tma_dispatch<true>(p, d_values, d_x, d_y, d_flag, d_dot_out, st)
+                               : spmv_tma_dispatch<false>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
       if (rc >= 0) return rc;
    }
    const unsigned grid = (unsigned)cdiv(nrows * kSpmvLanes, kSpmvThreads);

@@ -49,3 +49,11 @@ v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
 y = torch.empty_like(v)
 t = timeit(lambda: A.mult(v, y), 20)
 print(f"spmv: {t:.3f} ms frac {(36*A.nnz_blocks + 40*m.nnodes)/t/1e6/6451.2:.3f}")
+for cfg in os.environ.get("SPMV_CFGS", "6438,6428,6448,3228,3238,3248,6424,6434,6444").split(","):
+    os.environ["FEMB200_SPMV_CFG"] = cfg
+    try:
+        t = timeit(lambda: A.mult(v, y), 20)
+        print(f"spmv cfg {cfg} (R,S,L): {t:.3f} ms frac {(36*A.nnz_blocks + 40*m.nnodes)/t/1e6/6451.2:.3f} |y| {y.norm().item():.12e}", flush=True)
+    except Exception as ex:
+        print("spmv cfg", cfg, "failed", ex)
+os.environ.pop("FEMB200_SPMV_CFG", None)
