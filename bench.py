@@ -364,6 +364,10 @@ def run_b200(args):
         "gpu_launches": 2 * K,
         "clocks": clocks,
     }
+    if world == 1:
+        line["matrix_free"] = pa_probe(fem, form, bc, g, m, timed, peak)
+    if world == 1 and args.extras:
+        line["extras"] = extras(fem, timed, peak)
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(args.cpu_n, 3, 1)
         line["cpu_baseline"] = {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
@@ -371,6 +375,67 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
+
+
+def pa_probe(fem, form, bc, g, m, timed, peak):
+    """Matrix-free apply (AssemblePA / AddMultPA role) of the same operator on the same mesh."""
+    import torch
+    pa = fem.PAOperator(form, bcs=[fem.DirichletBC(bc, g)])
+    v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(v)
+    for _ in range(3):
+        pa.mult(v, y)
+    tot, _ = timed(lambda: pa.mult(v, y), 10)
+    ms = tot / 10
+    nbytes = m.nnodes * 32 + m.ncells * (8 * (2 * m.nv + 2) + 4 * m.nd + 4)
+    return {"pa_apply_ms": ms, "gdofs": m.ndofs / (ms * 1e-3) / 1e9, "gbs": nbytes / (ms * 1e-3) / 1e9,
+            "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": nbytes}
+
+
+def extras(fem, timed, peak):
+    """Other BASELINE configs on one GPU (developer flag --extras): config 3 (Q2 quads, matrix-free,
+    16.8 M elements) and the config-5 workload (damaged-tangent reassembly, closed form and AD)."""
+    import torch
+    from femb200 import mesh as fm
+    out = {}
+    n = 4096
+    m = fm.jitter(fm.structured_quads_q2(n), 0.2, seed=1234)
+    E = fm.young_per_cell(m.ncells)
+    bc, g = fm.dirichlet_markers(m)
+    form = fem.ElasticityForm(m, E, 0.3)
+    r = pa_probe(fem, form, bc, g, m, timed, peak)
+    pa = fem.PAOperator(form, bcs=[fem.DirichletBC(bc, g)])
+    cg = fem.CGSolver(rel_tol=0.0, max_iter=10)
+    cg.SetOperator(pa)
+    cg.SetPreconditioner("jacobi")
+    b = torch.ones(m.ndofs, dtype=torch.float64, device="cuda")
+    x = torch.empty_like(b)
+    cg.Mult(b, x, fixed_iters=10)
+    tot, _ = timed(lambda: cg.Mult(b, x, fixed_iters=10), 3)
+    r.update({"workload": f"Q2 quads n={n}: {m.ncells} elements, {m.ndofs} dofs, 3x3 Gauss, sum-factorised",
+              "pa_cg_iter_ms": tot / 3 / 11, "pa_cg_iter_gdofs": m.ndofs / (tot / 3 / 11 * 1e-3) / 1e9,
+              "survey_bytes_per_element": 596, "frac_at_survey_bytes": 596 * m.ncells / (r["pa_apply_ms"] * 1e-3) / 1e9 / peak})
+    out["config3_q2_matrix_free"] = r
+    del pa, cg, form, b, x
+    torch.cuda.empty_cache()
+    n = 1448
+    m = fm.jitter(fm.structured_triangles(n, order=2), 0.2, seed=1234)
+    E = fm.young_per_cell(m.ncells)
+    d = fm.damage_band(m)
+    u = 1e-3 * np.random.default_rng(0).standard_normal(m.ndofs)
+    res = {"workload": f"P2 n={n}, damage band on {100 * float((d[m.xdofmap].mean(axis=1) > 0).mean()):.1f} % of the cells, "
+                       "values-only reassembly on a frozen pattern"}
+    for variant, name in ((0, "closed_form"), (1, "ad")):
+        form = fem.ElasticityForm(m, E, 0.3, d=d, u=u, variant=variant)
+        A = fem.create_matrix(form)
+        for _ in range(2):
+            fem.assemble_matrix(A, form)
+        tot, _ = timed(lambda: fem.assemble_matrix(A, form), 5)
+        res[name + "_ms"] = tot / 5
+        res[name + "_gdofs"] = m.ndofs / (tot / 5 * 1e-3) / 1e9
+        del A, form
+    out["config5_damaged_reassembly_1gpu"] = res
+    return out
 
 
 def traffic_from_profile(which: str):
@@ -393,6 +458,7 @@ def main():
     ap.add_argument("--cg-iters", type=int, default=25)
     ap.add_argument("--cpu-n", type=int, default=512, help="cells per side of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time config 3 (Q2 matrix-free) and config 5 (damage)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
