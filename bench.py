@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1448, help="cells per side per GPU (1448 -> 4.19 M P2 triangles)")
+    ap.add_argument("--size", dest="n", type=int, default=1448, help="cells per side per GPU (1448 -> 4.19 M P2 triangles)")
     ap.add_argument("--cg-iters", type=int, default=25)
     ap.add_argument("--cpu-n", type=int, default=512, help="cells per side of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
