@@ -443,27 +443,43 @@ __global__ void dirichlet_kernel(int nbc, const int32_t *__restrict__ bc_nodes, 
 }
 
 // ---- Frobenius norm^2 and trace --------------------------------------------------
+// fro^2: one flat streaming pass over the value array; trace: one thread per node looks its
+// diagonal block up in the (sorted) block row.  Deterministic reductions.
 __global__ void __launch_bounds__(256)
-norms_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+fro_kernel(int64_t n2, const double2 *__restrict__ values, ReduceScratch red, double *__restrict__ out)
+{
+   double acc = 0.;
+   const int64_t stride = (int64_t)gridDim.x * 256;
+   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n2; i += stride)
+   {
+      const double2 v = ld_stream_d2(reinterpret_cast<const double *>(values + i));
+      acc += v.x * v.x + v.y * v.y;
+   }
+   block_reduce_finish<256>(acc, red, out);
+}
+
+__global__ void __launch_bounds__(256)
+trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
              const double *__restrict__ values, ReduceScratch red, double *__restrict__ out)
 {
-   double acc[2] = {0., 0.};  // fro^2, trace
-   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-   const int lane = threadIdx.x & 31;
-   for (int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < nnodes; I += nw)
+   double acc = 0.;
+   const int64_t stride = (int64_t)gridDim.x * 256;
+   for (int64_t I = (int64_t)blockIdx.x * 256 + threadIdx.x; I < nnodes; I += stride)
    {
       const int64_t bi = brp[I];
       const int deg = (int)(brp[I + 1] - bi);
-      const double2 *row = reinterpret_cast<const double2 *>(values + 4 * bi);
-      for (int t = lane; t < 2 * deg; t += 32)
+      int lo = 0, hi = deg;
+      while (lo < hi)
       {
-         const double2 v = row[t];
-         acc[0] += v.x * v.x + v.y * v.y;
+         const int mid = (lo + hi) >> 1;
+         if (bcol[bi + mid] < I)
+            lo = mid + 1;
+         else
+            hi = mid;
       }
-      for (int s = lane; s < deg; s += 32)
-         if (bcol[bi + s] == I) acc[1] += values[4 * bi + 2 * s] + values[4 * bi + 2 * deg + 2 * s + 1];
+      if (lo < deg && bcol[bi + lo] == I) acc += values[4 * bi + 2 * lo] + values[4 * bi + 2 * deg + 2 * lo + 1];
    }
-   block_reduce_finish_n<256, 2>(acc, red, out);
+   block_reduce_finish<256>(acc, red, out);
 }
 
 template <int ET, bool FAST, int CH, int TPN>
@@ -579,11 +595,14 @@ extern "C" int femb200_matrix_norms(const femb200_plan *p, const double *d_value
 {
    FEMB_CHECK(p && d_values && d_out, "matrix_norms: null argument");
    cudaStream_t st = as_stream(stream);
-   const int T = 256;
-   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(p->nnodes * 32, T), (int64_t)devinfo().sm_count * 8);
+   const int64_t n2 = 2 * p->nnzb;  // 16-byte units of the value array
+   const unsigned g1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n2, 256), (int64_t)devinfo().sm_count * 16));
+   const unsigned g2 = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->nnodes, 256), (int64_t)devinfo().sm_count * 16));
    ReduceScratch red;
-   if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
-   norms_kernel<<<grid, T, 0, st>>>(p->nnodes, p->brp, p->bcol, d_values, red, d_out);
+   if (int rc = reduce_scratch(std::max(g1, g2), st, &red)) return rc;
+   fro_kernel<<<g1, 256, 0, st>>>(n2, reinterpret_cast<const double2 *>(d_values), red, d_out);
+   FEMB_LAUNCH_CHECK();
+   trace_kernel<<<g2, 256, 0, st>>>(p->nnodes, p->brp, p->bcol, d_values, red, d_out + 1);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
