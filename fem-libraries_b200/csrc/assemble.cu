@@ -131,9 +131,9 @@ __global__ void cell_setup_kernel(int64_t ncells, const int32_t *__restrict__ xd
 
 __device__ __forceinline__ FastGeo fast_geo(const AsmArgs &A, const Visit &r)
 {
-   const double2 *p = reinterpret_cast<const double2 *>(A.cellrec + 4 * (int64_t)r.e);
-   const double2 a = p[0], b = p[1];
-   return FastGeo{a.x, a.y, b.x, b.y};
+   FastGeo g;
+   ld_d4(A.cellrec + 4 * (int64_t)r.e, g.g1x, g.g1y, g.g2x, g.g2y);
+   return g;
 }
 
 // column order of the blocks produced below: ROTATED local dofs, vertices (m, m1, m2)

@@ -63,6 +63,12 @@ __device__ __forceinline__ void st_stream_d2(double *p, double2 v)
    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// 256-bit global load (PTX ISA 8.8, sm_100+): one request, one line for a 32-byte record
+__device__ __forceinline__ void ld_d4(const double *p, double &a, double &b, double &c, double &d)
+{
+   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
