@@ -83,6 +83,8 @@ struct AsmArgs
    int64_t nnodes;
    const int32_t *nptr;
    const VisitRec *vrec;
+   const uint8_t *perm;
+   const uint16_t *voff;
    const int64_t *brp;
    const int32_t *xdofmap, *dofmap;
    const double *x;
@@ -93,7 +95,6 @@ struct AsmArgs
    const double *cellrec;
    int variant;
    double *values;
-   int debug;        // developer switch: 1 = skip the visits, 2 = skip the stream-out
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
 };
 
@@ -294,56 +295,41 @@ __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double (*
 // the lanes of a warp run the same number of visits; on the fast path the three
 // dependent load levels are issued for CH visits at a time.
 template <int ET, bool FAST, int CH, int TPN>
-__global__ void __launch_bounds__(256) assemble_kernel(AsmArgs A)
+__global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
 {
-   constexpr int nd = Elem<ET>::nd;
+   constexpr int nd = Elem<ET>::nd, R = kAsmR, THREADS = kAsmR * TPN;
    extern __shared__ double2 sv[];
-   __shared__ int s_hist[8], s_base[8];
    // fast path: two threads per node (one per scalar row); generic path: one
-   const int R = blockDim.x / TPN, tid = threadIdx.x;
+   const int tid = threadIdx.x;
    const int64_t n0 = (int64_t)blockIdx.x * R;
    const int nloc = (int)min((int64_t)R, A.nnodes - n0);
    const int64_t b0 = A.brp[n0];
+   const int32_t vbase = A.nptr[n0];
    const int units = 2 * (int)(A.brp[n0 + nloc] - b0);  // 16-byte units of this tile
    // tile metadata behind the staging area
-   int32_t *s_k0 = reinterpret_cast<int32_t *>(sv + A.stage_units);  // first visit of node i
-   int32_t *s_cnt = s_k0 + R;                                         // number of visits
-   int32_t *s_roff = s_cnt + R;                                       // unit offset of row 0, [R + 1]
-   uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_roff + R + 1);
-   if (tid < 8) s_hist[tid] = 0;
-   __syncthreads();
-   int my_off = 0, key = 0;
+   int32_t *s_cnt = reinterpret_cast<int32_t *>(sv + A.stage_units);  // number of visits of node i
+   int32_t *s_roff = s_cnt + R;                                        // unit offset of row 0, [R + 1]
+   int32_t *s_voff = s_roff + R + 1;                                   // [kAsmLevels] level offsets of the records
    if (tid < nloc)
    {
-      const int32_t k0 = A.nptr[n0 + tid], k1 = A.nptr[n0 + tid + 1];
-      s_k0[tid] = k0;
-      s_cnt[tid] = k1 - k0;
+      s_cnt[tid] = A.nptr[n0 + tid + 1] - A.nptr[n0 + tid];
       s_roff[tid] = 2 * (int)(A.brp[n0 + tid] - b0);
-      key = min(k1 - k0, 7);
-      my_off = atomicAdd(&s_hist[key], 1);
    }
    if (tid == 0) s_roff[nloc] = units;
-   __syncthreads();
-   if (tid < 8)
-   {
-      int base = 0;
-      for (int kk = 7; kk > tid; --kk) base += s_hist[kk];
-      s_base[tid] = base;
-   }
-   __syncthreads();
-   if (tid < nloc) s_perm[s_base[key] + my_off] = (uint16_t)tid;
-   __syncthreads();
+   if (tid < kAsmLevels) s_voff[tid] = A.voff[(int64_t)blockIdx.x * kAsmLevels + tid];
    // TPN == 2: lanes 0-15 of a warp own scalar row 0 of 16 nodes, lanes 16-31 row 1 of the same
-   // nodes: the 8 lanes of a shared-memory phase then belong to 8 different nodes
-   const int slot_node = TPN == 2 ? ((tid >> 5) << 4) + (tid & 15) : tid;
+   // nodes: the 8 lanes of a shared-memory phase then belong to 8 different nodes.  Ranks are the
+   // plan's order of decreasing visit count: the lanes of a warp run the same number of visits.
+   const int rank = TPN == 2 ? ((tid >> 5) << 4) + (tid & 15) : tid;
    const int half = TPN == 2 ? ((tid >> 4) & 1) : 0;
-   if (slot_node < nloc && A.debug != 1)
+   const int i = rank < nloc ? (int)A.perm[n0 + rank] : 0;
+   __syncthreads();
+   if (rank < nloc)
    {
-      const int i = s_perm[slot_node];
-      const int32_t k0 = s_k0[i];
       const int cnt = s_cnt[i];
       const int r0 = s_roff[i];
       const int r1 = r0 + ((s_roff[i + 1] - r0) >> 1);
+      const uint4 *rec = reinterpret_cast<const uint4 *>(A.vrec + vbase) + rank;
       if (FAST)
       {
          for (int c = 0; c < cnt; c += CH)
@@ -351,8 +337,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs A)
             uint4 raw[CH];
             FastGeo geo[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-               raw[j] = (c + j < cnt) ? *reinterpret_cast<const uint4 *>(A.vrec + k0 + c + j) : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < CH; ++j) raw[j] = (c + j < cnt) ? rec[s_voff[c + j]] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int j = 0; j < CH; ++j)
                if (c + j < cnt) geo[j] = fast_geo(A, Visit(raw[j]));
@@ -374,7 +359,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs A)
       {
          for (int c = 0; c < cnt; ++c)
          {
-            const Visit r(*reinterpret_cast<const uint4 *>(A.vrec + k0 + c));
+            const Visit r(rec[s_voff[c]]);
             double kb[nd][4];
             visit_generic<ET>(A, r, kb);
 #pragma unroll
@@ -386,10 +371,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmArgs A)
    // stream the finished tile out: one contiguous byte range of the CSR values
    double *dst = A.values + 4 * b0;
    const int padded = (units + 7) & ~7;
-   for (int i = tid; i < padded && A.debug != 2; i += blockDim.x)
+   for (int k = tid; k < padded; k += THREADS)
    {
-      const int u = swz(i);
-      if (u < units) st_stream_d2(dst + 2 * (int64_t)u, sv[i]);
+      const int u = swz(k);
+      if (u < units) st_stream_d2(dst + 2 * (int64_t)u, sv[k]);
    }
 }
 
@@ -485,27 +470,15 @@ trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__r
 template <int ET, bool FAST, int CH, int TPN>
 static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
-   // tile height R = threads per CTA: the largest candidate that keeps >= 4 CTAs per SM
+   static_assert(tile_r(1) == kAsmR, "tile_max_blocks[1] must describe kAsmR-row tiles");
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
-   auto tile_smem = [&](int r) {
-      const size_t units = (2 * (size_t)p->tile_max_blocks[r] + 7) & ~(size_t)7;
-      return 16 * units + 4 * (3 * (size_t)tile_r(r) + 1) + 2 * (size_t)tile_r(r) + 16;
-   };
-   int best = 0;
-   for (int r = 0; r < kNumTileR; ++r)
-      if (tile_smem(r) + 1024 <= budget / 4 && tile_r(r) <= 64) best = r;
-   const int maxR = 256 / TPN;
-   const char *env = getenv("FEMB200_TILE_R");
-   if (env)
-      for (int r = 0; r < kNumTileR; ++r)
-         if (atoi(env) == tile_r(r) && tile_r(r) <= maxR) best = r;
-   const int R = tile_r(best);
-   A.stage_units = (2 * p->tile_max_blocks[best] + 7) & ~7;
-   const size_t smem = tile_smem(best);
-   FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", R, smem, budget);
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   const unsigned grid = (unsigned)cdiv(p->nnodes, R);
-   assemble_kernel<ET, FAST, CH, TPN><<<grid, TPN * R, smem, st>>>(A);
+   A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
+   const size_t smem = 16 * (size_t)A.stage_units + 4 * (size_t)(2 * kAsmR + 1 + kAsmLevels) + 16;
+   FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", kAsmR, smem, budget);
+   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+   const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
+   assemble_kernel<ET, FAST, CH, TPN><<<grid, kAsmR * TPN, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -543,13 +516,12 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
    FEMB_CHECK(p && d_x && d_E && d_values, "assemble_matrix: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_matrix: x_stride must be 2 or 3, got %d", x_stride);
    AsmArgs A;
-   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.brp = p->brp;
+   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.perm = p->perm, A.voff = p->voff, A.brp = p->brp;
    A.xdofmap = p->xdofmap, A.dofmap = p->dofmap, A.x = d_x, A.xs = x_stride, A.E = d_E, A.lc = lame_coef(nu);
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);
    const bool linear = (d_dnod == nullptr) && !getenv("FEMB200_FORCE_GENERIC");
    A.cellrec = nullptr;
-   A.debug = getenv("FEMB200_ASM_DEBUG") ? atoi(getenv("FEMB200_ASM_DEBUG")) : 0;
    if (linear && p->etype != FEMB200_Q2)
    {
       femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan

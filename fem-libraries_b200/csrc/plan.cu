@@ -165,6 +165,37 @@ __global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__
    }
 }
 
+// --- tile-sorted storage order of the visit records -------------------------------------
+// one CTA of kAsmR threads per tile: rank the nodes by decreasing visit count (ties by index),
+// write perm and the level offsets, move every record to nptr[n0] + voff[j] + rank
+__global__ void __launch_bounds__(kAsmR)
+k_tile_sort(int64_t nnodes, const int32_t *__restrict__ nptr, const VisitRec *__restrict__ src,
+            VisitRec *__restrict__ dst, uint8_t *__restrict__ perm, uint16_t *__restrict__ voff,
+            int32_t *__restrict__ flags)
+{
+   __shared__ int s_cnt[kAsmR], s_off[kAsmLevels + 1];
+   const int i = threadIdx.x;
+   const int64_t n0 = (int64_t)blockIdx.x * kAsmR, node = n0 + i;
+   const int32_t k0 = node < nnodes ? nptr[node] : 0;
+   const int cnt = node < nnodes ? nptr[node + 1] - k0 : -1;
+   s_cnt[i] = cnt;
+   __syncthreads();
+   int rank = 0;
+   for (int t = 0; t < kAsmR; ++t) rank += (s_cnt[t] > cnt) || (s_cnt[t] == cnt && t < i);
+   perm[n0 + rank] = (uint8_t)i;  // padding nodes of the last tile rank last (cnt = -1)
+   if (cnt > kAsmLevels) atomicOr(flags, 1);
+   if (i <= kAsmLevels)
+   {  // s_off[j] = records in levels < j = sum over nodes of min(cnt, j)
+      int o = 0;
+      for (int t = 0; t < kAsmR; ++t) o += max(0, min(s_cnt[t], i));
+      s_off[i] = o;
+   }
+   __syncthreads();
+   if (i < kAsmLevels) voff[(int64_t)blockIdx.x * kAsmLevels + i] = (uint16_t)s_off[i];
+   const int32_t vbase = nptr[n0];
+   for (int j = 0; j < cnt && j < kAsmLevels; ++j) dst[vbase + s_off[j] + rank] = src[k0 + j];
+}
+
 // --- largest staging tile (in node blocks) for each candidate tile height R ------
 __global__ void k_tile_max(int64_t nnodes, const int64_t *__restrict__ brp, int32_t *__restrict__ out)
 {
@@ -244,6 +275,8 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    if (!p) return;
    cudaFree(p->nptr);
    cudaFree(p->vrec);
+   cudaFree(p->perm);
+   cudaFree(p->voff);
    cudaFree(p->brp);
    cudaFree(p->bcol);
    cudaFree(p->bc);
@@ -319,6 +352,23 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
    // 3. slot map + staging-tile sizes
    k_fill_slots<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
                                                               p->vrec);
+   {  // tile-sorted storage order (the slot map above was written node by node into a scratch copy)
+      const int64_t ntiles = cdiv(nnodes, kAsmR);
+      VisitRec *sorted = nullptr;
+      if (dev_alloc(&sorted, (size_t)nvis, &p->bytes) || dev_alloc(&p->perm, (size_t)ntiles * kAsmR, &p->bytes) ||
+          dev_alloc(&p->voff, (size_t)ntiles * kAsmLevels, &p->bytes))
+         return fail(1);
+      cudaMemsetAsync(flags, 0, sizeof(int32_t), st);
+      k_tile_sort<<<(unsigned)ntiles, kAsmR, 0, st>>>(nnodes, p->nptr, p->vrec, sorted, p->perm, p->voff, flags);
+      int32_t over = 0;
+      if (cudaMemcpyAsync(&over, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+         return fail(set_error("plan_create: tile sort failed: %s", cudaGetErrorString(cudaGetLastError())));
+      cudaFree(p->vrec);
+      p->bytes -= sizeof(VisitRec) * (size_t)nvis;
+      p->vrec = sorted;
+      if (over) return fail(set_error("plan_create: a node belongs to more than %d cells", kAsmLevels));
+   }
    k_tile_max<<<(unsigned)cdiv(cdiv(nnodes, tile_r(0)), T), T, 0, st>>>(nnodes, p->brp, flags + 2);
    if (cudaMemcpyAsync(p->tile_max_blocks, flags + 2, sizeof(int32_t) * kNumTileR, cudaMemcpyDeviceToHost, st) !=
            cudaSuccess ||

@@ -11,7 +11,11 @@ namespace femb {
 //            bit b set when this visit is the first (in list order) to contribute to
 //            slot[b], so it stores instead of adds
 //   word 2-3 slot of local dof b = 0..7 in block row I, one byte each
-// Visits are stored grouped by row node (nptr), ascending cell id inside a group.
+// nptr[I] .. nptr[I+1] counts the visits of node I (ascending cell id: the order of the sums).
+// STORAGE ORDER of vrec: tiles of kAsmR consecutive nodes; inside a tile the nodes are ranked by
+// decreasing visit count (perm[n0 + rank] = tile-local node) and the records are laid out level by
+// level: record (rank r, visit j) lives at nptr[n0] + voff[tile][j] + r, so the lanes of a warp
+// (consecutive ranks, same j) read consecutive 16-byte records.
 struct __align__(16) VisitRec
 {
    uint32_t e;
@@ -35,6 +39,8 @@ struct Visit
 };
 static_assert(sizeof(VisitRec) == 16, "VisitRec must be 16 bytes");
 
+constexpr int kAsmR = 64;      // node rows per assembly tile (fixed at plan time: vrec storage order)
+constexpr int kAsmLevels = 16; // visits per node supported by the tile-sorted layout
 constexpr int kNumTileR = 6;
 __host__ __device__ constexpr int tile_r(int r) { return r == 0 ? 32 : r == 1 ? 64 : r == 2 ? 96 : r == 3 ? 128 : r == 4 ? 192 : 256; }
 
@@ -47,7 +53,9 @@ struct femb200_plan
    int32_t max_deg = 0;
    const int32_t *dofmap = nullptr, *xdofmap = nullptr;  // borrowed
    int32_t *nptr = nullptr;                               // [nnodes+1]
-   femb::VisitRec *vrec = nullptr;                        // [nvisits]
+   femb::VisitRec *vrec = nullptr;                        // [nvisits], tile-sorted (see above)
+   uint8_t *perm = nullptr;                               // [ntiles * kAsmR] rank -> tile-local node
+   uint16_t *voff = nullptr;                              // [ntiles * kAsmLevels] level offsets in a tile
    int64_t *brp = nullptr;                                // [nnodes+1]
    int32_t *bcol = nullptr;                               // [nnzb]
    int32_t tile_max_blocks[femb::kNumTileR] = {0, 0, 0, 0, 0, 0};

@@ -35,7 +35,7 @@ def timeit(fn, k=10, w=3):
 
 ref = None
 for tpn, ch, R in itertools.product(os.environ.get("TPNS", "1,2").split(","), os.environ.get("CHS", "1,2,3").split(","), os.environ.get("RS", "64,96,128").split(",")):
-    os.environ["FEMB200_ASM_CH"], os.environ["FEMB200_TILE_R"], os.environ["FEMB200_ASM_TPN"] = ch, R, tpn
+    os.environ["FEMB200_ASM_CH"], os.environ["FEMB200_ASM_TPN"] = ch, tpn
     try:
         t = timeit(lambda: fem.assemble_matrix(A, form))
     except Exception as ex:
