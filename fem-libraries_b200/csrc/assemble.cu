@@ -137,15 +137,15 @@ __device__ __forceinline__ FastGeo fast_geo(const AsmArgs &A, const Visit &r)
    return g;
 }
 
-// column order of the blocks produced below: ROTATED local dofs, vertices (m, m1, m2)
-// then edges (3+m, 3+m1, 3+m2)
-__device__ __forceinline__ int rotated_index(int t, int a)
+// stored position (plan.cuh) of natural local dof b in the visit record of a row with local index a
+__device__ __forceinline__ int stored_position(int b, int a, int nd)
 {
+   if (nd > 6) return b;
    const int m = (a >= 3) ? a - 3 : a;
-   const int tt = (t >= 3) ? t - 3 : t;
-   int b = m + tt;
-   b = (b >= 3) ? b - 3 : b;
-   return (t >= 3) ? b + 3 : b;
+   const int bb = (b >= 3) ? b - 3 : b;
+   int tt = bb - m;
+   tt = (tt < 0) ? tt + 3 : tt;
+   return (b >= 3) ? tt + 3 : tt;
 }
 
 // row 0 of W^{cd} = |T| (lam g_c (x) g_d + mu g_d (x) g_c + mu (g_c . g_d) I)
@@ -174,8 +174,7 @@ __device__ __forceinline__ void fast_compute_stage(const AsmArgs &A, const Visit
    const double tl = A.lc.c2, tm = A.lc.c3;
    double k[2];
    auto put = [&](int t, const double *kk) {
-      const int b = rotated_index(t, a);
-      stage_put(sv, rbase + r.slot(b), h ? kk[1] : kk[0], h ? kk[0] : kk[1], r.is_first(b));
+      stage_put(sv, rbase + r.slot(t), h ? kk[1] : kk[0], h ? kk[0] : kk[1], r.is_first(t));  // rotated order
    };
    if (a < 3)
    {  // row = (rotated) vertex 0
@@ -363,7 +362,11 @@ __global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
             double kb[nd][4];
             visit_generic<ET>(A, r, kb);
 #pragma unroll
-            for (int b = 0; b < nd; ++b) stage_block(sv, r0, r1, r.slot(b), kb[b], r.is_first(b));
+            for (int b = 0; b < nd; ++b)
+            {
+               const int t = stored_position(b, (int)r.a, nd);
+               stage_block(sv, r0, r1, r.slot(t), kb[b], r.is_first(t));
+            }
          }
       }
    }

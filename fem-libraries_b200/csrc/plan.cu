@@ -119,6 +119,17 @@ __global__ void k_fill_cols(int64_t nnodes, int nd, const int32_t *__restrict__ 
    for (int s = 0; s < d; ++s) bcol[base + s] = loc[s];
 }
 
+// local dof of ROTATED column t for a row with local index a: the row's own vertex / edge becomes
+// number 0 of its group (vertices m, m+1, m+2 then edges 3+m, 3+m+1, 3+m+2, indices mod 3)
+__device__ __forceinline__ int rotated_local(int t, int a)
+{
+   const int m = (a >= 3) ? a - 3 : a;
+   const int tt = (t >= 3) ? t - 3 : t;
+   int b = m + tt;
+   b = (b >= 3) ? b - 3 : b;
+   return (t >= 3) ? b + 3 : b;
+}
+
 // --- slot map: position of every local dof b of visit (I, e, a) in block row I ---
 __global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
                              const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
@@ -139,8 +150,9 @@ __global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__
       r.first = 0;
       r.slot8 = 0;
       for (int b = 0; b < 8; ++b) r.slot[b] = 0;
-      for (int b = 0; b < nd; ++b)
-      {
+      for (int t = 0; t < nd; ++t)
+      {  // stored position t: triangles keep the columns in ROTATED order (plan.cuh), quads in natural order
+         const int b = nd <= 6 ? rotated_local(t, (int)r.a) : t;
          const int32_t J = dofmap[(int64_t)r.e * nd + b];
          int lo = 0, hi = deg;
          while (lo < hi)
@@ -151,14 +163,14 @@ __global__ void k_fill_slots(int64_t nnodes, int nd, const int32_t *__restrict__
             else
                hi = mid;
          }
-         if (b < 8)
-            r.slot[b] = (uint8_t)lo;
+         if (t < 8)
+            r.slot[t] = (uint8_t)lo;
          else
             r.slot8 = (uint8_t)lo;
          if (!((touched[lo >> 5] >> (lo & 31)) & 1u))
          {
             touched[lo >> 5] |= 1u << (lo & 31);
-            r.first |= (uint16_t)(1u << b);
+            r.first |= (uint16_t)(1u << t);
          }
       }
       vrec[k] = r;

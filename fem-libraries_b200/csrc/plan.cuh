@@ -10,7 +10,10 @@ namespace femb {
 //   word 1   a (bits 0-7) | slot of local dof 8 (bits 8-15, Q2 only) | first-touch mask (bits 16-31):
 //            bit b set when this visit is the first (in list order) to contribute to
 //            slot[b], so it stores instead of adds
-//   word 2-3 slot of local dof b = 0..7 in block row I, one byte each
+//   word 2-3 slot in block row I of the column stored at position t = 0..7, one byte each; triangles
+//            store the columns in ROTATED order (position t = local dof (m + t) mod 3 for the vertices,
+//            3 + (m + t - 3) mod 3 for the edges, m = a mod 3: the row's own vertex / edge comes first),
+//            quadrilaterals in natural order; the first-touch bits use the same positions
 // nptr[I] .. nptr[I+1] counts the visits of node I (ascending cell id: the order of the sums).
 // STORAGE ORDER of vrec: tiles of kAsmR consecutive nodes; inside a tile the nodes are ranked by
 // decreasing visit count (perm[n0 + rank] = tile-local node) and the records are laid out level by
