@@ -331,15 +331,27 @@ __global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
       const uint4 *rec = reinterpret_cast<const uint4 *>(A.vrec + vbase) + rank;
       if (FAST)
       {
+         // software pipeline over the visits: while batch c is computed and staged, the cell records
+         // of batch c + CH and the visit records of batch c + 2 CH are in flight
+         uint4 raw[CH], raw1[CH], raw2[CH];
+         FastGeo geo[CH], geo1[CH];
+         const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+         for (int j = 0; j < CH; ++j) raw1[j] = (j < cnt) ? rec[s_voff[j]] : none;
+#pragma unroll
+         for (int j = 0; j < CH; ++j) raw2[j] = (CH + j < cnt) ? rec[s_voff[CH + j]] : none;
+#pragma unroll
+         for (int j = 0; j < CH; ++j)
+            if (j < cnt) geo1[j] = fast_geo(A, Visit(raw1[j]));
          for (int c = 0; c < cnt; c += CH)
          {
-            uint4 raw[CH];
-            FastGeo geo[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) raw[j] = (c + j < cnt) ? rec[s_voff[c + j]] : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < CH; ++j) raw[j] = raw1[j], geo[j] = geo1[j], raw1[j] = raw2[j];
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-               if (c + j < cnt) geo[j] = fast_geo(A, Visit(raw[j]));
+               if (c + CH + j < cnt) geo1[j] = fast_geo(A, Visit(raw1[j]));
+#pragma unroll
+            for (int j = 0; j < CH; ++j) raw2[j] = (c + 2 * CH + j < cnt) ? rec[s_voff[c + 2 * CH + j]] : none;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
                if (c + j < cnt)
@@ -492,7 +504,7 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
-   const int ch = env ? atoi(env) : 2, tpn = env2 ? atoi(env2) : 2;
+   const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
    if (tpn == 2)
       switch (ch)
       {
