@@ -93,6 +93,7 @@ struct AsmArgs
    LameCoef lc;
    const double *dnod, *u;
    const double *cellrec;
+   const double *celld;  // records of the damaged cells (see cell_setup_damage_kernel)
    int variant;
    double *values;
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
@@ -128,6 +129,142 @@ __global__ void cell_setup_kernel(int64_t ncells, const int32_t *__restrict__ xd
    double2 *r = reinterpret_cast<double2 *>(rec + 4 * e);
    r[0] = make_double2((y2 - y0) * sc, -(x2 - x0) * sc);
    r[1] = make_double2(-(y1 - y0) * sc, (x1 - x0) * sc);
+}
+
+__device__ __forceinline__ int stored_position(int b, int a, int nd);
+
+// ---- damaged cells (d > 0 at some quadrature point): per-cell pre-pass ------------------
+// The tangent D_q (M.cc:736-872 closed form, or the dual-number Hessian M.cc:752-765) depends on
+// the cell only, but the gather assembly visits every cell once per node: evaluating it per visit
+// costs 6x the work.  This pre-pass evaluates it once per damaged cell and stores
+//   [g_1, g_2 | w_q D_q (9 doubles) for every quadrature point],  w_q = quadrature weight * |det J|;
+// the cell record of a damaged cell is replaced by {NaN, index of its record}.  Undamaged cells
+// keep the 32-byte fast-path record.
+template <int ET>
+__device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *phi, double &w2)
+{  // reference gradients, vertex basis and 2 * weight at point q of the rule of element.cuh
+   double xi, eta, w;
+   quad_point<ET>(q, xi, eta, w);
+   ref_grads<ET>(xi, eta, dN);
+   phi[0] = 1. - xi - eta, phi[1] = xi, phi[2] = eta;
+   w2 = 2. * w;
+}
+
+template <int ET>
+__global__ void cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap,
+                                         const int32_t *__restrict__ dofmap, const double *__restrict__ x, int xs,
+                                         const double *__restrict__ E, LameCoef lc, const double *__restrict__ dnod,
+                                         const double *__restrict__ u, int variant, double *__restrict__ rec,
+                                         double *__restrict__ celld, int32_t *__restrict__ count)
+{
+   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, W = 4 + 9 * nq;
+   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= ncells) return;
+   const int64_t v0 = xdofmap[3 * e], v1 = xdofmap[3 * e + 1], v2 = xdofmap[3 * e + 2];
+   const double x0 = x[v0 * xs], y0 = x[v0 * xs + 1];
+   const double x1 = x[v1 * xs], y1 = x[v1 * xs + 1];
+   const double x2 = x[v2 * xs], y2 = x[v2 * xs + 1];
+   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+   const double id = 1. / det, T = 0.5 * fabs(det), Ee = E[e];
+   const double g1[2] = {(y2 - y0) * id, -(x2 - x0) * id}, g2[2] = {-(y1 - y0) * id, (x1 - x0) * id};
+   const double dv[3] = {dnod[v0], dnod[v1], dnod[v2]};
+   double dq[nq];
+   bool damaged = false;
+#pragma unroll
+   for (int q = 0; q < nq; ++q)
+   {
+      double dN[nd][2], phi[3], w2;
+      tri_ref_grads<ET>(q, dN, phi, w2);
+      dq[q] = phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2];
+      damaged = damaged || dq[q] > 0.;
+   }
+   double2 *r = reinterpret_cast<double2 *>(rec + 4 * e);
+   if (!damaged)
+   {
+      const double sc = sqrt(T * Ee);
+      r[0] = make_double2(g1[0] * sc, g1[1] * sc);
+      r[1] = make_double2(g2[0] * sc, g2[1] * sc);
+      return;
+   }
+   const int idx = atomicAdd(count, 1);
+   r[0] = make_double2(__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double((long long)idx));
+   r[1] = make_double2(0., 0.);
+   double *o = celld + (int64_t)idx * W;
+   o[0] = g1[0], o[1] = g1[1], o[2] = g2[0], o[3] = g2[1];
+   const double lam = Ee * lc.c2, mu = Ee * lc.c3;
+   double ue[nd][2];
+#pragma unroll
+   for (int b = 0; b < nd; ++b)
+   {
+      const int64_t gd = 2 * (int64_t)dofmap[e * nd + b];
+      ue[b][0] = u ? u[gd] : 0., ue[b][1] = u ? u[gd + 1] : 0.;
+   }
+#pragma unroll 1
+   for (int q = 0; q < nq; ++q)
+   {
+      double dN[nd][2], phi[3], w2, D[9];
+      tri_ref_grads<ET>(q, dN, phi, w2);
+      if (dq[q] > 0.)
+      {
+         double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+#pragma unroll
+         for (int b = 0; b < nd; ++b)
+         {
+            const double Gx = dN[b][0] * g1[0] + dN[b][1] * g2[0], Gy = dN[b][0] * g1[1] + dN[b][1] * g2[1];
+            g00 += ue[b][0] * Gx, g01 += ue[b][0] * Gy;
+            g10 += ue[b][1] * Gx, g11 += ue[b][1] * Gy;
+         }
+         const double sh = 0.5 * (g01 + g10);
+         const double eps[4] = {g00, sh, sh, g11};
+         tangent(variant, lam, mu, dq[q], eps, D);
+      }
+      else
+         hooke_scaled(lam, mu, 1., D);
+      const double w = w2 * T;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[4 + 9 * q + k] = w * D[k];
+   }
+}
+
+// row slice of a damaged cell: scalar row h of local row a against the stored columns t
+template <int ET>
+__device__ __forceinline__ void damaged_compute_stage(const AsmArgs &A, const Visit &r, int idx, double2 *sv, int rbase,
+                                                      int h)
+{
+   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, W = 4 + 9 * nq;
+   const double *o = A.celld + (int64_t)idx * W;
+   const double g1x = o[0], g1y = o[1], g2x = o[2], g2y = o[3];
+   const int a = r.a;
+   double k0[nd], k1[nd];
+#pragma unroll
+   for (int t = 0; t < nd; ++t) k0[t] = k1[t] = 0.;
+#pragma unroll 1
+   for (int q = 0; q < nq; ++q)
+   {
+      double dN[nd][2], phi[3], w2;
+      tri_ref_grads<ET>(q, dN, phi, w2);
+      const double *D = o + 4 + 9 * q;
+      double gax = 0., gay = 0.;
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+         if (b == a) gax = dN[b][0] * g1x + dN[b][1] * g2x, gay = dN[b][0] * g1y + dN[b][1] * g2y;
+      // c = (row h of B_a) D, B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]   (M.cc:699-704)
+      const double c0 = h ? gay * D[3] + gax * D[6] : gax * D[0] + gay * D[6];
+      const double c1 = h ? gay * D[4] + gax * D[7] : gax * D[1] + gay * D[7];
+      const double c2 = h ? gay * D[5] + gax * D[8] : gax * D[2] + gay * D[8];
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+      {
+         const double gbx = dN[b][0] * g1x + dN[b][1] * g2x, gby = dN[b][0] * g1y + dN[b][1] * g2y;
+         const double v0 = c0 * gbx + c2 * gby, v1 = c1 * gby + c2 * gbx;
+         const int t = stored_position(b, a, nd);
+#pragma unroll
+         for (int s = 0; s < nd; ++s)
+            if (s == t) k0[s] += v0, k1[s] += v1;
+      }
+   }
+#pragma unroll
+   for (int t = 0; t < nd; ++t) stage_put(sv, rbase + r.slot(t), k0[t], k1[t], r.is_first(t));
 }
 
 __device__ __forceinline__ FastGeo fast_geo(const AsmArgs &A, const Visit &r)
@@ -293,7 +430,7 @@ __device__ inline void visit_generic(const AsmArgs &A, const Visit &r, double (*
 // DECREASING visit count (P2: vertex nodes have 6 incident cells, edge nodes 2), so
 // the lanes of a warp run the same number of visits; on the fast path the three
 // dependent load levels are issued for CH visits at a time.
-template <int ET, bool FAST, int CH, int TPN>
+template <int ET, bool FAST, int CH, int TPN, bool DMG>
 __global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
 {
    constexpr int nd = Elem<ET>::nd, R = kAsmR, THREADS = kAsmR * TPN;
@@ -356,7 +493,18 @@ __global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
             for (int j = 0; j < CH; ++j)
                if (c + j < cnt)
                {
-                  if (TPN == 2)
+                  if (DMG && geo[j].g1x != geo[j].g1x)
+                  {  // damaged cell: NaN marker + index of its per-cell tangent record
+                     const int idx = (int)__double_as_longlong(geo[j].g1y);
+                     if (TPN == 2)
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, half ? r1 : r0, half);
+                     else
+                     {
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, r0, 0);
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, r1, 1);
+                     }
+                  }
+                  else if (TPN == 2)
                      fast_compute_stage<ET>(A, Visit(raw[j]), geo[j], sv, half ? r1 : r0, half);
                   else
                   {
@@ -482,7 +630,7 @@ trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__r
    block_reduce_finish<256>(acc, red, out);
 }
 
-template <int ET, bool FAST, int CH, int TPN>
+template <int ET, bool FAST, int CH, int TPN, bool DMG = false>
 static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
    static_assert(tile_r(1) == kAsmR, "tile_max_blocks[1] must describe kAsmR-row tiles");
@@ -490,10 +638,10 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    const size_t smem = 16 * (size_t)A.stage_units + 4 * (size_t)(2 * kAsmR + 1 + kAsmLevels) + 16;
    FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", kAsmR, smem, budget);
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN, DMG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
-   assemble_kernel<ET, FAST, CH, TPN><<<grid, kAsmR * TPN, smem, st>>>(A);
+   assemble_kernel<ET, FAST, CH, TPN, DMG><<<grid, kAsmR * TPN, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -502,6 +650,7 @@ template <int ET, bool FAST>
 static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
 {
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
+   if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
    const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
@@ -535,9 +684,11 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
    A.xdofmap = p->xdofmap, A.dofmap = p->dofmap, A.x = d_x, A.xs = x_stride, A.E = d_E, A.lc = lame_coef(nu);
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);
-   const bool linear = (d_dnod == nullptr) && !getenv("FEMB200_FORCE_GENERIC");
-   A.cellrec = nullptr;
-   if (linear && p->etype != FEMB200_Q2)
+   // triangles take the per-cell pre-pass + fast kernel (damaged cells through their own per-cell
+   // tangent records); Q2 and FEMB200_FORCE_GENERIC take the per-quadrature-point kernel
+   const bool linear = (p->etype != FEMB200_Q2) && !getenv("FEMB200_FORCE_GENERIC");
+   A.cellrec = nullptr, A.celld = nullptr;
+   if (linear)
    {
       femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan
       if (!pm->cellrec)
@@ -545,8 +696,30 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
          FEMB_CUDA(cudaMalloc(&pm->cellrec, sizeof(double) * 4 * (size_t)p->ncells));
          pm->bytes += sizeof(double) * 4 * (size_t)p->ncells;
       }
-      cell_setup_kernel<<<(unsigned)cdiv(p->ncells, 256), 256, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, A.lc,
-                                                                        pm->cellrec);
+      const unsigned grid = (unsigned)cdiv(p->ncells, 128);
+      if (d_dnod)
+      {
+         const size_t W = 4 + 9 * (size_t)elem_nq(p->etype);
+         if (!pm->celld)
+         {
+            FEMB_CUDA(cudaMalloc(&pm->celld, sizeof(double) * W * (size_t)p->ncells));
+            FEMB_CUDA(cudaMalloc(&pm->celld_count, sizeof(int32_t)));
+            pm->bytes += sizeof(double) * W * (size_t)p->ncells;
+         }
+         FEMB_CUDA(cudaMemsetAsync(pm->celld_count, 0, sizeof(int32_t), st));
+         if (p->etype == FEMB200_P1)
+            cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E,
+                                                                       A.lc, d_dnod, d_u, variant, pm->cellrec, pm->celld,
+                                                                       pm->celld_count);
+         else
+            cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E,
+                                                                       A.lc, d_dnod, d_u, variant, pm->cellrec, pm->celld,
+                                                                       pm->celld_count);
+         A.celld = pm->celld;
+      }
+      else
+         cell_setup_kernel<<<(unsigned)cdiv(p->ncells, 256), 256, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E,
+                                                                           A.lc, pm->cellrec);
       FEMB_LAUNCH_CHECK();
       A.cellrec = pm->cellrec;
    }

@@ -294,6 +294,8 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
    cudaFree(p->cellrec);
+   cudaFree(p->celld);
+   cudaFree(p->celld_count);
    delete p;
 }
 

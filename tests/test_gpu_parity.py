@@ -223,9 +223,14 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
 
 @pytest.mark.parametrize("kind", ["P1", "P2", "Q2"])
 @pytest.mark.parametrize("variant", [0, 1])
-def test_assembly_damaged_tangent(kind, variant):
+@pytest.mark.parametrize("generic", [False, True])
+def test_assembly_damaged_tangent(kind, variant, generic, monkeypatch):
     """Config 5: damaged tangent (closed form M.cc:736-872, AD M.cc:752-765), values-only
-    reassembly on a frozen pattern."""
+    reassembly on a frozen pattern; per-cell pre-pass path (triangles) and per-quadrature-point path."""
+    if generic:
+        if kind == "Q2":
+            pytest.skip("Q2 always takes the per-quadrature-point path")
+        monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
     m = make_mesh(kind, 12)
     E = fm.young_per_cell(m.ncells)
     d = fm.damage_band(m)
