@@ -673,9 +673,9 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
 
 using namespace femb;
 
-extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
-                                       double nu, const double *d_dnod, const double *d_u, int variant,
-                                       double *d_values, void *stream)
+static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E, double nu,
+                                const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream,
+                                bool dirichlet)
 {
    FEMB_CHECK(p && d_x && d_E && d_values, "assemble_matrix: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_matrix: x_stride must be 2 or 3, got %d", x_stride);
@@ -736,8 +736,22 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
          rc = launch_assemble<FEMB200_Q2, false>(p, A, st);
    }
    if (rc) return rc;
-   if (p->bc && p->nbc > 0) return femb200_apply_dirichlet(p, d_values, 1.0, stream);
+   if (dirichlet && p->bc && p->nbc > 0) return femb200_apply_dirichlet(p, d_values, 1.0, stream);
    return 0;
+}
+
+extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
+                                       double nu, const double *d_dnod, const double *d_u, int variant,
+                                       double *d_values, void *stream)
+{
+   return assemble_matrix_impl(p, d_x, x_stride, d_E, nu, d_dnod, d_u, variant, d_values, stream, true);
+}
+
+extern "C" int femb200_assemble_matrix_nobc(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
+                                            double nu, const double *d_dnod, const double *d_u, int variant,
+                                            double *d_values, void *stream)
+{
+   return assemble_matrix_impl(p, d_x, x_stride, d_E, nu, d_dnod, d_u, variant, d_values, stream, false);
 }
 
 extern "C" int femb200_apply_dirichlet(const femb200_plan *p, double *d_values, double diag, void *stream)

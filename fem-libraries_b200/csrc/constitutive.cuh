@@ -142,6 +142,52 @@ __device__ inline void tangent(int variant, double l, double m, double d, const 
       hooke_scaled(l, m, 1., D);
 }
 
+// Stress (already multiplied by the weight w): asym_stress of the reference, non-AD path
+// (M.cc:207-329), including its identity-eigenvector branch (when |eps_xy| <= 1e-12
+// the larger eigenvalue is paired with the x axis whatever the strain).  eps = [e00,e01,e10,e11]
+// symmetrised; sig = [s00,s01,s10,s11].
+__device__ inline void asym_stress(double l, double m, double d, double w, const double *eps, double *sig)
+{
+   if (d > 0.)
+   {
+      const double I1 = eps[0] + eps[3];
+      const double I2 = eps[1] * eps[1] - eps[0] * eps[3];
+      sig[0] = sig[1] = sig[2] = sig[3] = 0.;
+      if (I1 > kLimit || I2 > kLimit || I1 < -kLimit || I2 < -kLimit)
+      {
+         const double delta = I1 * I1 + 4 * I2;
+         const double r = sqrt(fmax(0., delta));
+         const double e0 = (I1 + r) / 2., e1 = (I1 - r) / 2.;
+         const double a1 = (e0 >= 0) ? 1. : 0., a2 = (e1 >= 0) ? 1. : 0., a = ((e0 + e1) >= 0) ? 1. : 0.;
+         if (!((d == 1.) && (a == 1) && (a1 == 1) && (a2 == 1)))
+         {
+            double v00 = 1., v01 = 0., v10 = 0., v11 = 1.;
+            if (fabs(eps[2]) > kLimit)
+            {
+               v00 = e0 - eps[3], v01 = e1 - eps[3], v10 = v11 = eps[2];
+               const double n0 = sqrt(v00 * v00 + v10 * v10), n1 = sqrt(v01 * v01 + v11 * v11);
+               v00 /= n0, v10 /= n0, v01 /= n1, v11 /= n1;
+            }
+            const double temp = 2. * m * w, gamma = 0.5 * l / m;
+            const double c = 1 - a * d, c1 = 1 - a1 * d, c2 = 1 - a2 * d;
+            const double D0 = temp * (c1 + gamma * c), D1 = temp * gamma * c, D2 = temp * (c2 + gamma * c);
+            const double s0 = D0 * e0 + D1 * e1, s1 = D1 * e0 + D2 * e1;
+            sig[0] = v00 * s0 * v00 + v01 * s1 * v01;
+            sig[1] = v00 * s0 * v10 + v01 * s1 * v11;
+            sig[2] = sig[1];
+            sig[3] = v10 * s0 * v10 + v11 * s1 * v11;
+         }
+      }
+   }
+   else
+   {
+      const double m2plw = w * (2 * m + l), lw = l * w;
+      sig[0] = m2plw * eps[0] + lw * eps[3];
+      sig[3] = m2plw * eps[3] + lw * eps[0];
+      sig[1] = sig[2] = w * m * (eps[1] + eps[2]);
+   }
+}
+
 // Lame coefficients, the MFEM form (M.cc:1087-1098): lambda = E*c2, mu = E*c3
 struct LameCoef
 {

@@ -83,6 +83,31 @@ __device__ __forceinline__ void ref_grads(double xi, double eta, double (*dN)[2]
    }
 }
 
+// values of the nd scalar shape functions
+template <int ET>
+__device__ __forceinline__ void basis_values(double xi, double eta, double *N)
+{
+   if (ET == FEMB200_P1)
+   {
+      N[0] = 1. - xi - eta, N[1] = xi, N[2] = eta;
+   }
+   else if (ET == FEMB200_P2)
+   {
+      const double L0 = 1. - xi - eta, L1 = xi, L2 = eta;
+      N[0] = L0 * (2. * L0 - 1.), N[1] = L1 * (2. * L1 - 1.), N[2] = L2 * (2. * L2 - 1.);
+      N[3] = 4. * L1 * L2, N[4] = 4. * L0 * L2, N[5] = 4. * L0 * L1;
+   }
+   else
+   {
+      const double lx[3] = {2. * (xi - 0.5) * (xi - 1.), 4. * xi * (1. - xi), 2. * xi * (xi - 0.5)};
+      const double ly[3] = {2. * (eta - 0.5) * (eta - 1.), 4. * eta * (1. - eta), 2. * eta * (eta - 0.5)};
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+         for (int i = 0; i < 3; ++i) N[3 * j + i] = lx[i] * ly[j];
+   }
+}
+
 // geometry (vertex) basis: values and reference gradients
 template <int ET>
 __device__ __forceinline__ void geom_basis(double xi, double eta, double *phi, double (*dphi)[2])

@@ -1,0 +1,203 @@
+// vector.cu -- residual vector assembly and Dirichlet lifting.
+//
+// Role in the reference: the setF lambda of the FEniCSx driver (F.cc:817-845:
+// assemble_vector(F) -> apply_lifting(J, bcs, u, -1) -> ghost update -> set_bc(-1)) and
+// ParNonlinearForm::Mult -> damIntegrator::AssembleElementVector + asym_stress on the MFEM
+// side (M.cc:559-637, 207-329):
+//     r_e = sum_q w_q |det J_q| G_q sigma_q(u)  -  sum_q' w_q' |det J_q'| N(q') f(q')
+// stress term with the element's rule (P1: the single point the reference forces), load term
+// with the degree-2 3-point rule on triangles (M.cc:613-632) / 3x3 Gauss on quadrilaterals.
+//
+// B200 design: the same write-once gather as the matrix assembly.  One thread owns one node
+// I, walks the cells incident to I through the plan's visit records, keeps only the two
+// entries of r_e that belong to I, sums them in registers in ascending cell order and
+// writes b[2I..2I+1] once: no atomics, no zero-fill, deterministic.
+#include "constitutive.cuh"
+#include "element.cuh"
+#include "plan.cuh"
+
+namespace femb {
+
+struct VecArgs
+{
+   int64_t nnodes;
+   const int32_t *nptr;
+   const VisitRec *vrec;
+   const uint8_t *perm;
+   const uint16_t *voff;
+   const int32_t *xdofmap, *dofmap;
+   const double *x;
+   int xs;
+   const double *E;
+   LameCoef lc;
+   const double *dnod, *u, *fnod;
+   double *b;
+};
+
+template <int ET>
+__global__ void __launch_bounds__(kAsmR) assemble_vector_kernel(VecArgs A)
+{
+   constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq;
+   constexpr int LET = (ET == FEMB200_Q2) ? FEMB200_Q2 : FEMB200_P2;  // rule of the load term
+   constexpr int lq = Elem<LET>::nq;
+   __shared__ int32_t s_voff[kAsmLevels];
+   const int rank = threadIdx.x;
+   const int64_t n0 = (int64_t)blockIdx.x * kAsmR;
+   const int nloc = (int)min((int64_t)kAsmR, A.nnodes - n0);
+   if (rank < kAsmLevels) s_voff[rank] = A.voff[(int64_t)blockIdx.x * kAsmLevels + rank];
+   __syncthreads();
+   if (rank >= nloc) return;
+   const int64_t I = n0 + A.perm[n0 + rank];
+   const int cnt = A.nptr[I + 1] - A.nptr[I];
+   const uint4 *rec = reinterpret_cast<const uint4 *>(A.vrec + A.nptr[n0]) + rank;
+   double bx = 0., by = 0.;
+   for (int c = 0; c < cnt; ++c)
+   {
+      const Visit r(rec[s_voff[c]]);
+      const int64_t e = r.e;
+      const int a = r.a;
+      double xv[nv][2], dv[nv];
+#pragma unroll
+      for (int v = 0; v < nv; ++v)
+      {
+         const int64_t g = A.xdofmap[e * nv + v];
+         xv[v][0] = A.x[g * A.xs], xv[v][1] = A.x[g * A.xs + 1];
+         dv[v] = A.dnod ? A.dnod[g] : 0.;
+      }
+      double ue[nd][2], fe[nd][2];
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+      {
+         const int64_t g = A.dofmap[e * nd + b];
+         const double2 uu = reinterpret_cast<const double2 *>(A.u)[g];
+         ue[b][0] = uu.x, ue[b][1] = uu.y;
+         if (A.fnod)
+         {
+            const double2 ff = reinterpret_cast<const double2 *>(A.fnod)[g];
+            fe[b][0] = ff.x, fe[b][1] = ff.y;
+         }
+      }
+      const double Ee = A.E[e];
+      const double lam = Ee * A.lc.c2, mu = Ee * A.lc.c3;
+      double rx = 0., ry = 0.;
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q)
+      {
+         double G[nd][2], phi[nv];
+         const double w = qp_geometry<ET>(xv, q, G, phi);
+         double d = 0.;
+#pragma unroll
+         for (int v = 0; v < nv; ++v) d += phi[v] * dv[v];
+         double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+         double gax = 0., gay = 0.;
+#pragma unroll
+         for (int b = 0; b < nd; ++b)
+         {
+            g00 += ue[b][0] * G[b][0], g01 += ue[b][0] * G[b][1];
+            g10 += ue[b][1] * G[b][0], g11 += ue[b][1] * G[b][1];
+            if (b == a) gax = G[b][0], gay = G[b][1];
+         }
+         const double sh = 0.5 * (g01 + g10);
+         const double eps[4] = {g00, sh, sh, g11};
+         double sig[4];
+         asym_stress(lam, mu, d, w, eps, sig);
+         rx += gax * sig[0] + gay * sig[2];  // AddMult(gdshape, sig, res), M.cc:601
+         ry += gax * sig[1] + gay * sig[3];
+      }
+      if (A.fnod)
+      {
+#pragma unroll 1
+         for (int q = 0; q < lq; ++q)
+         {
+            double xi, eta, wq, N[nd], G[nd][2], phi[nv];
+            quad_point<LET>(q, xi, eta, wq);
+            basis_values<ET>(xi, eta, N);
+            // |det J| at the point: qp_geometry returns (its own rule's weight) * |det J|
+            double dphi[nv][2];
+            geom_basis<ET>(xi, eta, phi, dphi);
+            double J00 = 0., J01 = 0., J10 = 0., J11 = 0.;
+#pragma unroll
+            for (int v = 0; v < nv; ++v)
+            {
+               J00 += xv[v][0] * dphi[v][0], J01 += xv[v][0] * dphi[v][1];
+               J10 += xv[v][1] * dphi[v][0], J11 += xv[v][1] * dphi[v][1];
+            }
+            const double w = wq * fabs(J00 * J11 - J01 * J10);
+            (void)G;
+            double f0 = 0., f1 = 0., na = 0.;
+#pragma unroll
+            for (int b = 0; b < nd; ++b)
+            {
+               f0 += N[b] * fe[b][0], f1 += N[b] * fe[b][1];
+               if (b == a) na = N[b];
+            }
+            rx -= w * na * f0;  // AddMult_a_VWt(-wl, shape, f, res), M.cc:631
+            ry -= w * na * f1;
+         }
+      }
+      bx += rx, by += ry;
+   }
+   reinterpret_cast<double2 *>(A.b)[I] = make_double2(bx, by);
+}
+
+// w = (g - u) on the constrained dofs, 0 elsewhere
+__global__ void lift_w_kernel(int64_t n, const uint8_t *__restrict__ bc, const double *__restrict__ g,
+                              const double *__restrict__ u, double *__restrict__ w)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) w[i] = bc[i] ? g[i] - u[i] : 0.;
+}
+
+// b -= scale * y on the free dofs, b = scale * (g - u) on the constrained ones (set_bc)
+__global__ void lift_b_kernel(int64_t n, const uint8_t *__restrict__ bc, const double *__restrict__ w,
+                              const double *__restrict__ y, double scale, double *__restrict__ b)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) b[i] = bc[i] ? scale * w[i] : b[i] - scale * y[i];
+}
+
+int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
+                double *d_dot_out, cudaStream_t st);
+
+}  // namespace femb
+
+using namespace femb;
+
+extern "C" int femb200_assemble_vector(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
+                                       double nu, const double *d_dnod, const double *d_u, const double *d_fnod,
+                                       double *d_b, void *stream)
+{
+   FEMB_CHECK(p && d_x && d_E && d_u && d_b, "assemble_vector: null argument");
+   FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_vector: x_stride must be 2 or 3, got %d", x_stride);
+   VecArgs A;
+   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.perm = p->perm, A.voff = p->voff;
+   A.xdofmap = p->xdofmap, A.dofmap = p->dofmap, A.x = d_x, A.xs = x_stride, A.E = d_E, A.lc = lame_coef(nu);
+   A.dnod = d_dnod, A.u = d_u, A.fnod = d_fnod, A.b = d_b;
+   const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
+   cudaStream_t st = as_stream(stream);
+   switch (p->etype)
+   {
+      case FEMB200_P1: assemble_vector_kernel<FEMB200_P1><<<grid, kAsmR, 0, st>>>(A); break;
+      case FEMB200_P2: assemble_vector_kernel<FEMB200_P2><<<grid, kAsmR, 0, st>>>(A); break;
+      default: assemble_vector_kernel<FEMB200_Q2><<<grid, kAsmR, 0, st>>>(A);
+   }
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
+extern "C" int femb200_apply_lifting(const femb200_plan *p, const double *d_values_nobc, const double *d_g,
+                                     const double *d_u, double scale, double *d_b, double *d_work, void *stream)
+{
+   FEMB_CHECK(p && d_values_nobc && d_g && d_u && d_b && d_work, "apply_lifting: null argument");
+   FEMB_CHECK(p->bc != nullptr, "apply_lifting: no Dirichlet dofs set on the plan");
+   const int64_t n = 2 * p->nnodes;
+   cudaStream_t st = as_stream(stream);
+   double *w = d_work, *y = d_work + n;
+   const unsigned grid = (unsigned)cdiv(n, 256);
+   lift_w_kernel<<<grid, 256, 0, st>>>(n, p->bc, d_g, d_u, w);
+   FEMB_LAUNCH_CHECK();
+   if (int rc = spmv_launch(p, d_values_nobc, w, y, nullptr, nullptr, st)) return rc;
+   lift_b_kernel<<<grid, 256, 0, st>>>(n, p->bc, w, y, scale, d_b);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}

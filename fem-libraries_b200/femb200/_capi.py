@@ -31,6 +31,9 @@ SIGNATURES = {
     "femb200_plan_copy_block_csr": [vp, vp, vp, vp],
     "femb200_plan_scalar_csr": [vp, vp, vp, vp],
     "femb200_assemble_matrix": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp],
+    "femb200_assemble_matrix_nobc": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp],
+    "femb200_assemble_vector": [vp, vp, i32, vp, f64, vp, vp, vp, vp, vp],
+    "femb200_apply_lifting": [vp, vp, vp, vp, f64, vp, vp, vp],
     "femb200_plan_set_dirichlet": [vp, vp, vp],
     "femb200_apply_dirichlet": [vp, vp, f64, vp],
     "femb200_matrix_norms": [vp, vp, vp, vp],

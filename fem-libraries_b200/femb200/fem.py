@@ -16,6 +16,8 @@ MFEM driver, `manual.py` = the UFL form file; paths relative to /root/reference)
                                                tabulate_tensor_batched(form)
   MFEM side (M.cc:639, 1483-1546)
   damIntegrator::AssembleElementGrad           element_grad_batched(form)  (col-major, byNODES)
+  AssembleElementVector / setF lambda          assemble_vector(A, form, f), apply_lifting(A, b, g, u)
+  NewtonSolver (M.cc:1531-1549, F.cc:869-907)  NewtonSolver(form, bcs, f).solve()
   BilinearFormIntegrator::AssemblePA/AddMultPA PAOperator(form).AssemblePA()/AddMultPA()/Mult()
   CGSolver::SetRelTol/SetMaxIter/SetOperator/  CGSolver(...)
     SetPreconditioner/Mult                       (Jacobi instead of BoomerAMG: third party, out of scope)
@@ -244,6 +246,80 @@ def assemble_matrix(A: Matrix, form: ElasticityForm | None = None, bcs=None, dia
     if diag != 1.0 and A.bc_dev is not None:
         capi.call("femb200_apply_dirichlet", A.plan, _p(A.values), float(diag), _stream())
     return A
+
+
+def assemble_matrix_nobc(A: Matrix, form: ElasticityForm | None = None) -> Matrix:
+    """The unconstrained tangent (no Dirichlet rows/cols): what apply_lifting needs."""
+    form = A.form if form is None else form
+    capi.call("femb200_assemble_matrix_nobc", A.plan, _p(form.x), form.x_stride, _p(form.E), form.nu, _p(form.d),
+              _p(form.u), form.variant, _p(A.values), _stream())
+    return A
+
+
+def assemble_vector(A: Matrix, form: ElasticityForm | None = None, f=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Role of assemble_vector(F) (F.cc:825) / ParNonlinearForm::Mult -> AssembleElementVector
+    (M.cc:559-637): b = F(u) = int sigma(u):eps(v) - int f.v, no boundary treatment.  `f` is the
+    nodal body force (nnodes x 2, host or device) or None; the current iterate is form.u."""
+    form = A.form if form is None else form
+    if form.u is None:
+        form.set_u(np.zeros(2 * form.nnodes))
+    fd = to_device(f, np.float64)
+    if out is None:
+        out = torch.empty(2 * form.nnodes, dtype=torch.float64, device="cuda")
+    capi.call("femb200_assemble_vector", A.plan, _p(form.x), form.x_stride, _p(form.E), form.nu, _p(form.d),
+              _p(form.u), _p(fd), _p(out), _stream())
+    return out
+
+
+def apply_lifting(A: Matrix, b: torch.Tensor, g: torch.Tensor, u: torch.Tensor, scale: float = -1.0) -> torch.Tensor:
+    """apply_lifting(b, {J}, {bcs}, {u}, scale) + set_bc(b, bcs, u, scale) of the setF lambda
+    (F.cc:826-836): b -= scale * J[:, bc] (g - u)_bc on the free dofs, b[bc] = scale * (g - u)[bc].
+    A.values must hold the UNCONSTRAINED tangent (assemble_matrix_nobc)."""
+    work = torch.empty(2 * b.numel(), dtype=torch.float64, device="cuda")
+    capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(g), _p(u), float(scale), _p(b), _p(work), _stream())
+    return b
+
+
+class NewtonSolver:
+    """The Newton loop around the hot path (mfem::NewtonSolver, M.cc:1531-1549; dolfinx NewtonSolver,
+    F.cc:705-714,869-907): per iteration residual F(u) (+ lifting), tangent J(u), Jacobi-PCG solve,
+    u <- u - du.  Convergence as MFEM: |b| <= max(rel_tol |b_0|, abs_tol) (M.cc:1535-1541)."""
+
+    def __init__(self, form: ElasticityForm, bcs, f=None, rel_tol=1e-7, abs_tol=5e-8, max_iter=10, cg_rel_tol=1e-12,
+                 cg_max_iter=2000):
+        self.form, self.f = form, to_device(f, np.float64)
+        self.rel_tol, self.abs_tol, self.max_iter = rel_tol, abs_tol, max_iter
+        self.A = create_matrix(form)
+        self.A.set_bcs(bcs)
+        gv = np.zeros(self.A.ndofs)
+        for bc in ([bcs] if isinstance(bcs, DirichletBC) else bcs):
+            if bc.values is not None:
+                m = np.asarray(bc.marker) != 0
+                gv[m] = np.asarray(bc.values)[m]
+        self.g = to_device(gv, np.float64)
+        self.cg = CGSolver(rel_tol=cg_rel_tol, max_iter=cg_max_iter)
+        self.residual_norms, self.linear_iterations = [], []
+
+    def solve(self, u0=None) -> torch.Tensor:
+        form, A = self.form, self.A
+        u = torch.zeros(A.ndofs, dtype=torch.float64, device="cuda") if u0 is None else to_device(u0, np.float64).clone()
+        self.residual_norms, self.linear_iterations = [], []
+        for it in range(self.max_iter + 1):
+            form.u = u
+            b = assemble_vector(A, form, self.f)
+            assemble_matrix_nobc(A, form)
+            apply_lifting(A, b, self.g, u, -1.0)
+            self.residual_norms.append(float(b.norm().item()))
+            if self.residual_norms[-1] <= max(self.rel_tol * self.residual_norms[0], self.abs_tol) or it == self.max_iter:
+                break
+            capi.call("femb200_apply_dirichlet", A.plan, _p(A.values), 1.0, _stream())
+            self.cg.SetOperator(A)
+            self.cg.SetPreconditioner("jacobi")
+            du = self.cg.Mult(b)
+            self.linear_iterations.append(self.cg.GetNumIterations())
+            u = u - du
+        self.iterations = len(self.residual_norms) - 1
+        return u
 
 
 def tabulate_tensor_batched(form: ElasticityForm, layout: int = capi.ROWMAJOR_INTERLEAVED,

@@ -114,6 +114,9 @@ int femb200_plan_scalar_csr(const femb200_plan *plan, int64_t *d_rowptr, int32_t
  * ------------------------------------------------------------------------ */
 int femb200_assemble_matrix(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
                             const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream);
+/* the same without the Dirichlet treatment (the unconstrained tangent, needed by apply_lifting) */
+int femb200_assemble_matrix_nobc(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
+                                 const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream);
 /* Dirichlet dofs: d_bc is a per-dof marker (uint8, 2*nnodes).  Builds the compact
  * list of constrained nodes once (F.cc:640,664 create the DirichletBC objects
  * once); pass NULL to clear.  Synchronises the stream. */
@@ -122,6 +125,22 @@ int femb200_plan_set_dirichlet(femb200_plan *plan, const uint8_t *d_bc, void *st
 int femb200_apply_dirichlet(const femb200_plan *plan, double *d_values, double diag, void *stream);
 /* Frobenius norm^2 and trace of the assembled matrix into d_out[2] (device) */
 int femb200_matrix_norms(const femb200_plan *plan, const double *d_values, double *d_out, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Residual vector.
+ * Replaces: the setF lambda (F.cc:817-845) = assemble_vector(F) + apply_lifting(J,
+ * bcs, u, -1) + set_bc(-1), and ParNonlinearForm::Mult ->
+ * damIntegrator::AssembleElementVector + asym_stress (M.cc:559-637, 207-329).
+ *   d_b[2*nnodes] = sum_e r_e, r_e = int sigma(u):eps(v) - int f.v, written once;
+ *   d_u current iterate (required); d_fnod nodal body force (nnodes x 2) or NULL.
+ * apply_lifting: b -= scale * K[:, bc] (g - u)_bc on the free dofs and
+ *   b[bc] = scale * (g - u)[bc]  (dolfinx: scale = -1), with K the
+ *   UNCONSTRAINED tangent (femb200_assemble_matrix_nobc); d_work: 4*nnodes doubles.
+ * ------------------------------------------------------------------------ */
+int femb200_assemble_vector(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
+                            const double *d_dnod, const double *d_u, const double *d_fnod, double *d_b, void *stream);
+int femb200_apply_lifting(const femb200_plan *plan, const double *d_values_nobc, const double *d_g, const double *d_u,
+                          double scale, double *d_b, double *d_work, void *stream);
 
 /* ------------------------------------------------------------------------
  * Assembled operator apply.

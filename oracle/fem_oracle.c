@@ -701,6 +701,101 @@ void orc_p1_element_vector(const double *xv, double l, double m, double d, const
    }
 }
 
+/* Generic element residual (any family): stress term with the element's own rule
+ * (P1: the 1-point rule the reference forces, M.cc:1112,1151-1152), load term with the
+ * degree-2 3-point rule on triangles (M.cc:613-632) / 3x3 Gauss on quads, the nodal
+ * load interpolated with the element's own basis.  P2 / Q2 are extrapolations of the
+ * reference (P1 only); for P1 this equals orc_p1_element_vector.
+ * u: nd x 2 interleaved; dnod: nv nodal damage or NULL; fnod: nd x 2 or NULL. */
+void orc_element_vector(int etype, const double *xv, double lam, double mu, const double *dnod, const double *u,
+                        const double *fnod, double *r)
+{
+   const int nd = elem_nd(etype), nv = elem_nv(etype), nq = elem_nq(etype);
+   double pts[9][2], wts[9];
+   quad_rule(etype, pts, wts);
+   for (int i = 0; i < 2 * nd; ++i) r[i] = 0.;
+   for (int q = 0; q < nq; ++q)
+   {
+      double N[9], G[9][2], phi[4];
+      const double w = qp_geometry(etype, xv, pts[q][0], pts[q][1], wts[q], N, G, phi);
+      double d = 0.;
+      if (dnod)
+         for (int v = 0; v < nv; ++v) d += phi[v] * dnod[v];
+      double gu[2][2] = {{0., 0.}, {0., 0.}};
+      for (int a = 0; a < nd; ++a)
+         for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) gu[i][j] += u[2 * a + i] * G[a][j];
+      const double s = 0.5 * (gu[0][1] + gu[1][0]);
+      const double eps[4] = {gu[0][0], s, s, gu[1][1]};
+      double sig[4];
+      orc_stress(lam, mu, d, w, eps, sig);
+      for (int a = 0; a < nd; ++a)
+      {
+         r[2 * a + 0] += G[a][0] * sig[0] + G[a][1] * sig[2];
+         r[2 * a + 1] += G[a][0] * sig[1] + G[a][1] * sig[3];
+      }
+   }
+   if (fnod)
+   {
+      const int lrule = (etype == ORC_Q2) ? ORC_Q2 : ORC_P2;
+      const int lq = elem_nq(lrule);
+      quad_rule(lrule, pts, wts);
+      for (int q = 0; q < lq; ++q)
+      {
+         double N[9], G[9][2], phi[4];
+         const double w = qp_geometry(etype, xv, pts[q][0], pts[q][1], wts[q], N, G, phi);
+         double f[2] = {0., 0.};
+         for (int a = 0; a < nd; ++a)
+         {
+            f[0] += N[a] * fnod[2 * a];
+            f[1] += N[a] * fnod[2 * a + 1];
+         }
+         for (int a = 0; a < nd; ++a)
+         {
+            r[2 * a + 0] -= w * N[a] * f[0];
+            r[2 * a + 1] -= w * N[a] * f[1];
+         }
+      }
+   }
+}
+
+/* Global residual vector b = sum_e P_e^t r_e (role of assemble_vector(F), F.cc:825, and of
+ * ParNonlinearForm::Mult -> AssembleElementVector, M.cc:559-637), no boundary treatment.
+ * fnod: nnodes x 2 nodal load or NULL. */
+void orc_assemble_vector(int etype, int64_t ncells, int64_t nnodes, const double *x, const int32_t *xdofmap,
+                         const int32_t *dofmap, const double *E, double nu, const double *dnod, const double *u,
+                         const double *fnod, double *b)
+{
+   const int nd = elem_nd(etype), nv = elem_nv(etype);
+   for (int64_t i = 0; i < 2 * nnodes; ++i) b[i] = 0.;
+   for (int64_t e = 0; e < ncells; ++e)
+   {
+      double xv[8], dv[4], ue[18], fe[18], r[18];
+      for (int v = 0; v < nv; ++v)
+      {
+         const int32_t g = xdofmap[e * nv + v];
+         xv[2 * v] = x[2 * (int64_t)g];
+         xv[2 * v + 1] = x[2 * (int64_t)g + 1];
+         if (dnod) dv[v] = dnod[g];
+      }
+      for (int a = 0; a < nd; ++a)
+      {
+         const int64_t g = dofmap[e * nd + a];
+         ue[2 * a] = u[2 * g], ue[2 * a + 1] = u[2 * g + 1];
+         if (fnod) fe[2 * a] = fnod[2 * g], fe[2 * a + 1] = fnod[2 * g + 1];
+      }
+      double lam, mu;
+      orc_lame(E[e], nu, &lam, &mu);
+      orc_element_vector(etype, xv, lam, mu, dnod ? dv : NULL, ue, fnod ? fe : NULL, r);
+      for (int a = 0; a < nd; ++a)
+      {
+         const int64_t g = dofmap[e * nd + a];
+         b[2 * g] += r[2 * a];
+         b[2 * g + 1] += r[2 * a + 1];
+      }
+   }
+}
+
 /* ------------------------------------------------------------------------ */
 /* Sparsity pattern (role of dolfinx create_matrix, F.cc:688)                */
 /* rows in dof order, columns ascending and unique, structural, bs=2 dofs    */

@@ -137,6 +137,51 @@ def p1_element_vector(xv, lam, mu, d, u, fnod=None) -> np.ndarray:
     return r
 
 
+def element_vector(etype, xv, lam, mu, u, dnod=None, fnod=None) -> np.ndarray:
+    nd = (3, 6, 9)[etype]
+    r = np.zeros(2 * nd)
+    xv, u, dnod, fnod = _f64(xv), _f64(u), _f64(dnod), _f64(fnod)
+    lib().orc_element_vector(C.c_int(etype), _d(xv), C.c_double(lam), C.c_double(mu), _d(dnod), _d(u), _d(fnod), _d(r))
+    return r
+
+
+def assemble_vector(etype, x, xdofmap, dofmap, E, nu, u, dnod=None, fnod=None) -> np.ndarray:
+    """Unconstrained residual b = F(u) (F.cc:825 / M.cc:559-637)."""
+    x, E, u, dnod, fnod = _f64(x), _f64(E), _f64(u), _f64(dnod), _f64(fnod)
+    xd, dm = _i32(xdofmap), _i32(dofmap)
+    b = np.empty(2 * x.shape[0])
+    lib().orc_assemble_vector(C.c_int(etype), C.c_int64(dm.shape[0]), C.c_int64(x.shape[0]), _d(x), _i(xd), _i(dm),
+                              _d(E), C.c_double(nu), _d(dnod), _d(u), _d(fnod), _d(b))
+    return b
+
+
+def newton(etype, x, xdofmap, dofmap, E, nu, bc, g, dnod=None, fnod=None, variant=TANGENT_CLOSED, rel_tol=1e-7,
+           abs_tol=5e-8, max_iter=10, cg_rtol=1e-12, cg_maxit=4000):
+    """Newton loop of the reference (tolerances M.cc:1531-1543; BC treatment F.cc:817-862):
+    b = F(u); b -= (-1) J[:, bc] (g - u)_bc; b[bc] = -(g - u)_bc; J with BC rows/cols zeroed and unit diagonal;
+    solve J du = b with Jacobi-PCG; u <- u - du.  MFEM convergence: |b| <= max(rel_tol |b0|, abs_tol).
+    Returns u, iterations, residual norms."""
+    x = _f64(x)
+    nn = x.shape[0]
+    rowptr, colidx = build_pattern(nn, dofmap)
+    u = np.zeros(2 * nn)
+    c = np.asarray(bc) != 0
+    norms = []
+    for it in range(max_iter + 1):
+        b = assemble_vector(etype, x, xdofmap, dofmap, E, nu, u, dnod, fnod)
+        full = assemble_matrix(etype, x, xdofmap, dofmap, E, nu, rowptr, colidx, dnod=dnod, u=u, variant=variant)
+        w = np.where(c, g - u, 0.0)
+        b = b + spmv(rowptr, colidx, full, w)
+        b[c] = -(g - u)[c]
+        norms.append(float(np.linalg.norm(b)))
+        if norms[-1] <= max(rel_tol * norms[0], abs_tol) or it == max_iter:
+            break
+        vals = assemble_matrix(etype, x, xdofmap, dofmap, E, nu, rowptr, colidx, dnod=dnod, u=u, variant=variant, bc=bc)
+        du, _, _, conv = pcg(rowptr, colidx, vals, b, rtol=cg_rtol, maxit=cg_maxit, jacobi=True)
+        u = u - du
+    return u, len(norms) - 1, norms
+
+
 def build_pattern(nnodes: int, dofmap: np.ndarray):
     dm = _i32(dofmap)
     ncells, nd = dm.shape

@@ -476,3 +476,89 @@ def test_full_size_properties():
     np.testing.assert_array_equal(A.rowptr[:2 * nrows_nodes + 1].cpu().numpy(), rowptr[:2 * nrows_nodes + 1])
     np.testing.assert_array_equal(A.colidx[:hi].cpu().numpy(), colidx[:hi])
     assert relfro(got, want[:hi]) < TOL_VALUES
+
+
+# ---------------------------------------------------------------------------
+# residual vector, lifting, Newton
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [("P1", 14), ("P2", 11), ("Q2", 7)])
+@pytest.mark.parametrize("damaged", [False, True])
+def test_residual_vector_and_lifting(kind, n, damaged):
+    m = make_mesh(kind, n, ny=n + 2)
+    E = fm.young_per_cell(m.ncells)
+    rng = np.random.default_rng(8)
+    u = 1e-3 * rng.standard_normal(m.ndofs)
+    d = fm.damage_band(m) if damaged else None
+    fnod = fm.body_force(m)
+    f = fem()
+    form = f.ElasticityForm(m, E, 0.3, d=d, u=u)
+    A = f.create_matrix(form)
+    for load in (None, fnod):
+        want = oracle.assemble_vector(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, u, dnod=d,
+                                      fnod=None if load is None else load.ravel())
+        got = f.assemble_vector(A, form, load).cpu().numpy()
+        assert relfro(got, want) < 1e-12
+    # lifting + set_bc (F.cc:826-836): b += J[:, bc] (g - u)_bc on free dofs, b[bc] = -(g - u)[bc]
+    bc, g = fm.dirichlet_markers(m)
+    A.set_bcs([f.DirichletBC(bc, g)])
+    rowptr, colidx, full = oracle_assemble(m, E, d=d, u=u)
+    c = bc != 0
+    b0 = oracle.assemble_vector(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, u, dnod=d, fnod=fnod.ravel())
+    want = b0 + oracle.spmv(rowptr, colidx, full, np.where(c, g - u, 0.0))
+    want[c] = -(g - u)[c]
+    f.assemble_matrix_nobc(A, form)
+    assert relfro(A.values.cpu().numpy(), full) < TOL_VALUES
+    b = f.assemble_vector(A, form, fnod)
+    f.apply_lifting(A, b, f.to_device(g, np.float64), f.to_device(u, np.float64), -1.0)
+    assert relfro(b.cpu().numpy(), want) < 1e-12
+    np.testing.assert_array_equal(b.cpu().numpy()[c], want[c])
+
+
+def test_p1_residual_against_reference_goldens():
+    """The residual kernel on one-cell meshes against the reference's own asym_stress + load term
+    (tests/golden/ref_p1_vectors.json, generated by running M.cc:207-329,559-637)."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_p1_vectors.json")) as fh:
+        gold = json.load(fh)
+    un = lambda a: np.array([float.fromhex(v) for v in a])
+    f = fem()
+    cases = gold["damaged"]
+    nc = len(cases)
+    xs = np.concatenate([un(c["xv"]).reshape(3, 2) for c in cases])
+    cells = np.arange(3 * nc, dtype=np.int32).reshape(nc, 3)
+    E = np.array([2 * float.fromhex(c["mu"]) * 1.3 for c in cases])
+    dn = np.repeat([float.fromhex(c["d"]) for c in cases], 3)
+    u = np.concatenate([np.stack([un(c["elfun"])[:3], un(c["elfun"])[3:]], axis=1).ravel() for c in cases])
+    m = fm.Mesh(fm.P1, xs, cells, cells)
+    form = f.ElasticityForm(m, E, 0.3, d=dn, u=u)
+    A = f.create_matrix(form)
+    got = f.assemble_vector(A, form).cpu().numpy().reshape(nc, 3, 2)
+    for k, c in enumerate(cases):
+        want = un(c["elvect_noload"])                      # byNODES
+        want_i = np.stack([want[:3], want[3:]], axis=1)
+        scale = max(np.linalg.norm(want_i), 1e-6 * float.fromhex(c["lam"]) * 1e-3)
+        # "isotropic": eps_xx == eps_yy, eps_xy == 0 -> delta = I1^2 + 4 I2 cancels to rounding noise and
+        # r = sqrt(noise) ~ 1e-11 enters the eigenvalues: the reference formula itself is only good to
+        # ~1e-8 there (FMA contraction on the device vs none on the host decides the last bits)
+        tol = 1e-6 if c["kind"] == "isotropic" else 1e-12
+        assert np.linalg.norm(got[k] - want_i) / scale < tol, c["kind"]
+
+
+@pytest.mark.parametrize("kind,n", [("P1", 10), ("P2", 8)])
+def test_newton_against_oracle(kind, n):
+    """A full Newton solve of the damaged problem (residual, lifting, tangent, PCG) on the GPU against
+    the same loop written with the oracle: same iteration count, same solution."""
+    m = make_mesh(kind, n)
+    E = fm.young_per_cell(m.ncells)
+    bc, g = fm.dirichlet_markers(m)
+    d = fm.damage_band(m)
+    fnod = fm.body_force(m)
+    want, it_o, norms_o = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, bc, g, dnod=d, fnod=fnod.ravel())
+    f = fem()
+    form = f.ElasticityForm(m, E, 0.3, d=d)
+    ns = f.NewtonSolver(form, [f.DirichletBC(bc, g)], f=fnod)
+    u = ns.solve().cpu().numpy()
+    assert ns.iterations == it_o and 2 <= it_o <= 8
+    assert relfro(u, want) < 1e-9
+    assert abs(ns.residual_norms[0] - norms_o[0]) < 1e-10 * norms_o[0]
+    np.testing.assert_allclose(u[bc != 0], g[bc != 0], rtol=0, atol=1e-14)
