@@ -562,3 +562,22 @@ def test_newton_against_oracle(kind, n):
     assert relfro(u, want) < 1e-9
     assert abs(ns.residual_norms[0] - norms_o[0]) < 1e-10 * norms_o[0]
     np.testing.assert_allclose(u[bc != 0], g[bc != 0], rtol=0, atol=1e-14)
+
+
+def test_config1_square_msh_newton(square):
+    """BASELINE config 1: P1 on the reference's own mesh, materials by physical tag (M.cc:1086-1098),
+    x = 0 clamped / x = 1 pulled by 0.01 (F.cc:627-664), body force of M.cc:1431-1440, a synthetic
+    damage band (the reference's damage-field construction is out of scope): GPU Newton vs oracle Newton."""
+    m = square_mesh(square)
+    E = oracle.E_table()[square["tag"] % 200]
+    bc, g = fm.dirichlet_markers(m)
+    assert bc.sum() > 0 and (g != 0).sum() > 0
+    d = fm.damage_band(m)
+    fnod = fm.body_force(m)
+    want, it_o, norms_o = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, bc, g, dnod=d, fnod=fnod.ravel())
+    f = fem()
+    ns = f.NewtonSolver(f.ElasticityForm(m, E, 0.3, d=d), [f.DirichletBC(bc, g)], f=fnod)
+    u = ns.solve().cpu().numpy()
+    assert ns.iterations == it_o
+    assert relfro(u, want) < 1e-9
+    assert ns.residual_norms[-1] <= max(1e-7 * ns.residual_norms[0], 5e-8)

@@ -192,3 +192,31 @@ def test_pcg_mfem_semantics():
     # zero right-hand side converges in zero iterations
     _, it3, _, conv3 = oracle.pcg(rowptr, colidx, vals, np.zeros_like(b))
     assert conv3 and it3 == 0
+
+
+def test_oracle_newton_consistency():
+    """The residual is the derivative-consistent partner of the tangent: Newton converges in one
+    step on the linear problem and quadratically with damage; the imposed values are reached."""
+    m = fm.jitter(fm.structured_triangles(6, order=2), 0.2, seed=3)
+    E = fm.young_per_cell(m.ncells)
+    bc, g = fm.dirichlet_markers(m)
+    f = fm.body_force(m).ravel()
+    u0, it0, n0 = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, bc, g, fnod=f)
+    assert it0 == 1 and n0[1] < 1e-9 * n0[0]
+    u1, it1, n1 = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, bc, g, dnod=fm.damage_band(m), fnod=f)
+    assert 2 <= it1 <= 6 and n1[-1] <= max(1e-7 * n1[0], 5e-8)
+    assert n1[2] / n1[1] < 0.1 * n1[1] / n1[0] * 10  # super-linear decrease
+    np.testing.assert_allclose(u1[bc != 0], g[bc != 0], atol=1e-14)
+    # finite-difference check of the tangent against the residual (unconstrained, d > 0)
+    rng = np.random.default_rng(0)
+    u = 1e-3 * rng.standard_normal(m.ndofs)
+    d = fm.damage_band(m)
+    rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+    K = sp.csr_matrix((oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rowptr, colidx, dnod=d, u=u),
+                       colidx, rowptr), shape=(m.ndofs, m.ndofs))
+    v = rng.standard_normal(m.ndofs)
+    h = 1e-7
+    Fp = oracle.assemble_vector(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, u + h * 1e-3 * v, dnod=d)
+    Fm = oracle.assemble_vector(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, u - h * 1e-3 * v, dnod=d)
+    fd = (Fp - Fm) / (2 * h * 1e-3)
+    assert np.linalg.norm(fd - K @ v) / np.linalg.norm(K @ v) < 1e-5
