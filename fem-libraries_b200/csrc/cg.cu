@@ -348,3 +348,27 @@ extern "C" int femb200_gather(int64_t nnodes_out, const int32_t *d_node_idx, con
    FEMB_LAUNCH_CHECK();
    return 0;
 }
+
+// dst[idx[k]] = src[k] over nodes of `width` doubles (2 or 3): uploads the coordinates of the
+// geometry vertices only (dolfinx keeps the P1 geometry apart from the P2 space: mesh.geometry.x
+// holds the vertices, F.cc:213), the edge nodes of a straight-sided P2 mesh are never read
+namespace femb {
+__global__ void scatter_rows_kernel(int64_t n, int width, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                                    double *__restrict__ dst)
+{
+   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= n) return;
+   const int64_t j = idx[k];
+   for (int c = 0; c < width; ++c) dst[j * width + c] = src[k * width + c];
+}
+}  // namespace femb
+
+extern "C" int femb200_scatter_rows(int64_t n, int width, const int32_t *d_idx, const double *d_src, double *d_dst,
+                                    void *stream)
+{
+   FEMB_CHECK(n >= 0 && width >= 1 && width <= 3 && (n == 0 || (d_idx && d_src && d_dst)), "scatter_rows: bad argument");
+   if (n == 0) return 0;
+   femb::scatter_rows_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(n, width, d_idx, d_src, d_dst);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}

@@ -55,6 +55,7 @@ SIGNATURES = {
     "femb200_pa_apply": [vp, vp, vp, vp],
     "femb200_pa_diagonal": [vp, vp, vp],
     "femb200_gather": [i64, vp, vp, vp, vp],
+    "femb200_scatter_rows": [i64, i32, vp, vp, vp, vp],
     "femb200_plan_set_row_range": [vp, i64, i64],
 }
 _SPECIAL = {

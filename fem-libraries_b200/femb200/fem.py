@@ -128,6 +128,21 @@ class ElasticityForm:
     def set_coordinates(self, x):
         self.x = to_device(x, np.float64)
 
+    @property
+    def geometry_vertices(self) -> np.ndarray:
+        """Sorted node ids of the geometry vertices (the nodes xdofmap refers to)."""
+        if getattr(self, "_gv", None) is None:
+            self._gv = np.unique(np.asarray(self.mesh.xdofmap)).astype(np.int32)
+            self._gv_dev = to_device(self._gv, np.int32)
+        return self._gv
+
+    def set_geometry(self, xv: torch.Tensor):
+        """Refresh the coordinates of the geometry vertices only (role of mesh.geometry.x, which holds
+        the P1 geometry, F.cc:213): xv is (len(geometry_vertices), x_stride) on the device or host."""
+        gv = self.geometry_vertices
+        xvd = xv if (isinstance(xv, torch.Tensor) and xv.is_cuda) else to_device(xv, np.float64)
+        capi.call("femb200_scatter_rows", len(gv), self.x_stride, _p(self._gv_dev), _p(xvd), _p(self.x), _stream())
+
 
 class Matrix:
     """CSR matrix in the dolfinx convention (rows in dof order, columns ascending,

@@ -209,6 +209,9 @@ int femb200_cg_update_dir(int64_t n, const double *d_scal, const double *d_r, co
  * dofs of a halo message before ncclSend (role of the dolfinx Scatterer behind
  * VecGhostUpdate(INSERT, FORWARD), F.cc:865-866) */
 int femb200_gather(int64_t nnodes_out, const int32_t *d_node_idx, const double *d_src, double *d_dst, void *stream);
+/* d_dst[d_idx[k]] = d_src[k] over rows of `width` doubles: refreshes the coordinates of the geometry
+ * vertices only (dolfinx mesh.geometry.x holds the P1 geometry, F.cc:213) */
+int femb200_scatter_rows(int64_t n, int width, const int32_t *d_idx, const double *d_src, double *d_dst, void *stream);
 /* restrict femb200_spmv / femb200_cg_apply to the node rows [row_lo, row_hi)
  * (the rows this rank owns); rows outside are left untouched */
 int femb200_plan_set_row_range(femb200_plan *plan, int64_t row_lo, int64_t row_hi);

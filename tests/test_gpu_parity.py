@@ -581,3 +581,19 @@ def test_config1_square_msh_newton(square):
     assert ns.iterations == it_o
     assert relfro(u, want) < 1e-9
     assert ns.residual_norms[-1] <= max(1e-7 * ns.residual_norms[0], 5e-8)
+
+
+def test_set_geometry_vertices_only():
+    """Refreshing only the geometry vertices (dolfinx mesh.geometry.x) gives the matrix of the moved mesh."""
+    f = fem()
+    m0 = make_mesh("P2", 9, jit=0.0)
+    m1 = make_mesh("P2", 9, jit=0.2, seed=11)
+    E = fm.young_per_cell(m0.ncells)
+    form = f.ElasticityForm(m0, E)
+    A = f.create_matrix(form)
+    gv = form.geometry_vertices
+    assert len(gv) == 10 * 10
+    form.set_geometry(m1.x[gv])
+    f.assemble_matrix(A, form)
+    _, _, want = oracle_assemble(m1, E)
+    assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
