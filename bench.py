@@ -168,6 +168,35 @@ def cpu_reference(n_sample: int, steps: int, warmup: int, spmv_reps: int = 5):
     return best
 
 
+def reference_element_kernel_rate(n_elems: int = 400000):
+    """The reference's OWN element code (damIntegrator::AssembleElementGrad, M.cc:639-916, compiled in place
+    into oracle/_ref by oracle/ref_shim/build_ref.sh), one host thread, P1 triangles, d = 0: elements per
+    second, next to the 5.5 M elements/s/core the reference publishes (curve_time.txt col 84).  None when
+    oracle/_ref does not exist on this box."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_B.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    if not hasattr(L, "ref_element_grad_batch"):
+        return None
+    dp = C.POINTER(C.c_double)
+    L.ref_element_grad_batch.argtypes = [C.c_long, dp, dp, dp, dp, dp]
+    rng = np.random.default_rng(0)
+    xv = np.tile(np.array([0.0, 0.0, 1.0, 0.1, 0.2, 0.9]), (n_elems, 1)) + 0.05 * rng.random((n_elems, 6))
+    lam, mu, d = np.full(n_elems, 4.0e7), np.full(n_elems, 2.7e7), np.zeros(n_elems)
+    out = np.empty((n_elems, 36))
+    P = lambda a: a.ctypes.data_as(dp)
+    L.ref_element_grad_batch(1000, P(xv), P(lam), P(mu), P(d), P(out))
+    t = time.perf_counter()
+    L.ref_element_grad_batch(n_elems, P(xv), P(lam), P(mu), P(d), P(out))
+    dt = time.perf_counter() - t
+    return {"melems_per_s_per_core": n_elems / dt / 1e6, "elements": n_elems,
+            "what": "the reference's own damIntegrator::AssembleElementGrad (M.cc:639-916, P1, d = 0) compiled in place "
+                    "against the MFEM stand-in of oracle/ref_shim, 1 thread, -O3 -DNDEBUG",
+            "published_melems_per_s_per_core": 5.5}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -374,7 +403,8 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(args.cpu_n, 3, 1)
         line["cpu_baseline"] = {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                                "sample": r["sample"], "spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"]}
+                                "sample": r["sample"], "spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"],
+                                "reference_element_kernel": reference_element_kernel_rate()}
     print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()

@@ -15,7 +15,7 @@ CXX=${CXX:-g++}
 [ -x /usr/bin/g++ ] && CXX=/usr/bin/g++
 [ -f "$SRC" ] || { echo "oracle/_ref: $SRC not found, skipped"; exit 0; }
 mkdir -p "$OUT"
-FLAGS="-x c++ -std=c++17 -O2 -fPIC -shared -I$HERE -w"
+FLAGS="-x c++ -std=c++17 -O3 -DNDEBUG -fPIC -shared -I$HERE -w"   # the reference flags (MFEM/setting.mk.in:4)
 ( sed -n '1,330p;487,953p' "$SRC"; cat "$HERE/ref_driver.cc" ) | $CXX $FLAGS -o "$OUT/libref_B.so" -
 ( sed -n '1,330p;487,953p' "$SRC" | sed 's|^#define USE_B$|//#define USE_B|'; cat "$HERE/ref_driver.cc" ) | $CXX $FLAGS -o "$OUT/libref_blocks.so" -
 echo "oracle/_ref: built libref_B.so libref_blocks.so from $SRC"

@@ -52,6 +52,32 @@ void ref_element_grad(const double *xv, double lam, double mu, double d, const d
    for (int i = 0; i < 36; ++i) elmat[i] = K.GetData()[i];
 }
 
+// n elements through ONE integrator object, as ParNonlinearForm::GetGradient drives it (M.cc:1546):
+// xv [n][6], lam/mu/d [n], elmat [n][36] (d = 0 -> elfun is not read).  For timing the reference's
+// element kernel on the host cores.
+void ref_element_grad_batch(long n, const double *xv, const double *lam, const double *mu, const double *d,
+                            double *elmat)
+{
+   mfem::ConstantCoefficient l(0.), m(0.);
+   mfem::QuadratureFunctionCoefficient dam(0.);
+   mfem::VectorQuadratureFunctionCoefficient load;
+   load.values.assign(6, 0.);
+   mfem::IntegrationPoint ip = centroid_point();
+   mfem::IntegrationRule ir(3);
+   load_rule(ir);
+   damIntegrator integ(l, m, dam, ip, &ir, load);
+   mfem::FiniteElement el;
+   mfem::Vector u(6);
+   mfem::DenseMatrix K;
+   for (long e = 0; e < n; ++e)
+   {
+      l.constant = lam[e], m.constant = mu[e], dam.constant = d[e];
+      mfem::ElementTransformation Tr(xv + 6 * e);
+      integ.AssembleElementGrad(el, Tr, u, K);
+      for (int i = 0; i < 36; ++i) elmat[36 * e + i] = K.GetData()[i];
+   }
+}
+
 void ref_element_vector(const double *xv, double lam, double mu, double d, const double *elfun, const double *fq,
                         double *elvect)
 {
