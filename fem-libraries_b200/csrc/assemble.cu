@@ -607,7 +607,7 @@ fro_kernel(int64_t n2, const double2 *__restrict__ values, ReduceScratch red, do
 }
 
 __global__ void __launch_bounds__(256)
-trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const uint8_t *__restrict__ dslot,
              const double *__restrict__ values, ReduceScratch red, double *__restrict__ out)
 {
    double acc = 0.;
@@ -615,17 +615,8 @@ trace_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__r
    for (int64_t I = (int64_t)blockIdx.x * 256 + threadIdx.x; I < nnodes; I += stride)
    {
       const int64_t bi = brp[I];
-      const int deg = (int)(brp[I + 1] - bi);
-      int lo = 0, hi = deg;
-      while (lo < hi)
-      {
-         const int mid = (lo + hi) >> 1;
-         if (bcol[bi + mid] < I)
-            lo = mid + 1;
-         else
-            hi = mid;
-      }
-      if (lo < deg && bcol[bi + lo] == I) acc += values[4 * bi + 2 * lo] + values[4 * bi + 2 * deg + 2 * lo + 1];
+      const int deg = (int)(brp[I + 1] - bi), s = dslot[I];
+      if (s < deg) acc += values[4 * bi + 2 * s] + values[4 * bi + 2 * deg + 2 * s + 1];
    }
    block_reduce_finish<256>(acc, red, out);
 }
@@ -776,7 +767,7 @@ extern "C" int femb200_matrix_norms(const femb200_plan *p, const double *d_value
    if (int rc = reduce_scratch(std::max(g1, g2), st, &red)) return rc;
    fro_kernel<<<g1, 256, 0, st>>>(n2, reinterpret_cast<const double2 *>(d_values), red, d_out);
    FEMB_LAUNCH_CHECK();
-   trace_kernel<<<g2, 256, 0, st>>>(p->nnodes, p->brp, p->bcol, d_values, red, d_out + 1);
+   trace_kernel<<<g2, 256, 0, st>>>(p->nnodes, p->brp, p->dslot, d_values, red, d_out + 1);
    FEMB_LAUNCH_CHECK();
    return 0;
 }

@@ -5,66 +5,230 @@
 // M.cc:559,639; partial assembly is only discussed at doc.tex:1445-1449), so the
 // contract is SURVEY.md A.9:  y_e = sum_q w_q |det J_q| B_q (D (B_q^t x_e)).
 //
-// "AssemblePA" stores per cell the straight-sided geometry (nv vertices) and the
-// Lame pair: 10 doubles (Q2) / 8 doubles (triangles), read contiguously; J_q is
-// rebuilt per quadrature point (bilinear / affine, a handful of FMAs), which is
-// fewer bytes than storing (J^-1, w) per point.  "AddMultPA": one thread per
-// cell, E-vector gathered with 16-byte loads, sum-factorised contractions for Q2
-// (1-D 3x3 tables), results added with fp64 red.global.add.  Dirichlet dofs are
-// handled like the assembled operator (rows/cols zeroed, diag on the diagonal)
-// through a per-cell bit mask of constrained local dofs.
+// "AssemblePA" (pa_create) builds, once:
+//  * a cell order: cells sorted by the Morton code of their centroid, cut into TILES of CT
+//    consecutive cells (compact 2-D patches on any mesh with spatial locality);
+//  * per tile the sorted list of its unique nodes, the cell -> local node map (16-bit) and its
+//    transpose (local node -> the (cell, local dof) pairs that touch it);
+//  * per cell (tile order) the straight-sided geometry (nv vertices) and the Lame pair:
+//    10 doubles (Q2) / 8 doubles (triangles); J_q is rebuilt per quadrature point (bilinear /
+//    affine, a handful of FMAs), which is fewer bytes than storing (J^-1, w) per point.
+// "AddMultPA" (pa_apply): one CTA per tile, one thread per cell.  The tile's x values are staged in
+// shared memory once (coalesced runs of consecutive nodes), every cell computes its element
+// product (sum-factorised for Q2: 1-D 3x3 tables) into a shared E-vector, then one thread per
+// tile node sums the contributions of the tile's cells.  Nodes interior to a tile (the vast
+// majority) are written with one plain 16-byte store; only nodes on a tile boundary use
+// red.global.add.f64 into entries zeroed by a small pre-kernel (compact list built at setup).
+// Dirichlet dofs are handled like the assembled operator (rows/cols zeroed, diag on the
+// diagonal) through a per-cell bit mask of constrained local dofs.
 #include <algorithm>
+#include <cub/block/block_discontinuity.cuh>
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 
 #include "constitutive.cuh"
 #include "element.cuh"
 #include "plan.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 
 struct femb200_pa
 {
    int etype = 0, nd = 0, nv = 0;
    int64_t nnodes = 0, ncells = 0;
    const int32_t *dofmap = nullptr;  // borrowed
-   double *geo = nullptr;            // [ncells][2 nv + 2]: vertices, lambda, mu
-   uint32_t *cmask = nullptr;        // [ncells] constrained local dofs (bit 2a+i) or null
+   int ct = 0;                       // cells per tile
+   int64_t ntiles = 0;
+   int max_uniq = 0;                 // largest number of unique nodes in a tile
+   int32_t *cperm = nullptr;         // [ncells] tile order -> caller's cell index
+   double *geo = nullptr;            // [ncells][2 nv + 2]: vertices, lambda, mu (tile order)
+   int32_t *tcount = nullptr;        // [ntiles] unique nodes of the tile
+   int32_t *tnodes = nullptr;        // [ntiles][ct nd] global node of local node k; bit 31: shared with another tile
+   uint16_t *tptr = nullptr;         // [ntiles][ct nd + 8]: [0] = unique nodes, [1 + k] = first entry of node k in trefs
+   uint16_t *trefs = nullptr;        // [ntiles][ct nd] (local dof a) * ct + (cell in tile), grouped by local node
+   uint16_t *lidx = nullptr;         // [ntiles][nd][ct] local node of (cell in tile, a)
+   int32_t *shared_nodes = nullptr;  // nodes touched by more than one tile
+   int32_t nshared = 0;
+   uint32_t *cmask = nullptr;        // [ncells] constrained local dofs (bit 2a+i), tile order, or null
    uint8_t *bc = nullptr;            // [2 nnodes] or null
    int32_t *bc_dofs = nullptr;       // compact list of constrained dofs
    int32_t nbc = 0;
    double diag = 1.0;
+   size_t bytes = 0;
 };
 
 namespace femb {
 
-constexpr int kPaThreads = 128;
+constexpr int kPaThreads = 128;  // = cells per tile
 
+// ---- setup: cell order --------------------------------------------------------------
+__global__ void pa_centroid_kernel(int64_t ncells, int nv, const int32_t *__restrict__ xdofmap,
+                                   const double *__restrict__ x, int xs, float *__restrict__ cx, float *__restrict__ cy)
+{
+   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= ncells) return;
+   double sx = 0., sy = 0.;
+   for (int v = 0; v < nv; ++v)
+   {
+      const int64_t n = xdofmap[e * nv + v];
+      sx += x[n * xs], sy += x[n * xs + 1];
+   }
+   cx[e] = (float)(sx / nv), cy[e] = (float)(sy / nv);
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+   v &= 0xffffu;
+   v = (v | (v << 8)) & 0x00ff00ffu;
+   v = (v | (v << 4)) & 0x0f0f0f0fu;
+   v = (v | (v << 2)) & 0x33333333u;
+   v = (v | (v << 1)) & 0x55555555u;
+   return v;
+}
+
+// bb = (min x, max x, min y, max y) of the centroids
+__global__ void pa_morton_kernel(int64_t ncells, const float *__restrict__ cx, const float *__restrict__ cy,
+                                 const float *__restrict__ bb, uint32_t *__restrict__ key, int32_t *__restrict__ id)
+{
+   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= ncells) return;
+   const float sx = bb[1] > bb[0] ? 65535.f / (bb[1] - bb[0]) : 0.f, sy = bb[3] > bb[2] ? 65535.f / (bb[3] - bb[2]) : 0.f;
+   const uint32_t qx = (uint32_t)fminf(fmaxf((cx[e] - bb[0]) * sx, 0.f), 65535.f);
+   const uint32_t qy = (uint32_t)fminf(fmaxf((cy[e] - bb[2]) * sy, 0.f), 65535.f);
+   key[e] = spread16(qx) | (spread16(qy) << 1);
+   id[e] = (int32_t)e;
+}
+
+// ---- setup: per-tile node lists -------------------------------------------------------
+// One CTA per tile sorts the (node, a * CT + t) pairs of its cells by node: the heads of the runs
+// are the tile's unique nodes (ascending), the sorted values are the node -> (cell, dof) lists.
+template <int ND, int CT>
+__global__ void __launch_bounds__(CT)
+pa_tile_build_kernel(int64_t ncells, int64_t nnodes, int end_bit, const int32_t *__restrict__ dofmap,
+                     const int32_t *__restrict__ cperm, int32_t *__restrict__ tnodes, uint16_t *__restrict__ tptr,
+                     uint16_t *__restrict__ trefs, uint16_t *__restrict__ lidx, int32_t *__restrict__ tcount,
+                     int32_t *__restrict__ ntouch)
+{
+   using Sort = cub::BlockRadixSort<uint32_t, CT, ND, uint16_t>;
+   using Disc = cub::BlockDiscontinuity<uint32_t, CT>;
+   using Scan = cub::BlockScan<int, CT>;
+   __shared__ union
+   {
+      typename Sort::TempStorage sort;
+      typename Disc::TempStorage disc;
+      typename Scan::TempStorage scan;
+   } tmp;
+   constexpr int S = CT * ND;
+   const int64_t tile = blockIdx.x;
+   const int t = threadIdx.x;
+   const int64_t e = tile * CT + t;
+   const uint32_t none = (uint32_t)nnodes;
+   uint32_t key[ND];
+   uint16_t val[ND];
+   const int64_t row = e < ncells ? (int64_t)cperm[e] * ND : 0;
+#pragma unroll
+   for (int a = 0; a < ND; ++a)
+   {
+      key[a] = e < ncells ? (uint32_t)dofmap[row + a] : none;
+      val[a] = (uint16_t)(a * CT + t);
+   }
+   Sort(tmp.sort).Sort(key, val, 0, end_bit);
+   __syncthreads();
+   int flag[ND];
+   Disc(tmp.disc).FlagHeads(flag, key, cub::Inequality());
+   __syncthreads();
+   int cnt = 0;
+#pragma unroll
+   for (int j = 0; j < ND; ++j)
+   {
+      if (key[j] == none) flag[j] = 0;
+      cnt += flag[j];
+   }
+   int lid, total;
+   Scan(tmp.scan).ExclusiveSum(cnt, lid, total);
+   lid -= 1;  // index of the run that is open when this thread's items start
+   const int64_t base = tile * S;
+   uint16_t *tp = tptr + tile * (S + 8) + 1;
+#pragma unroll
+   for (int j = 0; j < ND; ++j)
+   {
+      if (key[j] == none) continue;
+      const int pos = t * ND + j;
+      if (flag[j])
+      {
+         ++lid;
+         tnodes[base + lid] = (int32_t)key[j];
+         tp[lid] = (uint16_t)pos;
+         atomicAdd(ntouch + key[j], 1);
+      }
+      trefs[base + pos] = val[j];
+      lidx[base + val[j]] = (uint16_t)lid;
+   }
+   if (t == 0)
+   {
+      const int64_t left = ncells - tile * CT;
+      tp[total] = (uint16_t)((left < CT ? (int)left : CT) * ND);
+      tp[-1] = (uint16_t)total;
+      tcount[tile] = total;
+   }
+}
+
+__global__ void pa_tile_flag_kernel(int64_t ntiles, int S, const int32_t *__restrict__ tcount,
+                                    const int32_t *__restrict__ ntouch, int32_t *__restrict__ tnodes)
+{
+   const int64_t tile = blockIdx.x;
+   const int n = tcount[tile];
+   for (int k = threadIdx.x; k < n; k += blockDim.x)
+   {
+      const int32_t node = tnodes[tile * S + k];
+      if (ntouch[node] > 1) tnodes[tile * S + k] = node | (int32_t)0x80000000;
+   }
+}
+
+__global__ void pa_shared_list_kernel(int64_t nnodes, const int32_t *__restrict__ ntouch, int32_t *__restrict__ list,
+                                      int32_t *__restrict__ count)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nnodes || ntouch[i] <= 1) return;
+   const int32_t p = atomicAdd(count, 1);
+   if (list) list[p] = (int32_t)i;
+}
+
+// ---- setup: per-cell data in tile order ----------------------------------------------
 template <int ET>
-__global__ void pa_setup_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, const double *__restrict__ x,
-                                int xs, const double *__restrict__ E, LameCoef lc, double *__restrict__ geo)
+__global__ void pa_setup_kernel(int64_t ncells, const int32_t *__restrict__ cperm, const int32_t *__restrict__ xdofmap,
+                                const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
+                                double *__restrict__ geo)
 {
    constexpr int nv = Elem<ET>::nv, W = 2 * nv + 2;
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= ncells) return;
+   const int64_t src = cperm[e];
    double *g = geo + e * W;
 #pragma unroll
    for (int v = 0; v < nv; ++v)
    {
-      const int64_t n = xdofmap[e * nv + v];
+      const int64_t n = xdofmap[src * nv + v];
       g[2 * v] = x[n * xs];
       g[2 * v + 1] = x[n * xs + 1];
    }
-   g[2 * nv] = E[e] * lc.c2;      // lambda, M.cc:1093-1098
-   g[2 * nv + 1] = E[e] * lc.c3;  // mu
+   g[2 * nv] = E[src] * lc.c2;      // lambda, M.cc:1093-1098
+   g[2 * nv + 1] = E[src] * lc.c3;  // mu
 }
 
-__global__ void pa_cmask_kernel(int64_t ncells, int nd, const int32_t *__restrict__ dofmap,
-                                const uint8_t *__restrict__ bc, uint32_t *__restrict__ cmask)
+__global__ void pa_cmask_kernel(int64_t ncells, int nd, const int32_t *__restrict__ cperm,
+                                const int32_t *__restrict__ dofmap, const uint8_t *__restrict__ bc,
+                                uint32_t *__restrict__ cmask)
 {
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= ncells) return;
+   const int64_t src = cperm[e];
    uint32_t m = 0;
    for (int a = 0; a < nd; ++a)
    {
-      const int64_t n = dofmap[e * nd + a];
+      const int64_t n = dofmap[src * nd + a];
       if (bc[2 * n]) m |= 1u << (2 * a);
       if (bc[2 * n + 1]) m |= 1u << (2 * a + 1);
    }
@@ -231,59 +395,213 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-template <int ET, bool DOT>
-__global__ void __launch_bounds__(kPaThreads)
-pa_apply_kernel(int64_t ncells, const int32_t *__restrict__ dofmap, const double *__restrict__ geo,
-                const uint32_t *__restrict__ cmask, const double *__restrict__ x, double *__restrict__ y,
-                const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out)
+// byte offsets of the CTA's shared-memory buffers (from the host) and the bulk-copy sizes
+struct PaLayout
 {
-   constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, W = 2 * nv + 2;
+   int geo, li, cm;      // per-cell inputs of the current tile (one buffer)
+   int nb, nb_bytes;     // 3 buffers of {tn, tp}: node ids and node -> refs offsets
+   int tp;               // offset of tp inside one of them
+   int tr, tr_bytes;     // 2 buffers of trefs
+   int xs, xs_bytes;     // 2 buffers of x values
+   int ye;               // element results
+   int b_tn, b_tp;       // bytes copied per tile for tn / tp
+};
+
+struct PaArgs
+{
+   int64_t ncells;
+   int ntiles;
+   const int32_t *tnodes;
+   const uint16_t *tptr, *trefs, *lidx;
+   const double *geo;
+   const uint32_t *cmask;
+   const double *x;
+   double *y;
+   const double *flag;
+   PaLayout L;
+};
+
+__global__ void pa_zero_shared_kernel(int n, const int32_t *__restrict__ list, double *__restrict__ y,
+                                      const double *__restrict__ flag)
+{
    if (flag && *flag != 0.) return;
-   const int64_t e = (int64_t)blockIdx.x * kPaThreads + threadIdx.x;
-   double part = 0.;
-   if (e < ncells)
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) reinterpret_cast<double2 *>(y)[list[i]] = make_double2(0., 0.);
+}
+
+// Persistent CTAs, one thread per cell of a tile.  Thread 0 streams the tile plans and per-cell
+// data (contiguous byte ranges) into shared memory with bulk copies one to two tiles ahead; the x
+// values of tile i+1 are gathered with 16-byte cp.async while tile i is computed, so no thread
+// waits on DRAM in steady state.  Per tile: inputs -> registers | element products -> ye |
+// one thread per tile node sums its contributions and stores (interior) or reduces (tile boundary).
+template <int ET, bool DOT>
+__global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, ReduceScratch red, double *__restrict__ out)
+{
+   constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, W = 2 * nv + 2, CT = kPaThreads, S = CT * nd;
+   extern __shared__ __align__(128) unsigned char pa_sm[];
+   __shared__ uint64_t fullG, fullN[3], fullT[2];
+   if (A.flag && *A.flag != 0.) return;
+   const int tid = threadIdx.x;
+   const PaLayout &L = A.L;
+   if (tid == 0)
    {
-      int32_t dof[nd];
+      mbar_init(&fullG, 1);
 #pragma unroll
-      for (int a = 0; a < nd; ++a) dof[a] = dofmap[e * nd + a];
-      const uint32_t m = cmask ? cmask[e] : 0u;
-      double g[W];
-      const double2 *g2 = reinterpret_cast<const double2 *>(geo + e * W);
-#pragma unroll
-      for (int k = 0; k < W / 2; ++k)
+      for (int s = 0; s < 3; ++s) mbar_init(&fullN[s], 1);
+      mbar_init(&fullT[0], 1), mbar_init(&fullT[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   const int first = blockIdx.x, stride = gridDim.x;
+   const int nmine = first < A.ntiles ? (A.ntiles - first + stride - 1) / stride : 0;
+   const uint32_t b_cm = A.cmask ? CT * 4 : 0;
+   auto tile_of = [&](int it) { return first + (int64_t)it * stride; };
+   // thread 0 only
+   auto load_N = [&](int it) {
+      unsigned char *dst = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
+      const int64_t tile = tile_of(it);
+      mbar_expect_tx(&fullN[it % 3], (uint32_t)(L.b_tn + L.b_tp));
+      bulk_g2s(dst, A.tnodes + tile * S, (uint32_t)L.b_tn, &fullN[it % 3]);
+      bulk_g2s(dst + L.tp, A.tptr + tile * (S + 8), (uint32_t)L.b_tp, &fullN[it % 3]);
+   };
+   auto load_T = [&](int it) {
+      mbar_expect_tx(&fullT[it & 1], S * 2);
+      bulk_g2s(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes, A.trefs + tile_of(it) * S, S * 2, &fullT[it & 1]);
+   };
+   auto load_G = [&](int it) {
+      const int64_t tile = tile_of(it);
+      mbar_expect_tx(&fullG, CT * W * 8 + S * 2 + b_cm);
+      bulk_g2s(pa_sm + L.li, A.lidx + tile * S, S * 2, &fullG);
+      bulk_g2s(pa_sm + L.geo, A.geo + tile * (CT * W), CT * W * 8, &fullG);
+      if (b_cm) bulk_g2s(pa_sm + L.cm, A.cmask + tile * CT, b_cm, &fullG);
+   };
+   const double2 *x2 = reinterpret_cast<const double2 *>(A.x);
+   double2 *y2 = reinterpret_cast<double2 *>(A.y);
+   double2 *ye = reinterpret_cast<double2 *>(pa_sm + L.ye);
+   // gather the x values of tile it (its node list must have landed)
+   auto gather_x = [&](int it) {
+      const unsigned char *nb = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
+      const int nu = reinterpret_cast<const uint16_t *>(nb + L.tp)[0];
+      const int32_t *tn = reinterpret_cast<const int32_t *>(nb);
+      double2 *xs = reinterpret_cast<double2 *>(pa_sm + L.xs + (size_t)(it & 1) * L.xs_bytes);
+      for (int k = tid; k < nu; k += CT) cp_async16(xs + k, x2 + (tn[k] & 0x7fffffff));
+   };
+   double part = 0.;
+   if (nmine > 0)
+   {
+      if (tid == 0)
       {
-         const double2 v = g2[k];
-         g[2 * k] = v.x, g[2 * k + 1] = v.y;
+         load_N(0);
+         if (nmine > 1) load_N(1);
+         load_T(0);
+         load_G(0);
       }
-      double ux[nd], uy[nd], yx[nd], yy[nd];
-      const double2 *x2 = reinterpret_cast<const double2 *>(x);
-#pragma unroll
-      for (int a = 0; a < nd; ++a)
+      mbar_wait(&fullN[0], 0);
+      gather_x(0);
+   }
+   cp_async_commit();
+   for (int it = 0; it < nmine; ++it)
+   {
+      cp_async_wait<0>();
+      __syncthreads();  // A: x of tile it visible; every thread is done with tile it - 1
+      if (tid == 0)
       {
-         const double2 v = x2[dof[a]];
-         ux[a] = ((m >> (2 * a)) & 1u) ? 0. : v.x;
-         uy[a] = ((m >> (2 * a + 1)) & 1u) ? 0. : v.y;
+         if (it + 2 < nmine) load_N(it + 2);
+         if (it + 1 < nmine) load_T(it + 1);
       }
-      if (ET == FEMB200_Q2)
-         local_apply_q2(g, ux, uy, yx, yy);
-      else
-         local_apply_tri<ET>(g, ux, uy, yx, yy);
-#pragma unroll
-      for (int a = 0; a < nd; ++a)
+      const int64_t e = tile_of(it) * CT + tid;
+      const bool valid = e < A.ncells;
+      const double2 *xs = reinterpret_cast<const double2 *>(pa_sm + L.xs + (size_t)(it & 1) * L.xs_bytes);
+      mbar_wait(&fullG, it & 1);
+      uint32_t m = 0u;
+      double g[W], ux[nd], uy[nd];
       {
-         double *yp = y + 2 * (int64_t)dof[a];
-         if (!((m >> (2 * a)) & 1u))
+         const uint16_t *lp = reinterpret_cast<const uint16_t *>(pa_sm + L.li) + tid;
+         if (A.cmask) m = reinterpret_cast<const uint32_t *>(pa_sm + L.cm)[tid];
+         const double2 *g2 = reinterpret_cast<const double2 *>(pa_sm + L.geo) + tid * (W / 2);
+#pragma unroll
+         for (int k = 0; k < W / 2; ++k)
          {
-            red_add_f64(yp, yx[a]);
-            if (DOT) part += ux[a] * yx[a];
+            const double2 v = g2[k];
+            g[2 * k] = v.x, g[2 * k + 1] = v.y;
          }
-         if (!((m >> (2 * a + 1)) & 1u))
+#pragma unroll
+         for (int a = 0; a < nd; ++a)
          {
-            red_add_f64(yp + 1, yy[a]);
-            if (DOT) part += uy[a] * yy[a];
+            const double2 v = xs[valid ? lp[a * CT] : 0];
+            ux[a] = v.x, uy[a] = v.y;
          }
+      }
+      __syncthreads();  // B1: the per-cell inputs are in registers
+      if (it + 1 < nmine)
+      {
+         if (tid == 0) load_G(it + 1);
+         mbar_wait(&fullN[(it + 1) % 3], ((it + 1) / 3) & 1);
+         gather_x(it + 1);
+      }
+      cp_async_commit();
+      if (valid)
+      {
+         double yx[nd], yy[nd];
+         if (m != 0u)
+         {
+#pragma unroll
+            for (int a = 0; a < nd; ++a)
+            {
+               if ((m >> (2 * a)) & 1u) ux[a] = 0.;
+               if ((m >> (2 * a + 1)) & 1u) uy[a] = 0.;
+            }
+         }
+         if (ET == FEMB200_Q2)
+            local_apply_q2(g, ux, uy, yx, yy);
+         else
+            local_apply_tri<ET>(g, ux, uy, yx, yy);
+         if (m != 0u)
+         {
+#pragma unroll
+            for (int a = 0; a < nd; ++a)
+            {
+               if ((m >> (2 * a)) & 1u) yx[a] = 0.;
+               if ((m >> (2 * a + 1)) & 1u) yy[a] = 0.;
+            }
+         }
+#pragma unroll
+         for (int a = 0; a < nd; ++a) ye[a * CT + tid] = make_double2(yx[a], yy[a]);
+      }
+      __syncthreads();  // B2: ye complete
+      // one thread per tile node: sum the contributions of the tile's cells (fixed order)
+      const unsigned char *nb = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
+      const int32_t *tn = reinterpret_cast<const int32_t *>(nb);
+      const uint16_t *tp = reinterpret_cast<const uint16_t *>(nb + L.tp);
+      const uint16_t *tr = reinterpret_cast<const uint16_t *>(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes);
+      mbar_wait(&fullT[it & 1], (it >> 1) & 1);
+      const int nu = tp[0];
+      for (int k = tid; k < nu; k += CT)
+      {
+         const int p0 = tp[1 + k], p1 = tp[2 + k];
+         double2 acc = ye[tr[p0]];
+         for (int p = p0 + 1; p < p1; ++p)
+         {
+            const double2 v = ye[tr[p]];
+            acc.x += v.x, acc.y += v.y;
+         }
+         const int32_t id = tn[k];
+         if (DOT)
+         {  // <x, y> = sum over (tile, node) of x_node . partial: masked dofs contribute zeros
+            const double2 xv = xs[k];
+            part += xv.x * acc.x + xv.y * acc.y;
+         }
+         if (id < 0)
+         {
+            double *yp = A.y + 2 * (int64_t)(id & 0x7fffffff);
+            red_add_f64(yp, acc.x);
+            red_add_f64(yp + 1, acc.y);
+         }
+         else
+            y2[id] = acc;
       }
    }
+   cp_async_wait<0>();
    if (DOT) block_reduce_finish<kPaThreads>(part, red, out);
 }
 
@@ -311,8 +629,8 @@ pa_bc_fix_kernel(int nbc, const int32_t *__restrict__ list, double diag, const d
 
 template <int ET>
 __global__ void __launch_bounds__(kPaThreads)
-pa_diag_kernel(int64_t ncells, const int32_t *__restrict__ dofmap, const double *__restrict__ geo,
-               const uint32_t *__restrict__ cmask, double *__restrict__ diag)
+pa_diag_kernel(int64_t ncells, const int32_t *__restrict__ cperm, const int32_t *__restrict__ dofmap,
+               const double *__restrict__ geo, const uint32_t *__restrict__ cmask, double *__restrict__ diag)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq, W = 2 * nv + 2;
    const int64_t e = (int64_t)blockIdx.x * kPaThreads + threadIdx.x;
@@ -344,7 +662,7 @@ pa_diag_kernel(int64_t ncells, const int32_t *__restrict__ dofmap, const double 
 #pragma unroll
    for (int a = 0; a < nd; ++a)
    {
-      double *dp = diag + 2 * (int64_t)dofmap[e * nd + a];
+      double *dp = diag + 2 * (int64_t)dofmap[(int64_t)cperm[e] * nd + a];
       if (!((m >> (2 * a)) & 1u)) red_add_f64(dp, kd[a][0]);
       if (!((m >> (2 * a + 1)) & 1u)) red_add_f64(dp + 1, kd[a][1]);
    }
@@ -356,21 +674,58 @@ __global__ void pa_diag_bc_kernel(int nbc, const int32_t *__restrict__ list, dou
    if (k < nbc) d[list[k]] = diag;
 }
 
+static PaLayout pa_layout(const femb200_pa *pa)
+{
+   const int CT = kPaThreads, S = CT * pa->nd, W = 2 * pa->nv + 2;
+   auto up = [](int v) { return (v + 127) & ~127; };
+   PaLayout L;
+   int o = 0;
+   L.geo = o, o += up(CT * W * 8);
+   L.li = o, o += up(S * 2);
+   L.cm = o, o += up(CT * 4);
+   L.b_tn = ((pa->max_uniq + 3) & ~3) * 4;
+   L.b_tp = ((pa->max_uniq + 2 + 7) & ~7) * 2;
+   L.tp = up(L.b_tn);
+   L.nb_bytes = L.tp + up(L.b_tp);
+   L.nb = o, o += 3 * L.nb_bytes;
+   L.tr_bytes = up(S * 2);
+   L.tr = o, o += 2 * L.tr_bytes;
+   L.xs_bytes = up(pa->max_uniq * 16);
+   L.xs = o, o += 2 * L.xs_bytes;
+   L.ye = o;
+   return L;
+}
+
 template <int ET>
 static int pa_apply_t(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
                       cudaStream_t st)
 {
-   const unsigned grid = (unsigned)cdiv(pa->ncells, kPaThreads);
+   const PaLayout L = pa_layout(pa);
+   const size_t smem = (size_t)L.ye + sizeof(double2) * (size_t)kPaThreads * Elem<ET>::nd;
+   const size_t lim = devinfo().smem_optin - 1024;
+   FEMB_CHECK(smem <= lim, "pa_apply: tile needs %zu bytes of shared memory", smem);
+   static bool attr_done = false;
+   if (!attr_done)
+   {
+      FEMB_CUDA(cudaFuncSetAttribute(pa_tile_kernel<ET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+      FEMB_CUDA(cudaFuncSetAttribute(pa_tile_kernel<ET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+      attr_done = true;
+   }
+   int per_sm = 1;
+   if (d_dot_out)
+      FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pa_tile_kernel<ET, true>, kPaThreads, smem));
+   else
+      FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pa_tile_kernel<ET, false>, kPaThreads, smem));
+   const unsigned grid = (unsigned)std::min<int64_t>(pa->ntiles, (int64_t)devinfo().sm_count * std::max(1, per_sm));
+   PaArgs A{pa->ncells, (int)pa->ntiles, pa->tnodes, pa->tptr, pa->trefs, pa->lidx, pa->geo, pa->cmask, d_x, d_y, d_flag, L};
    if (d_dot_out)
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red)) return rc;
-      pa_apply_kernel<ET, true><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->dofmap, pa->geo, pa->cmask, d_x, d_y,
-                                                              d_flag, red, d_dot_out);
+      pa_tile_kernel<ET, true><<<grid, kPaThreads, smem, st>>>(A, red, d_dot_out);
    }
    else
-      pa_apply_kernel<ET, false><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->dofmap, pa->geo, pa->cmask, d_x, d_y,
-                                                               d_flag, ReduceScratch{nullptr, nullptr}, nullptr);
+      pa_tile_kernel<ET, false><<<grid, kPaThreads, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -378,8 +733,12 @@ static int pa_apply_t(const femb200_pa *pa, const double *d_x, double *d_y, cons
 int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
                     cudaStream_t st)
 {
-   // y = 0 (a converged CG leaves y stale: harmless, nothing reads it any more)
-   FEMB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * 2 * (size_t)pa->nnodes, st));
+   // only the nodes shared between tiles are accumulated with reductions: zero those
+   if (pa->nshared > 0)
+   {
+      pa_zero_shared_kernel<<<(unsigned)cdiv(pa->nshared, 256), 256, 0, st>>>(pa->nshared, pa->shared_nodes, d_y, d_flag);
+      FEMB_LAUNCH_CHECK();
+   }
    int rc;
    switch (pa->etype)
    {
@@ -396,6 +755,97 @@ int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const 
    return 0;
 }
 
+// ---- setup driver -------------------------------------------------------------------
+template <typename T>
+static int pa_alloc(femb200_pa *pa, T **p, size_t n)
+{
+   const size_t b = sizeof(T) * (n ? n : 1);
+   if (cudaMalloc(p, b) != cudaSuccess) return set_error("pa_create: cudaMalloc of %zu bytes failed", b);
+   pa->bytes += b;
+   return 0;
+}
+
+template <int ND>
+static void pa_tile_build(femb200_pa *pa, int end_bit, int32_t *ntouch, cudaStream_t st)
+{
+   pa_tile_build_kernel<ND, kPaThreads><<<(unsigned)pa->ntiles, kPaThreads, 0, st>>>(
+      pa->ncells, pa->nnodes, end_bit, pa->dofmap, pa->cperm, pa->tnodes, pa->tptr, pa->trefs, pa->lidx, pa->tcount,
+      ntouch);
+}
+
+static int pa_build_tiles(femb200_pa *pa, const int32_t *d_xdofmap, const double *d_x, int xs, cudaStream_t st)
+{
+   const int64_t nc = pa->ncells;
+   const int CT = kPaThreads, S = CT * pa->nd;
+   pa->ct = CT;
+   pa->ntiles = cdiv(nc, CT);
+   // 1. Morton order of the cell centroids
+   float *cx = nullptr, *cy = nullptr, *bb = nullptr;
+   uint32_t *key = nullptr, *key2 = nullptr;
+   int32_t *id = nullptr, *ntouch = nullptr, *count = nullptr;
+   void *tmp = nullptr;
+   auto cleanup = [&](int rc) {
+      cudaFree(cx), cudaFree(cy), cudaFree(bb), cudaFree(key), cudaFree(key2), cudaFree(id), cudaFree(ntouch);
+      cudaFree(count), cudaFree(tmp);
+      return rc;
+   };
+   size_t scratch = 0;
+   femb200_pa dummy;  // setup scratch is not counted in pa->bytes
+   if (pa_alloc(&dummy, &cx, (size_t)nc) || pa_alloc(&dummy, &cy, (size_t)nc) || pa_alloc(&dummy, &bb, 4) ||
+       pa_alloc(&dummy, &key, (size_t)nc) || pa_alloc(&dummy, &key2, (size_t)nc) || pa_alloc(&dummy, &id, (size_t)nc) ||
+       pa_alloc(&dummy, &ntouch, (size_t)pa->nnodes) || pa_alloc(&dummy, &count, 1) || pa_alloc(pa, &pa->cperm, (size_t)nc))
+      return cleanup(1);
+   const unsigned gc = (unsigned)cdiv(nc, 256);
+   pa_centroid_kernel<<<gc, 256, 0, st>>>(nc, pa->nv, d_xdofmap, d_x, xs, cx, cy);
+   size_t need = 0, n1 = 0;
+   cub::DeviceReduce::Min(nullptr, need, cx, bb, (int)nc, st);
+   cub::DeviceRadixSort::SortPairs(nullptr, n1, key, key2, id, pa->cperm, (int)nc, 0, 32, st);
+   scratch = std::max(need, n1);
+   if (cudaMalloc(&tmp, scratch) != cudaSuccess) return cleanup(set_error("pa_create: cudaMalloc of %zu bytes failed", scratch));
+   cub::DeviceReduce::Min(tmp, scratch, cx, bb + 0, (int)nc, st);
+   cub::DeviceReduce::Max(tmp, scratch, cx, bb + 1, (int)nc, st);
+   cub::DeviceReduce::Min(tmp, scratch, cy, bb + 2, (int)nc, st);
+   cub::DeviceReduce::Max(tmp, scratch, cy, bb + 3, (int)nc, st);
+   pa_morton_kernel<<<gc, 256, 0, st>>>(nc, cx, cy, bb, key, id);
+   cub::DeviceRadixSort::SortPairs(tmp, scratch, key, key2, id, pa->cperm, (int)nc, 0, 32, st);
+   // 2. per-tile node lists
+   const size_t nt = (size_t)pa->ntiles;
+   if (pa_alloc(pa, &pa->tcount, nt) || pa_alloc(pa, &pa->tnodes, nt * S) || pa_alloc(pa, &pa->tptr, nt * (S + 8)) ||
+       pa_alloc(pa, &pa->trefs, nt * S) || pa_alloc(pa, &pa->lidx, nt * S))
+      return cleanup(1);
+   cudaMemsetAsync(ntouch, 0, sizeof(int32_t) * (size_t)pa->nnodes, st);
+   int end_bit = 1;
+   while (end_bit < 32 && (pa->nnodes >> end_bit) != 0) ++end_bit;
+   switch (pa->nd)
+   {
+      case 3: pa_tile_build<3>(pa, end_bit, ntouch, st); break;
+      case 6: pa_tile_build<6>(pa, end_bit, ntouch, st); break;
+      default: pa_tile_build<9>(pa, end_bit, ntouch, st);
+   }
+   pa_tile_flag_kernel<<<(unsigned)pa->ntiles, 128, 0, st>>>(pa->ntiles, S, pa->tcount, ntouch, pa->tnodes);
+   // 3. nodes shared between tiles, largest tile
+   int32_t *mx = count;
+   cub::DeviceReduce::Max(tmp, scratch, pa->tcount, mx, (int)pa->ntiles, st);
+   int32_t h = 0;
+   cudaMemcpyAsync(&h, mx, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+   if (cudaStreamSynchronize(st) != cudaSuccess)
+      return cleanup(set_error("pa_create: tile build failed: %s", cudaGetErrorString(cudaGetLastError())));
+   pa->max_uniq = h;
+   cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+   const unsigned gn = (unsigned)cdiv(pa->nnodes, 256);
+   pa_shared_list_kernel<<<gn, 256, 0, st>>>(pa->nnodes, ntouch, nullptr, count);
+   cudaMemcpyAsync(&h, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+   if (cudaStreamSynchronize(st) != cudaSuccess)
+      return cleanup(set_error("pa_create: shared-node count failed: %s", cudaGetErrorString(cudaGetLastError())));
+   pa->nshared = h;
+   if (pa_alloc(pa, &pa->shared_nodes, (size_t)h)) return cleanup(1);
+   cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+   pa_shared_list_kernel<<<gn, 256, 0, st>>>(pa->nnodes, ntouch, pa->shared_nodes, count);
+   if (cudaStreamSynchronize(st) != cudaSuccess)
+      return cleanup(set_error("pa_create: shared-node list failed: %s", cudaGetErrorString(cudaGetLastError())));
+   return cleanup(0);
+}
+
 }  // namespace femb
 
 using namespace femb;
@@ -403,7 +853,14 @@ using namespace femb;
 extern "C" void femb200_pa_destroy(femb200_pa *pa)
 {
    if (!pa) return;
+   cudaFree(pa->cperm);
    cudaFree(pa->geo);
+   cudaFree(pa->tcount);
+   cudaFree(pa->tnodes);
+   cudaFree(pa->tptr);
+   cudaFree(pa->trefs);
+   cudaFree(pa->lidx);
+   cudaFree(pa->shared_nodes);
    cudaFree(pa->cmask);
    cudaFree(pa->bc);
    cudaFree(pa->bc_dofs);
@@ -423,19 +880,26 @@ extern "C" int femb200_pa_create(int etype, int64_t nnodes, int64_t ncells, cons
    femb200_pa *pa = new femb200_pa();
    pa->etype = etype, pa->nd = elem_nd(etype), pa->nv = elem_nv(etype);
    pa->nnodes = nnodes, pa->ncells = ncells, pa->dofmap = d_dofmap;
-   const size_t W = 2 * (size_t)pa->nv + 2;
-   if (cudaMalloc(&pa->geo, sizeof(double) * W * (size_t)ncells) != cudaSuccess)
+   FEMB_CHECK(ncells < (int64_t)1 << 31 && nnodes < (int64_t)1 << 31, "pa_create: mesh too large for 32-bit local indices");
+   cudaStream_t st = as_stream(stream);
+   if (pa_build_tiles(pa, d_xdofmap, d_x, x_stride, st))
    {
       femb200_pa_destroy(pa);
-      return set_error("pa_create: cudaMalloc of %zu bytes failed", sizeof(double) * W * (size_t)ncells);
+      return 1;
+   }
+   const size_t W = 2 * (size_t)pa->nv + 2;
+   const size_t padded = (size_t)pa->ntiles * kPaThreads;
+   if (pa_alloc(pa, &pa->geo, W * padded) || cudaMemsetAsync(pa->geo, 0, sizeof(double) * W * padded, st) != cudaSuccess)
+   {
+      femb200_pa_destroy(pa);
+      return 1;
    }
    const LameCoef lc = lame_coef(nu);
    const unsigned grid = (unsigned)cdiv(ncells, 256);
-   cudaStream_t st = as_stream(stream);
    if (etype == FEMB200_Q2)
-      pa_setup_kernel<FEMB200_Q2><<<grid, 256, 0, st>>>(ncells, d_xdofmap, d_x, x_stride, d_E, lc, pa->geo);
+      pa_setup_kernel<FEMB200_Q2><<<grid, 256, 0, st>>>(ncells, pa->cperm, d_xdofmap, d_x, x_stride, d_E, lc, pa->geo);
    else
-      pa_setup_kernel<FEMB200_P1><<<grid, 256, 0, st>>>(ncells, d_xdofmap, d_x, x_stride, d_E, lc, pa->geo);
+      pa_setup_kernel<FEMB200_P1><<<grid, 256, 0, st>>>(ncells, pa->cperm, d_xdofmap, d_x, x_stride, d_E, lc, pa->geo);
    if (cudaGetLastError() != cudaSuccess)
    {
       femb200_pa_destroy(pa);
@@ -455,9 +919,11 @@ extern "C" int femb200_pa_set_dirichlet(femb200_pa *pa, const uint8_t *d_bc, dou
    if (!d_bc) return 0;
    const int64_t nd = 2 * pa->nnodes;
    FEMB_CUDA(cudaMalloc(&pa->bc, (size_t)nd));
-   FEMB_CUDA(cudaMalloc(&pa->cmask, sizeof(uint32_t) * (size_t)pa->ncells));
+   FEMB_CUDA(cudaMalloc(&pa->cmask, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads));
+   FEMB_CUDA(cudaMemsetAsync(pa->cmask, 0, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads, st));
    FEMB_CUDA(cudaMemcpyAsync(pa->bc, d_bc, (size_t)nd, cudaMemcpyDeviceToDevice, st));
-   pa_cmask_kernel<<<(unsigned)cdiv(pa->ncells, 256), 256, 0, st>>>(pa->ncells, pa->nd, pa->dofmap, pa->bc, pa->cmask);
+   pa_cmask_kernel<<<(unsigned)cdiv(pa->ncells, 256), 256, 0, st>>>(pa->ncells, pa->nd, pa->cperm, pa->dofmap, pa->bc,
+                                                                    pa->cmask);
    int32_t *count = nullptr;
    FEMB_CUDA(cudaMalloc(&count, sizeof(int32_t)));
    FEMB_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
@@ -495,13 +961,13 @@ extern "C" int femb200_pa_diagonal(const femb200_pa *pa, double *d_diag, void *s
    switch (pa->etype)
    {
       case FEMB200_P1:
-         pa_diag_kernel<FEMB200_P1><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->dofmap, pa->geo, pa->cmask, d_diag);
+         pa_diag_kernel<FEMB200_P1><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->cperm, pa->dofmap, pa->geo, pa->cmask, d_diag);
          break;
       case FEMB200_P2:
-         pa_diag_kernel<FEMB200_P2><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->dofmap, pa->geo, pa->cmask, d_diag);
+         pa_diag_kernel<FEMB200_P2><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->cperm, pa->dofmap, pa->geo, pa->cmask, d_diag);
          break;
       default:
-         pa_diag_kernel<FEMB200_Q2><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->dofmap, pa->geo, pa->cmask, d_diag);
+         pa_diag_kernel<FEMB200_Q2><<<grid, kPaThreads, 0, st>>>(pa->ncells, pa->cperm, pa->dofmap, pa->geo, pa->cmask, d_diag);
    }
    FEMB_LAUNCH_CHECK();
    if (pa->nbc > 0)

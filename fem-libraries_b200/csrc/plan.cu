@@ -109,14 +109,20 @@ __global__ void k_degree(int64_t nnodes, int nd, const int32_t *__restrict__ dof
 
 __global__ void k_fill_cols(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
                             const int32_t *__restrict__ nptr, const uint32_t *__restrict__ vis,
-                            const int64_t *__restrict__ brp, int32_t *__restrict__ bcol)
+                            const int64_t *__restrict__ brp, int32_t *__restrict__ bcol, uint8_t *__restrict__ dslot)
 {
    const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (I >= nnodes) return;
    int32_t loc[kMaxDeg];
    const int d = gather_neighbours(I, nd, dofmap, nptr, vis, loc);
    const int64_t base = brp[I];
-   for (int s = 0; s < d; ++s) bcol[base + s] = loc[s];
+   int ds = 255;
+   for (int s = 0; s < d; ++s)
+   {
+      bcol[base + s] = loc[s];
+      if (loc[s] == I) ds = s;
+   }
+   dslot[I] = (uint8_t)ds;
 }
 
 // local dof of ROTATED column t for a row with local index a: the row's own vertex / edge becomes
@@ -291,6 +297,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->voff);
    cudaFree(p->brp);
    cudaFree(p->bcol);
+   cudaFree(p->dslot);
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
    cudaFree(p->cellrec);
@@ -359,9 +366,11 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       return fail(set_error("plan_create: pattern build failed: %s", cudaGetErrorString(cudaGetLastError())));
    if (hflags[0]) return fail(set_error("plan_create: a node has more than %d neighbour nodes", kMaxDeg));
    p->max_deg = hflags[1];
-   if (dev_alloc(&p->bcol, (size_t)p->nnzb + 8, &p->bytes) || dev_alloc(&p->vrec, (size_t)nvis, &p->bytes))
+   if (dev_alloc(&p->bcol, (size_t)p->nnzb + 8, &p->bytes) || dev_alloc(&p->vrec, (size_t)nvis, &p->bytes) ||
+       dev_alloc(&p->dslot, (size_t)nnodes, &p->bytes))
       return fail(1);
-   k_fill_cols<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol);
+   k_fill_cols<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
+                                                            p->dslot);
 
    // 3. slot map + staging-tile sizes
    k_fill_slots<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,

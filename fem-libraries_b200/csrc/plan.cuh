@@ -61,6 +61,7 @@ struct femb200_plan
    uint16_t *voff = nullptr;                              // [ntiles * kAsmLevels] level offsets in a tile
    int64_t *brp = nullptr;                                // [nnodes+1]
    int32_t *bcol = nullptr;                               // [nnzb]
+   uint8_t *dslot = nullptr;                              // [nnodes] slot of the diagonal block in its row (255: none)
    int32_t tile_max_blocks[femb::kNumTileR] = {0, 0, 0, 0, 0, 0};
    // Dirichlet
    uint8_t *bc = nullptr;        // [2*nnodes] or null

@@ -15,6 +15,7 @@
 
 #include "plan.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 
 namespace femb {
 
@@ -89,41 +90,6 @@ spmv_kernel(int64_t row_lo, int64_t nnodes, const int64_t *__restrict__ brp, con
 // ---------------------------------------------------------------------------
 constexpr int kTmaConsumers = 256;
 constexpr int kTmaThreads = kTmaConsumers + 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-   asm volatile(
-       "{\n"
-       ".reg .pred P1;\n"
-       "LAB_WAIT:\n"
-       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-       "@P1 bra DONE;\n"
-       "bra LAB_WAIT;\n"
-       "DONE:\n"
-       "}" ::"r"(smem_u32(bar)),
-       "r"(parity)
-       : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(dst)),
-                "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                : "memory");
-}
 
 struct SpmvTile
 {
@@ -252,30 +218,16 @@ spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp,
    if (DOT) block_reduce_finish<kTmaThreads>(part, red, out);
 }
 
-__global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+__global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const uint8_t *__restrict__ dslot,
                             const double *__restrict__ values, double *__restrict__ diag)
 {
    const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (I >= nnodes) return;
    const int64_t bi = brp[I];
-   const int deg = (int)(brp[I + 1] - bi);
-   int lo = 0, hi = deg;
-   while (lo < hi)
-   {
-      const int mid = (lo + hi) >> 1;
-      if (bcol[bi + mid] < I)
-         lo = mid + 1;
-      else
-         hi = mid;
-   }
-   double d0 = 0., d1 = 0.;
-   if (lo < deg && bcol[bi + lo] == I)
-   {
-      d0 = values[4 * bi + 2 * lo];
-      d1 = values[4 * bi + 2 * deg + 2 * lo + 1];
-   }
-   diag[2 * I] = d0;
-   diag[2 * I + 1] = d1;
+   const int deg = (int)(brp[I + 1] - bi), s = dslot[I];
+   double2 d = make_double2(0., 0.);
+   if (s < deg) d = make_double2(values[4 * bi + 2 * s], values[4 * bi + 2 * deg + 2 * s + 1]);
+   reinterpret_cast<double2 *>(diag)[I] = d;
 }
 
 template <bool DOT, int R, int S, int L>
@@ -382,7 +334,7 @@ extern "C" int femb200_extract_diagonal(const femb200_plan *p, const double *d_v
 {
    FEMB_CHECK(p && d_values && d_diag, "extract_diagonal: null argument");
    const int T = 256;
-   diag_kernel<<<(unsigned)cdiv(p->nnodes, T), T, 0, as_stream(stream)>>>(p->nnodes, p->brp, p->bcol, d_values, d_diag);
+   diag_kernel<<<(unsigned)cdiv(p->nnodes, T), T, 0, as_stream(stream)>>>(p->nnodes, p->brp, p->dslot, d_values, d_diag);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
