@@ -47,7 +47,7 @@ struct femb200_pa
    int32_t *tcount = nullptr;        // [ntiles] unique nodes of the tile
    int32_t *tnodes = nullptr;        // [ntiles][ct nd] global node of local node k; bit 31: shared with another tile
    uint16_t *tptr = nullptr;         // [ntiles][ct nd + 8]: [0] = unique nodes, [1 + k] = first entry of node k in trefs
-   uint16_t *trefs = nullptr;        // [ntiles][ct nd] (local dof a) * ct + (cell in tile), grouped by local node
+   uint16_t *trefs = nullptr;        // [ntiles][nd][ct] position of (cell in tile, a) in the node-sorted E-vector
    uint16_t *lidx = nullptr;         // [ntiles][nd][ct] local node of (cell in tile, a)
    int32_t *shared_nodes = nullptr;  // nodes touched by more than one tile
    int32_t nshared = 0;
@@ -58,6 +58,10 @@ struct femb200_pa
    double diag = 1.0;
    size_t bytes = 0;
 };
+
+#ifndef PA_EXP
+#define PA_EXP 0
+#endif
 
 namespace femb {
 
@@ -103,7 +107,8 @@ __global__ void pa_morton_kernel(int64_t ncells, const float *__restrict__ cx, c
 
 // ---- setup: per-tile node lists -------------------------------------------------------
 // One CTA per tile sorts the (node, a * CT + t) pairs of its cells by node: the heads of the runs
-// are the tile's unique nodes (ascending), the sorted values are the node -> (cell, dof) lists.
+// are the tile's unique nodes (ascending); the sorted position of a pair is where the cell's
+// contribution is stored, so that the contributions to one node are contiguous.
 template <int ND, int CT>
 __global__ void __launch_bounds__(CT)
 pa_tile_build_kernel(int64_t ncells, int64_t nnodes, int end_bit, const int32_t *__restrict__ dofmap,
@@ -163,7 +168,7 @@ pa_tile_build_kernel(int64_t ncells, int64_t nnodes, int end_bit, const int32_t 
          tp[lid] = (uint16_t)pos;
          atomicAdd(ntouch + key[j], 1);
       }
-      trefs[base + pos] = val[j];
+      trefs[base + val[j]] = (uint16_t)pos;
       lidx[base + val[j]] = (uint16_t)lid;
    }
    if (t == 0)
@@ -290,57 +295,85 @@ __device__ __forceinline__ void local_apply_tri(const double *g, const double *u
    }
 }
 
-// Q2: sum factorisation with the 1-D tables of the three Lagrange (GLL) basis
-// functions at the three Gauss points
-__device__ __forceinline__ void q2_tables(double (*B)[3], double (*dB)[3])
+// Q2: sum factorisation with the 1-D tables of the three Lagrange (GLL) basis functions at the
+// three Gauss points t0 < 1/2 < t2.  The tables are
+//    B  = [b0 b1 b2; 0 1 0; b2 b1 b0]        dB = [d0 d1 d2; -1 0 1; -d2 -d1 -d0]
+// (the middle Gauss point is the middle node), which the contractions below exploit.
+namespace q2 {
+constexpr double s = 0.7745966692414834;
+constexpr double t = 0.5 * (1. - s);
+constexpr double b0 = 2. * (t - 0.5) * (t - 1.), b1 = 4. * t * (1. - t), b2 = 2. * t * (t - 0.5);
+constexpr double d0 = 4. * t - 3., d1 = 4. - 8. * t, d2 = 4. * t - 1.;
+// values at the three points of  sum_i B[q][i] u_i  and  sum_i dB[q][i] u_i
+__device__ __forceinline__ void interp(double u0, double u1, double u2, double *v)
 {
-   const double s = 0.7745966692414834;
-   const double xq[3] = {0.5 * (1. - s), 0.5, 0.5 * (1. + s)};
-#pragma unroll
-   for (int q = 0; q < 3; ++q)
-   {
-      const double t = xq[q];
-      B[q][0] = 2. * (t - 0.5) * (t - 1.), B[q][1] = 4. * t * (1. - t), B[q][2] = 2. * t * (t - 0.5);
-      dB[q][0] = 4. * t - 3., dB[q][1] = 4. - 8. * t, dB[q][2] = 4. * t - 1.;
-   }
+   v[0] = b0 * u0 + b1 * u1 + b2 * u2;
+   v[1] = u1;
+   v[2] = b2 * u0 + b1 * u1 + b0 * u2;
+}
+__device__ __forceinline__ void deriv(double u0, double u1, double u2, double *v)
+{
+   v[0] = d0 * u0 + d1 * u1 + d2 * u2;
+   v[1] = u2 - u0;
+   v[2] = -d2 * u0 - d1 * u1 - d0 * u2;
+}
+// transposes: out_i = sum_q B[q][i] a_q,  out_i = sum_q dB[q][i] a_q
+__device__ __forceinline__ void interp_t(double a0, double a1, double a2, double *v)
+{
+   v[0] = b0 * a0 + b2 * a2;
+   v[1] = b1 * (a0 + a2) + a1;
+   v[2] = b2 * a0 + b0 * a2;
+}
+__device__ __forceinline__ void deriv_t_add(double a0, double a1, double a2, double *v)
+{
+   v[0] += d0 * a0 - a1 - d2 * a2;
+   v[1] += d1 * (a0 - a2);
+   v[2] += d2 * a0 + a1 - d0 * a2;
+}
+}  // namespace q2
+
+// 1 / d to ~1 ulp: hardware seed + two Newton steps (no slow-path call)
+__device__ __forceinline__ double fast_rcp(double d)
+{
+   double x;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+   x = fma(fma(-d, x, 1.), x, x);
+   x = fma(fma(-d, x, 1.), x, x);
+   return x;
 }
 
 __device__ __forceinline__ void local_apply_q2(const double *g, const double *ux, const double *uy, double *yx,
                                                double *yy)
 {
-   double B[3][3], dB[3][3];
-   q2_tables(B, dB);
-   const double s = 0.7745966692414834;
-   const double xq[3] = {0.5 * (1. - s), 0.5, 0.5 * (1. + s)};
+   const double xq[3] = {q2::t, 0.5, 1. - q2::t};
    const double wq[3] = {5. / 18., 8. / 18., 5. / 18.};
    const double lam = g[8], mu = g[9];
-   // reference gradients at the 9 points: a[q][0..3] = (dux/dxi, dux/deta, duy/dxi, duy/deta)
+   // reference gradients at the 9 points: a[3 qy + qx] = (dux/dxi, dux/deta, duy/dxi, duy/deta)
    double a[9][4];
+#pragma unroll
+   for (int c = 0; c < 2; ++c)
    {
-      double t0[3][3], t1[3][3];  // [qx][j]
+      const double *u = c ? uy : ux;
+      double t0[3][3], t1[3][3];  // [j][qx]: values / xi-derivatives along node row j
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+      for (int j = 0; j < 3; ++j)
       {
-         const double *u = c ? uy : ux;
+         q2::interp(u[3 * j], u[3 * j + 1], u[3 * j + 2], t0[j]);
+         q2::deriv(u[3 * j], u[3 * j + 1], u[3 * j + 2], t1[j]);
+      }
 #pragma unroll
-         for (int qx = 0; qx < 3; ++qx)
+      for (int qx = 0; qx < 3; ++qx)
+      {
+         double v[3], w[3];
+         q2::interp(t1[0][qx], t1[1][qx], t1[2][qx], v);  // d/dxi at (qx, qy = 0..2)
+         q2::deriv(t0[0][qx], t0[1][qx], t0[2][qx], w);   // d/deta
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-            {
-               t0[qx][j] = B[qx][0] * u[3 * j] + B[qx][1] * u[3 * j + 1] + B[qx][2] * u[3 * j + 2];
-               t1[qx][j] = dB[qx][0] * u[3 * j] + dB[qx][1] * u[3 * j + 1] + dB[qx][2] * u[3 * j + 2];
-            }
-#pragma unroll
-         for (int qy = 0; qy < 3; ++qy)
-#pragma unroll
-            for (int qx = 0; qx < 3; ++qx)
-            {
-               a[3 * qy + qx][2 * c] = t1[qx][0] * B[qy][0] + t1[qx][1] * B[qy][1] + t1[qx][2] * B[qy][2];
-               a[3 * qy + qx][2 * c + 1] = t0[qx][0] * dB[qy][0] + t0[qx][1] * dB[qy][1] + t0[qx][2] * dB[qy][2];
-            }
+         for (int qy = 0; qy < 3; ++qy) a[3 * qy + qx][2 * c] = v[qy], a[3 * qy + qx][2 * c + 1] = w[qy];
       }
    }
-   // point work: a[q] <- (px0, px1, py0, py1) = J^-1 (w sigma) rows
+   // point work: a[q] <- (px0, px1, py0, py1) = adj(J) (w / |det|) sigma(adj(J)^t grad_ref u)
+   const double ax = g[2] - g[0], bx = g[6] - g[4], cx = g[4] - g[0], dx = g[6] - g[2];
+   const double ay = g[3] - g[1], by = g[7] - g[5], cy = g[5] - g[1], dy = g[7] - g[3];
 #pragma unroll
    for (int qy = 0; qy < 3; ++qy)
 #pragma unroll
@@ -348,45 +381,42 @@ __device__ __forceinline__ void local_apply_q2(const double *g, const double *ux
       {
          const double xi = xq[qx], eta = xq[qy];
          // bilinear geometry, vertices (0,0),(1,0),(0,1),(1,1)
-         const double J00 = (1. - eta) * (g[2] - g[0]) + eta * (g[6] - g[4]);
-         const double J01 = (1. - xi) * (g[4] - g[0]) + xi * (g[6] - g[2]);
-         const double J10 = (1. - eta) * (g[3] - g[1]) + eta * (g[7] - g[5]);
-         const double J11 = (1. - xi) * (g[5] - g[1]) + xi * (g[7] - g[3]);
+         const double J00 = ax + eta * (bx - ax), J01 = cx + xi * (dx - cx);
+         const double J10 = ay + eta * (by - ay), J11 = cy + xi * (dy - cy);
          const double det = J00 * J11 - J01 * J10;
-         const double id = 1. / det;
-         const double i00 = J11 * id, i01 = -J01 * id, i10 = -J10 * id, i11 = J00 * id;  // J^-1[m][k]
+         // J^-1 = adj / det with adj = [J11 -J01; -J10 J00]: the two 1/det and w |det| fold into w / |det|
+         const double sc = wq[qx] * wq[qy] * fast_rcp(fabs(det));
          double *aq = a[3 * qy + qx];
-         // physical gradient: d u / d x_k = sum_m (du/dxi_m) Jinv[m][k]
-         const double uxx = aq[0] * i00 + aq[1] * i10, uxy = aq[0] * i01 + aq[1] * i11;
-         const double uyx = aq[2] * i00 + aq[3] * i10, uyy = aq[2] * i01 + aq[3] * i11;
+         const double uxx = aq[0] * J11 - aq[1] * J10, uxy = aq[1] * J00 - aq[0] * J01;
+         const double uyx = aq[2] * J11 - aq[3] * J10, uyy = aq[3] * J00 - aq[2] * J01;
          double sxx, syy, sxy;
-         hooke_stress(lam, mu, wq[qx] * wq[qy] * fabs(det), uxx, uyy, uxy + uyx, sxx, syy, sxy);
-         // back to reference directions: p_m = sum_k Jinv[m][k] sigma_{c k}
-         aq[0] = i00 * sxx + i01 * sxy;
-         aq[1] = i10 * sxx + i11 * sxy;
-         aq[2] = i00 * sxy + i01 * syy;
-         aq[3] = i10 * sxy + i11 * syy;
+         hooke_stress(lam, mu, sc, uxx, uyy, uxy + uyx, sxx, syy, sxy);
+         aq[0] = J11 * sxx - J01 * sxy;
+         aq[1] = J00 * sxy - J10 * sxx;
+         aq[2] = J11 * sxy - J01 * syy;
+         aq[3] = J00 * syy - J10 * sxy;
       }
    // transpose contractions
 #pragma unroll
    for (int c = 0; c < 2; ++c)
    {
       double *y = c ? yy : yx;
-      double t0[3][3], t1[3][3];  // [qx][j]: sum over qy
+      double t1[3][3], t0[3][3];  // [qx][j]
 #pragma unroll
       for (int qx = 0; qx < 3; ++qx)
-#pragma unroll
-         for (int j = 0; j < 3; ++j)
-         {
-            t1[qx][j] = B[0][j] * a[qx][2 * c] + B[1][j] * a[3 + qx][2 * c] + B[2][j] * a[6 + qx][2 * c];
-            t0[qx][j] = dB[0][j] * a[qx][2 * c + 1] + dB[1][j] * a[3 + qx][2 * c + 1] + dB[2][j] * a[6 + qx][2 * c + 1];
-         }
+      {
+         q2::interp_t(a[qx][2 * c], a[3 + qx][2 * c], a[6 + qx][2 * c], t1[qx]);
+         t0[qx][0] = t0[qx][1] = t0[qx][2] = 0.;
+         q2::deriv_t_add(a[qx][2 * c + 1], a[3 + qx][2 * c + 1], a[6 + qx][2 * c + 1], t0[qx]);
+      }
 #pragma unroll
       for (int j = 0; j < 3; ++j)
-#pragma unroll
-         for (int i = 0; i < 3; ++i)
-            y[3 * j + i] = dB[0][i] * t1[0][j] + dB[1][i] * t1[1][j] + dB[2][i] * t1[2][j] + B[0][i] * t0[0][j] +
-                           B[1][i] * t0[1][j] + B[2][i] * t0[2][j];
+      {
+         double v[3];
+         q2::interp_t(t0[0][j], t0[1][j], t0[2][j], v);
+         q2::deriv_t_add(t1[0][j], t1[1][j], t1[2][j], v);
+         y[3 * j] = v[0], y[3 * j + 1] = v[1], y[3 * j + 2] = v[2];
+      }
    }
 }
 
@@ -552,10 +582,15 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
                if ((m >> (2 * a + 1)) & 1u) uy[a] = 0.;
             }
          }
+#if PA_EXP & 1
+#pragma unroll
+         for (int a = 0; a < nd; ++a) yx[a] = ux[a] * g[a % W], yy[a] = uy[a];
+#else
          if (ET == FEMB200_Q2)
             local_apply_q2(g, ux, uy, yx, yy);
          else
             local_apply_tri<ET>(g, ux, uy, yx, yy);
+#endif
          if (m != 0u)
          {
 #pragma unroll
@@ -565,40 +600,64 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
                if ((m >> (2 * a + 1)) & 1u) yy[a] = 0.;
             }
          }
+         // contributions go to their node-sorted positions
+         const uint16_t *pp = reinterpret_cast<const uint16_t *>(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes) + tid;
+         mbar_wait(&fullT[it & 1], (it >> 1) & 1);
 #pragma unroll
-         for (int a = 0; a < nd; ++a) ye[a * CT + tid] = make_double2(yx[a], yy[a]);
+         for (int a = 0; a < nd; ++a) ye[pp[a * CT]] = make_double2(yx[a], yy[a]);
       }
       __syncthreads();  // B2: ye complete
-      // one thread per tile node: sum the contributions of the tile's cells (fixed order)
+      // one thread per tile node: sum its (contiguous) contributions in a fixed order; KU nodes in flight
       const unsigned char *nb = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
       const int32_t *tn = reinterpret_cast<const int32_t *>(nb);
       const uint16_t *tp = reinterpret_cast<const uint16_t *>(nb + L.tp);
-      const uint16_t *tr = reinterpret_cast<const uint16_t *>(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes);
-      mbar_wait(&fullT[it & 1], (it >> 1) & 1);
-      const int nu = tp[0];
-      for (int k = tid; k < nu; k += CT)
+      const int nu = (PA_EXP & 2) ? 0 : tp[0];
+      constexpr int KU = ET == FEMB200_Q2 ? 5 : 3;
+      for (int k0 = tid; k0 < nu; k0 += KU * CT)
       {
-         const int p0 = tp[1 + k], p1 = tp[2 + k];
-         double2 acc = ye[tr[p0]];
-         for (int p = p0 + 1; p < p1; ++p)
+         int p0[KU], p1[KU];
+         double2 acc[KU];
+#pragma unroll
+         for (int j = 0; j < KU; ++j)
          {
-            const double2 v = ye[tr[p]];
-            acc.x += v.x, acc.y += v.y;
+            const int k = k0 + j * CT;
+            p0[j] = k < nu ? tp[1 + k] : 0;
+            p1[j] = k < nu ? tp[2 + k] : 0;
+            acc[j] = make_double2(0., 0.);
          }
-         const int32_t id = tn[k];
-         if (DOT)
-         {  // <x, y> = sum over (tile, node) of x_node . partial: masked dofs contribute zeros
-            const double2 xv = xs[k];
-            part += xv.x * acc.x + xv.y * acc.y;
-         }
-         if (id < 0)
+         for (int r = 0;; ++r)
          {
-            double *yp = A.y + 2 * (int64_t)(id & 0x7fffffff);
-            red_add_f64(yp, acc.x);
-            red_add_f64(yp + 1, acc.y);
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < KU; ++j)
+               if (p0[j] + r < p1[j])
+               {
+                  const double2 v = ye[p0[j] + r];
+                  acc[j].x += v.x, acc[j].y += v.y;
+                  any = true;
+               }
+            if (!any) break;
          }
-         else
-            y2[id] = acc;
+#pragma unroll
+         for (int j = 0; j < KU; ++j)
+         {
+            const int k = k0 + j * CT;
+            if (k >= nu) continue;
+            const int32_t id = tn[k];
+            if (DOT)
+            {  // <x, y> = sum over (tile, node) of x_node . partial: masked dofs contribute zeros
+               const double2 xv = xs[k];
+               part += xv.x * acc[j].x + xv.y * acc[j].y;
+            }
+            if (id < 0)
+            {
+               double *yp = A.y + 2 * (int64_t)(id & 0x7fffffff);
+               red_add_f64(yp, acc[j].x);
+               red_add_f64(yp + 1, acc[j].y);
+            }
+            else
+               y2[id] = acc[j];
+         }
       }
    }
    cp_async_wait<0>();

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfemb200.so")
+LIB_PATH = os.environ.get("FEMB200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfemb200.so")
 
 P1, P2, Q2 = 0, 1, 2
 ROWMAJOR_INTERLEAVED, COLMAJOR_BYNODES = 0, 1
