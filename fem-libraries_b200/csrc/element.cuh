@@ -129,13 +129,13 @@ __device__ __forceinline__ void geom_basis(double xi, double eta, double *phi, d
    }
 }
 
-// everything needed at quadrature point q: G (nd x 2), phi (nv), weight
+// physical gradients G (nd x 2) and vertex basis phi (nv) at the reference point (xi, eta);
+// returns |det J|
 template <int ET>
-__device__ __forceinline__ double qp_geometry(const double (*xv)[2], int q, double (*G)[2], double *phi)
+__device__ __forceinline__ double point_geometry(const double (*xv)[2], double xi, double eta, double (*G)[2],
+                                                 double *phi)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv;
-   double xi, eta, wq;
-   quad_point<ET>(q, xi, eta, wq);
    double dN[nd][2], dphi[nv][2];
    ref_grads<ET>(xi, eta, dN);
    geom_basis<ET>(xi, eta, phi, dphi);
@@ -156,7 +156,16 @@ __device__ __forceinline__ double qp_geometry(const double (*xv)[2], int q, doub
       G[a][0] = dN[a][0] * i00 + dN[a][1] * i10;
       G[a][1] = dN[a][0] * i01 + dN[a][1] * i11;
    }
-   return wq * fabs(det);
+   return fabs(det);
+}
+
+// everything needed at quadrature point q: G (nd x 2), phi (nv), weight
+template <int ET>
+__device__ __forceinline__ double qp_geometry(const double (*xv)[2], int q, double (*G)[2], double *phi)
+{
+   double xi, eta, wq;
+   quad_point<ET>(q, xi, eta, wq);
+   return wq * point_geometry<ET>(xv, xi, eta, G, phi);
 }
 
 // 2x2 block  w * B_a D B_b^t  with B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]

@@ -19,6 +19,9 @@ MFEM driver, `manual.py` = the UFL form file; paths relative to /root/reference)
   AssembleElementVector / setF lambda          assemble_vector(A, form, f), apply_lifting(A, b, g, u)
   NewtonSolver (M.cc:1531-1549, F.cc:869-907)  NewtonSolver(form, bcs, f).solve()
   BilinearFormIntegrator::AssemblePA/AddMultPA PAOperator(form).AssemblePA()/AddMultPA()/Mult()
+  damage smoothing (M.cc:1258-1315)            DamageSmoother(mesh).smooth(d, niter)
+  strainTensor / stressTensor -> DG0 fields    cell_strain_stress(form)
+    (M.cc:333-430,1551-1563; F.cc:909-942)
   CGSolver::SetRelTol/SetMaxIter/SetOperator/  CGSolver(...)
     SetPreconditioner/Mult                       (Jacobi instead of BoomerAMG: third party, out of scope)
 
@@ -374,6 +377,54 @@ def tabulate_tensor(A: np.ndarray, w: np.ndarray, c: np.ndarray, coordinate_dofs
     Ae = tabulate_tensor_batched(form).cpu().numpy().reshape(-1)
     Av = np.asarray(A).reshape(-1)
     Av += Ae
+
+
+class DamageSmoother:
+    """The reference's damage-field smoothing over the vertex graph of the triangulation
+    (M.cc:1209-1315; the Python driver builds a SciPy adjacency matrix for it, F.py:160-199):
+    niter double sweeps d_l = max(sum over edge neighbours / edge count, d_l), the first of each
+    pair only where d_l < 0.01.  The graph is the block pattern of a P1 plan on the geometry
+    vertices, built once on the device; `d` is indexed by node id like ElasticityForm.d."""
+
+    def __init__(self, mesh: Mesh):
+        _require_cuda()
+        if mesh.nv != 3:
+            raise ValueError("damage smoothing is defined on triangulations (the reference has no quads)")
+        self.nnodes = mesh.nnodes
+        self._tri = to_device(mesh.xdofmap, np.int32)
+        self._plan = C.c_void_p()
+        capi.call("femb200_plan_create", capi.P1, mesh.nnodes, mesh.ncells, _p(self._tri), _p(self._tri), _stream(),
+                  C.byref(self._plan))
+        self._work = torch.empty(self.nnodes, dtype=torch.float64, device="cuda")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None and self._plan.value:
+                capi.lib().femb200_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    def smooth(self, d, niter: int = 8, threshold: float = 0.01) -> torch.Tensor:
+        """niter = 8 * (max_refine + 1) in the reference (M.cc:1258).  Returns a new device tensor."""
+        dd = to_device(d, np.float64).clone()
+        if dd.numel() != self.nnodes:
+            raise ValueError(f"d has {dd.numel()} entries, expected one per node ({self.nnodes})")
+        capi.call("femb200_smooth_damage", self._plan, _p(dd), _p(self._work), int(niter), float(threshold), _stream())
+        return dd
+
+
+def cell_strain_stress(form: ElasticityForm, stress: bool = True):
+    """DG0 output fields of the reference (strainTensor / stressTensor projected on a 3-component
+    DG0 space, M.cc:333-430,1551-1563; strain/stress expressions interpolated into S, F.cc:909-942):
+    (ncells, 3) device tensors (xx, xy, yy) evaluated at the cell centroid for the current form.u."""
+    if form.u is None:
+        raise ValueError("form.u (the displacement) is not set")
+    eps = torch.empty((form.ncells, 3), dtype=torch.float64, device="cuda")
+    sig = torch.empty((form.ncells, 3), dtype=torch.float64, device="cuda") if stress else None
+    capi.call("femb200_cell_strain_stress", form.etype, form.ncells, _p(form.xdofmap), _p(form.dofmap), _p(form.x),
+              form.x_stride, _p(form.E), form.nu, _p(form.d), _p(form.u), _p(eps), _p(sig), _stream())
+    return eps, sig
 
 
 class PAOperator:

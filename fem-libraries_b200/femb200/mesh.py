@@ -207,3 +207,64 @@ def damage_band(mesh: Mesh) -> np.ndarray:
     x, y = mesh.x[:, 0], mesh.x[:, 1]
     d = np.maximum(0.0, 1.0 - np.abs(y - 0.5 - 0.1 * np.sin(6.0 * x)) / 0.05)
     return np.minimum(d, 0.95)
+
+
+def read_gmsh22(path: str) -> Mesh:
+    """Gmsh 2.2 ASCII reader for triangulations (role of `Mesh(mesh_file, 1, 0, true)`, M.cc:1017-1020,
+    and of the gmsh -> XDMF conversion + `read_mesh` / `read_meshtags`, gmsh_to_xdmf_neper_dam.py:1-16,
+    F.cc:153-193): 2-node lines (type 1) and 3-node triangles (type 2) with their first (physical)
+    tag.  Returns a P1 Mesh; meta holds `cell_tags` (ncells), `facets` (nfacets, 2) and `facet_tags`.
+    Orientation is left as in the file: the element kernels use |det J|."""
+    with open(path) as f:
+        tok = f.read().split("\n")
+    sec = {}
+    i = 0
+    while i < len(tok):
+        ln = tok[i].strip()
+        if ln.startswith("$") and not ln.startswith("$End"):
+            j = i + 1
+            while j < len(tok) and tok[j].strip() != "$End" + ln[1:]:
+                j += 1
+            sec[ln[1:]] = tok[i + 1:j]
+            i = j
+        i += 1
+    if "MeshFormat" in sec and not sec["MeshFormat"][0].split()[0].startswith("2"):
+        raise ValueError(f"{path}: only the Gmsh 2.x ASCII format is supported")
+    nn = int(sec["Nodes"][0])
+    rows = np.array([r.split() for r in sec["Nodes"][1:1 + nn]], dtype=np.float64)
+    ids = rows[:, 0].astype(np.int64)
+    remap = np.full(int(ids.max()) + 1, -1, dtype=np.int64)
+    remap[ids] = np.arange(nn)
+    x = np.ascontiguousarray(rows[:, 1:3])
+    tris, ttag, lines, ltag = [], [], [], []
+    ne = int(sec["Elements"][0])
+    for r in sec["Elements"][1:1 + ne]:
+        p = [int(t) for t in r.split()]
+        et, ntags = p[1], p[2]
+        tag = p[3] if ntags > 0 else 0
+        nodes = p[3 + ntags:]
+        if et == 2:
+            tris.append(nodes), ttag.append(tag)
+        elif et == 1:
+            lines.append(nodes), ltag.append(tag)
+    if not tris:
+        raise ValueError(f"{path}: no triangles")
+    tri = remap[np.array(tris, dtype=np.int64)].astype(np.int32)
+    meta = {"kind": "gmsh22", "cell_tags": np.array(ttag, dtype=np.int32),
+            "facets": remap[np.array(lines, dtype=np.int64).reshape(-1, 2)].astype(np.int32),
+            "facet_tags": np.array(ltag, dtype=np.int32)}
+    return Mesh(P1, x, tri, tri.copy(), 0, 0, meta)
+
+
+def young_from_tags(cell_tags: np.ndarray) -> np.ndarray:
+    """E per cell from the physical tag: E_range[tag % 200] (M.cc:1580-1583, F.py:221)."""
+    return young_table()[np.asarray(cell_tags, dtype=np.int64) % 200].copy()
+
+
+def damage_seed(mesh: Mesh, facet_tags, max_dam: float = 1.0) -> np.ndarray:
+    """Initial nodal damage: MAX_DAM on the nodes of the facets carrying one of `facet_tags`
+    (M.cc:1160-1205,1251-1255; F.py:113-127; the square mesh uses tag 4, M.cc:1164-1167)."""
+    d = np.zeros(mesh.nnodes)
+    sel = np.isin(mesh.meta["facet_tags"], np.asarray(facet_tags))
+    d[np.unique(mesh.meta["facets"][sel])] = max_dam
+    return d

@@ -233,6 +233,25 @@ int femb200_pa_set_dirichlet(femb200_pa *pa, const uint8_t *d_bc, double diag, v
 int femb200_pa_apply(const femb200_pa *pa, const double *d_x, double *d_y, void *stream);
 int femb200_pa_diagonal(const femb200_pa *pa, double *d_diag, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Field operators either side of the hot path.
+ * smooth_damage: the reference's damage-field smoothing over the vertex graph
+ * (M.cc:1258-1315; F.py:160-199): niter double sweeps d_l = max(sum over edge
+ * neighbours / degree, d_l), the first sweep of a pair only where d_l < threshold
+ * (0.01 in the reference).  `plan` is the P1 plan of the triangulation (its block
+ * pattern is the edge graph plus the diagonal); d_d [nnodes] in/out, d_work
+ * [nnodes] scratch.  The reference runs niter = 8 * (max_refine + 1).
+ * cell_strain_stress: DG0 output fields (strainTensor / stressTensor,
+ * M.cc:333-430,1551-1563; F.cc:909-942): symmetric gradient of u and asym_stress
+ * at the cell centroid, three doubles (xx, xy, yy) per cell; d_strain or d_stress
+ * may be NULL; d_dnod (nodal damage on the geometry vertices) may be NULL (d = 0).
+ * ------------------------------------------------------------------------ */
+int femb200_smooth_damage(const femb200_plan *plan, double *d_d, double *d_work, int niter, double threshold,
+                          void *stream);
+int femb200_cell_strain_stress(int etype, int64_t ncells, const int32_t *d_xdofmap, const int32_t *d_dofmap,
+                               const double *d_x, int x_stride, const double *d_E, double nu, const double *d_dnod,
+                               const double *d_u, double *d_strain, double *d_stress, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

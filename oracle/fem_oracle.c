@@ -797,6 +797,83 @@ void orc_assemble_vector(int etype, int64_t ncells, int64_t nnodes, const double
 }
 
 /* ------------------------------------------------------------------------ */
+/* Field operators either side of the hot path      */
+/* ------------------------------------------------------------------------ */
+
+/* Damage-field smoothing, serial semantics of M.cc:1258-1315 (same algorithm with a SciPy
+ * adjacency product at F.py:160-199).  adjptr/adj: the vertex graph (edge neighbours of every
+ * vertex, ascending, no self).  niter double sweeps, each reading the previous field in full
+ * (the reference fills the scratch vector vv before updating, M.cc:1270-1291):
+ *   sweep A: s_l = [d_l < thr] sum_n d_n ; d_l = max(s_l * (1/deg_l), d_l)   (thr = 0.01, M.cc:1274)
+ *   sweep B: s_l = sum_n d_n             ; d_l = max(s_l * (1/deg_l), d_l)
+ * The reference multiplies by the precomputed reciprocal of the edge count (M.cc:1247,1292).
+ * Its summation order is MFEM's vertex-to-edge table order (not available here); the oracle sums
+ * in ascending neighbour order ("parity unpinned" for the last bits). */
+void orc_smooth_damage(int64_t nverts, const int64_t *adjptr, const int32_t *adj, double *d, int niter, double thr)
+{
+   double *t = (double *)malloc(sizeof(double) * (size_t)(nverts > 0 ? nverts : 1));
+   for (int it = 0; it < niter; ++it)
+      for (int sweep = 0; sweep < 2; ++sweep)
+      {
+         const double *in = sweep ? t : d;
+         double *out = sweep ? d : t;
+         for (int64_t l = 0; l < nverts; ++l)
+         {
+            const int64_t deg = adjptr[l + 1] - adjptr[l];
+            double s = 0.;
+            if (sweep == 1 || in[l] < thr)
+               for (int64_t k = adjptr[l]; k < adjptr[l + 1]; ++k) s += in[adj[k]];
+            const double inv = deg > 0 ? 1. / (double)deg : 0.;
+            const double v = s * inv;
+            out[l] = v > in[l] ? v : in[l];
+         }
+      }
+   free(t);
+}
+
+/* DG0 strain and stress output fields (strainTensor / stressTensor, M.cc:333-430 projected on a
+ * DG0 space at M.cc:1551-1563; F.cc:909-942): per cell the symmetrised gradient of u
+ * (M.cc:343-349) and asym_stress with weight one (M.cc:415-427) at the DG0 node = cell centroid,
+ * stored (xx, xy, yy).  dnod: nodal damage (indexed like x) or NULL.  strain/stress may be NULL. */
+void orc_cell_strain_stress(int etype, int64_t ncells, const double *x, const int32_t *xdofmap, const int32_t *dofmap,
+                            const double *E, double nu, const double *dnod, const double *u, double *strain,
+                            double *stress)
+{
+   const int nd = elem_nd(etype), nv = elem_nv(etype);
+   const double xi = etype == ORC_Q2 ? 0.5 : 1. / 3., eta = xi;
+   for (int64_t e = 0; e < ncells; ++e)
+   {
+      double xv[8], N[9], G[9][2], phi[4];
+      for (int v = 0; v < nv; ++v)
+      {
+         const int64_t g = xdofmap[e * nv + v];
+         xv[2 * v] = x[2 * g], xv[2 * v + 1] = x[2 * g + 1];
+      }
+      qp_geometry(etype, xv, xi, eta, 1., N, G, phi);
+      double d = 0.;
+      if (dnod)
+         for (int v = 0; v < nv; ++v) d += phi[v] * dnod[xdofmap[e * nv + v]];
+      double gu[2][2] = {{0., 0.}, {0., 0.}};
+      for (int a = 0; a < nd; ++a)
+      {
+         const int64_t g = dofmap[e * nd + a];
+         for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) gu[i][j] += u[2 * g + i] * G[a][j];
+      }
+      const double sh = 0.5 * (gu[0][1] + gu[1][0]);
+      if (strain) strain[3 * e] = gu[0][0], strain[3 * e + 1] = sh, strain[3 * e + 2] = gu[1][1];
+      if (stress)
+      {
+         const double eps[4] = {gu[0][0], sh, sh, gu[1][1]};
+         double lam, mu, sig[4];
+         orc_lame(E[e], nu, &lam, &mu);
+         orc_stress(lam, mu, d, 1., eps, sig);
+         stress[3 * e] = sig[0], stress[3 * e + 1] = sig[1], stress[3 * e + 2] = sig[3];
+      }
+   }
+}
+
+/* ------------------------------------------------------------------------ */
 /* Sparsity pattern (role of dolfinx create_matrix, F.cc:688)                */
 /* rows in dof order, columns ascending and unique, structural, bs=2 dofs    */
 /* (2*node + comp).  Call with colidx == NULL to get rowptr and nnz.          */

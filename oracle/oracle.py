@@ -245,3 +245,35 @@ def pcg(rowptr, colidx, values, b, rtol=1e-12, atol=0.0, maxit=2000, jacobi=True
                          C.c_double(atol), C.c_int(maxit), C.c_int(1 if jacobi else 0), C.byref(it), C.byref(fn),
                          C.c_int(nthreads))
     return x, it.value, fn.value, bool(conv)
+
+
+def vertex_graph(nverts: int, tri: np.ndarray):
+    """Edge graph of a triangulation as CSR (adjptr int64, adj int32): the neighbours of every
+    vertex, ascending, no self (role of the vertex_edge / edge_vertex tables, M.cc:1209-1213)."""
+    t = np.asarray(tri, dtype=np.int64)
+    a = np.concatenate([t[:, 0], t[:, 1], t[:, 2], t[:, 1], t[:, 2], t[:, 0]])
+    b = np.concatenate([t[:, 1], t[:, 2], t[:, 0], t[:, 0], t[:, 1], t[:, 2]])
+    key = np.unique(a * nverts + b)
+    rows, cols = key // nverts, key % nverts
+    adjptr = np.zeros(nverts + 1, dtype=np.int64)
+    np.add.at(adjptr, rows + 1, 1)
+    return np.cumsum(adjptr), cols.astype(np.int32)
+
+
+def smooth_damage(nverts: int, tri: np.ndarray, d0: np.ndarray, niter: int = 8, thr: float = 0.01) -> np.ndarray:
+    """Damage-field smoothing (M.cc:1258-1315, F.py:160-199) on the vertex graph of `tri`."""
+    adjptr, adj = vertex_graph(nverts, tri)
+    d = np.array(d0, dtype=np.float64, copy=True)
+    lib().orc_smooth_damage(C.c_int64(nverts), _l(adjptr), _i(adj), _d(d), C.c_int(niter), C.c_double(thr))
+    return d
+
+
+def cell_strain_stress(etype, x, xdofmap, dofmap, E, nu, u, dnod=None):
+    """DG0 strain and stress (xx, xy, yy) per cell at the centroid (M.cc:333-430,1551-1563)."""
+    x, E, u, dnod = _f64(np.asarray(x)[:, :2]), _f64(E), _f64(u), _f64(dnod)
+    xd, dm = _i32(xdofmap), _i32(dofmap)
+    nc = dm.shape[0]
+    strain, stress_ = np.empty((nc, 3)), np.empty((nc, 3))
+    lib().orc_cell_strain_stress(C.c_int(etype), C.c_int64(nc), _d(x), _i(xd), _i(dm), _d(E), C.c_double(nu), _d(dnod),
+                                 _d(u), _d(strain), _d(stress_))
+    return strain, stress_

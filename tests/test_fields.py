@@ -1,0 +1,147 @@
+"""Field operators either side of the hot path: damage-field smoothing
+(M.cc:1258-1315, F.py:160-199), DG0 strain / stress output fields (M.cc:333-430,1551-1563),
+Gmsh-2.2 ingestion (M.cc:1017-1020).  CPU part: the oracle against hand-computed answers and the
+pinned P1 residual; GPU part: the CUDA kernels against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from femb200 import mesh as fm
+
+
+def write_msh22(path, x, tri, tri_tag, edges, edge_tag):
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(x))
+        for i, p in enumerate(x):
+            f.write("%d %.17g %.17g 0\n" % (i + 1, p[0], p[1]))
+        f.write("$EndNodes\n$Elements\n%d\n" % (len(tri) + len(edges)))
+        k = 1
+        for e, t in zip(edges, edge_tag):
+            f.write("%d 1 2 %d %d %d %d\n" % (k, t, t, e[0] + 1, e[1] + 1))
+            k += 1
+        for c, t in zip(tri, tri_tag):
+            f.write("%d 2 2 %d %d %d %d %d\n" % (k, t, t, c[0] + 1, c[1] + 1, c[2] + 1))
+            k += 1
+        f.write("$EndElements\n")
+
+
+def square_as_mesh(square, tmp_path):
+    p = os.path.join(tmp_path, "square.msh")
+    write_msh22(p, square["x"], square["tri"], square["tag"], square["edges"], square["edge_tag"])
+    return fm.read_gmsh22(p)
+
+
+# ---------------------------------------------------------------------------
+# CPU: reader, oracle
+# ---------------------------------------------------------------------------
+def test_gmsh_reader_roundtrip(square, tmp_path):
+    m = square_as_mesh(square, str(tmp_path))
+    assert m.etype == fm.P1 and m.nnodes == 62 and m.ncells == 98
+    np.testing.assert_array_equal(m.x, square["x"])
+    np.testing.assert_array_equal(m.dofmap, square["tri"])
+    np.testing.assert_array_equal(m.meta["cell_tags"], square["tag"])
+    np.testing.assert_array_equal(m.meta["facets"], square["edges"])
+    np.testing.assert_array_equal(m.meta["facet_tags"], square["edge_tag"])
+    E = fm.young_from_tags(m.meta["cell_tags"])
+    tab = fm.young_table()
+    assert set(np.unique(E)) == {tab[1], tab[2]}                            # physical faces 1 and 2
+    d0 = fm.damage_seed(m, [4])                                             # M.cc:1164-1167
+    assert d0.sum() == 8.0 and set(np.unique(d0)) == {0.0, 1.0}             # 7 segments of tag 4 -> 8 nodes
+
+
+def test_smoothing_path_graph_by_hand():
+    # 5 vertices in a strip of triangles is awkward to do by hand; use two triangles sharing an
+    # edge: vertices 0-1-2 and 1-2-3.  deg = (2, 3, 3, 2).  d0 = (1, 0, 0, 0).
+    tri = np.array([[0, 1, 2], [1, 2, 3]], dtype=np.int32)
+    d = oracle.smooth_damage(4, tri, np.array([1., 0., 0., 0.]), niter=1)
+    # sweep A (only where d < 0.01): s = (-, 1, 1, 0) -> d = (1, 1/3, 1/3, 0)
+    # sweep B: s = (2/3, 1 + 1/3, 1 + 1/3, 2/3) -> d = max(s / deg, d) = (1, 4/9, 4/9, 1/3)
+    third = 1. * (1. / 3.)
+    a = (1. + third) * (1. / 3.)
+    np.testing.assert_array_equal(d, [1.0, a, a, (third + third) * 0.5])
+
+
+def test_smoothing_properties_square(square):
+    nv = len(square["x"])
+    d0 = np.zeros(nv)
+    d0[np.unique(square["edges"][square["edge_tag"] == 4])] = 1.0
+    prev = d0
+    for it in (1, 2, 8):
+        d = oracle.smooth_damage(nv, square["tri"], d0, niter=it)
+        assert np.all(d >= prev - 0.0) and np.all(d <= 1.0) and np.all(d[d0 == 1.0] == 1.0)
+        assert (d > 0).sum() >= (prev > 0).sum()
+        prev = d
+    assert (prev > 0).sum() > (d0 > 0).sum()
+
+
+def test_strain_stress_linear_field_and_pinned_residual(square):
+    x, tri = square["x"], square["tri"]
+    E = fm.young_table()[square["tag"] % 200]
+    A = np.array([[0.01, 0.004], [-0.002, -0.003]])
+    u = (x @ A.T).reshape(-1)
+    rng = np.random.default_rng(5)
+    dn = np.where(rng.random(len(x)) < 0.4, rng.random(len(x)) * 0.9, 0.0)
+    eps, sig = oracle.cell_strain_stress(oracle.P1, x, tri, tri, E, 0.3, u, dnod=dn)
+    np.testing.assert_allclose(eps, np.tile([A[0, 0], 0.5 * (A[0, 1] + A[1, 0]), A[1, 1]], (len(tri), 1)), rtol=0,
+                               atol=1e-15)
+    # the stress output and the (reference-pinned) P1 residual are the same asym_stress:
+    # r_e = |T| G sigma  (M.cc:586-611)
+    for e in range(len(tri)):
+        xv = x[tri[e]]
+        l, m = oracle.lame(E[e], 0.3)
+        d = dn[tri[e]].mean()
+        r = oracle.p1_element_vector(xv.reshape(-1), l, m, d, u.reshape(-1, 2)[tri[e]].reshape(-1))
+        J = np.array([xv[1] - xv[0], xv[2] - xv[0]]).T
+        G = np.array([[-1., -1.], [1., 0.], [0., 1.]]) @ np.linalg.inv(J)
+        S = np.array([[sig[e, 0], sig[e, 1]], [sig[e, 1], sig[e, 2]]])
+        want = 0.5 * abs(np.linalg.det(J)) * (G @ S)
+        np.testing.assert_allclose(np.asarray(r).reshape(3, 2), want, rtol=1e-11, atol=1e-9 * abs(want).max())
+
+
+# ---------------------------------------------------------------------------
+# GPU: CUDA kernels against the oracle
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_smoothing_square_bit_exact(square, tmp_path):
+    from femb200 import fem
+    m = square_as_mesh(square, str(tmp_path))
+    d0 = fm.damage_seed(m, [4])
+    sm = fem.DamageSmoother(m)
+    for it in (0, 1, 8):
+        got = sm.smooth(d0, niter=it).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.smooth_damage(m.nnodes, m.xdofmap, d0, niter=it))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order,n", [(1, 37), (2, 21)])
+def test_gpu_smoothing_structured_bit_exact(order, n):
+    from femb200 import fem
+    m = fm.jitter(fm.structured_triangles(n, n + 3, order=order), 0.2, seed=2)
+    rng = np.random.default_rng(11)
+    d0 = np.zeros(m.nnodes)
+    verts = np.unique(m.xdofmap)
+    d0[rng.choice(verts, size=max(3, len(verts) // 40), replace=False)] = 1.0
+    got = fem.DamageSmoother(m).smooth(d0, niter=8).cpu().numpy()
+    want = oracle.smooth_damage(m.nnodes, m.xdofmap, d0, niter=8)
+    np.testing.assert_array_equal(got, want)
+    assert np.all(got[np.setdiff1d(np.arange(m.nnodes), verts)] == 0.0)    # P2 edge nodes carry no damage
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n", [("P1", 33), ("P2", 19), ("Q2", 14)])
+def test_gpu_strain_stress(kind, n):
+    from femb200 import fem
+    m = fm.structured_triangles(n, n + 2, order=1 if kind == "P1" else 2) if kind != "Q2" else fm.structured_quads_q2(n, n + 2)
+    m = fm.jitter(m, 0.2, seed=4)
+    E = fm.young_per_cell(m.ncells)
+    rng = np.random.default_rng(9)
+    u = 1e-3 * rng.standard_normal(m.ndofs)
+    dn = fm.damage_band(m)
+    form = fem.ElasticityForm(m, E, 0.3, d=dn, u=u)
+    eps, sig = fem.cell_strain_stress(form)
+    weps, wsig = oracle.cell_strain_stress(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, u, dnod=dn)
+    assert (dn[m.xdofmap].mean(axis=1) > 0).any()
+    np.testing.assert_allclose(eps.cpu().numpy(), weps, rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(sig.cpu().numpy(), wsig, rtol=1e-11, atol=1e-9 * np.abs(wsig).max())
