@@ -54,6 +54,67 @@ __global__ void k_sort_visits(int64_t nnodes, const int32_t *__restrict__ nptr, 
    }
 }
 
+// Triangles: re-order the visits of every VERTEX row rotationally (a fan around the node): cell k
+// shares one of its two fan edges (I, V) with cell k+1, so the contribution of consecutive visits to
+// that edge's columns can be carried in registers by the assembly kernel instead of being read back
+// from the staging image (see k_fast_records).  Orientation-agnostic: the walk leaves every cell by
+// the fan vertex it did not enter by.  It starts at a boundary cell of an open fan (a fan vertex
+// that belongs to one cell only; the smallest such vertex), else at the smallest fan vertex (closed
+// fan; the lower of its two cells); where the walk breaks it restarts at the smallest remaining
+// cell.  Edge rows (two cells) keep ascending cell order.  The order depends on the relative order
+// of node / cell numbers only: deterministic, and identical on every partition of a mesh.
+__global__ void k_order_visits(int64_t nnodes, int nd, const int32_t *__restrict__ dofmap,
+                               const int32_t *__restrict__ nptr, uint32_t *__restrict__ tmp)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes) return;
+   const int32_t lo = nptr[I];
+   const int cnt = nptr[I + 1] - lo;
+   if (cnt < 2 || cnt > kAsmLevels) return;
+   uint32_t v[kAsmLevels];
+   int32_t p1[kAsmLevels], p2[kAsmLevels];
+   for (int k = 0; k < cnt; ++k)
+   {
+      v[k] = tmp[lo + k];
+      const int a = (int)(v[k] & 15u);
+      if (a >= 3) return;  // an edge row
+      const int64_t e = v[k] >> 4;
+      p1[k] = dofmap[e * nd + (a + 1) % 3];
+      p2[k] = dofmap[e * nd + (a + 2) % 3];
+   }
+   auto occurrences = [&](int32_t vert) {
+      int n = 0;
+      for (int j = 0; j < cnt; ++j) n += (p1[j] == vert) + (p2[j] == vert);
+      return n;
+   };
+   // start cell and entry vertex
+   int cur = -1;
+   int32_t entry = 0;
+   for (int pass = 0; pass < 2 && cur < 0; ++pass)  // pass 0: open-fan ends, pass 1: any vertex
+      for (int k = 0; k < cnt; ++k)
+         for (int side = 0; side < 2; ++side)
+         {
+            const int32_t vert = side ? p2[k] : p1[k];
+            if (pass == 0 && occurrences(vert) != 1) continue;
+            if (cur < 0 || vert < entry) cur = k, entry = vert;
+         }
+   uint32_t used = 0u;
+   for (int out = 0; out < cnt; ++out)
+   {
+      tmp[lo + out] = v[cur];
+      used |= 1u << cur;
+      const int32_t exitv = (entry == p1[cur]) ? p2[cur] : p1[cur];
+      int nxt = -1;
+      for (int j = 0; j < cnt; ++j)
+         if (!((used >> j) & 1u) && nxt < 0 && (p1[j] == exitv || p2[j] == exitv)) nxt = j;
+      entry = exitv;
+      if (nxt < 0)  // the walk breaks: smallest remaining cell (v[] is in ascending cell order)
+         for (int j = 0; j < cnt; ++j)
+            if (!((used >> j) & 1u) && nxt < 0) nxt = j, entry = p1[j];
+      cur = nxt;
+   }
+}
+
 // --- neighbour sets -------------------------------------------------------------
 // sorted unique neighbour nodes of row node I into loc[]; returns the count, or
 // -1 when kMaxDeg is exceeded
@@ -214,6 +275,90 @@ k_tile_sort(int64_t nnodes, const int32_t *__restrict__ nptr, const VisitRec *__
    for (int j = 0; j < cnt && j < kAsmLevels; ++j) dst[vbase + s_off[j] + rank] = src[k0 + j];
 }
 
+// --- fast-path records (plan.cuh): staging addresses resolved at plan time ----------------
+// one CTA of kAsmR threads per tile, thread = rank.  Put semantics of the fast kernel:
+//  * the diagonal block (position 0 of a vertex row, 3 of an edge row) is accumulated in registers
+//    over all visits and stored once after the last one: never "put";
+//  * a vertex row has two "sides" per visit, the columns of its two fan edges: side 0 = positions
+//    (1, 5) (vertex 1', midpoint of edge (0', 1')), side 1 = positions (2, 4).  carry-out: the side
+//    this visit shares with the NEXT visit stays in registers; carry-in: the previous visit's carried
+//    pair is added to the side it shares with this visit before that side is put;
+//  * an edge row (two cells) carries its two end-vertex columns (positions 1, 2) from the first to
+//    the second visit; carry-in side 1 means the second cell sees the ends in the same order;
+//  * first-touch bits describe the puts that actually happen, in visit order.
+// The pairing is verified here on the slots; where it does not hold the columns are put as usual.
+__global__ void __launch_bounds__(kAsmR)
+k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const int64_t *__restrict__ brp,
+               const uint8_t *__restrict__ perm, const uint16_t *__restrict__ voff, const VisitRec *__restrict__ vrec,
+               uint4 *__restrict__ frec)
+{
+   const int rank = threadIdx.x;
+   const int64_t n0 = (int64_t)blockIdx.x * kAsmR;
+   const int nloc = (int)min((int64_t)kAsmR, nnodes - n0);
+   if (rank >= nloc) return;
+   const int64_t node = n0 + perm[n0 + rank];
+   const int cnt = nptr[node + 1] - nptr[node];
+   const int deg = (int)(brp[node + 1] - brp[node]);
+   const int r0 = 2 * (int)(brp[node] - brp[n0]);  // first 16-byte unit of scalar row 0 in the tile image
+   const int32_t vbase = nptr[n0];
+   const uint16_t *vo = voff + (int64_t)blockIdx.x * kAsmLevels;
+   uint32_t touched[(kMaxDeg + 31) / 32];
+   for (int t = 0; t < (kMaxDeg + 31) / 32; ++t) touched[t] = 0u;
+   bool cin = false;
+   int cin_side = 0;
+   for (int j = 0; j < cnt; ++j)
+   {
+      const int64_t k = (int64_t)vbase + vo[j] + rank;
+      const VisitRec r = vrec[k];
+      const bool vert = r.a < 3;
+      const int diag = vert ? 0 : 3;
+      bool cout = false;
+      int cout_side = 0, next_side = 0;
+      if (j + 1 < cnt)
+      {
+         const VisitRec q = vrec[(int64_t)vbase + vo[j + 1] + rank];
+         if (vert && q.a < 3)
+         {
+            for (int rs = 0; rs < 2 && !cout; ++rs)
+               for (int qs = 0; qs < 2 && !cout; ++qs)
+               {
+                  if (cin && rs == cin_side) continue;  // that side already holds the previous carry
+                  const bool same_v = r.slot[1 + rs] == q.slot[1 + qs];
+                  const bool same_e = nd == 3 || r.slot[5 - rs] == q.slot[5 - qs];
+                  if (same_v && same_e) cout = true, cout_side = rs, next_side = qs;
+               }
+         }
+         else if (!vert && q.a >= 3 && !cin)
+         {
+            if (r.slot[1] == q.slot[2] && r.slot[2] == q.slot[1]) cout = true, next_side = 0;
+            if (r.slot[1] == q.slot[1] && r.slot[2] == q.slot[2]) cout = true, next_side = 1;
+         }
+      }
+      uint32_t first = 0u;
+      for (int t = 0; t < nd && t < 6; ++t)
+      {
+         if (t == diag) continue;
+         const bool carried = cout && (vert ? (t == 1 + cout_side || (nd > 3 && t == 5 - cout_side)) : (t == 1 || t == 2));
+         if (carried) continue;
+         const int s = r.slot[t];
+         if (!((touched[s >> 5] >> (s & 31)) & 1u))
+         {
+            touched[s >> 5] |= 1u << (s & 31);
+            first |= 1u << t;
+         }
+      }
+      for (int h = 0; h < 2; ++h)
+      {
+         uint32_t ent[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz(r0 + h * deg + (int)r.slot[t]);
+         frec[2 * k + h] = make_uint4(r.e, ent[0] | (first & 0xfu) | (cout_side ? 0x8000u : 0u) | (ent[1] << 16),
+                                      ent[2] | ((first >> 4) & 0x3u) | (cin ? 4u : 0u) | (cout ? 8u : 0u) | (ent[3] << 16),
+                                      ent[4] | (r.a & 0x7u) | (cin_side ? 8u : 0u) | (ent[5] << 16));
+      }
+      cin = cout, cin_side = next_side;
+   }
+}
+
 // --- largest staging tile (in node blocks) for each candidate tile height R ------
 __global__ void k_tile_max(int64_t nnodes, const int64_t *__restrict__ brp, int32_t *__restrict__ out)
 {
@@ -293,6 +438,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    if (!p) return;
    cudaFree(p->nptr);
    cudaFree(p->vrec);
+   cudaFree(p->frec);
    cudaFree(p->perm);
    cudaFree(p->voff);
    cudaFree(p->brp);
@@ -353,6 +499,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
    cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)nnodes + 1), st);
    k_fill_visits<<<(unsigned)cdiv(nvis, T), T, 0, st>>>(nvis, nd, d_dofmap, p->nptr, cnt, tmpvis);
    k_sort_visits<<<(unsigned)cdiv(nnodes, T), T, 0, st>>>(nnodes, p->nptr, tmpvis);
+   if (etype != FEMB200_Q2) k_order_visits<<<(unsigned)cdiv(nnodes, T), T, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis);
 
    // 2. block degrees -> brp -> bcol
    if (dev_alloc(&deg, (size_t)nnodes + 1, &scratch) || dev_alloc(&p->brp, (size_t)nnodes + 4, &p->bytes))
@@ -399,6 +546,15 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       return fail(set_error("plan_create: slot map build failed: %s", cudaGetErrorString(cudaGetLastError())));
 
    p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
+   // fast-path records: triangles whose kAsmR-row staging image is addressable with 15-bit byte offsets
+   if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 4) < 32768)
+   {
+      if (dev_alloc(&p->frec, 2 * (size_t)nvis, &p->bytes)) return fail(1);
+      k_fast_records<<<(unsigned)cdiv(nnodes, kAsmR), kAsmR, 0, st>>>(nnodes, nd, p->nptr, p->brp, p->perm, p->voff,
+                                                                     p->vrec, p->frec);
+      if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+         return fail(set_error("plan_create: fast record build failed: %s", cudaGetErrorString(cudaGetLastError())));
+   }
 
    cudaFree(cnt);
    cudaFree(deg);

@@ -42,6 +42,27 @@ struct Visit
 };
 static_assert(sizeof(VisitRec) == 16, "VisitRec must be 16 bytes");
 
+// staging swizzle on 16-byte units: spreads the systematically aligned row starts of neighbouring
+// threads over different bank groups; an involution inside aligned groups of 8 units, so the
+// stream-out stays coalesced.  key = bit-reversed low 3 bits of the aligned 8-unit group index
+// (chosen by simulating the staging accesses of P1 / P2 tiles: fewest shared-memory wavefronts)
+__host__ __device__ __forceinline__ int swz(int u)
+{
+   const int g = u >> 3;
+   return u ^ (((g & 1) << 2) | (g & 2) | ((g >> 2) & 1));
+}
+
+// Fast-path record of one (visit, scalar row h) pair, triangles only: everything the row thread
+// needs in one 16-byte load, with the staging addresses resolved at plan time:
+//   x        cell id e
+//   y, z, w  six 16-bit entries (positions t = 0..5, rotated order as in VisitRec): BYTE offset of the
+//            16-byte staging unit of column t in the tile image (already swizzled; a multiple of 16
+//            below 32768).  The free bits of the even entries carry  y: first-touch bits of t = 0..3
+//            (bits 0-3), carry-out side (bit 15);  z: first-touch bits of t = 4, 5 (bits 0-1), carry-in
+//            (bit 2), carry-out (bit 3);  w: local index a of the row node (bits 0-2), carry-in side
+//            (bit 3).  Put / carry semantics: k_fast_records in plan.cu.
+// Storage: record (tile, level j, rank r, h) at 2 * (nptr[n0] + voff[tile][j] + r) + h: the 32 lanes
+// of a warp (16 ranks x 2 rows) read 512 contiguous bytes.
 constexpr int kAsmR = 64;      // node rows per assembly tile (fixed at plan time: vrec storage order)
 constexpr int kAsmLevels = 16; // visits per node supported by the tile-sorted layout
 constexpr int kNumTileR = 6;
@@ -57,6 +78,7 @@ struct femb200_plan
    const int32_t *dofmap = nullptr, *xdofmap = nullptr;  // borrowed
    int32_t *nptr = nullptr;                               // [nnodes+1]
    femb::VisitRec *vrec = nullptr;                        // [nvisits], tile-sorted (see above)
+   uint4 *frec = nullptr;                                 // [2 nvisits] fast-path records (triangles) or null
    uint8_t *perm = nullptr;                               // [ntiles * kAsmR] rank -> tile-local node
    uint16_t *voff = nullptr;                              // [ntiles * kAsmLevels] level offsets in a tile
    int64_t *brp = nullptr;                                // [nnodes+1]
