@@ -74,6 +74,8 @@ struct AsmArgs
    const int32_t *nptr;
    const VisitRec *vrec;
    const uint4 *frec;
+   const TileHdr *thdr;
+   int flevels;  // levels (visits per node) of the fixed-stride fast-record layout
    const uint8_t *perm;
    const uint16_t *voff;
    const int64_t *brp;
@@ -372,22 +374,23 @@ template <int ET>
 __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uint4 raw, const FastGeo &g,
                                                      unsigned char *sv, int h, FastCarry &C)
 {
-   const int a = (int)(raw.w & 7u);
-   const int m = (a >= 3) ? a - 3 : a;  // rotation: own vertex / own edge becomes number 0
+   // gradients of the visit's vertices 1' and 2' (local numbers from the record; 0' is the row's own
+   // vertex, or the vertex opposite to the row's own edge)
+   const int i1 = (int)(raw.w & 3u), i2 = (int)((raw.w >> 2) & 3u);
    const double h0x = -g.g1x - g.g2x, h0y = -g.g1y - g.g2y;
-   const double a1x = m == 0 ? g.g1x : (m == 1 ? g.g2x : h0x), a1y = m == 0 ? g.g1y : (m == 1 ? g.g2y : h0y);
-   const double a2x = m == 0 ? g.g2x : (m == 1 ? h0x : g.g1x), a2y = m == 0 ? g.g2y : (m == 1 ? h0y : g.g1y);
+   const double a1x = i1 == 0 ? h0x : (i1 == 1 ? g.g1x : g.g2x), a1y = i1 == 0 ? h0y : (i1 == 1 ? g.g1y : g.g2y);
+   const double a2x = i2 == 0 ? h0x : (i2 == 1 ? g.g1x : g.g2x), a2y = i2 == 0 ? h0y : (i2 == 1 ? g.g1y : g.g2y);
    // scalar row h = 1 is row 0 with x and y exchanged in every gradient and in every output pair:
    // all values below are in the exchanged frame, put() and the diagonal store swap them back
    const double g1[2] = {h ? a1y : a1x, h ? a1x : a1y};
    const double g2[2] = {h ? a2y : a2x, h ? a2x : a2y};
    const double tl = A.lc.c2, tm = A.lc.c3;
-   const bool cin = (raw.z >> 2) & 1u, cout = (raw.z >> 3) & 1u;
-   const bool cin_side = (raw.w >> 3) & 1u, cout_side = (raw.y >> 15) & 1u;
-   auto put = [&](int t, double k0, double k1) {
+   const bool cout = (raw.z >> 1) & 1u;
+   // t = position (address entry), b = index of the put (first-touch bit)
+   auto put = [&](int t, int b, double k0, double k1) {
       const uint32_t w = t < 2 ? raw.y : (t < 4 ? raw.z : raw.w);
       const uint32_t off = (t & 1) ? (w >> 16) : (w & 0x7ff0u);
-      const bool first = t < 4 ? ((raw.y >> t) & 1u) : ((raw.z >> (t - 4)) & 1u);
+      const bool first = b < 4 ? ((raw.y >> b) & 1u) : (raw.z & 1u);
       double2 *p = reinterpret_cast<double2 *>(sv + off);
       const double va = h ? k1 : k0, vb = h ? k0 : k1;
       if (first)
@@ -399,8 +402,8 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
          *p = v;
       }
    };
-   if (a < 3)
-   {  // row = (rotated) vertex 0
+   if (!((raw.z >> 2) & 1u))
+   {  // row = vertex 0'
       const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
       double w00[2], w01[2], w02[2];
       w_row(g0, g0, tl, tm, w00);
@@ -410,34 +413,26 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
       // side 0 = columns of the fan edge (0', 1'): vertex 1' (position 1), its midpoint (position 5);
       // side 1 = fan edge (0', 2'): positions 2 and 4.  P1 (M.cc:885-887) has the vertex columns only.
       const double c3 = ET == FEMB200_P1 ? 1. : -1. / 3., c43 = 4. / 3.;
-      double sv0[2] = {c3 * w01[0], c3 * w01[1]}, se0[2] = {c43 * w01[0], c43 * w01[1]};
-      double sv1[2] = {c3 * w02[0], c3 * w02[1]}, se1[2] = {c43 * w02[0], c43 * w02[1]};
-      if (cin)
+      put(1, 0, c3 * w01[0] + C.cv[0], c3 * w01[1] + C.cv[1]);
+      if (ET != FEMB200_P1)
       {
-         if (cin_side)
-            sv1[0] += C.cv[0], sv1[1] += C.cv[1], se1[0] += C.ce[0], se1[1] += C.ce[1];
-         else
-            sv0[0] += C.cv[0], sv0[1] += C.cv[1], se0[0] += C.ce[0], se0[1] += C.ce[1];
+         put(5, 4, c43 * w01[0] + C.ce[0], c43 * w01[1] + C.ce[1]);
+         put(3, 2, 0., 0.);  // edge 0' = (1', 2') is opposite: structural zero
       }
-      const bool keep0 = cout && !cout_side, keep1 = cout && cout_side;
-      if (keep0)
-         C.cv[0] = sv0[0], C.cv[1] = sv0[1], C.ce[0] = se0[0], C.ce[1] = se0[1];
+      if (cout)
+      {
+         C.cv[0] = c3 * w02[0], C.cv[1] = c3 * w02[1];
+         if (ET != FEMB200_P1) C.ce[0] = c43 * w02[0], C.ce[1] = c43 * w02[1];
+      }
       else
       {
-         put(1, sv0[0], sv0[1]);
-         if (ET != FEMB200_P1) put(5, se0[0], se0[1]);
+         put(2, 1, c3 * w02[0], c3 * w02[1]);
+         if (ET != FEMB200_P1) put(4, 3, c43 * w02[0], c43 * w02[1]);
+         C.cv[0] = C.cv[1] = C.ce[0] = C.ce[1] = 0.;
       }
-      if (keep1)
-         C.cv[0] = sv1[0], C.cv[1] = sv1[1], C.ce[0] = se1[0], C.ce[1] = se1[1];
-      else
-      {
-         put(2, sv1[0], sv1[1]);
-         if (ET != FEMB200_P1) put(4, se1[0], se1[1]);
-      }
-      if (ET != FEMB200_P1) put(3, 0., 0.);  // rotated edge 0' = (1', 2') is opposite: structural zero
    }
    else
-   {  // row = (rotated) edge 0 = (1,2); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
+   {  // row = edge 0' = (1', 2'); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
       double w11[2], w12[2], w21[2], w22[2];
       w_row(g1, g1, tl, tm, w11);
       w_row(g1, g2, tl, tm, w12);
@@ -446,74 +441,63 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
       const double c43 = 4. / 3.;
       const double sy[2] = {w12[0] + w21[0], w12[1] + w21[1]};  // S = W12 + W21
       C.dg[0] += c43 * (2. * w11[0] + sy[0] + 2. * w22[0]), C.dg[1] += c43 * (2. * w11[1] + sy[1] + 2. * w22[1]);
-      put(0, 0., 0.);  // opposite vertex: structural zero
-      // end vertices 1' (= p) -> 4/3 W^{21}; 2' (= q) -> 4/3 W^{12}
-      double v1[2] = {c43 * w21[0], c43 * w21[1]}, v2[2] = {c43 * w12[0], c43 * w12[1]};
-      if (cin)
-      {  // cv / ce = the first cell's p / q columns; side 0: this cell sees p and q exchanged
-         if (cin_side)
-            v1[0] += C.cv[0], v1[1] += C.cv[1], v2[0] += C.ce[0], v2[1] += C.ce[1];
-         else
-            v1[0] += C.ce[0], v1[1] += C.ce[1], v2[0] += C.cv[0], v2[1] += C.cv[1];
-      }
+      put(0, 0, 0., 0.);  // opposite vertex: structural zero
+      put(4, 3, -c43 * (2. * w11[0] + sy[0]), -c43 * (2. * w11[1] + sy[1]));
+      put(5, 4, -c43 * (sy[0] + 2. * w22[0]), -c43 * (sy[1] + 2. * w22[1]));
+      // end vertices 1' -> 4/3 W^{21}; 2' -> 4/3 W^{12}, plus what the first cell of the edge carried
+      const double v1[2] = {c43 * w21[0] + C.cv[0], c43 * w21[1] + C.cv[1]};
+      const double v2[2] = {c43 * w12[0] + C.ce[0], c43 * w12[1] + C.ce[1]};
       if (cout)
          C.cv[0] = v1[0], C.cv[1] = v1[1], C.ce[0] = v2[0], C.ce[1] = v2[1];
       else
       {
-         put(1, v1[0], v1[1]);
-         put(2, v2[0], v2[1]);
+         put(1, 1, v1[0], v1[1]);
+         put(2, 2, v2[0], v2[1]);
+         C.cv[0] = C.cv[1] = C.ce[0] = C.ce[1] = 0.;
       }
-      put(4, -c43 * (2. * w11[0] + sy[0]), -c43 * (2. * w11[1] + sy[1]));
-      put(5, -c43 * (sy[0] + 2. * w22[0]), -c43 * (sy[1] + 2. * w22[1]));
    }
 }
 
-// Fast kernel (undamaged triangles): two threads per node (one per scalar row), tile-sorted
-// per-row records, three-stage software pipeline over the visits.
+// Fast kernel (undamaged triangles): two threads per node (one per scalar row: lanes 0-15 of a warp
+// own row 0 of 16 nodes, lanes 16-31 row 1 of the same nodes), nodes ranked by decreasing visit
+// count.  The records live in a fixed-stride layout (tile, level, rank, row), so their addresses
+// depend on the block and thread index only: the dependent chain of a tile is record -> cell record
+// -> first put (the tile header is needed by the stream-out only), with the cell record one visit
+// and the record two visits ahead.
 template <int ET>
 __global__ void __launch_bounds__(kAsmR * 2, 7) assemble_fast_kernel(AsmArgs A)
 {
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
    extern __shared__ double2 sv[];
    const int tid = threadIdx.x;
-   const int64_t n0 = (int64_t)blockIdx.x * R;
-   const int nloc = (int)min((int64_t)R, A.nnodes - n0);
-   const int64_t b0 = A.brp[n0];
-   const int32_t vbase = A.nptr[n0];
-   const int units = 2 * (int)(A.brp[n0 + nloc] - b0);  // 16-byte units of this tile
-   int32_t *s_cnt = reinterpret_cast<int32_t *>(sv + A.stage_units);  // number of visits of node i
-   int32_t *s_voff = s_cnt + R;                                        // [kAsmLevels] level offsets of the records
-   if (tid < nloc) s_cnt[tid] = A.nptr[n0 + tid + 1] - A.nptr[n0 + tid];
-   if (tid < kAsmLevels) s_voff[tid] = 2 * (int32_t)A.voff[(int64_t)blockIdx.x * kAsmLevels + tid];
+   const TileHdr *hdr = A.thdr + blockIdx.x;
+   const int64_t b0 = hdr->b0;
+   const int units = hdr->units;  // 16-byte units of this tile
    const int rank = ((tid >> 5) << 4) + (tid & 15);
    const int half = (tid >> 4) & 1;
-   const int i = rank < nloc ? (int)A.perm[n0 + rank] : 0;
-   __syncthreads();
-   if (rank < nloc)
    {
-      const int cnt = s_cnt[i];
-      const uint4 *rec = A.frec + 2 * (int64_t)vbase + 2 * rank + half;
+      const uint4 *rec = A.frec + ((int64_t)blockIdx.x * A.flevels * R + rank) * 2 + half;
+      constexpr int LS = 2 * R;  // records per level
       unsigned char *img = reinterpret_cast<unsigned char *>(sv);
       const uint4 none = make_uint4(0u, 0u, 0u, 0u);
-      // software pipeline: while visit c is computed and staged, the cell record of visit c + 1 and
-      // the fast record of visit c + 2 are in flight
       uint4 raw = none, raw1, raw2;
       FastGeo geo, geo1;
       FastCarry C;
       C.dg[0] = C.dg[1] = C.cv[0] = C.cv[1] = C.ce[0] = C.ce[1] = 0.;
-      raw1 = (0 < cnt) ? rec[s_voff[0]] : none;
-      raw2 = (1 < cnt) ? rec[s_voff[1]] : none;
-      if (0 < cnt) ld_d4(A.cellrec + 4 * (int64_t)raw1.x, geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
+      raw1 = rec[0];
+      raw2 = A.flevels > 1 ? rec[LS] : none;
+      const int cnt = (int)(raw1.x >> 28);  // visits of this row (0: padding)
+      if (0 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
       for (int c = 0; c < cnt; ++c)
       {
          raw = raw1, geo = geo1, raw1 = raw2;
-         if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)raw1.x, geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
-         raw2 = (c + 2 < cnt) ? rec[s_voff[c + 2]] : none;
+         if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
+         raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
          fast_compute_stage_f<ET>(A, raw, geo, img, half, C);
       }
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
-         const uint32_t off = (raw.w & 7u) >= 3u ? (raw.z >> 16) : (raw.y & 0x7ff0u);
+         const uint32_t off = (raw.z & 4u) ? (raw.z >> 16) : (raw.y & 0x7ff0u);
          *reinterpret_cast<double2 *>(img + off) = make_double2(half ? C.dg[1] : C.dg[0], half ? C.dg[0] : C.dg[1]);
       }
    }
@@ -801,7 +785,8 @@ template <int ET>
 static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
-   const size_t smem = 16 * (size_t)A.stage_units + 4 * (size_t)(kAsmR + kAsmLevels) + 16;
+   A.flevels = p->flevels;
+   const size_t smem = 16 * (size_t)A.stage_units;
    FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
    assemble_fast_kernel<ET><<<(unsigned)cdiv(p->nnodes, kAsmR), kAsmR * 2, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
@@ -813,7 +798,11 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
 {
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
    if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
-   if (ET != FEMB200_Q2 && A.frec && !getenv("FEMB200_ASM_OLD")) return launch_assemble_fast<ET == FEMB200_Q2 ? FEMB200_P2 : ET>(p, A, st);
+   if (ET != FEMB200_Q2 && A.frec && !getenv("FEMB200_ASM_OLD"))
+   {
+      constexpr int TRI = ET == FEMB200_Q2 ? FEMB200_P2 : ET;
+      return launch_assemble_fast<TRI>(p, A, st);
+   }
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
    const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
@@ -843,7 +832,7 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
    FEMB_CHECK(p && d_x && d_E && d_values, "assemble_matrix: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_matrix: x_stride must be 2 or 3, got %d", x_stride);
    AsmArgs A;
-   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.frec = p->frec, A.perm = p->perm, A.voff = p->voff, A.brp = p->brp;
+   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.frec = p->frec, A.thdr = p->thdr, A.perm = p->perm, A.voff = p->voff, A.brp = p->brp;
    A.xdofmap = p->xdofmap, A.dofmap = p->dofmap, A.x = d_x, A.xs = x_stride, A.E = d_E, A.lc = lame_coef(nu);
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);

@@ -279,18 +279,20 @@ k_tile_sort(int64_t nnodes, const int32_t *__restrict__ nptr, const VisitRec *__
 // one CTA of kAsmR threads per tile, thread = rank.  Put semantics of the fast kernel:
 //  * the diagonal block (position 0 of a vertex row, 3 of an edge row) is accumulated in registers
 //    over all visits and stored once after the last one: never "put";
-//  * a vertex row has two "sides" per visit, the columns of its two fan edges: side 0 = positions
-//    (1, 5) (vertex 1', midpoint of edge (0', 1')), side 1 = positions (2, 4).  carry-out: the side
-//    this visit shares with the NEXT visit stays in registers; carry-in: the previous visit's carried
-//    pair is added to the side it shares with this visit before that side is put;
-//  * an edge row (two cells) carries its two end-vertex columns (positions 1, 2) from the first to
-//    the second visit; carry-in side 1 means the second cell sees the ends in the same order;
+//  * every visit has two "sides", the columns that go with its two other vertices 1' and 2':
+//    side 0 = positions (1, 5), side 1 = positions (2, 4) for a vertex row (vertex, midpoint of the
+//    fan edge); positions 1 and 2 (the two ends) for an edge row.  The kernel ALWAYS adds its carry
+//    registers to side 0 and, when the carry-out bit is set, keeps side 1 (vertex row) / both ends
+//    (edge row) in registers for the next visit instead of putting them.  To make that static
+//    pairing hold, this pass may FLIP a visit: vertices 1' and 2' (hence positions 1 <-> 2, 4 <-> 5)
+//    exchange their roles, which the closed form of the element matrix allows (it is symmetric
+//    under relabelling); the record carries the local vertex numbers of 1' and 2';
 //  * first-touch bits describe the puts that actually happen, in visit order.
 // The pairing is verified here on the slots; where it does not hold the columns are put as usual.
 __global__ void __launch_bounds__(kAsmR)
 k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const int64_t *__restrict__ brp,
                const uint8_t *__restrict__ perm, const uint16_t *__restrict__ voff, const VisitRec *__restrict__ vrec,
-               uint4 *__restrict__ frec)
+               int flevels, uint4 *__restrict__ frec)
 {
    const int rank = threadIdx.x;
    const int64_t n0 = (int64_t)blockIdx.x * kAsmR;
@@ -304,59 +306,102 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
    const uint16_t *vo = voff + (int64_t)blockIdx.x * kAsmLevels;
    uint32_t touched[(kMaxDeg + 31) / 32];
    for (int t = 0; t < (kMaxDeg + 31) / 32; ++t) touched[t] = 0u;
+   const bool p2 = nd > 3;
    bool cin = false;
-   int cin_side = 0;
+   int carry_v = -1, carry_e = -1;  // slots of the columns held in the carry registers
    for (int j = 0; j < cnt; ++j)
    {
-      const int64_t k = (int64_t)vbase + vo[j] + rank;
-      const VisitRec r = vrec[k];
+      const VisitRec r = vrec[(int64_t)vbase + vo[j] + rank];
       const bool vert = r.a < 3;
       const int diag = vert ? 0 : 3;
+      const int m = vert ? r.a : r.a - 3;
+      VisitRec q = r;
+      const bool has_next = j + 1 < cnt;
+      if (has_next) q = vrec[(int64_t)vbase + vo[j + 1] + rank];
+      const bool same_kind = has_next && ((q.a < 3) == vert);
+      // does side `rs` of this visit (natural numbering) coincide with a side of the next visit?
+      auto side_matches_next = [&](int rs) {
+         if (!same_kind) return false;
+         for (int qs = 0; qs < 2; ++qs)
+            if (r.slot[1 + rs] == q.slot[1 + qs] && (!p2 || !vert || r.slot[5 - rs] == q.slot[5 - qs])) return true;
+         return false;
+      };
+      int flip = 0;
       bool cout = false;
-      int cout_side = 0, next_side = 0;
-      if (j + 1 < cnt)
+      if (vert)
       {
-         const VisitRec q = vrec[(int64_t)vbase + vo[j + 1] + rank];
-         if (vert && q.a < 3)
-         {
-            for (int rs = 0; rs < 2 && !cout; ++rs)
-               for (int qs = 0; qs < 2 && !cout; ++qs)
-               {
-                  if (cin && rs == cin_side) continue;  // that side already holds the previous carry
-                  const bool same_v = r.slot[1 + rs] == q.slot[1 + qs];
-                  const bool same_e = nd == 3 || r.slot[5 - rs] == q.slot[5 - qs];
-                  if (same_v && same_e) cout = true, cout_side = rs, next_side = qs;
-               }
+         if (cin)
+         {  // side 0 must be the side that is in the carry registers
+            flip = (r.slot[1] == carry_v && (!p2 || r.slot[5] == carry_e)) ? 0 : 1;
+            cout = side_matches_next(1 - flip);  // natural side 1 - flip becomes side 1
          }
-         else if (!vert && q.a >= 3 && !cin)
-         {
-            if (r.slot[1] == q.slot[2] && r.slot[2] == q.slot[1]) cout = true, next_side = 0;
-            if (r.slot[1] == q.slot[1] && r.slot[2] == q.slot[2]) cout = true, next_side = 1;
-         }
+         else if (side_matches_next(1))
+            cout = true;
+         else if (side_matches_next(0))
+            cout = true, flip = 1;
       }
+      else
+      {
+         if (cin) flip = (r.slot[1] == carry_v) ? 0 : 1;  // see the ends in the order of the first cell
+         else
+            cout = same_kind && ((r.slot[1] == q.slot[1] && r.slot[2] == q.slot[2]) ||
+                                 (r.slot[1] == q.slot[2] && r.slot[2] == q.slot[1]));
+      }
+      // positions after the flip
+      int sl[6];
+      for (int t = 0; t < 6; ++t) sl[t] = r.slot[t];
+      if (flip)
+      {
+         sl[1] = r.slot[2], sl[2] = r.slot[1];
+         sl[4] = r.slot[5], sl[5] = r.slot[4];
+      }
+      const int i1 = (m + (flip ? 2 : 1)) % 3, i2 = (m + (flip ? 1 : 2)) % 3;  // local numbers of 1', 2'
       uint32_t first = 0u;
+      int bit = 0;
       for (int t = 0; t < nd && t < 6; ++t)
       {
          if (t == diag) continue;
-         const bool carried = cout && (vert ? (t == 1 + cout_side || (nd > 3 && t == 5 - cout_side)) : (t == 1 || t == 2));
-         if (carried) continue;
-         const int s = r.slot[t];
-         if (!((touched[s >> 5] >> (s & 31)) & 1u))
+         const bool carried = cout && (vert ? (t == 2 || t == 4) : (t == 1 || t == 2));
+         if (!carried && !((touched[sl[t] >> 5] >> (sl[t] & 31)) & 1u))
          {
-            touched[s >> 5] |= 1u << (s & 31);
-            first |= 1u << t;
+            touched[sl[t] >> 5] |= 1u << (sl[t] & 31);
+            first |= 1u << bit;
          }
+         ++bit;
       }
       for (int h = 0; h < 2; ++h)
       {
          uint32_t ent[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz(r0 + h * deg + (int)r.slot[t]);
-         frec[2 * k + h] = make_uint4(r.e, ent[0] | (first & 0xfu) | (cout_side ? 0x8000u : 0u) | (ent[1] << 16),
-                                      ent[2] | ((first >> 4) & 0x3u) | (cin ? 4u : 0u) | (cout ? 8u : 0u) | (ent[3] << 16),
-                                      ent[4] | (r.a & 0x7u) | (cin_side ? 8u : 0u) | (ent[5] << 16));
+         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz(r0 + h * deg + sl[t]);
+         frec[(((int64_t)blockIdx.x * flevels + j) * kAsmR + rank) * 2 + h] =
+            make_uint4(r.e | ((uint32_t)cnt << 28), ent[0] | (first & 0xfu) | (ent[1] << 16),
+                       ent[2] | ((first >> 4) & 0x1u) | (cout ? 2u : 0u) | (vert ? 0u : 4u) | (ent[3] << 16),
+                       ent[4] | (uint32_t)i1 | ((uint32_t)i2 << 2) | (ent[5] << 16));
       }
-      cin = cout, cin_side = next_side;
+      cin = cout;
+      if (cout) carry_v = vert ? sl[2] : sl[1], carry_e = vert ? (p2 ? sl[4] : -1) : sl[2];
    }
+}
+
+__global__ void k_tile_hdr(int64_t nnodes, int64_t ntiles, const int32_t *__restrict__ nptr,
+                           const int64_t *__restrict__ brp, const uint16_t *__restrict__ voff, TileHdr *__restrict__ hdr,
+                           int32_t *__restrict__ maxcnt)
+{
+   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= ntiles) return;
+   const int64_t n0 = t * kAsmR, n1 = min(n0 + (int64_t)kAsmR, nnodes);
+   TileHdr h;
+   h.b0 = brp[n0];
+   h.vbase = nptr[n0];
+   h.nvis = nptr[n1] - nptr[n0];
+   h.units = 2 * (int32_t)(brp[n1] - brp[n0]);
+   h.pad = 0;
+   for (int j = 0; j < kAsmLevels; ++j) h.voff[j] = voff[t * kAsmLevels + j];
+   for (int j = 0; j < 4; ++j) h.pad2[j] = 0;
+   hdr[t] = h;
+   int m = 0;
+   for (int64_t i = n0; i < n1; ++i) m = max(m, nptr[i + 1] - nptr[i]);
+   atomicMax(maxcnt, m);
 }
 
 // --- largest staging tile (in node blocks) for each candidate tile height R ------
@@ -439,6 +484,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->nptr);
    cudaFree(p->vrec);
    cudaFree(p->frec);
+   cudaFree(p->thdr);
    cudaFree(p->perm);
    cudaFree(p->voff);
    cudaFree(p->brp);
@@ -547,13 +593,28 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
 
    p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
    // fast-path records: triangles whose kAsmR-row staging image is addressable with 15-bit byte offsets
+   // and whose nodes belong to fewer than 16 cells
    if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 4) < 32768)
    {
-      if (dev_alloc(&p->frec, 2 * (size_t)nvis, &p->bytes)) return fail(1);
-      k_fast_records<<<(unsigned)cdiv(nnodes, kAsmR), kAsmR, 0, st>>>(nnodes, nd, p->nptr, p->brp, p->perm, p->voff,
-                                                                     p->vrec, p->frec);
+      const int64_t ntiles = cdiv(nnodes, kAsmR);
+      if (dev_alloc(&p->thdr, (size_t)ntiles, &p->bytes)) return fail(1);
+      cudaMemsetAsync(flags, 0, sizeof(int32_t), st);
+      k_tile_hdr<<<(unsigned)cdiv(ntiles, T), T, 0, st>>>(nnodes, ntiles, p->nptr, p->brp, p->voff, p->thdr, flags);
+      int32_t maxcnt = 0;
+      cudaMemcpyAsync(&maxcnt, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
       if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
-         return fail(set_error("plan_create: fast record build failed: %s", cudaGetErrorString(cudaGetLastError())));
+         return fail(set_error("plan_create: tile header build failed: %s", cudaGetErrorString(cudaGetLastError())));
+      if (maxcnt >= 1 && maxcnt < 16)
+      {
+         p->flevels = maxcnt;
+         const size_t nrec = (size_t)ntiles * (size_t)maxcnt * kAsmR * 2;
+         if (dev_alloc(&p->frec, nrec, &p->bytes)) return fail(1);
+         cudaMemsetAsync(p->frec, 0, sizeof(uint4) * nrec, st);
+         k_fast_records<<<(unsigned)ntiles, kAsmR, 0, st>>>(nnodes, nd, p->nptr, p->brp, p->perm, p->voff, p->vrec,
+                                                          p->flevels, p->frec);
+         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+            return fail(set_error("plan_create: fast record build failed: %s", cudaGetErrorString(cudaGetLastError())));
+      }
    }
 
    cudaFree(cnt);

@@ -5,6 +5,8 @@
 
 namespace femb {
 
+constexpr int kAsmLevelsFwd = 16;  // = kAsmLevels (declared below)
+
 // One visit = (row node I, incident cell e, local index a of I in e).  16 bytes:
 //   word 0   cell id e
 //   word 1   a (bits 0-7) | slot of local dof 8 (bits 8-15, Q2 only) | first-touch mask (bits 16-31):
@@ -57,14 +59,31 @@ __host__ __device__ __forceinline__ int swz(int u)
 //   x        cell id e
 //   y, z, w  six 16-bit entries (positions t = 0..5, rotated order as in VisitRec): BYTE offset of the
 //            16-byte staging unit of column t in the tile image (already swizzled; a multiple of 16
-//            below 32768).  The free bits of the even entries carry  y: first-touch bits of t = 0..3
-//            (bits 0-3), carry-out side (bit 15);  z: first-touch bits of t = 4, 5 (bits 0-1), carry-in
-//            (bit 2), carry-out (bit 3);  w: local index a of the row node (bits 0-2), carry-in side
-//            (bit 3).  Put / carry semantics: k_fast_records in plan.cu.
-// Storage: record (tile, level j, rank r, h) at 2 * (nptr[n0] + voff[tile][j] + r) + h: the 32 lanes
-// of a warp (16 ranks x 2 rows) read 512 contiguous bytes.
+//            below 32768).  The free low nibbles of the even entries carry
+//              y: first-touch bits of the first four puts;
+//              z: first-touch bit of the fifth put (bit 0), carry-out (bit 1), edge row (bit 2);
+//              w: local vertex numbers of the visit's vertices 1' (bits 0-1) and 2' (bits 2-3).
+//            The five puts are positions 1..5 of a vertex row, 0, 1, 2, 4, 5 of an edge row (the diagonal
+//            block never goes through the image).  Put / carry / flip semantics: k_fast_records.
+//   The top four bits of x hold the number of visits of the row (cells are numbered below 2^28).
+// Storage: fixed stride, record (tile, level j, rank r, h) at ((tile * flevels + j) * kAsmR + r) * 2 + h
+// with flevels = the largest visit count of the mesh (zero padding where a row has fewer visits):
+// the address depends on the block and thread index only, and the 32 lanes of a warp (16 ranks x
+// 2 rows) read 512 contiguous bytes.
+// Per-tile header of the streaming assembly kernel: everything a CTA needs to know about a tile in
+// one 64-byte bulk copy.
+struct __align__(64) TileHdr
+{
+   int64_t b0;                  // first node block of the tile (brp[n0])
+   int32_t vbase, nvis, units;  // first visit record, number of visits, 16-byte units of the tile image
+   int32_t pad;
+   uint16_t voff[kAsmLevelsFwd];  // level offsets (records in levels < j)
+   uint16_t pad2[4];
+};
 constexpr int kAsmR = 64;      // node rows per assembly tile (fixed at plan time: vrec storage order)
 constexpr int kAsmLevels = 16; // visits per node supported by the tile-sorted layout
+static_assert(kAsmLevels == kAsmLevelsFwd, "TileHdr::voff");
+static_assert(sizeof(TileHdr) == 64, "TileHdr must be 64 bytes");
 constexpr int kNumTileR = 6;
 __host__ __device__ constexpr int tile_r(int r) { return r == 0 ? 32 : r == 1 ? 64 : r == 2 ? 96 : r == 3 ? 128 : r == 4 ? 192 : 256; }
 
@@ -79,6 +98,8 @@ struct femb200_plan
    int32_t *nptr = nullptr;                               // [nnodes+1]
    femb::VisitRec *vrec = nullptr;                        // [nvisits], tile-sorted (see above)
    uint4 *frec = nullptr;                                 // [2 nvisits] fast-path records (triangles) or null
+   femb::TileHdr *thdr = nullptr;                         // [ntiles] tile headers (with frec)
+   int32_t flevels = 0;                                   // levels of the fixed-stride frec layout (max visits per node)
    uint8_t *perm = nullptr;                               // [ntiles * kAsmR] rank -> tile-local node
    uint16_t *voff = nullptr;                              // [ntiles * kAsmLevels] level offsets in a tile
    int64_t *brp = nullptr;                                // [nnodes+1]

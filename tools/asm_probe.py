@@ -21,9 +21,9 @@ for kind, n in [(k, int(v)) for k, v in (a.split(":") for a in os.environ.get("C
     A = fem.create_matrix(form)
     nb = 8 * A.nnz + 32 * m.ncells + 16 * m.nnodes
     res = {}
-    for tag, env in (("old", "1"), ("new", None)):
-        if env: os.environ["FEMB200_ASM_OLD"] = env
-        else: os.environ.pop("FEMB200_ASM_OLD", None)
+    for tag, env in (("old", {"FEMB200_ASM_OLD": "1"}), ("new", {})):
+        for k in ("FEMB200_ASM_OLD", "FEMB200_ASM_NOSTREAM"): os.environ.pop(k, None)
+        os.environ.update(env)
         t = timeit(lambda: fem.assemble_matrix(A, form))
         res[tag] = A.values.clone()
         print(f"{kind} n={n} {tag}: {t:.3f} ms  {m.ndofs / t / 1e6:.2f} GDOF/s  frac {nb / t / 1e6 / 6451.2:.3f}  plan {A.plan_bytes/1e6:.0f} MB", flush=True)
