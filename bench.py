@@ -234,6 +234,10 @@ def run_b200(args):
 
     m, E, bc, g, part = build_problem(n, rank, world)
     form = fem.ElasticityForm(m, E, 0.3)
+    # load the library's CUDA module (lazy, one-off) outside the pattern-build timing
+    from femb200 import mesh as _fm
+    _tiny = _fm.structured_triangles(4, order=2)
+    fem.create_matrix(fem.ElasticityForm(_tiny, _fm.young_per_cell(_tiny.ncells), 0.3))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     A = fem.create_matrix(form)
@@ -339,25 +343,60 @@ def run_b200(args):
     hx = torch.from_numpy(np.ascontiguousarray(m.x[gv])).pin_memory()
     dxv = torch.empty(hx.shape, dtype=torch.float64, device="cuda")
     hE = torch.from_numpy(np.ascontiguousarray(E)).pin_memory()
-    hout = torch.empty(2, dtype=torch.float64).pin_memory()
-    dout = torch.empty(2, dtype=torch.float64, device="cuda")
+    # Two steps in flight: a copy stream uploads the inputs of step k + 1 (double-buffered device
+    # inputs) while the compute stream assembles step k; every step's H2D copies, its assembly, its
+    # checksum and the D2H read of that checksum are inside the timed region, and the host reads the
+    # result of step k - 1 before it enqueues step k + 1.
+    copy_stream = torch.cuda.Stream()
+    comp = torch.cuda.current_stream()
+    dxv = [torch.empty(hx.shape, dtype=torch.float64, device="cuda") for _ in range(2)]
+    dE = [torch.empty(hE.shape, dtype=torch.float64, device="cuda") for _ in range(2)]
+    hout = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in range(2)]
+    dout = [torch.empty(2, dtype=torch.float64, device="cuda") for _ in range(2)]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0}
 
     def e2e_step():
-        dxv.copy_(hx, non_blocking=True)               # H2D: vertex coordinates of this step
-        form.set_geometry(dxv)
-        form.E.copy_(hE, non_blocking=True)            # H2D: material field of this step
+        k = state["k"]
+        b = k & 1
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(ev_done[b])         # the buffers of step k - 2 are free
+            dxv[b].copy_(hx, non_blocking=True)            # H2D: vertex coordinates of this step
+            dE[b].copy_(hE, non_blocking=True)             # H2D: material field of this step
+            ev_up[b].record(copy_stream)
+        comp.wait_event(ev_up[b])
+        form.set_geometry(dxv[b])
+        form.set_E(dE[b])
         fem.assemble_matrix(A, form)
-        fem.capi.call("femb200_matrix_norms", A.plan, fem._p(A.values), fem._p(dout), fem._stream())
-        hout.copy_(dout, non_blocking=True)            # D2H: (|K|_F^2, trace K)
-        torch.cuda.current_stream().synchronize()
+        fem.capi.call("femb200_matrix_norms", A.plan, fem._p(A.values), fem._p(dout[b]), fem._stream())
+        hout[b].copy_(dout[b], non_blocking=True)          # D2H: (|K|_F^2, trace K)
+        ev_done[b].record(comp)
+        if k >= 1:
+            ev_done[1 - b].synchronize()                   # the host consumes the result of step k - 1
+            state["last"] = (float(hout[1 - b][0]), float(hout[1 - b][1]))
+        state["k"] = k + 1
+
+    def e2e_drain():
+        torch.cuda.synchronize()
+        b = (state["k"] - 1) & 1
+        state["last"] = (float(hout[b][0]), float(hout[b][1]))
 
     for _ in range(max(1, min(W, 2))):
         e2e_step()
-    e2e_total, _ = timed(e2e_step, K)
+    e2e_drain()
+
+    def e2e_all():
+        for _ in range(K):
+            e2e_step()
+        e2e_drain()
+
+    e2e_total, _ = timed(e2e_all, 1)
     e2e_ms = e2e_total / K
     e2e_value = total_dofs / (e2e_ms * 1e-3) / 1e9
     h2d = hx.numel() * 8 + hE.numel() * 8
-    fro, tr = float(np.sqrt(hout[0].item())), float(hout[1].item())
+    fro, tr = float(np.sqrt(state["last"][0])), float(state["last"][1])
 
     if rank != 0:
         if world > 1:
@@ -382,7 +421,7 @@ def run_b200(args):
                    "l2": "inputs + outputs per step (3.5 GB) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"strips x{world}" if world > 1 else "single GPU", "cg_iters": args.cg_iters,
                    "pattern_build_ms": pattern_ms},
-        "roofline": {"kernel": "assemble_kernel<P2,fast> (+ cell_setup_kernel, dirichlet_kernel)", "bound": "hbm", "achieved": a_gbs,
+        "roofline": {"kernel": "assemble_fast_kernel<P2> (+ cell_setup_kernel, dirichlet_kernel)", "bound": "hbm", "achieved": a_gbs,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a_gbs / peak,
                      "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": kernel_ms,
                      "traffic": traffic_from_profile("assemble") if (n == 1448 and world == 1) else None},
