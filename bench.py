@@ -430,8 +430,10 @@ def run_b200(args):
                "cg_iter_ms": cg_iter_ms, "cg_iter_gbs": c_gbs, "cg_iter_frac": c_gbs / peak,
                "cg_iter_gdofs": total_dofs / (cg_iter_ms * 1e-3) / 1e9, "precond": "jacobi", "iters": args.cg_iters},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 16, "what": "pinned host vertex coordinates + E -> device, set_geometry, "
-                                                  "assemble_matrix(A, form, bcs), matrix_norms, 16-byte read back", "fro": fro, "trace": tr},
+                "d2h_bytes_per_step": 16, "what": "per step: pinned host vertex coordinates + E -> device (copy stream, "
+                                                  "double-buffered, overlapping the previous step's assembly), set_geometry, "
+                                                  "assemble_matrix(A, form, bcs), matrix_norms, 16-byte read back consumed by "
+                                                  "the host; K steps timed as a whole", "fro": fro, "trace": tr},
         "gpu_launches": 3 * K,  # cell_setup + assemble + dirichlet per step
         "clocks": clocks,
     }
