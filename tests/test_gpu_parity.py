@@ -168,6 +168,46 @@ def test_assembly_unstructured_and_ragged():
         assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
 
 
+def relabel_cells(m, rng):
+    """Random cell order and a random relabelling (rotation and/or reflection) of every cell's vertices:
+    mixed orientations, every rotation of the row node, broken fans."""
+    perms = np.array([[0, 1, 2], [1, 2, 0], [2, 0, 1], [0, 2, 1], [2, 1, 0], [1, 0, 2]])
+    p = perms[rng.integers(0, 6, size=m.ncells)]
+    order = rng.permutation(m.ncells)
+    rows = np.arange(m.ncells)[:, None]
+    xd = m.xdofmap[rows, p][order]
+    dm = m.dofmap[rows, p] if m.etype == fm.P1 else np.hstack([m.dofmap[rows, p], m.dofmap[rows, 3 + p]])
+    return fm.Mesh(m.etype, m.x, np.ascontiguousarray(xd, dtype=np.int32), np.ascontiguousarray(dm[order], dtype=np.int32),
+                   m.nx, m.ny), order
+
+
+@pytest.mark.parametrize("kind,n", [("P1", 13), ("P2", 11), ("P2", 40)])
+@pytest.mark.parametrize("old", [False, True])
+def test_assembly_random_orientation(kind, n, old, square, monkeypatch):
+    """The fast kernel carries fan-edge columns in registers along a rotational walk of every vertex fan,
+    flipping vertex labels where the orientation demands it: meshes with random cell order and random
+    per-cell vertex labelling (and the clockwise square.msh) against the oracle; the older record format
+    (FEMB200_ASM_OLD) on the same meshes."""
+    if old:
+        monkeypatch.setenv("FEMB200_ASM_OLD", "1")
+    f = fem()
+    rng = np.random.default_rng(17 + n)
+    meshes = [relabel_cells(make_mesh(kind, n, ny=n + 2), rng)[0]]
+    if kind == "P1":
+        meshes.append(relabel_cells(square_mesh(square), rng)[0])
+    for m in meshes:
+        E = 1e7 * (1 + rng.random(m.ncells))
+        bc = fm.dirichlet_markers(m)[0] if m.nx else None
+        rowptr, colidx, want = oracle_assemble(m, E, bc=bc)
+        form = f.ElasticityForm(m, E)
+        A = f.create_matrix(form)
+        np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
+        np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
+        A.values.fill_(float("nan"))
+        f.assemble_matrix(A, form, bcs=[f.DirichletBC(bc)] if bc is not None else None)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
 def test_assembly_square_msh_known_answers(square, kat):
     m = square_mesh(square)
     E = oracle.E_table()[square["tag"] % 200]
@@ -207,6 +247,7 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
     if kind in ("P1", "P2"):
         # the developer variants of the fast kernel and the generic per-quadrature-point path
         # must give the same matrix
+        monkeypatch.setenv("FEMB200_ASM_OLD", "1")     # the generic-record kernel (still used for damaged cells)
         for tpn, ch in (("1", "1"), ("1", "3"), ("2", "1"), ("2", "3")):
             monkeypatch.setenv("FEMB200_ASM_TPN", tpn)
             monkeypatch.setenv("FEMB200_ASM_CH", ch)
@@ -215,6 +256,7 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
             assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
         monkeypatch.delenv("FEMB200_ASM_TPN")
         monkeypatch.delenv("FEMB200_ASM_CH")
+        monkeypatch.delenv("FEMB200_ASM_OLD")
         monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
         A.values.fill_(float("nan"))
         f.assemble_matrix(A, form)
