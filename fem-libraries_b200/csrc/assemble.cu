@@ -128,11 +128,11 @@ __device__ __forceinline__ int stored_position(int b, int a, int nd);
 
 // ---- damaged cells (d > 0 at some quadrature point): per-cell pre-pass ------------------
 // The tangent D_q (M.cc:736-872 closed form, or the dual-number Hessian M.cc:752-765) depends on
-// the cell only, but the gather assembly visits every cell once per node: evaluating it per visit
-// costs 6x the work.  This pre-pass evaluates it once per damaged cell and stores
-//   [g_1, g_2 | w_q D_q (9 doubles) for every quadrature point],  w_q = quadrature weight * |det J|;
-// the cell record of a damaged cell is replaced by {NaN, index of its record}.  Undamaged cells
-// keep the 32-byte fast-path record.
+// the cell only, but the gather assembly visits every cell once per node and scalar row: this
+// pre-pass classifies the cells (cell_setup_damage_kernel: undamaged cells keep the 32-byte
+// fast-path record, damaged ones get {NaN, index} and go on a compact list) and integrates the full
+// element tangent of every damaged cell once (cell_tangent_kernel); a damaged visit then copies its
+// row slice.
 template <int ET>
 __device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *phi, double &w2)
 {  // reference gradients, vertex basis and 2 * weight at point q of the rule of element.cuh
@@ -145,119 +145,131 @@ __device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *ph
 
 template <int ET>
 __global__ void cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap,
-                                         const int32_t *__restrict__ dofmap, const double *__restrict__ x, int xs,
-                                         const double *__restrict__ E, LameCoef lc, const double *__restrict__ dnod,
-                                         const double *__restrict__ u, int variant, double *__restrict__ rec,
-                                         double *__restrict__ celld, int32_t *__restrict__ count)
+                                         const double *__restrict__ x, int xs, const double *__restrict__ E,
+                                         const double *__restrict__ dnod, double *__restrict__ rec,
+                                         int32_t *__restrict__ dlist, int32_t *__restrict__ count)
 {
-   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, W = 4 + 9 * nq;
+   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq;
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= ncells) return;
    const int64_t v0 = xdofmap[3 * e], v1 = xdofmap[3 * e + 1], v2 = xdofmap[3 * e + 2];
-   const double x0 = x[v0 * xs], y0 = x[v0 * xs + 1];
-   const double x1 = x[v1 * xs], y1 = x[v1 * xs + 1];
-   const double x2 = x[v2 * xs], y2 = x[v2 * xs + 1];
-   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
-   const double id = 1. / det, T = 0.5 * fabs(det), Ee = E[e];
-   const double g1[2] = {(y2 - y0) * id, -(x2 - x0) * id}, g2[2] = {-(y1 - y0) * id, (x1 - x0) * id};
    const double dv[3] = {dnod[v0], dnod[v1], dnod[v2]};
-   double dq[nq];
    bool damaged = false;
 #pragma unroll
    for (int q = 0; q < nq; ++q)
    {
       double dN[nd][2], phi[3], w2;
       tri_ref_grads<ET>(q, dN, phi, w2);
-      dq[q] = phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2];
-      damaged = damaged || dq[q] > 0.;
+      damaged = damaged || (phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2]) > 0.;
    }
    double2 *r = reinterpret_cast<double2 *>(rec + 4 * e);
-   if (!damaged)
-   {
-      const double sc = sqrt(T * Ee);
-      r[0] = make_double2(g1[0] * sc, g1[1] * sc);
-      r[1] = make_double2(g2[0] * sc, g2[1] * sc);
+   if (damaged)
+   {  // NaN marker + index of the cell's tangent record (filled by cell_tangent_kernel)
+      const int idx = atomicAdd(count, 1);
+      dlist[idx] = (int32_t)e;
+      r[0] = make_double2(__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double((long long)idx));
+      r[1] = make_double2(0., 0.);
       return;
    }
-   const int idx = atomicAdd(count, 1);
-   r[0] = make_double2(__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double((long long)idx));
-   r[1] = make_double2(0., 0.);
-   double *o = celld + (int64_t)idx * W;
-   o[0] = g1[0], o[1] = g1[1], o[2] = g2[0], o[3] = g2[1];
-   const double lam = Ee * lc.c2, mu = Ee * lc.c3;
-   double ue[nd][2];
+   const double x0 = x[v0 * xs], y0 = x[v0 * xs + 1];
+   const double x1 = x[v1 * xs], y1 = x[v1 * xs + 1];
+   const double x2 = x[v2 * xs], y2 = x[v2 * xs + 1];
+   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+   const double sc = sqrt(0.5 * fabs(det) * E[e]) / det;
+   r[0] = make_double2((y2 - y0) * sc, -(x2 - x0) * sc);
+   r[1] = make_double2(-(y1 - y0) * sc, (x1 - x0) * sc);
+}
+
+// Element tangent K_e = sum_q w_q |det J| B_q D_q B_q^t of every damaged cell (closed-form tangent
+// M.cc:736-872 or the dual-number Hessian M.cc:752-765; M.cc:699-704, 885-887 for B D B^t), row-major
+// 2nd x 2nd with interleaved dofs: the gather kernel then copies the row slices it needs instead of
+// integrating them once per visit.  Grid-stride over the compact list of damaged cells.
+template <int ET>
+__global__ void __launch_bounds__(128)
+cell_tangent_kernel(const int32_t *__restrict__ dlist, const int32_t *__restrict__ count,
+                    const int32_t *__restrict__ xdofmap, const int32_t *__restrict__ dofmap,
+                    const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
+                    const double *__restrict__ dnod, const double *__restrict__ u, int variant,
+                    double *__restrict__ celld)
+{
+   constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq;
+   const int n = *count;
+   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+   {
+      const int64_t e = dlist[idx];
+      double xv[nv][2], dv[nv];
 #pragma unroll
-   for (int b = 0; b < nd; ++b)
-   {
-      const int64_t gd = 2 * (int64_t)dofmap[e * nd + b];
-      ue[b][0] = u ? u[gd] : 0., ue[b][1] = u ? u[gd + 1] : 0.;
-   }
-#pragma unroll 1
-   for (int q = 0; q < nq; ++q)
-   {
-      double dN[nd][2], phi[3], w2, D[9];
-      tri_ref_grads<ET>(q, dN, phi, w2);
-      if (dq[q] > 0.)
+      for (int v = 0; v < nv; ++v)
       {
-         double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+         const int64_t g = xdofmap[e * nv + v];
+         xv[v][0] = x[g * xs], xv[v][1] = x[g * xs + 1];
+         dv[v] = dnod[g];
+      }
+      const double lam = E[e] * lc.c2, mu = E[e] * lc.c3;
+      double ue[nd][2];
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+      {
+         const int64_t gd = 2 * (int64_t)dofmap[e * nd + b];
+         ue[b][0] = u ? u[gd] : 0., ue[b][1] = u ? u[gd + 1] : 0.;
+      }
+      double G[nq][nd][2], D[nq][9];
+#pragma unroll
+      for (int q = 0; q < nq; ++q)
+      {
+         double phi[nv];
+         const double w = qp_geometry<ET>(xv, q, G[q], phi);
+         double d = 0.;
+#pragma unroll
+         for (int v = 0; v < nv; ++v) d += phi[v] * dv[v];
+         if (d > 0.)
+         {
+            double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+#pragma unroll
+            for (int b = 0; b < nd; ++b)
+            {
+               g00 += ue[b][0] * G[q][b][0], g01 += ue[b][0] * G[q][b][1];
+               g10 += ue[b][1] * G[q][b][0], g11 += ue[b][1] * G[q][b][1];
+            }
+            const double sh = 0.5 * (g01 + g10);
+            const double eps[4] = {g00, sh, sh, g11};
+            tangent(variant, lam, mu, d, eps, D[q]);
+         }
+         else
+            hooke_scaled(lam, mu, 1., D[q]);
+#pragma unroll
+         for (int k = 0; k < 9; ++k) D[q][k] *= w;
+      }
+      double *K = celld + (int64_t)idx * (4 * nd * nd);
+#pragma unroll
+      for (int a = 0; a < nd; ++a)
 #pragma unroll
          for (int b = 0; b < nd; ++b)
          {
-            const double Gx = dN[b][0] * g1[0] + dN[b][1] * g2[0], Gy = dN[b][0] * g1[1] + dN[b][1] * g2[1];
-            g00 += ue[b][0] * Gx, g01 += ue[b][0] * Gy;
-            g10 += ue[b][1] * Gx, g11 += ue[b][1] * Gy;
-         }
-         const double sh = 0.5 * (g01 + g10);
-         const double eps[4] = {g00, sh, sh, g11};
-         tangent(variant, lam, mu, dq[q], eps, D);
-      }
-      else
-         hooke_scaled(lam, mu, 1., D);
-      const double w = w2 * T;
+            double k[4] = {0., 0., 0., 0.};
 #pragma unroll
-      for (int k = 0; k < 9; ++k) o[4 + 9 * q + k] = w * D[k];
+            for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], 1., k);
+            reinterpret_cast<double2 *>(K + (2 * a) * (2 * nd) + 2 * b)[0] = make_double2(k[0], k[1]);
+            reinterpret_cast<double2 *>(K + (2 * a + 1) * (2 * nd) + 2 * b)[0] = make_double2(k[2], k[3]);
+         }
    }
 }
 
-// row slice of a damaged cell: scalar row h of local row a against the stored columns t
+// row slice of a damaged cell: scalar row h of local row a, copied from the cell's tangent record
 template <int ET>
 __device__ __forceinline__ void damaged_compute_stage(const AsmArgs &A, const Visit &r, int idx, double2 *sv, int rbase,
                                                       int h)
 {
-   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, W = 4 + 9 * nq;
-   const double *o = A.celld + (int64_t)idx * W;
-   const double g1x = o[0], g1y = o[1], g2x = o[2], g2y = o[3];
+   constexpr int nd = Elem<ET>::nd;
    const int a = r.a;
-   double k0[nd], k1[nd];
+   const double2 *K = reinterpret_cast<const double2 *>(A.celld + (int64_t)idx * (4 * nd * nd) + (2 * a + h) * (2 * nd));
 #pragma unroll
-   for (int t = 0; t < nd; ++t) k0[t] = k1[t] = 0.;
-#pragma unroll 1
-   for (int q = 0; q < nq; ++q)
+   for (int b = 0; b < nd; ++b)
    {
-      double dN[nd][2], phi[3], w2;
-      tri_ref_grads<ET>(q, dN, phi, w2);
-      const double *D = o + 4 + 9 * q;
-      double gax = 0., gay = 0.;
-#pragma unroll
-      for (int b = 0; b < nd; ++b)
-         if (b == a) gax = dN[b][0] * g1x + dN[b][1] * g2x, gay = dN[b][0] * g1y + dN[b][1] * g2y;
-      // c = (row h of B_a) D, B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]   (M.cc:699-704)
-      const double c0 = h ? gay * D[3] + gax * D[6] : gax * D[0] + gay * D[6];
-      const double c1 = h ? gay * D[4] + gax * D[7] : gax * D[1] + gay * D[7];
-      const double c2 = h ? gay * D[5] + gax * D[8] : gax * D[2] + gay * D[8];
-#pragma unroll
-      for (int b = 0; b < nd; ++b)
-      {
-         const double gbx = dN[b][0] * g1x + dN[b][1] * g2x, gby = dN[b][0] * g1y + dN[b][1] * g2y;
-         const double v0 = c0 * gbx + c2 * gby, v1 = c1 * gby + c2 * gbx;
-         const int t = stored_position(b, a, nd);
-#pragma unroll
-         for (int s = 0; s < nd; ++s)
-            if (s == t) k0[s] += v0, k1[s] += v1;
-      }
+      const double2 kv = K[b];
+      const int t = stored_position(b, a, nd);
+      stage_put(sv, rbase + r.slot(t), kv.x, kv.y, r.is_first(t));
    }
-#pragma unroll
-   for (int t = 0; t < nd; ++t) stage_put(sv, rbase + r.slot(t), k0[t], k1[t], r.is_first(t));
 }
 
 __device__ __forceinline__ FastGeo fast_geo(const AsmArgs &A, const Visit &r)
@@ -370,9 +382,12 @@ struct FastCarry
    double dg[2], cv[2], ce[2];
 };
 
-template <int ET>
-__device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uint4 raw, const FastGeo &g,
-                                                     unsigned char *sv, int h, FastCarry &C)
+// Values of the row slice of one visit, positions t = 0..5 of the record's numbering (0', 1', 2', then
+// the edges opposite to them), for scalar row h, in the EXCHANGED frame of row h: for h = 1 the two
+// entries of every pair are swapped (row 1 of the closed form is row 0 with x and y exchanged in every
+// gradient and every output pair); emit_row_slice() swaps them back when it stores.
+template <int ET, bool EDGE>
+__device__ __forceinline__ void fast_values(const AsmArgs &A, const uint4 raw, const FastGeo &g, int h, double (*v)[2])
 {
    // gradients of the visit's vertices 1' and 2' (local numbers from the record; 0' is the row's own
    // vertex, or the vertex opposite to the row's own edge)
@@ -380,11 +395,69 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
    const double h0x = -g.g1x - g.g2x, h0y = -g.g1y - g.g2y;
    const double a1x = i1 == 0 ? h0x : (i1 == 1 ? g.g1x : g.g2x), a1y = i1 == 0 ? h0y : (i1 == 1 ? g.g1y : g.g2y);
    const double a2x = i2 == 0 ? h0x : (i2 == 1 ? g.g1x : g.g2x), a2y = i2 == 0 ? h0y : (i2 == 1 ? g.g1y : g.g2y);
-   // scalar row h = 1 is row 0 with x and y exchanged in every gradient and in every output pair:
-   // all values below are in the exchanged frame, put() and the diagonal store swap them back
    const double g1[2] = {h ? a1y : a1x, h ? a1x : a1y};
    const double g2[2] = {h ? a2y : a2x, h ? a2x : a2y};
    const double tl = A.lc.c2, tm = A.lc.c3;
+   if (!EDGE)
+   {  // row = vertex 0'
+      const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
+      double w01[2], w02[2];
+      w_row(g0, g0, tl, tm, v[0]);
+      w_row(g0, g1, tl, tm, w01);
+      w_row(g0, g2, tl, tm, w02);
+      // P1: K_ab = W^{ab} (M.cc:885-887); P2: vertex / vertex -1/3 W, vertex / adjacent edge 4/3 W,
+      // vertex / opposite edge 0
+      const double c3 = ET == FEMB200_P1 ? 1. : -1. / 3., c43 = 4. / 3.;
+      v[1][0] = c3 * w01[0], v[1][1] = c3 * w01[1];
+      v[2][0] = c3 * w02[0], v[2][1] = c3 * w02[1];
+      if (ET != FEMB200_P1)
+      {
+         v[3][0] = v[3][1] = 0.;
+         v[4][0] = c43 * w02[0], v[4][1] = c43 * w02[1];
+         v[5][0] = c43 * w01[0], v[5][1] = c43 * w01[1];
+      }
+   }
+   else
+   {  // row = edge 0' = (1', 2'); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
+      double w11[2], w12[2], w21[2], w22[2];
+      w_row(g1, g1, tl, tm, w11);
+      w_row(g1, g2, tl, tm, w12);
+      w_row(g2, g1, tl, tm, w21);  // = row of (W^{12})^t
+      w_row(g2, g2, tl, tm, w22);
+      const double c43 = 4. / 3.;
+      const double sy[2] = {w12[0] + w21[0], w12[1] + w21[1]};  // S = W12 + W21
+      v[0][0] = v[0][1] = 0.;  // opposite vertex
+      v[1][0] = c43 * w21[0], v[1][1] = c43 * w21[1];
+      v[2][0] = c43 * w12[0], v[2][1] = c43 * w12[1];
+      v[3][0] = c43 * (2. * w11[0] + sy[0] + 2. * w22[0]), v[3][1] = c43 * (2. * w11[1] + sy[1] + 2. * w22[1]);
+      v[4][0] = -c43 * (2. * w11[0] + sy[0]), v[4][1] = -c43 * (2. * w11[1] + sy[1]);
+      v[5][0] = -c43 * (sy[0] + 2. * w22[0]), v[5][1] = -c43 * (sy[1] + 2. * w22[1]);
+   }
+}
+
+// The same slice for a damaged cell: copied from the cell's tangent record (cell_tangent_kernel).
+template <int ET>
+__device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw, int idx, int h, double (*v)[2])
+{
+   constexpr int nd = Elem<ET>::nd;
+   const int i1 = (int)(raw.w & 3u), i2 = (int)((raw.w >> 2) & 3u), i0 = 3 - i1 - i2;
+   const int a = ((raw.z >> 2) & 1u) ? 3 + i0 : i0;  // local dof of the row
+   const double2 *K = reinterpret_cast<const double2 *>(A.celld + (int64_t)idx * (4 * nd * nd) + (2 * a + h) * (2 * nd));
+#pragma unroll
+   for (int t = 0; t < nd; ++t)
+   {
+      const int b = (t >= 3 ? 3 : 0) + (t % 3 == 0 ? i0 : (t % 3 == 1 ? i1 : i2));  // local dof at position t
+      const double2 kv = K[b];
+      v[t][0] = h ? kv.y : kv.x, v[t][1] = h ? kv.x : kv.y;  // exchanged frame
+   }
+}
+
+// Accumulates / carries / stages the slice: the diagonal block goes to registers (C.dg); the carry
+// registers are added to side 0; side 1 is carried when the record says so (plan.cu, k_fast_records).
+template <int ET, bool EDGE>
+__device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *sv, int h, FastCarry &C,
+                                               const double (*v)[2])
+{
    const bool cout = (raw.z >> 1) & 1u;
    // t = position (address entry), b = index of the put (first-touch bit)
    auto put = [&](int t, int b, double k0, double k1) {
@@ -397,56 +470,40 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
          *p = make_double2(va, vb);
       else
       {
-         double2 v = *p;
-         v.x += va, v.y += vb;
-         *p = v;
+         double2 x = *p;
+         x.x += va, x.y += vb;
+         *p = x;
       }
    };
-   if (!((raw.z >> 2) & 1u))
-   {  // row = vertex 0'
-      const double g0[2] = {-g1[0] - g2[0], -g1[1] - g2[1]};
-      double w00[2], w01[2], w02[2];
-      w_row(g0, g0, tl, tm, w00);
-      w_row(g0, g1, tl, tm, w01);
-      w_row(g0, g2, tl, tm, w02);
-      C.dg[0] += w00[0], C.dg[1] += w00[1];
-      // side 0 = columns of the fan edge (0', 1'): vertex 1' (position 1), its midpoint (position 5);
-      // side 1 = fan edge (0', 2'): positions 2 and 4.  P1 (M.cc:885-887) has the vertex columns only.
-      const double c3 = ET == FEMB200_P1 ? 1. : -1. / 3., c43 = 4. / 3.;
-      put(1, 0, c3 * w01[0] + C.cv[0], c3 * w01[1] + C.cv[1]);
+   if (!EDGE)
+   {  // vertex row: side 0 = positions (1, 5), side 1 = positions (2, 4)
+      C.dg[0] += v[0][0], C.dg[1] += v[0][1];
+      put(1, 0, v[1][0] + C.cv[0], v[1][1] + C.cv[1]);
       if (ET != FEMB200_P1)
       {
-         put(5, 4, c43 * w01[0] + C.ce[0], c43 * w01[1] + C.ce[1]);
-         put(3, 2, 0., 0.);  // edge 0' = (1', 2') is opposite: structural zero
+         put(5, 4, v[5][0] + C.ce[0], v[5][1] + C.ce[1]);
+         put(3, 2, v[3][0], v[3][1]);
       }
       if (cout)
       {
-         C.cv[0] = c3 * w02[0], C.cv[1] = c3 * w02[1];
-         if (ET != FEMB200_P1) C.ce[0] = c43 * w02[0], C.ce[1] = c43 * w02[1];
+         C.cv[0] = v[2][0], C.cv[1] = v[2][1];
+         if (ET != FEMB200_P1) C.ce[0] = v[4][0], C.ce[1] = v[4][1];
       }
       else
       {
-         put(2, 1, c3 * w02[0], c3 * w02[1]);
-         if (ET != FEMB200_P1) put(4, 3, c43 * w02[0], c43 * w02[1]);
+         put(2, 1, v[2][0], v[2][1]);
+         if (ET != FEMB200_P1) put(4, 3, v[4][0], v[4][1]);
          C.cv[0] = C.cv[1] = C.ce[0] = C.ce[1] = 0.;
       }
    }
    else
-   {  // row = edge 0' = (1', 2'); uses sum_d W^{cd} = 0 to stay within W11, W12, W21, W22
-      double w11[2], w12[2], w21[2], w22[2];
-      w_row(g1, g1, tl, tm, w11);
-      w_row(g1, g2, tl, tm, w12);
-      w_row(g2, g1, tl, tm, w21);  // = row of (W^{12})^t
-      w_row(g2, g2, tl, tm, w22);
-      const double c43 = 4. / 3.;
-      const double sy[2] = {w12[0] + w21[0], w12[1] + w21[1]};  // S = W12 + W21
-      C.dg[0] += c43 * (2. * w11[0] + sy[0] + 2. * w22[0]), C.dg[1] += c43 * (2. * w11[1] + sy[1] + 2. * w22[1]);
-      put(0, 0, 0., 0.);  // opposite vertex: structural zero
-      put(4, 3, -c43 * (2. * w11[0] + sy[0]), -c43 * (2. * w11[1] + sy[1]));
-      put(5, 4, -c43 * (sy[0] + 2. * w22[0]), -c43 * (sy[1] + 2. * w22[1]));
-      // end vertices 1' -> 4/3 W^{21}; 2' -> 4/3 W^{12}, plus what the first cell of the edge carried
-      const double v1[2] = {c43 * w21[0] + C.cv[0], c43 * w21[1] + C.cv[1]};
-      const double v2[2] = {c43 * w12[0] + C.ce[0], c43 * w12[1] + C.ce[1]};
+   {  // edge row: the two end columns (positions 1, 2) go from the first cell to the second
+      C.dg[0] += v[3][0], C.dg[1] += v[3][1];
+      put(0, 0, v[0][0], v[0][1]);
+      put(4, 3, v[4][0], v[4][1]);
+      put(5, 4, v[5][0], v[5][1]);
+      const double v1[2] = {v[1][0] + C.cv[0], v[1][1] + C.cv[1]};
+      const double v2[2] = {v[2][0] + C.ce[0], v[2][1] + C.ce[1]};
       if (cout)
          C.cv[0] = v1[0], C.cv[1] = v1[1], C.ce[0] = v2[0], C.ce[1] = v2[1];
       else
@@ -464,8 +521,8 @@ __device__ __forceinline__ void fast_compute_stage_f(const AsmArgs &A, const uin
 // depend on the block and thread index only: the dependent chain of a tile is record -> cell record
 // -> first put (the tile header is needed by the stream-out only), with the cell record one visit
 // and the record two visits ahead.
-template <int ET>
-__global__ void __launch_bounds__(kAsmR * 2, 7) assemble_fast_kernel(AsmArgs A)
+template <int ET, bool DMG>
+__global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7) assemble_fast_kernel(AsmArgs A)
 {
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
    extern __shared__ double2 sv[];
@@ -493,7 +550,37 @@ __global__ void __launch_bounds__(kAsmR * 2, 7) assemble_fast_kernel(AsmArgs A)
          raw = raw1, geo = geo1, raw1 = raw2;
          if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
          raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
-         fast_compute_stage_f<ET>(A, raw, geo, img, half, C);
+         // damaged cell: NaN marker + index of its per-cell tangent record
+         const bool dam = DMG && geo.g1x != geo.g1x;
+         const int didx = dam ? (int)__double_as_longlong(geo.g1y) : 0;
+         if (!((raw.z >> 2) & 1u))
+         {  // vertex row
+            double v[Elem<ET>::nd][2];
+            if (dam)
+            {
+               damaged_values<ET>(A, raw, didx, half, v);
+               emit_row_slice<ET, false>(raw, img, half, C, v);
+            }
+            else
+            {
+               fast_values<ET, false>(A, raw, geo, half, v);
+               emit_row_slice<ET, false>(raw, img, half, C, v);
+            }
+         }
+         else if (ET != FEMB200_P1)
+         {  // edge row
+            double v[Elem<ET>::nd][2];
+            if (dam)
+            {
+               damaged_values<ET>(A, raw, didx, half, v);
+               emit_row_slice<ET, true>(raw, img, half, C, v);
+            }
+            else
+            {
+               fast_values<ET, true>(A, raw, geo, half, v);
+               emit_row_slice<ET, true>(raw, img, half, C, v);
+            }
+         }
       }
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
@@ -781,14 +868,14 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    return 0;
 }
 
-template <int ET>
+template <int ET, bool DMG>
 static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    A.flevels = p->flevels;
    const size_t smem = 16 * (size_t)A.stage_units;
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   assemble_fast_kernel<ET><<<(unsigned)cdiv(p->nnodes, kAsmR), kAsmR * 2, smem, st>>>(A);
+   FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   assemble_fast_kernel<ET, DMG><<<(unsigned)cdiv(p->nnodes, kAsmR), kAsmR * 2, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -797,12 +884,12 @@ template <int ET, bool FAST>
 static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
 {
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
-   if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
    if (ET != FEMB200_Q2 && A.frec && !getenv("FEMB200_ASM_OLD"))
    {
       constexpr int TRI = ET == FEMB200_Q2 ? FEMB200_P2 : ET;
-      return launch_assemble_fast<TRI>(p, A, st);
+      return A.celld ? launch_assemble_fast<TRI, true>(p, A, st) : launch_assemble_fast<TRI, false>(p, A, st);
    }
+   if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
    // developer switches: visits batched per load level (CH), threads per node (TPN)
    const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
    const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
@@ -851,22 +938,30 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
       const unsigned grid = (unsigned)cdiv(p->ncells, 128);
       if (d_dnod)
       {
-         const size_t W = 4 + 9 * (size_t)elem_nq(p->etype);
+         const size_t W = 4 * (size_t)p->nd * p->nd;  // one element tangent per damaged cell (worst case: all)
          if (!pm->celld)
          {
             FEMB_CUDA(cudaMalloc(&pm->celld, sizeof(double) * W * (size_t)p->ncells));
-            FEMB_CUDA(cudaMalloc(&pm->celld_count, sizeof(int32_t)));
-            pm->bytes += sizeof(double) * W * (size_t)p->ncells;
+            FEMB_CUDA(cudaMalloc(&pm->celld_count, sizeof(int32_t) * (1 + (size_t)p->ncells)));
+            pm->bytes += (sizeof(double) * W + sizeof(int32_t)) * (size_t)p->ncells;
          }
+         int32_t *dlist = pm->celld_count + 1;
          FEMB_CUDA(cudaMemsetAsync(pm->celld_count, 0, sizeof(int32_t), st));
+         const unsigned g2 = (unsigned)std::min<int64_t>(cdiv(p->ncells, 128), (int64_t)devinfo().sm_count * 16);
          if (p->etype == FEMB200_P1)
-            cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E,
-                                                                       A.lc, d_dnod, d_u, variant, pm->cellrec, pm->celld,
-                                                                       pm->celld_count);
+         {
+            cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, d_dnod,
+                                                                       pm->cellrec, dlist, pm->celld_count);
+            cell_tangent_kernel<FEMB200_P1><<<g2, 128, 0, st>>>(dlist, pm->celld_count, p->xdofmap, p->dofmap, d_x, x_stride,
+                                                                d_E, A.lc, d_dnod, d_u, variant, pm->celld);
+         }
          else
-            cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E,
-                                                                       A.lc, d_dnod, d_u, variant, pm->cellrec, pm->celld,
-                                                                       pm->celld_count);
+         {
+            cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, d_dnod,
+                                                                       pm->cellrec, dlist, pm->celld_count);
+            cell_tangent_kernel<FEMB200_P2><<<g2, 128, 0, st>>>(dlist, pm->celld_count, p->xdofmap, p->dofmap, d_x, x_stride,
+                                                                d_E, A.lc, d_dnod, d_u, variant, pm->celld);
+         }
          A.celld = pm->celld;
       }
       else

@@ -111,8 +111,8 @@ struct femb200_plan
    int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
    int32_t nbc = 0;
    size_t bytes = 0;
-   double *celld = nullptr;    // damaged cells: [ncells][4 + 9 nq] (grad l1, grad l2, w_q D_q), lazily allocated
-   int32_t *celld_count = nullptr;
+   double *celld = nullptr;    // damaged cells: [ncells][2nd x 2nd] element tangents (row-major, interleaved dofs), lazily allocated
+   int32_t *celld_count = nullptr;  // [1 + ncells]: number of damaged cells, then their list
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
    int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
    int32_t row_tile_max[2] = {0, 0};  // largest 32- / 64-row tile (in node blocks) of the tiling that starts at row_lo
