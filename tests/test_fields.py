@@ -145,3 +145,31 @@ def test_gpu_strain_stress(kind, n):
     assert (dn[m.xdofmap].mean(axis=1) > 0).any()
     np.testing.assert_allclose(eps.cpu().numpy(), weps, rtol=1e-13, atol=1e-16)
     np.testing.assert_allclose(sig.cpu().numpy(), wsig, rtol=1e-11, atol=1e-9 * np.abs(wsig).max())
+
+
+@pytest.mark.gpu
+def test_gpu_reference_driver_sequence(square, tmp_path):
+    """BASELINE config 1 end to end: the reference driver's stages (mesh file, materials by tag, damage seed +
+    smoothing, BCs, load, Newton, strain/stress) through examples/mechanic2d_square.py against the same
+    sequence written with the oracle."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mechanic2d_square", os.path.join(root, "examples", "mechanic2d_square.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    p = os.path.join(str(tmp_path), "square.msh")
+    ex.fixture_msh(p)
+    out = ex.run(p, verbose=False)
+    m = out["mesh"]
+    np.testing.assert_array_equal(m.x, square["x"])
+    d = oracle.smooth_damage(m.nnodes, m.xdofmap, out["d0"], niter=8)
+    np.testing.assert_array_equal(out["d"].cpu().numpy(), d)
+    assert 0 < (d > 0).sum() < m.nnodes and d.max() == 1.0
+    want, it_o, norms_o = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, out["E"], 0.3, out["bc"], out["g"], dnod=d,
+                                        fnod=out["load"].ravel())
+    u = out["u"].cpu().numpy()
+    assert out["newton"].iterations == it_o
+    assert np.linalg.norm(u - want) / np.linalg.norm(want) < 1e-9
+    eps, sig = oracle.cell_strain_stress(m.etype, m.x, m.xdofmap, m.dofmap, out["E"], 0.3, u, dnod=d)
+    np.testing.assert_allclose(out["strain"].cpu().numpy(), eps, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(out["stress"].cpu().numpy(), sig, rtol=1e-9, atol=1e-9 * np.abs(sig).max())
