@@ -369,8 +369,7 @@ def run_b200(args):
         comp.wait_event(ev_up[b])
         form.set_geometry(dxv[b])
         form.set_E(dE[b])
-        fem.assemble_matrix(A, form)
-        fem.capi.call("femb200_matrix_norms", A.plan, fem._p(A.values), fem._p(dout[b]), fem._stream())
+        fem.assemble_matrix(A, form, norms_out=dout[b])   # assembly + Dirichlet, (|K|_F^2, trace K) fused in
         hout[b].copy_(dout[b], non_blocking=True)          # D2H: (|K|_F^2, trace K)
         ev_done[b].record(comp)
         if k >= 1:
@@ -432,7 +431,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16, "what": "per step: pinned host vertex coordinates + E -> device (copy stream, "
                                                   "double-buffered, overlapping the previous step's assembly), set_geometry, "
-                                                  "assemble_matrix(A, form, bcs), matrix_norms, 16-byte read back consumed by "
+                                                  "assemble_matrix(A, form, bcs, norms_out) (Frobenius norm and trace fused into the assembly pass), 16-byte read back consumed by "
                                                   "the host; K steps timed as a whole", "fro": fro, "trace": tr},
         "gpu_launches": 3 * K,  # cell_setup + assemble + dirichlet per step
         "clocks": clocks,

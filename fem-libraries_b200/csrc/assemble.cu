@@ -521,8 +521,9 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
 // depend on the block and thread index only: the dependent chain of a tile is record -> cell record
 // -> first put (the tile header is needed by the stream-out only), with the cell record one visit
 // and the record two visits ahead.
-template <int ET, bool DMG>
-__global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7) assemble_fast_kernel(AsmArgs A)
+template <int ET, bool DMG, bool NORMS>
+__global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7)
+assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out)
 {
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
    extern __shared__ double2 sv[];
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7) assemble_fast_kernel(A
    const int units = hdr->units;  // 16-byte units of this tile
    const int rank = ((tid >> 5) << 4) + (tid & 15);
    const int half = (tid >> 4) & 1;
+   double nrm[2] = {0., 0.};  // NORMS: this thread's share of sum v^2 and of the trace
    {
       const uint4 *rec = A.frec + ((int64_t)blockIdx.x * A.flevels * R + rank) * 2 + half;
       constexpr int LS = 2 * R;  // records per level
@@ -586,6 +588,7 @@ __global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7) assemble_fast_kernel(A
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
          const uint32_t off = (raw.z & 4u) ? (raw.z >> 16) : (raw.y & 0x7ff0u);
          *reinterpret_cast<double2 *>(img + off) = make_double2(half ? C.dg[1] : C.dg[0], half ? C.dg[0] : C.dg[1]);
+         nrm[1] = C.dg[0];  // the diagonal entry of this scalar row (exchanged frame: first of the pair)
       }
    }
    __syncthreads();
@@ -595,7 +598,91 @@ __global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7) assemble_fast_kernel(A
    for (int k = tid; k < padded; k += THREADS)
    {
       const int u = swz(k);
-      if (u < units) st_stream_d2(dst + 2 * (int64_t)u, sv[k]);
+      if (u < units)
+      {
+         const double2 val = sv[k];
+         st_stream_d2(dst + 2 * (int64_t)u, val);
+         if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
+      }
+   }
+   // fused (|K|_F^2, trace K) of the unconstrained matrix: deterministic two-stage reduction
+   if (NORMS) block_reduce_finish_n<THREADS, 2>(nrm, red, norms_out);
+}
+
+// ---- (|K|_F^2, trace K) of the CONSTRAINED matrix from the fused sums of the unconstrained one ----
+// One warp per constrained node I, before dirichlet_kernel changes the values: sums v^2 over the
+// entries that will be overwritten (rows of the constrained dofs of I, and their columns in the rows
+// of dofs that are not constrained themselves: every entry once) and the diagonal entries that will
+// become `diag`; norms_fix_finish_kernel then corrects the fused sums in a fixed order.
+__global__ void norms_fix_kernel(int nbc, const int32_t *__restrict__ bc_nodes, const uint8_t *__restrict__ bc,
+                                 const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+                                 const double *__restrict__ values, double *__restrict__ partials)
+{
+   const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+   if (w >= nbc) return;
+   const int64_t I = bc_nodes[w];
+   const bool m0 = bc[2 * I], m1 = bc[2 * I + 1];
+   const int64_t bi = brp[I];
+   const int deg = (int)(brp[I + 1] - bi);
+   const double *row0 = values + 4 * bi, *row1 = row0 + 2 * deg;
+   double s2 = 0., sd = 0., cnt = 0.;
+   for (int s = lane; s < deg; s += 32)
+   {
+      const int64_t J = bcol[bi + s];
+      if (m0) s2 += row0[2 * s] * row0[2 * s] + row0[2 * s + 1] * row0[2 * s + 1];
+      if (m1) s2 += row1[2 * s] * row1[2 * s] + row1[2 * s + 1] * row1[2 * s + 1];
+      if (J == I)
+      {
+         if (m0) sd += row0[2 * s], cnt += 1.;
+         if (m1) sd += row1[2 * s + 1], cnt += 1.;
+         // the unconstrained dof of a half-constrained node: its entry in the constrained column
+         if (m0 && !m1) s2 += row1[2 * s] * row1[2 * s];
+         if (m1 && !m0) s2 += row0[2 * s + 1] * row0[2 * s + 1];
+         continue;
+      }
+      // column I of row J (the pattern is symmetric): rows of J that are not constrained themselves
+      const bool j0 = bc[2 * J], j1 = bc[2 * J + 1];
+      const int64_t bj = brp[J];
+      const int degj = (int)(brp[J + 1] - bj);
+      int lo = 0, hi = degj;
+      while (lo < hi)
+      {
+         const int mid = (lo + hi) >> 1;
+         if (bcol[bj + mid] < I)
+            lo = mid + 1;
+         else
+            hi = mid;
+      }
+      if (lo < degj && bcol[bj + lo] == I)
+      {
+         const double *c0 = values + 4 * bj, *c1 = c0 + 2 * degj;
+         if (m0)
+         {
+            if (!j0) s2 += c0[2 * lo] * c0[2 * lo];
+            if (!j1) s2 += c1[2 * lo] * c1[2 * lo];
+         }
+         if (m1)
+         {
+            if (!j0) s2 += c0[2 * lo + 1] * c0[2 * lo + 1];
+            if (!j1) s2 += c1[2 * lo + 1] * c1[2 * lo + 1];
+         }
+      }
+   }
+   s2 = warp_sum(s2), sd = warp_sum(sd), cnt = warp_sum(cnt);
+   if (lane == 0) partials[3 * w] = s2, partials[3 * w + 1] = sd, partials[3 * w + 2] = cnt;
+}
+
+__global__ void __launch_bounds__(256)
+norms_fix_finish_kernel(int nbc, const double *__restrict__ partials, double diag, double *__restrict__ out)
+{
+   __shared__ double sh[8];
+   double s2 = 0., sd = 0., cnt = 0.;
+   for (int k = threadIdx.x; k < nbc; k += 256) s2 += partials[3 * k], sd += partials[3 * k + 1], cnt += partials[3 * k + 2];
+   const double t2 = block_sum<256>(s2, sh), td = block_sum<256>(sd, sh), tc = block_sum<256>(cnt, sh);
+   if (threadIdx.x == 0)
+   {
+      out[0] += tc * diag * diag - t2;
+      out[1] += tc * diag - td;
    }
 }
 
@@ -869,25 +956,39 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 }
 
 template <int ET, bool DMG>
-static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st)
+static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    A.flevels = p->flevels;
    const size_t smem = 16 * (size_t)A.stage_units;
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   assemble_fast_kernel<ET, DMG><<<(unsigned)cdiv(p->nnodes, kAsmR), kAsmR * 2, smem, st>>>(A);
+   const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
+   if (d_norms)
+   {
+      ReduceScratch red;
+      if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
+      FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      assemble_fast_kernel<ET, DMG, true><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
+   }
+   else
+   {
+      FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      assemble_fast_kernel<ET, DMG, false><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
+   }
    FEMB_LAUNCH_CHECK();
    return 0;
 }
 
+// *fused: in: the caller wants (|K|_F^2, trace K) in d_norms; out: whether the kernel produced them
 template <int ET, bool FAST>
-static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st)
+static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t st, double *d_norms, bool *fused)
 {
+   *fused = false;
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
    if (ET != FEMB200_Q2 && A.frec && !getenv("FEMB200_ASM_OLD"))
    {
       constexpr int TRI = ET == FEMB200_Q2 ? FEMB200_P2 : ET;
-      return A.celld ? launch_assemble_fast<TRI, true>(p, A, st) : launch_assemble_fast<TRI, false>(p, A, st);
+      *fused = d_norms != nullptr;
+      return A.celld ? launch_assemble_fast<TRI, true>(p, A, st, d_norms) : launch_assemble_fast<TRI, false>(p, A, st, d_norms);
    }
    if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
    // developer switches: visits batched per load level (CH), threads per node (TPN)
@@ -914,7 +1015,7 @@ using namespace femb;
 
 static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E, double nu,
                                 const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream,
-                                bool dirichlet)
+                                bool dirichlet, double *d_norms = nullptr)
 {
    FEMB_CHECK(p && d_x && d_E && d_values, "assemble_matrix: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_matrix: x_stride must be 2 or 3, got %d", x_stride);
@@ -971,19 +1072,38 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
       A.cellrec = pm->cellrec;
    }
    int rc;
+   bool fused = false;
    switch (p->etype)
    {
       case FEMB200_P1:
-         rc = linear ? launch_assemble<FEMB200_P1, true>(p, A, st) : launch_assemble<FEMB200_P1, false>(p, A, st);
+         rc = linear ? launch_assemble<FEMB200_P1, true>(p, A, st, d_norms, &fused)
+                     : launch_assemble<FEMB200_P1, false>(p, A, st, d_norms, &fused);
          break;
       case FEMB200_P2:
-         rc = linear ? launch_assemble<FEMB200_P2, true>(p, A, st) : launch_assemble<FEMB200_P2, false>(p, A, st);
+         rc = linear ? launch_assemble<FEMB200_P2, true>(p, A, st, d_norms, &fused)
+                     : launch_assemble<FEMB200_P2, false>(p, A, st, d_norms, &fused);
          break;
       default:
-         rc = launch_assemble<FEMB200_Q2, false>(p, A, st);
+         rc = launch_assemble<FEMB200_Q2, false>(p, A, st, d_norms, &fused);
    }
    if (rc) return rc;
-   if (dirichlet && p->bc && p->nbc > 0) return femb200_apply_dirichlet(p, d_values, 1.0, stream);
+   const bool constrained = dirichlet && p->bc && p->nbc > 0;
+   if (d_norms && fused && constrained)
+   {  // correct the fused sums of the unconstrained matrix for the entries the Dirichlet kernel overwrites
+      femb200_plan *pm = const_cast<femb200_plan *>(p);
+      if (!pm->norm_partials)
+      {
+         FEMB_CUDA(cudaMalloc(&pm->norm_partials, sizeof(double) * 3 * (size_t)p->nbc));
+         pm->bytes += sizeof(double) * 3 * (size_t)p->nbc;
+      }
+      norms_fix_kernel<<<(unsigned)cdiv((int64_t)p->nbc * 32, 128), 128, 0, st>>>(p->nbc, p->bc_nodes, p->bc, p->brp, p->bcol,
+                                                                                  d_values, pm->norm_partials);
+      norms_fix_finish_kernel<<<1, 256, 0, st>>>(p->nbc, pm->norm_partials, 1.0, d_norms);
+      FEMB_LAUNCH_CHECK();
+   }
+   if (constrained)
+      if (int rc2 = femb200_apply_dirichlet(p, d_values, 1.0, stream)) return rc2;
+   if (d_norms && !fused) return femb200_matrix_norms(p, d_values, d_norms, stream);  // other kernels: separate pass
    return 0;
 }
 
@@ -992,6 +1112,14 @@ extern "C" int femb200_assemble_matrix(const femb200_plan *p, const double *d_x,
                                        double *d_values, void *stream)
 {
    return assemble_matrix_impl(p, d_x, x_stride, d_E, nu, d_dnod, d_u, variant, d_values, stream, true);
+}
+
+extern "C" int femb200_assemble_matrix_norms(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
+                                             double nu, const double *d_dnod, const double *d_u, int variant,
+                                             double *d_values, double *d_norms, void *stream)
+{
+   FEMB_CHECK(d_norms != nullptr, "assemble_matrix_norms: null output");
+   return assemble_matrix_impl(p, d_x, x_stride, d_E, nu, d_dnod, d_u, variant, d_values, stream, true, d_norms);
 }
 
 extern "C" int femb200_assemble_matrix_nobc(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,

@@ -492,6 +492,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->dslot);
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
+   cudaFree(p->norm_partials);
    cudaFree(p->cellrec);
    cudaFree(p->celld);
    cudaFree(p->celld_count);
@@ -669,6 +670,8 @@ extern "C" int femb200_plan_set_dirichlet(femb200_plan *p, const uint8_t *d_bc, 
 {
    FEMB_CHECK(p != nullptr, "plan_set_dirichlet: null plan");
    cudaStream_t st = as_stream(stream);
+   cudaFree(p->norm_partials);
+   p->norm_partials = nullptr;
    cudaFree(p->bc_nodes);
    p->bc_nodes = nullptr;
    p->nbc = 0;

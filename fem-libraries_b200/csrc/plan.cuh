@@ -110,6 +110,7 @@ struct femb200_plan
    uint8_t *bc = nullptr;        // [2*nnodes] or null
    int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
    int32_t nbc = 0;
+   double *norm_partials = nullptr;  // [3 nbc] scratch of femb200_assemble_matrix_norms
    size_t bytes = 0;
    double *celld = nullptr;    // damaged cells: [ncells][2nd x 2nd] element tangents (row-major, interleaved dofs), lazily allocated
    int32_t *celld_count = nullptr;  // [1 + ncells]: number of damaged cells, then their list

@@ -57,6 +57,7 @@ SIGNATURES = {
     "femb200_gather": [i64, vp, vp, vp, vp],
     "femb200_scatter_rows": [i64, i32, vp, vp, vp, vp],
     "femb200_plan_set_row_range": [vp, i64, i64],
+    "femb200_assemble_matrix_norms": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp, vp],
     "femb200_smooth_damage": [vp, vp, vp, i32, f64, vp],
     "femb200_cell_strain_stress": [i32, i64, vp, vp, vp, i32, vp, f64, vp, vp, vp, vp, vp],
 }

@@ -252,13 +252,21 @@ def create_matrix(form: ElasticityForm) -> Matrix:
     return Matrix(form)
 
 
-def assemble_matrix(A: Matrix, form: ElasticityForm | None = None, bcs=None, diag: float = 1.0) -> Matrix:
+def assemble_matrix(A: Matrix, form: ElasticityForm | None = None, bcs=None, diag: float = 1.0,
+                    norms_out: torch.Tensor | None = None) -> Matrix:
     """Role of the setJ lambda (F.cc:847-862): MatZeroEntries + assemble_matrix(
     set_block_fn(A, ADD_VALUES), J, bcs) + set_diagonal(..., 1.) + MatAssembly.
-    One write-once gather kernel + (if any) the Dirichlet kernel."""
+    One write-once gather kernel + (if any) the Dirichlet kernel.  `norms_out` (2 doubles on the
+    device) receives (|K|_F^2, trace K) of the assembled matrix, fused into the same pass."""
     form = A.form if form is None else form
     if bcs is not None:
         A.set_bcs(bcs)
+    if norms_out is not None:
+        if diag != 1.0:
+            raise ValueError("norms_out needs the unit Dirichlet diagonal")
+        capi.call("femb200_assemble_matrix_norms", A.plan, _p(form.x), form.x_stride, _p(form.E), form.nu, _p(form.d),
+                  _p(form.u), form.variant, _p(A.values), _p(norms_out), _stream())
+        return A
     capi.call("femb200_assemble_matrix", A.plan, _p(form.x), form.x_stride, _p(form.E), form.nu, _p(form.d),
               _p(form.u), form.variant, _p(A.values), _stream())
     if diag != 1.0 and A.bc_dev is not None:

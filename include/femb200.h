@@ -114,7 +114,13 @@ int femb200_plan_scalar_csr(const femb200_plan *plan, int64_t *d_rowptr, int32_t
  * ------------------------------------------------------------------------ */
 int femb200_assemble_matrix(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
                             const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream);
-/* the same without the Dirichlet treatment (the unconstrained tangent, needed by apply_lifting) */
+/* assemble_matrix + (|K|_F^2, trace K) of the assembled (constrained) matrix in d_norms[0..1]: on the
+ * fast path the sums are fused into the stream-out of the assembly kernel (values still in registers)
+ * and corrected for the Dirichlet rows / columns, instead of a second pass over the value array */
+int femb200_assemble_matrix_norms(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
+                                  const double *d_dnod, const double *d_u, int variant, double *d_values, double *d_norms,
+                                  void *stream);
+/* assemble_matrix without the Dirichlet treatment (the unconstrained tangent, needed by apply_lifting) */
 int femb200_assemble_matrix_nobc(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
                                  const double *d_dnod, const double *d_u, int variant, double *d_values, void *stream);
 /* Dirichlet dofs: d_bc is a per-dof marker (uint8, 2*nnodes).  Builds the compact

@@ -208,6 +208,33 @@ def test_assembly_random_orientation(kind, n, old, square, monkeypatch):
         assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
 
 
+@pytest.mark.parametrize("kind,n,with_bc", [("P2", 23, True), ("P2", 23, False), ("P1", 31, True), ("Q2", 9, True)])
+def test_assembly_fused_norms(kind, n, with_bc):
+    """assemble_matrix(..., norms_out): (|K|_F^2, trace K) fused into the assembly pass (fast kernel) or
+    computed by the separate kernels (Q2) equal the norms of the assembled matrix, Dirichlet rows included."""
+    f = fem()
+    import torch
+    m = make_mesh(kind, n, ny=n + 1)
+    E = fm.young_per_cell(m.ncells)
+    bc, g = fm.dirichlet_markers(m)
+    if with_bc:   # also a half-constrained node: only its x dof
+        free = np.nonzero(bc[0::2] == 0)[0]
+        bc[2 * free[len(free) // 2]] = 1
+    form = f.ElasticityForm(m, E)
+    A = f.create_matrix(form)
+    out = torch.zeros(2, dtype=torch.float64, device="cuda")
+    f.assemble_matrix(A, form, bcs=[f.DirichletBC(bc)] if with_bc else None, norms_out=out)
+    vals = A.values.cpu().numpy()
+    _, _, want = oracle_assemble(m, E, bc=bc if with_bc else None)
+    assert relfro(vals, want) < TOL_VALUES
+    K = A.to_scipy()
+    f2, tr = out.cpu().numpy()
+    assert abs(f2 - (vals ** 2).sum()) < 1e-12 * (vals ** 2).sum()
+    assert abs(tr - K.diagonal().sum()) < 1e-12 * abs(K.diagonal().sum())
+    fro, tr2 = A.norms()
+    assert abs(np.sqrt(f2) - fro) < 1e-12 * fro and abs(tr - tr2) < 1e-12 * abs(tr2)
+
+
 def test_assembly_square_msh_known_answers(square, kat):
     m = square_mesh(square)
     E = oracle.E_table()[square["tag"] % 200]
