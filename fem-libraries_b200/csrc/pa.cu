@@ -432,7 +432,7 @@ struct PaLayout
    int nb, nb_bytes;     // 3 buffers of {tn, tp}: node ids and node -> refs offsets
    int tp;               // offset of tp inside one of them
    int tr, tr_bytes;     // 2 buffers of trefs
-   int xs, xs_bytes;     // 2 buffers of x values
+   int xs, xs_bytes;     // x values of the current tile
    int ye;               // element results
    int b_tn, b_tp;       // bytes copied per tile for tn / tp
 };
@@ -461,11 +461,11 @@ __global__ void pa_zero_shared_kernel(int n, const int32_t *__restrict__ list, d
 
 // Persistent CTAs, one thread per cell of a tile.  Thread 0 streams the tile plans and per-cell
 // data (contiguous byte ranges) into shared memory with bulk copies one to two tiles ahead; the x
-// values of tile i+1 are gathered with 16-byte cp.async while tile i is computed, so no thread
-// waits on DRAM in steady state.  Per tile: inputs -> registers | element products -> ye |
+// values of tile i+1 are gathered with 16-byte cp.async (into the buffer tile i has just emptied into
+// registers) while tile i is computed, so no thread waits on DRAM in steady state.  Per tile: inputs -> registers | element products -> ye |
 // one thread per tile node sums its contributions and stores (interior) or reduces (tile boundary).
 template <int ET, bool DOT>
-__global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, ReduceScratch red, double *__restrict__ out)
+__global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, ReduceScratch red, double *__restrict__ out)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, W = 2 * nv + 2, CT = kPaThreads, S = CT * nd;
    extern __shared__ __align__(128) unsigned char pa_sm[];
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
       const unsigned char *nb = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
       const int nu = reinterpret_cast<const uint16_t *>(nb + L.tp)[0];
       const int32_t *tn = reinterpret_cast<const int32_t *>(nb);
-      double2 *xs = reinterpret_cast<double2 *>(pa_sm + L.xs + (size_t)(it & 1) * L.xs_bytes);
+      double2 *xs = reinterpret_cast<double2 *>(pa_sm + L.xs);
       for (int k = tid; k < nu; k += CT) cp_async16(xs + k, x2 + (tn[k] & 0x7fffffff));
    };
    double part = 0.;
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
       }
       const int64_t e = tile_of(it) * CT + tid;
       const bool valid = e < A.ncells;
-      const double2 *xs = reinterpret_cast<const double2 *>(pa_sm + L.xs + (size_t)(it & 1) * L.xs_bytes);
+      const double2 *xs = reinterpret_cast<const double2 *>(pa_sm + L.xs);
       mbar_wait(&fullG, it & 1);
       uint32_t m = 0u;
       double g[W], ux[nd], uy[nd];
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
             ux[a] = v.x, uy[a] = v.y;
          }
       }
-      __syncthreads();  // B1: the per-cell inputs are in registers
+      __syncthreads();  // B1: the per-cell inputs are in registers: the input buffers (G, xs) are free
       if (it + 1 < nmine)
       {
          if (tid == 0) load_G(it + 1);
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(kPaThreads, 3) pa_tile_kernel(PaArgs A, Reduce
             const int32_t id = tn[k];
             if (DOT)
             {  // <x, y> = sum over (tile, node) of x_node . partial: masked dofs contribute zeros
-               const double2 xv = xs[k];
+               const double2 xv = x2[id & 0x7fffffff];  // an L2 hit: gathered for this tile a moment ago
                part += xv.x * acc[j].x + xv.y * acc[j].y;
             }
             if (id < 0)
@@ -750,7 +750,7 @@ static PaLayout pa_layout(const femb200_pa *pa)
    L.tr_bytes = up(S * 2);
    L.tr = o, o += 2 * L.tr_bytes;
    L.xs_bytes = up(pa->max_uniq * 16);
-   L.xs = o, o += 2 * L.xs_bytes;
+   L.xs = o, o += L.xs_bytes;
    L.ye = o;
    return L;
 }
