@@ -235,6 +235,45 @@ def test_assembly_fused_norms(kind, n, with_bc):
     assert abs(np.sqrt(f2) - fro) < 1e-12 * fro and abs(tr - tr2) < 1e-12 * abs(tr2)
 
 
+def fan_mesh(k, order):
+    """k triangles around one centre node (valence k), P1 or P2."""
+    ang = 2 * np.pi * np.arange(k) / k
+    x = np.vstack([[0., 0.], np.c_[np.cos(ang), np.sin(ang)] * (1 + 0.1 * np.cos(3 * ang))[:, None]])
+    tri = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], dtype=np.int32)
+    if order == 1:
+        return fm.Mesh(fm.P1, x, tri, tri.copy())
+    edges = {}
+    def mid(a, b):
+        key = (min(a, b), max(a, b))
+        if key not in edges:
+            edges[key] = len(x) + len(edges)
+        return edges[key]
+    dm = np.array([[t[0], t[1], t[2], mid(t[1], t[2]), mid(t[0], t[2]), mid(t[0], t[1])] for t in tri], dtype=np.int32)
+    xm = np.zeros((len(x) + len(edges), 2))
+    xm[:len(x)] = x
+    for (a, b), i in edges.items():
+        xm[i] = 0.5 * (x[a] + x[b])
+    return fm.Mesh(fm.P2, xm, tri, dm)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("k", [3, 15, 16])
+def test_assembly_high_valence_fan(k, order):
+    """A node shared by k cells: 15 is the largest valence of the fast-record kernel, 16 the largest of the
+    plan (the older record format takes over); closed fan with a single closure."""
+    f = fem()
+    m = fan_mesh(k, order)
+    rng = np.random.default_rng(k)
+    E = 1e7 * (1 + rng.random(m.ncells))
+    rowptr, colidx, want = oracle_assemble(m, E)
+    form = f.ElasticityForm(m, E)
+    A = f.create_matrix(form)
+    np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
+    A.values.fill_(float("nan"))
+    f.assemble_matrix(A, form)
+    assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
 def test_assembly_square_msh_known_answers(square, kat):
     m = square_mesh(square)
     E = oracle.E_table()[square["tag"] % 200]
