@@ -605,8 +605,23 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
       }
    }
-   // fused (|K|_F^2, trace K) of the unconstrained matrix: deterministic two-stage reduction
-   if (NORMS) block_reduce_finish_n<THREADS, 2>(nrm, red, norms_out);
+   // fused (|K|_F^2, trace K) of the unconstrained matrix: one partial pair per CTA, summed in a fixed
+   // order by norms_sum_kernel
+   if (NORMS)
+   {
+      __shared__ double sh[THREADS / 32];
+      const double f2 = block_sum<THREADS>(nrm[0], sh), tr = block_sum<THREADS>(nrm[1], sh);
+      if (tid == 0) red.partials[blockIdx.x] = f2, red.partials[(size_t)gridDim.x + blockIdx.x] = tr;
+   }
+}
+
+__global__ void __launch_bounds__(1024) norms_sum_kernel(const double *__restrict__ partials, unsigned n, double *__restrict__ out)
+{
+   __shared__ double sh[32];
+   double a = 0., b = 0.;
+   for (unsigned i = threadIdx.x; i < n; i += 1024) a += partials[i], b += partials[(size_t)n + i];
+   const double ta = block_sum<1024>(a, sh), tb = block_sum<1024>(b, sh);
+   if (threadIdx.x == 0) out[0] = ta, out[1] = tb;
 }
 
 // ---- (|K|_F^2, trace K) of the CONSTRAINED matrix from the fused sums of the unconstrained one ----
@@ -968,6 +983,7 @@ static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t s
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
       FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       assemble_fast_kernel<ET, DMG, true><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
+      norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
    }
    else
    {
