@@ -58,6 +58,12 @@ SIGNATURES = {
     "femb200_scatter_rows": [i64, i32, vp, vp, vp, vp],
     "femb200_plan_set_row_range": [vp, i64, i64],
     "femb200_assemble_matrix_norms": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp, vp],
+    "femb200_create_pattern": [i32, i64, i64, vp, vp, vp, C.POINTER(vp)],
+    "femb200_element_grad_batched": [i32, i64, vp, vp, i32, vp, vp, vp, f64, vp, vp, i32, vp],
+    "femb200_assemble_pa": [i32, i64, i64, vp, vp, vp, i32, vp, f64, vp, C.POINTER(vp)],
+    "femb200_add_mult_pa": [vp, i64, vp, vp, vp, vp],
+    "femb200_cg": [vp, i32, vp, vp, vp, vp, i64, f64, f64, i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                   C.POINTER(C.c_int), vp],
     "femb200_smooth_damage": [vp, vp, vp, i32, f64, vp],
     "femb200_cell_strain_stress": [i32, i64, vp, vp, vp, i32, vp, f64, vp, vp, vp, vp, vp],
 }

@@ -481,7 +481,10 @@ class PAOperator:
     Mult = mult
 
     def AddMultPA(self, x: torch.Tensor, y: torch.Tensor) -> None:
-        y += self.mult(x)
+        """y += A x (mfem AddMultPA semantics)."""
+        if getattr(self, "_work", None) is None:
+            self._work = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        capi.call("femb200_add_mult_pa", self._pa, self.ndofs, _p(x), _p(y), _p(self._work), _stream())
 
     def diagonal(self) -> torch.Tensor:
         d = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")

@@ -258,6 +258,28 @@ int femb200_cell_strain_stress(int etype, int64_t ncells, const int32_t *d_xdofm
                                const double *d_x, int x_stride, const double *d_E, double nu, const double *d_dnod,
                                const double *d_u, double *d_strain, double *d_stress, void *stream);
 
+/* ------------------------------------------------------------------------
+ * The same entry points under the names SURVEY.md 8b gives the boundary.
+ *   create_pattern       = plan_create        (dolfinx create_matrix, F.cc:688)
+ *   element_grad_batched = tabulate_tensor_batched in the MFEM layout: elmat column-major,
+ *                          dofs byNODES (damIntegrator::AssembleElementGrad, M.cc:639,673)
+ *   assemble_pa          = pa_create          (BilinearFormIntegrator::AssemblePA)
+ *   add_mult_pa          : y += A x           (AddMultPA; d_work: ndofs doubles of scratch)
+ *   cg                   = pcg with its own scratch and Jacobi set-up (CGSolver::Mult /
+ *                          KSPSolve; precond FEMB200_PRECOND_NONE | _JACOBI); synchronises
+ * ------------------------------------------------------------------------ */
+int femb200_create_pattern(int etype, int64_t nnodes, int64_t ncells, const int32_t *d_dofmap, const int32_t *d_xdofmap,
+                           void *stream, femb200_plan **out);
+int femb200_element_grad_batched(int etype, int64_t ncells, double *d_elmat, const double *d_x, int x_stride,
+                                 const int32_t *d_xdofmap, const int32_t *d_dofmap, const double *d_E, double nu,
+                                 const double *d_dnod, const double *d_u, int variant, void *stream);
+int femb200_assemble_pa(int etype, int64_t nnodes, int64_t ncells, const int32_t *d_dofmap, const int32_t *d_xdofmap,
+                        const double *d_x, int x_stride, const double *d_E, double nu, void *stream, femb200_pa **out);
+int femb200_add_mult_pa(const femb200_pa *pa, int64_t ndofs, const double *d_x, double *d_y, double *d_work, void *stream);
+int femb200_cg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const double *d_b,
+               double *d_x, int64_t n, double rtol, double atol, int maxit, int precond, int *iters, double *final_res,
+               int *converged, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -705,3 +705,57 @@ def test_set_geometry_vertices_only():
     f.assemble_matrix(A, form)
     _, _, want = oracle_assemble(m1, E)
     assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+
+
+def test_survey_named_entry_points():
+    """The boundary under the names of SURVEY.md 8b (create_pattern, element_grad_batched, assemble_pa /
+    add_mult_pa, cg) gives what the plan / pa / pcg entry points give."""
+    import ctypes as C
+    import torch
+    f = fem()
+    capi = f.capi
+    m = make_mesh("P2", 14, ny=11)
+    E = fm.young_per_cell(m.ncells)
+    bc, g = fm.dirichlet_markers(m)
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form, bcs=[f.DirichletBC(bc)])
+    st = f._stream()
+    # create_pattern
+    plan = C.c_void_p()
+    capi.call("femb200_create_pattern", m.etype, m.nnodes, m.ncells, f._p(form.dofmap), f._p(form.xdofmap), st, C.byref(plan))
+    nnz = C.c_int64()
+    capi.call("femb200_plan_sizes", plan, None, None, None, C.byref(nnz), None, None)
+    assert nnz.value == A.nnz
+    capi.lib().femb200_plan_destroy(plan)
+    # element_grad_batched = the MFEM layout of the batched element kernel
+    n2 = 2 * m.nd
+    out = torch.empty((m.ncells, n2, n2), dtype=torch.float64, device="cuda")
+    capi.call("femb200_element_grad_batched", m.etype, m.ncells, f._p(out), f._p(form.x), form.x_stride, f._p(form.xdofmap),
+              f._p(form.dofmap), f._p(form.E), 0.3, None, None, 0, st)
+    assert torch.equal(out, f.element_grad_batched(form))
+    # assemble_pa / add_mult_pa: y += A x
+    pa = C.c_void_p()
+    capi.call("femb200_assemble_pa", m.etype, m.nnodes, m.ncells, f._p(form.dofmap), f._p(form.xdofmap), f._p(form.x),
+              form.x_stride, f._p(form.E), 0.3, st, C.byref(pa))
+    bcd = f.to_device(bc, np.uint8)
+    capi.call("femb200_pa_set_dirichlet", pa, f._p(bcd), 1.0, st)
+    x = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
+    y0 = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
+    y, work = y0.clone(), torch.empty_like(y0)
+    capi.call("femb200_add_mult_pa", pa, m.ndofs, f._p(x), f._p(y), f._p(work), st)
+    want = y0 + A.mult(x)
+    assert ((y - want).norm() / want.norm()).item() < 1e-12
+    # cg (Jacobi) on both operator kinds against CGSolver
+    b = f.to_device(np.where(bc != 0, g, 1.0), np.float64)
+    cgs = f.CGSolver(rel_tol=1e-12, max_iter=4000)
+    cgs.SetOperator(A)
+    cgs.SetPreconditioner("jacobi")
+    xref = cgs.Mult(b)
+    for kind, op, vals, pl in ((capi.OP_CSR, None, A.values, A.plan), (capi.OP_PA, pa, None, None)):
+        xs = torch.zeros_like(b)
+        it, conv, fin = C.c_int(), C.c_int(), C.c_double()
+        capi.call("femb200_cg", pl, kind, op, f._p(vals), f._p(b), f._p(xs), m.ndofs, 1e-12, 0.0, 4000, 1, C.byref(it),
+                  C.byref(fin), C.byref(conv), st)
+        assert conv.value == 1 and abs(it.value - cgs.GetNumIterations()) <= 2
+        assert ((xs - xref).norm() / xref.norm()).item() < TOL_CG
+    capi.lib().femb200_pa_destroy(pa)
