@@ -1006,23 +1006,10 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
       *fused = d_norms != nullptr;
       return A.celld ? launch_assemble_fast<TRI, true>(p, A, st, d_norms) : launch_assemble_fast<TRI, false>(p, A, st, d_norms);
    }
+   // older record format (16-byte visit records, staging addresses computed per block): plans without
+   // fast records (a node in 16 cells, a staging image over 32 KB) and the FEMB200_ASM_OLD switch
    if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
-   // developer switches: visits batched per load level (CH), threads per node (TPN)
-   const char *env = getenv("FEMB200_ASM_CH"), *env2 = getenv("FEMB200_ASM_TPN");
-   const int ch = env ? atoi(env) : 1, tpn = env2 ? atoi(env2) : 2;
-   if (tpn == 2)
-      switch (ch)
-      {
-         case 1: return launch_assemble_ch<ET, FAST, 1, 2>(p, A, st);
-         case 3: return launch_assemble_ch<ET, FAST, 3, 2>(p, A, st);
-         default: return launch_assemble_ch<ET, FAST, 2, 2>(p, A, st);
-      }
-   switch (ch)
-   {
-      case 1: return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
-      case 3: return launch_assemble_ch<ET, FAST, 3, 1>(p, A, st);
-      default: return launch_assemble_ch<ET, FAST, 2, 1>(p, A, st);
-   }
+   return launch_assemble_ch<ET, FAST, 1, 2>(p, A, st);
 }
 
 }  // namespace femb

@@ -311,17 +311,12 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
         np.testing.assert_array_equal(got[touched], want[touched])
         assert set(np.unique(want[touched])) == {0.0, 1.0}
     if kind in ("P1", "P2"):
-        # the developer variants of the fast kernel and the generic per-quadrature-point path
+        # the older record format of the fast kernel and the generic per-quadrature-point path
         # must give the same matrix
-        monkeypatch.setenv("FEMB200_ASM_OLD", "1")     # the generic-record kernel (still used for damaged cells)
-        for tpn, ch in (("1", "1"), ("1", "3"), ("2", "1"), ("2", "3")):
-            monkeypatch.setenv("FEMB200_ASM_TPN", tpn)
-            monkeypatch.setenv("FEMB200_ASM_CH", ch)
-            A.values.fill_(float("nan"))
-            f.assemble_matrix(A, form)
-            assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
-        monkeypatch.delenv("FEMB200_ASM_TPN")
-        monkeypatch.delenv("FEMB200_ASM_CH")
+        monkeypatch.setenv("FEMB200_ASM_OLD", "1")
+        A.values.fill_(float("nan"))
+        f.assemble_matrix(A, form)
+        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
         monkeypatch.delenv("FEMB200_ASM_OLD")
         monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
         A.values.fill_(float("nan"))
