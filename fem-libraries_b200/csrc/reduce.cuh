@@ -40,7 +40,8 @@ __device__ __forceinline__ double block_sum(double v, double *sh /* [THREADS/32]
 // Sum `part` over the whole grid into out[0].  Must be reached by every thread of
 // every CTA of the launch.
 template <int THREADS, int NV = 1>
-__device__ __forceinline__ void block_reduce_finish_n(const double (&part)[NV], ReduceScratch red, double *out)
+__device__ __forceinline__ void block_reduce_finish_n(const double (&part)[NV], ReduceScratch red, double *out,
+                                                      bool accumulate = false)
 {
    __shared__ double sh[THREADS / 32];
    __shared__ bool last;
@@ -66,16 +67,16 @@ __device__ __forceinline__ void block_reduce_finish_n(const double (&part)[NV], 
       const volatile double *p = red.partials + (size_t)k * gridDim.x;
       for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) s += p[i];
       const double t = block_sum<THREADS>(s, sh);
-      if (threadIdx.x == 0) out[k] = t;
+      if (threadIdx.x == 0) out[k] = accumulate ? out[k] + t : t;
    }
    if (threadIdx.x == 0) *red.ticket = 0u;
 }
 
 template <int THREADS>
-__device__ __forceinline__ void block_reduce_finish(double part, ReduceScratch red, double *out)
+__device__ __forceinline__ void block_reduce_finish(double part, ReduceScratch red, double *out, bool accumulate = false)
 {
    const double p[1] = {part};
-   block_reduce_finish_n<THREADS, 1>(p, red, out);
+   block_reduce_finish_n<THREADS, 1>(p, red, out, accumulate);
 }
 
 }  // namespace femb

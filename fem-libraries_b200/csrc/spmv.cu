@@ -26,7 +26,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_kernel(int64_t row_lo, int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
             const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
-            const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out)
+            const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out, bool accumulate = false)
 {
    if (flag && *flag != 0.) return;  // converged CG: become a no-op (uniform over the grid)
    const int lane = threadIdx.x & (kSpmvLanes - 1);
@@ -75,7 +75,7 @@ spmv_kernel(int64_t row_lo, int64_t nnodes, const int64_t *__restrict__ brp, con
          part = xi.x * y0 + xi.y * y1;
       }
    }
-   if (DOT) block_reduce_finish<kSpmvThreads>(part, red, out);
+   if (DOT) block_reduce_finish<kSpmvThreads>(part, red, out, accumulate);
 }
 
 // ---------------------------------------------------------------------------
@@ -328,6 +328,34 @@ extern "C" int femb200_spmv_dot(const femb200_plan *p, const double *d_values, c
    FEMB_CHECK(p && d_values && d_x && d_y && d_dot, "spmv_dot: null argument");
    FEMB_CHECK(d_x != d_y, "spmv_dot: x and y must not alias");
    return spmv_launch(p, d_values, d_x, d_y, nullptr, d_dot, as_stream(stream));
+}
+
+// y = A x on an arbitrary range of node rows (no tiling state needed: the plain kernel), optionally
+// d_dot (+)= <x, y> over those rows and gated by a convergence flag: the boundary rows of a rank, which
+// wait for the halo while the interior rows (femb200_spmv / cg_apply on the plan's row range) run.
+extern "C" int femb200_spmv_rows(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
+                                 int64_t row_lo, int64_t row_hi, double *d_dot, int accumulate, const double *d_flag,
+                                 void *stream)
+{
+   FEMB_CHECK(p && d_values && d_x && d_y, "spmv_rows: null argument");
+   FEMB_CHECK(d_x != d_y, "spmv_rows: x and y must not alias");
+   FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "spmv_rows: bad range [%lld, %lld)",
+              (long long)row_lo, (long long)row_hi);
+   cudaStream_t st = as_stream(stream);
+   if (row_hi == row_lo) return 0;
+   const unsigned grid = (unsigned)cdiv((row_hi - row_lo) * kSpmvLanes, kSpmvThreads);
+   if (d_dot)
+   {
+      ReduceScratch red;
+      if (int rc = reduce_scratch(grid, st, &red)) return rc;
+      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(row_lo, row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag, red,
+                                                        d_dot, accumulate != 0);
+   }
+   else
+      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(row_lo, row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag,
+                                                         ReduceScratch{nullptr, nullptr}, nullptr);
+   FEMB_LAUNCH_CHECK();
+   return 0;
 }
 
 extern "C" int femb200_extract_diagonal(const femb200_plan *p, const double *d_values, double *d_diag, void *stream)

@@ -39,6 +39,7 @@ SIGNATURES = {
     "femb200_matrix_norms": [vp, vp, vp, vp],
     "femb200_spmv": [vp, vp, vp, vp, vp],
     "femb200_spmv_dot": [vp, vp, vp, vp, vp, vp],
+    "femb200_spmv_rows": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp],
     "femb200_extract_diagonal": [vp, vp, vp, vp],
     "femb200_jacobi_setup": [i64, vp, vp, vp],
     "femb200_pcg": [vp, i32, vp, vp, vp, vp, i64, f64, f64, i32, vp, i32, i32, vp, C.POINTER(C.c_int),

@@ -173,12 +173,26 @@ class DistCG:
     search direction + all-reduce of the three dot products."""
 
     def __init__(self, A, part: StripPartition, rel_tol=1e-12, abs_tol=0.0, max_iter=2000, check_every=25,
-                 jacobi=True, group=None):
+                 jacobi=True, group=None, overlap: bool = False):
         self.A, self.part = A, part
         self.rel_tol, self.abs_tol, self.max_iter, self.check_every = rel_tol, abs_tol, max_iter, check_every
         self.halo = Halo(part, group)
         self.group = group
-        A.set_row_range(part.own_lo, part.own_hi)
+        # Owned rows that read ghost values (strip layout: the two lattice rows above the bottom ghost row, the
+        # lattice row below the top ghost rows) are applied after the halo exchange; all the other owned rows --
+        # the plan's row range -- run while the exchange is in flight on a second stream.
+        mx = 2 * part.nx + 1
+        self.bottom = (part.own_lo, min(part.own_lo + 2 * mx, part.own_hi)) if part.rank > 0 else (part.own_lo, part.own_lo)
+        self.top = (max(part.own_hi - mx, self.bottom[1]), part.own_hi) if part.rank < part.world - 1 else (part.own_hi, part.own_hi)
+        # (measured at 2 GPUs: 0.854 ms per iteration with the overlap, 0.848 ms without -- the communication
+        # cost of an iteration is the latency of its three all-reduces, not the 93 KB halo -- hence off by default)
+        self.overlap = bool(overlap) and part.world > 1 and A.values.is_cuda
+        if self.overlap:
+            A.set_row_range(self.bottom[1], self.top[0])
+            self.side = torch.cuda.Stream()
+            self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
+        else:
+            A.set_row_range(part.own_lo, part.own_hi)
         nl = 2 * part.mesh.nnodes
         dev = A.values.device
         self.r = torch.zeros(nl, dtype=torch.float64, device=dev)
@@ -200,6 +214,27 @@ class DistCG:
         if self.part.world > 1:
             td.all_reduce(self.scal[idx:idx + 1], group=self.group)
 
+    def mult(self, v: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """y[owned] = (A v)[owned] with the ghost update of v: halo exchange on the second stream while the
+        interior rows run, then the rows next to the ghosts (the operator apply of one CG iteration)."""
+        A, st = self.A, self._st
+        if not self.overlap:
+            self.halo.forward(v)
+            capi.call("femb200_spmv", A.plan, _p(A.values), _p(v), _p(y), st())
+            return y
+        main = torch.cuda.current_stream()
+        self.ev_ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_ready)
+            self.halo.forward(v)
+            self.ev_halo.record(self.side)
+        capi.call("femb200_spmv", A.plan, _p(A.values), _p(v), _p(y), st())
+        main.wait_event(self.ev_halo)
+        for lo, hi in (self.bottom, self.top):
+            if hi > lo:
+                capi.call("femb200_spmv_rows", A.plan, _p(A.values), _p(v), _p(y), lo, hi, None, 0, None, st())
+        return y
+
     def solve(self, b: torch.Tensor, x: torch.Tensor, fixed_iters: int = 0) -> torch.Tensor:
         p = self.part
         o, n = 2 * p.own_lo, 2 * p.n_owned
@@ -212,8 +247,24 @@ class DistCG:
         capi.call("femb200_cg_scalar_step", _p(scal), 0, st())
 
         def apply():
-            self.halo.forward(self.d)
-            capi.call("femb200_cg_apply", A.plan, capi.OP_CSR, None, _p(A.values), _p(self.d), _p(self.z), _p(scal), st())
+            if not self.overlap:
+                self.halo.forward(self.d)
+                capi.call("femb200_cg_apply", A.plan, capi.OP_CSR, None, _p(A.values), _p(self.d), _p(self.z), _p(scal), st())
+            else:
+                main = torch.cuda.current_stream()
+                self.ev_ready.record(main)                       # the search direction is final
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(self.ev_ready)
+                    self.halo.forward(self.d)                    # NCCL send/recv of the interface rows
+                    self.ev_halo.record(self.side)
+                # interior rows: Ad and the partial <d, A d>, while the halo is in flight
+                capi.call("femb200_cg_apply", A.plan, capi.OP_CSR, None, _p(A.values), _p(self.d), _p(self.z), _p(scal), st())
+                main.wait_event(self.ev_halo)
+                flag = _off(scal, capi.SC_FLAG)
+                for lo, hi in (self.bottom, self.top):           # rows that read ghost values; dot accumulated
+                    if hi > lo:
+                        capi.call("femb200_spmv_rows", A.plan, _p(A.values), _p(self.d), _p(self.z), lo, hi,
+                                  _off(scal, capi.SC_RED_DEN), 1, flag, st())
             self._allreduce(capi.SC_RED_DEN)
             capi.call("femb200_cg_scalar_step", _p(scal), 1, st())
 

@@ -158,6 +158,11 @@ int femb200_spmv(const femb200_plan *plan, const double *d_values, const double 
 /* y = A x and d_dot[0] = <x, y> in the same pass (deterministic reduction) */
 int femb200_spmv_dot(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, double *d_dot,
                      void *stream);
+/* y = A x on the node rows [row_lo, row_hi) only (any range); d_dot (or NULL) receives <x, y> over those rows,
+ * added to its content when `accumulate`; d_flag (or NULL): no-op when *d_flag != 0 (converged CG).  For the
+ * boundary rows of a rank, which wait for the halo while the interior rows run. */
+int femb200_spmv_rows(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, int64_t row_lo,
+                      int64_t row_hi, double *d_dot, int accumulate, const double *d_flag, void *stream);
 int femb200_extract_diagonal(const femb200_plan *plan, const double *d_values, double *d_diag, void *stream);
 /* d_dinv[i] = 1 / d_diag[i] (Jacobi preconditioner) */
 int femb200_jacobi_setup(int64_t n, const double *d_diag, double *d_dinv, void *stream);

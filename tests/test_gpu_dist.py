@@ -96,8 +96,25 @@ def _nccl_worker(rank, world, port, out):
         b[bcg != 0] = gg[bcg != 0]
         bl = fem.to_device(b[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)], np.float64)
         x = torch.zeros_like(bl)
-        cg = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000)
+        cg0 = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000)            # plain: halo, then all owned rows
+        x0 = torch.zeros_like(bl)
+        cg0.solve(bl, x0)
+        cg = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000, overlap=True)
+        # the overlapped operator apply (interior rows during the halo exchange, then the rows next to the
+        # ghosts) against the oracle's global product on the owned rows
+        vg = np.random.default_rng(3).standard_normal(mg.ndofs)
+        vl = fem.to_device(vg[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)].copy(), np.float64)
+        vl[:2 * p.own_lo] = float("nan")
+        vl[2 * p.own_hi:] = float("nan")                      # ghosts must come from the neighbours
+        yl = torch.full_like(vl, float("nan"))
+        cg.mult(vl, yl)
+        torch.cuda.synchronize()
+        wantl = oracle.spmv(rowptr, colidx, vals, vg)[2 * (p.node_offset + p.own_lo):2 * (p.node_offset + p.own_hi)]
+        gotl = yl[2 * p.own_lo:2 * p.own_hi].cpu().numpy()
+        assert np.isfinite(gotl).all() and np.linalg.norm(gotl - wantl) <= 1e-12 * np.linalg.norm(wantl)
         cg.solve(bl, x)
+        assert cg0.converged and abs(cg0.iterations - cg.iterations) <= 1
+        assert ((x0 - x)[2 * p.own_lo:2 * p.own_hi].norm() / x[2 * p.own_lo:2 * p.own_hi].norm()).item() < 1e-10
         xs = dist.gather_owned(p, x)
         if rank == 0:
             want, it, _, conv = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=4000, jacobi=True)
