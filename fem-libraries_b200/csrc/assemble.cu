@@ -74,8 +74,10 @@ struct AsmArgs
    const int32_t *nptr;
    const VisitRec *vrec;
    const uint4 *frec;
+   const uint8_t *tcnt;
    const TileHdr *thdr;
    int flevels;  // levels (visits per node) of the fixed-stride fast-record layout
+   int prefetch_tiles;  // record prefetch distance in tiles (0: off)
    const uint8_t *perm;
    const uint16_t *voff;
    const int64_t *brp;
@@ -543,9 +545,21 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       FastGeo geo, geo1;
       FastCarry C;
       C.dg[0] = C.dg[1] = C.cv[0] = C.cv[1] = C.ce[0] = C.ce[1] = 0.;
+      // The records are read once, from DRAM, at the head of every tile's dependent chain: the records of the
+      // tile `prefetch_tiles` ahead (1.5 - 2 waves of resident CTAs) are pulled into L2; that tile's visit
+      // count for this rank comes from the plan's byte table, loaded together with the first record.
+      const bool pf = A.prefetch_tiles > 0 && (int64_t)blockIdx.x + A.prefetch_tiles < (int64_t)gridDim.x;
+      const int cfut = pf ? (int)A.tcnt[((int64_t)blockIdx.x + A.prefetch_tiles) * R + rank] : 0;
       raw1 = rec[0];
       raw2 = A.flevels > 1 ? rec[LS] : none;
       const int cnt = (int)(raw1.x >> 28);  // visits of this row (0: padding)
+      if (cfut > 0)
+      {
+         const uint4 *nx = rec + (int64_t)A.prefetch_tiles * A.flevels * LS;
+#pragma unroll
+         for (int j = 0; j < 8; ++j)
+            if (j < cfut) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + j * LS));
+      }
       if (0 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
       for (int c = 0; c < cnt; ++c)
       {
@@ -975,6 +989,10 @@ static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t s
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    A.flevels = p->flevels;
+   {
+      const char *env = getenv("FEMB200_ASM_PREFETCH");
+      A.prefetch_tiles = env ? atoi(env) : 8 * devinfo().sm_count;  // a good wave of resident CTAs ahead
+   }
    const size_t smem = 16 * (size_t)A.stage_units;
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
    if (d_norms)
@@ -1023,7 +1041,7 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
    FEMB_CHECK(p && d_x && d_E && d_values, "assemble_matrix: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "assemble_matrix: x_stride must be 2 or 3, got %d", x_stride);
    AsmArgs A;
-   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.frec = p->frec, A.thdr = p->thdr, A.perm = p->perm, A.voff = p->voff, A.brp = p->brp;
+   A.nnodes = p->nnodes, A.nptr = p->nptr, A.vrec = p->vrec, A.frec = p->frec, A.tcnt = p->tcnt, A.thdr = p->thdr, A.perm = p->perm, A.voff = p->voff, A.brp = p->brp;
    A.xdofmap = p->xdofmap, A.dofmap = p->dofmap, A.x = d_x, A.xs = x_stride, A.E = d_E, A.lc = lame_coef(nu);
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);

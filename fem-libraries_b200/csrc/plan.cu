@@ -292,7 +292,7 @@ k_tile_sort(int64_t nnodes, const int32_t *__restrict__ nptr, const VisitRec *__
 __global__ void __launch_bounds__(kAsmR)
 k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const int64_t *__restrict__ brp,
                const uint8_t *__restrict__ perm, const uint16_t *__restrict__ voff, const VisitRec *__restrict__ vrec,
-               int flevels, uint4 *__restrict__ frec)
+               int flevels, uint4 *__restrict__ frec, uint8_t *__restrict__ tcnt)
 {
    const int rank = threadIdx.x;
    const int64_t n0 = (int64_t)blockIdx.x * kAsmR;
@@ -300,6 +300,7 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
    if (rank >= nloc) return;
    const int64_t node = n0 + perm[n0 + rank];
    const int cnt = nptr[node + 1] - nptr[node];
+   tcnt[n0 + rank] = (uint8_t)cnt;
    const int deg = (int)(brp[node + 1] - brp[node]);
    const int r0 = 2 * (int)(brp[node] - brp[n0]);  // first 16-byte unit of scalar row 0 in the tile image
    const int32_t vbase = nptr[n0];
@@ -484,6 +485,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->nptr);
    cudaFree(p->vrec);
    cudaFree(p->frec);
+   cudaFree(p->tcnt);
    cudaFree(p->thdr);
    cudaFree(p->perm);
    cudaFree(p->voff);
@@ -609,10 +611,11 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       {
          p->flevels = maxcnt;
          const size_t nrec = (size_t)ntiles * (size_t)maxcnt * kAsmR * 2;
-         if (dev_alloc(&p->frec, nrec, &p->bytes)) return fail(1);
+         if (dev_alloc(&p->frec, nrec, &p->bytes) || dev_alloc(&p->tcnt, (size_t)ntiles * kAsmR, &p->bytes)) return fail(1);
          cudaMemsetAsync(p->frec, 0, sizeof(uint4) * nrec, st);
+         cudaMemsetAsync(p->tcnt, 0, (size_t)ntiles * kAsmR, st);
          k_fast_records<<<(unsigned)ntiles, kAsmR, 0, st>>>(nnodes, nd, p->nptr, p->brp, p->perm, p->voff, p->vrec,
-                                                          p->flevels, p->frec);
+                                                          p->flevels, p->frec, p->tcnt);
          if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
             return fail(set_error("plan_create: fast record build failed: %s", cudaGetErrorString(cudaGetLastError())));
       }

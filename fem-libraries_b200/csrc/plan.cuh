@@ -98,6 +98,7 @@ struct femb200_plan
    int32_t *nptr = nullptr;                               // [nnodes+1]
    femb::VisitRec *vrec = nullptr;                        // [nvisits], tile-sorted (see above)
    uint4 *frec = nullptr;                                 // [2 nvisits] fast-path records (triangles) or null
+   uint8_t *tcnt = nullptr;                               // [ntiles * kAsmR] visit count of (tile, rank) (with frec)
    femb::TileHdr *thdr = nullptr;                         // [ntiles] tile headers (with frec)
    int32_t flevels = 0;                                   // levels of the fixed-stride frec layout (max visits per node)
    uint8_t *perm = nullptr;                               // [ntiles * kAsmR] rank -> tile-local node
