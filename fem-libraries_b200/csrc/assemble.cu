@@ -25,9 +25,18 @@
 //   vertex p / edge (p,q):  4/3 W^{pq};  vertex / opposite edge: 0
 //   edge (p,q) / edge (r,s): 4/3 [(1+d_qs) W^{pr} + (1+d_qr) W^{ps} + (1+d_ps) W^{qr} + (1+d_pr) W^{qs}]
 // which is what the 3-point rule integrates exactly.  The row
-// owner relabels the triangle cyclically so that its own local index is vertex 0
-// / edge 0: only 3 W blocks are needed per visit.  Damaged tangents (d > 0, D
-// varying per point) and Q2 take the generic per-quadrature-point path.
+// owner relabels the triangle so that its own local index is vertex 0 / edge 0:
+// only 3 W blocks are needed per visit.
+//
+// Kernels in this file:
+//   assemble_fast_kernel   triangles (the timed path): two threads per node, one 16-byte "fast record"
+//                          per (visit, scalar row) with every address resolved at plan time, diagonal and
+//                          fan-edge columns carried in registers, L2 prefetch of the next wave's records;
+//                          damaged cells (d > 0) copy the row slices of per-cell element tangents
+//                          (cell_setup_damage_kernel + cell_tangent_kernel);
+//   assemble_kernel        the generic-record form: Q2 and FEMB200_FORCE_GENERIC (per-quadrature-point
+//                          integration per visit) and plans without fast records;
+//   dirichlet_kernel, fro / trace kernels, the fused-norm correction kernels.
 #include <algorithm>
 
 #include "constitutive.cuh"
