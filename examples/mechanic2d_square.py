@@ -12,7 +12,10 @@ stage, with the stage numbers of their timers:
                        (Jacobi-)PCG at 1e-12 (M.cc:1502-1528; BoomerAMG is third party, out of scope)
   8.1  strain/stress   DG0 fields at the cell centroids (M.cc:1551-1563, F.cc:909-942)
 
-    python examples/mechanic2d_square.py [path/to/square.msh]
+    python examples/mechanic2d_square.py [path/to/square.msh [path/to/mfem_disp_0]]
+
+With a second argument the displacement is compared with an OUT_COMP dump of the reference (M.cc:1660-1725) and the
+reference's own two error norms are printed (femb200.compare).
 
 Without an argument the mesh is rebuilt from tests/golden/square_mesh.json (the fixture derived from
 common/data/square.msh of the reference).
@@ -26,7 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "fem-libraries_b200")]
-from femb200 import fem, mesh as fm  # noqa: E402
+from femb200 import compare, fem, mesh as fm  # noqa: E402
 
 
 def fixture_msh(path: str) -> None:
@@ -71,7 +74,10 @@ def run(msh_path: str, max_refine: int = 0, damaged_facet_tags=(4,), verbose: bo
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        run(sys.argv[1])
+        out = run(sys.argv[1])
+        if len(sys.argv) > 2:                                                # IN_COMP (M.cc:1689-1725)
+            l2x, l2y = compare.compare_disp_file(sys.argv[2], out["mesh"].x, out["u"].cpu().numpy())
+            print(f"Error L2 x:{l2x}\nError L2 y:{l2y}")
     else:
         with tempfile.TemporaryDirectory() as tmp:
             p = os.path.join(tmp, "square.msh")

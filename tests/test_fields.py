@@ -173,3 +173,29 @@ def test_gpu_reference_driver_sequence(square, tmp_path):
     eps, sig = oracle.cell_strain_stress(m.etype, m.x, m.xdofmap, m.dofmap, out["E"], 0.3, u, dnod=d)
     np.testing.assert_allclose(out["strain"].cpu().numpy(), eps, rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(out["stress"].cpu().numpy(), sig, rtol=1e-9, atol=1e-9 * np.abs(sig).max())
+
+
+def test_comparison_harness_roundtrip(square, tmp_path):
+    """OUT_COMP / IN_COMP files of the reference (M.cc:1660-1725, F.cc:1036-1130): write, read back, and the
+    two matching rules give the per-component L2 norms of a known perturbation."""
+    from femb200 import compare
+    x = square["x"]
+    rng = np.random.default_rng(1)
+    u = 1e-2 * rng.standard_normal((len(x), 2))
+    p = os.path.join(str(tmp_path), "mfem_disp_0")
+    compare.write_disp_file(p, x, u.ravel())
+    assert os.path.getsize(p) == 32 * len(x)                                 # four raw doubles per vertex
+    xr, ur = compare.read_disp_file(p)
+    np.testing.assert_array_equal(xr, x)
+    np.testing.assert_array_equal(ur, u)
+    du = 1e-6 * rng.standard_normal(u.shape)
+    want = (np.sqrt((du[:, 0] ** 2).sum()), np.sqrt((du[:, 1] ** 2).sum()))
+    got = compare.compare_disp_file(p, x, (u + du).ravel())
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    perm = rng.permutation(len(x))                                           # FEniCSx rule: other dof order
+    got = compare.compare_disp_file(p, x[perm] * (1 + 1e-9), (u + du)[perm].ravel(), match="coords")
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    with pytest.raises(ValueError, match="vertex"):
+        compare.compare_disp_file(p, x + 1e-3, u.ravel())
+    with pytest.raises(ValueError, match="no vertex"):
+        compare.compare_disp_file(p, x + 1e-3, u.ravel(), match="coords")
