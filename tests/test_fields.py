@@ -199,3 +199,30 @@ def test_comparison_harness_roundtrip(square, tmp_path):
         compare.compare_disp_file(p, x + 1e-3, u.ravel())
     with pytest.raises(ValueError, match="no vertex"):
         compare.compare_disp_file(p, x + 1e-3, u.ravel(), match="coords")
+
+
+def test_gmsh_reader_errors_and_sparse_ids(tmp_path):
+    """Reader edge cases: non-contiguous node ids, elements of other types ignored, no triangles, wrong format."""
+    p = os.path.join(str(tmp_path), "a.msh")
+    with open(p, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n4\n10 0 0 0\n20 1 0 0\n30 0 1 0\n45 1 1 0\n$EndNodes\n"
+                "$Elements\n4\n1 15 2 9 9 10\n2 1 2 7 7 10 20\n3 2 2 3 3 10 20 30\n4 2 2 5 5 20 45 30\n$EndElements\n")
+    m = fm.read_gmsh22(p)
+    assert m.nnodes == 4 and m.ncells == 2
+    np.testing.assert_array_equal(m.dofmap, [[0, 1, 2], [1, 3, 2]])
+    np.testing.assert_array_equal(m.meta["cell_tags"], [3, 5])
+    np.testing.assert_array_equal(m.meta["facets"], [[0, 1]])
+    np.testing.assert_array_equal(fm.damage_seed(m, [7]), [1., 1., 0., 0.])
+    np.testing.assert_array_equal(fm.damage_seed(m, [8]), [0., 0., 0., 0.])
+    tab = fm.young_table()
+    np.testing.assert_array_equal(fm.young_from_tags(np.array([3, 205])), [tab[3], tab[5]])
+    q = os.path.join(str(tmp_path), "b.msh")
+    with open(q, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n2\n1 0 0 0\n2 1 0 0\n$EndNodes\n$Elements\n1\n1 1 2 1 1 1 2\n$EndElements\n")
+    with pytest.raises(ValueError, match="no triangles"):
+        fm.read_gmsh22(q)
+    r = os.path.join(str(tmp_path), "c.msh")
+    with open(r, "w") as f:
+        f.write("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n0\n$EndNodes\n$Elements\n0\n$EndElements\n")
+    with pytest.raises(ValueError, match="2.x"):
+        fm.read_gmsh22(r)
