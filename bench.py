@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- the hot path of the mechanic2d elasticity examples on N B200s.
 
-Workload (BASELINE.json configs[1]): P2 triangles, structured n x n cells split
-by the right diagonal (n = 1448 -> 4 193 408 elements, 16 785 218 dofs, 385 886 212
-CSR non-zeros per GPU), jittered vertices, the reference's 200-value Young-modulus
-table, nu = 0.3, Dirichlet x = 0 / x = 1.  At N > 1 every rank owns an n x n strip of
-a [0,1] x [0,N] domain (weak scaling), assembles it without communication (one
-ghost row of cells) and runs CG with NCCL halo exchange + all-reduce.
+Workload (BASELINE.json configs[3], the configuration the north-star target is quoted on): P2 triangles on
+the structured n x n mesh split by the right diagonal, n = 5792 -> 67 094 528 elements, 268 424 450 dofs,
+6 173 067 268 CSR non-zeros; jittered vertices, the reference's 200-value Young-modulus table, nu = 0.3,
+Dirichlet x = 0 / x = 1.  The SAME global mesh at every N: `--gpus N` cuts it into N strips of cell rows
+(strong scaling); N = 1 holds all of it on one GPU (49 GB of values).
 
-One timed STEP = one full matrix assembly (element integration + scatter into
-the CSR + Dirichlet rows/cols), the setJ lambda of the reference (F.cc:847-862).
-`value` = dofs assembled per second over all ranks (GDOF/s).  The same run also
-times the operator apply inside CG (SpMV alone and whole PCG iterations) and
-reports them, with their own roofline, under "cg".
+One timed STEP = one pass of the hot path = one Newton linearisation:
+    full tangent assembly (element integration + write-once gather into the CSR + Dirichlet rows/columns,
+    the setJ lambda F.cc:847-862)  +  `--cg-iters` (25) Jacobi-PCG iterations on it (operator apply with
+    the ghost update of the search direction and the all-reduce of the dot products: CGSolver::Mult
+    M.cc:1502-1528 / KSP cg F.cc:718-722).
+`value` = dofs / step time (GDOF/s), whole job.  The same run times the assembly alone, the SpMV alone and
+the PCG iterations alone (sub-keys "assembly", "cg", each with its own roofline), checks parity in-run at
+every N (golden norms of the oracle, rigid-body modes through the distributed operator, recurrence vs true
+residual of the PCG), and at N = 1 also reports BASELINE configs[2] (Q2 matrix-free), configs[4] (damaged
+reassembly at 10 / 50 / 100 % damage), the FP64 roofline of the element kernels and the CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size n]
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -33,8 +38,9 @@ for p in (ROOT, os.path.join(ROOT, "fem-libraries_b200")):
 
 import numpy as np  # noqa: E402
 
-METRIC = "assembly GDOF/s (P2 elasticity, CSR) with CG SpMV GB/s alongside"
+METRIC = "assembly GDOF/s & CG SpMV GB/s (% HBM roofline): P2 elasticity Newton linearisation (CSR assembly + PCG)"
 UNIT = "GDOF/s"
+GOLDEN = os.path.join(ROOT, "tests", "golden", "config_norms.json")
 
 
 def measured_peaks():
@@ -46,7 +52,7 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------
-# algorithmic bytes (DESIGN.md, SURVEY.md 8d)
+# algorithmic bytes (DESIGN.md section 4, SURVEY.md 8d)
 # ---------------------------------------------------------------------------
 def assembly_bytes(nnz: int, ncells: int, nnodes: int) -> int:
     """write nnz values once + read connectivity (6 x int32), E (8 B) per cell and
@@ -60,11 +66,10 @@ def spmv_bytes(nnz_blocks: int, nnodes: int) -> int:
     return 36 * nnz_blocks + nnodes * (8 + 16 + 16)
 
 
-def cg_iter_bytes(nnz_blocks: int, nnodes: int, jacobi: bool = True) -> int:
+def cg_iter_bytes(nnz_blocks: int, nnodes: int) -> int:
     """SpMV + update_xr (read d, Ad, x, r, dinv; write x, r) + update_dir (read r, dinv,
     d; write d), 16 B per node per vector pass."""
-    passes = (7 if jacobi else 6) + (4 if jacobi else 3)
-    return spmv_bytes(nnz_blocks, nnodes) + passes * 16 * nnodes
+    return spmv_bytes(nnz_blocks, nnodes) + 11 * 16 * nnodes
 
 
 class ClockSampler:
@@ -115,56 +120,62 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(n: int, rank: int, world: int):
-    """Rank-local mesh (with its ghost layers at N > 1), materials and Dirichlet data."""
-    from femb200 import mesh as fm
-    if world == 1:
-        m = fm.jitter(fm.structured_triangles(n, order=2), 0.2, seed=1234)
-        E = fm.young_per_cell(m.ncells)
-        bc, g = fm.dirichlet_markers(m)
-        return m, E, bc, g, None
-    from femb200 import dist
-    part = dist.strip_partition(n, n * world, order=2, rank=rank, world=world, jitter_amp=0.2, seed=1234)
-    return part.mesh, part.E, part.bc, part.g, part
+def host_threads() -> int:
+    """Cores this process may use: the affinity mask, NOT OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1
+    to its workers, which made the round-1 reference arm single-threaded at N > 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ---------------------------------------------------------------------------
 # reference arm: the CPU restatement of the reference (oracle) on the host cores
 # ---------------------------------------------------------------------------
-def cpu_reference(n_sample: int, steps: int, warmup: int, spmv_reps: int = 5):
+def cpu_reference(n_sample: int, steps: int, warmup: int, cg_iters: int):
+    """The same step on the host: oracle assembly (domain-decomposed over the threads, as the reference's MPI
+    ranks) + `cg_iters` Jacobi-PCG iterations (OpenMP SpMV, dots, axpys), all-core and one-thread figures, median
+    and best of `steps` repetitions."""
     from oracle import oracle
-    from femb200 import mesh as fm
-    m = fm.jitter(fm.structured_triangles(n_sample, order=2), 0.2, seed=1234)
-    E = fm.young_per_cell(m.ncells)
-    bc, _ = fm.dirichlet_markers(m)
+    from femb200 import dist
+    nt_all = host_threads()
+    part = dist.strip_partition(n_sample, n_sample, 2, 0, 1)
+    m, E, bc, g = part.mesh, part.E, part.bc, part.g
     rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
     vals = np.empty(int(rowptr[-1]))
-    nt_all = oracle.num_threads()
-    best = None
-    for nt in sorted({1, nt_all}):
-        ts = []
-        for i in range(warmup + steps):
-            t = time.perf_counter()
-            oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rowptr, colidx, bc=bc, nthreads=nt,
-                                   values=vals)
-            if i >= warmup:
-                ts.append(time.perf_counter() - t)
-        t_asm = float(np.mean(ts))
+    b = np.where(bc != 0, g, 1.0)
+    out = {}
+    for nt in sorted({1, nt_all}, reverse=True):
+        k = steps if nt == nt_all else max(1, min(steps, 2))     # the one-thread figure is context: keep it short
+        w = warmup if nt == nt_all else 0
+        ta, tc = [], []
+        for i in range(w + k):
+            t0 = time.perf_counter()
+            oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rowptr, colidx, bc=bc, nthreads=nt, values=vals)
+            t1 = time.perf_counter()
+            oracle.pcg(rowptr, colidx, vals, b, rtol=0.0, atol=0.0, maxit=cg_iters, jacobi=True, nthreads=nt)
+            t2 = time.perf_counter()
+            if i >= w:
+                ta.append(t1 - t0), tc.append(t2 - t1)
+        ts = np.array(ta) + np.array(tc)
         v = np.random.default_rng(0).standard_normal(m.ndofs)
         y = np.empty(m.ndofs)
         oracle.spmv(rowptr, colidx, vals, v, nthreads=nt, y=y)
-        t = time.perf_counter()
-        for _ in range(spmv_reps):
+        t0 = time.perf_counter()
+        reps = 5 if nt == nt_all else 2
+        for _ in range(reps):
             oracle.spmv(rowptr, colidx, vals, v, nthreads=nt, y=y)
-        t_spmv = (time.perf_counter() - t) / spmv_reps
-        rec = {"threads": nt, "assembly_s": t_asm, "assembly_gdofs": m.ndofs / t_asm / 1e9, "spmv_s": t_spmv,
-               "spmv_gbs": (12 * int(rowptr[-1]) + 24 * m.ndofs + 8) / t_spmv / 1e9,
-               "spmv_gdofs": m.ndofs / t_spmv / 1e9}
-        if best is None or rec["assembly_gdofs"] > best["assembly_gdofs"]:
-            best = rec
-    best["sample"] = (f"P2 n={n_sample} ({m.ncells} elements, {m.ndofs} dofs) of the n=1448 workload, "
-                      f"{steps} assemblies after {warmup} warm-ups, oracle/fem_oracle.c -O3 OpenMP")
-    best["ms_per_step"] = 1e3 * best["assembly_s"]
+        t_spmv = (time.perf_counter() - t0) / reps
+        out[nt] = {"threads": nt, "step_s_median": float(np.median(ts)), "step_s_best": float(ts.min()),
+                   "step_gdofs": m.ndofs / float(np.median(ts)) / 1e9, "assembly_s": float(np.median(ta)),
+                   "assembly_gdofs": m.ndofs / float(np.median(ta)) / 1e9, "cg_iter_s": float(np.median(tc)) / (cg_iters + 1),
+                   "spmv_s": t_spmv, "spmv_gbs": (12 * int(rowptr[-1]) + 24 * m.ndofs + 8) / t_spmv / 1e9,
+                   "spmv_gdofs": m.ndofs / t_spmv / 1e9, "repetitions": k}
+    best = out[nt_all]
+    best["one_thread"] = out.get(1) if nt_all != 1 else None
+    best["sample"] = (f"P2 n={n_sample} ({m.ncells} elements, {m.ndofs} dofs), same mesh family / materials / BCs as the "
+                      f"GPU arm; step = assembly + {cg_iters} Jacobi-PCG iterations; oracle/fem_oracle.c -O3 OpenMP, "
+                      f"{nt_all} threads (os.sched_getaffinity), median of {best['repetitions']}")
     return best
 
 
@@ -197,20 +208,26 @@ def reference_element_kernel_rate(n_elems: int = 400000):
             "published_melems_per_s_per_core": 5.5}
 
 
+def workload_text(n: int, rows: int) -> str:
+    return (f"P2 triangles, structured {n} x {rows} cells ({2 * n * rows} elements, {2 * (2 * n + 1) * (2 * rows + 1)} dofs), "
+            "jittered, E = reference 200-value table, nu = 0.3, Dirichlet x = 0 / x = 1 (BASELINE configs[3] at n = 5792)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(args.cpu_n, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": r["assembly_gdofs"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "P2 triangles, structured n=1448 (4 193 408 elements), assembly + CG SpMV",
-                       "timed_on": r["sample"]},
-            "cpu_baseline": {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                             "sample": r["sample"]},
-            "cg": {"spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"]},
-            "e2e": {"value": r["assembly_gdofs"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    r = cpu_reference(args.cpu_n, args.steps, args.warmup, args.cg_iters)
+    line = {"impl": "reference", "metric": METRIC, "value": r["step_gdofs"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["step_s_median"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(args.n, args.n), "timed_on": r["sample"], "cg_iters": args.cg_iters},
+            "cpu_baseline": {"value": r["step_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                             "sample": r["sample"], "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
+            "assembly": {"gdofs": r["assembly_gdofs"], "ms": 1e3 * r["assembly_s"]},
+            "cg": {"spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"], "cg_iter_ms": 1e3 * r["cg_iter_s"]},
+            "one_thread": r["one_thread"],
+            "e2e": {"value": r["step_gdofs"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -218,60 +235,47 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as td
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from femb200 import fem
-    K, W, n = args.steps, max(args.warmup, 0), args.n
+class Env:
+    """rank / world, barrier, max-over-ranks timing."""
 
-    m, E, bc, g, part = build_problem(n, rank, world)
-    form = fem.ElasticityForm(m, E, 0.3)
-    # load the library's CUDA module (lazy, one-off) outside the pattern-build timing
-    from femb200 import mesh as _fm
-    _tiny = _fm.structured_triangles(4, order=2)
-    fem.create_matrix(fem.ElasticityForm(_tiny, _fm.young_per_cell(_tiny.ncells), 0.3))
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    A = fem.create_matrix(form)
-    A.set_bcs([fem.DirichletBC(bc, g)])
-    torch.cuda.synchronize()
-    pattern_ms = 1e3 * (time.perf_counter() - t0)
-    owned_nodes = m.nnodes if part is None else part.n_owned
-    owned_dofs = 2 * owned_nodes
-    owned_cells = m.ncells if part is None else part.n_owned_cells
+    def __init__(self):
+        import torch
+        import torch.distributed as td
+        self.torch, self.td = torch, td
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            td.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.td.barrier()
+        self.torch.cuda.synchronize()
 
-    def maxtime(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        td.all_reduce(t, op=td.ReduceOp.MAX)
+    def maxf(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
         return float(t.item())
 
-    def sumint(v: int) -> int:
-        if world == 1:
+    def sumi(self, v: int) -> int:
+        if self.world == 1:
             return v
-        t = torch.tensor([v], dtype=torch.int64, device="cuda")
-        td.all_reduce(t)
+        t = self.torch.tensor([v], dtype=self.torch.int64, device="cuda")
+        self.td.all_reduce(t)
         return int(t.item())
 
-    def timed(fn, k):
-        """k calls bracketed by barrier + synchronize; device time by CUDA events on the
-        launching stream; returns (total ms max over ranks, per-call ms list of this rank)."""
+    def timed(self, fn, k):
+        """k calls bracketed by barrier + synchronize; device time by CUDA events on the launching stream;
+        returns (total ms, max over ranks; per-call ms of this rank)."""
+        torch = self.torch
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
-        barrier()
+        self.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for a, b in evs:
@@ -279,258 +283,429 @@ def run_b200(args):
             fn()
             b.record()
         e.record()
-        barrier()
-        return maxtime(s.elapsed_time(e)), [a.elapsed_time(b) for a, b in evs]
+        self.barrier()
+        return self.maxf(s.elapsed_time(e)), [a.elapsed_time(b) for a, b in evs]
 
-    # ---- assembly: the timed step -----------------------------------------
-    def step():
+    def close(self):
+        if self.world > 1:
+            self.td.destroy_process_group()
+
+
+def parity_checks(env, fem, dist, A, form, part, op, n, rows, bvec):
+    """In-run parity (every N): (1) all-reduced |K|_F^2 and trace K of the constrained matrix against the oracle's
+    golden sums for this workload (tests/golden/config_norms.json, when n is listed there); (2) rigid-body modes
+    through the DISTRIBUTED operator: K_unconstrained t = 0 for the two translations and the rotation (exact
+    property of any elasticity tangent; exercises assembly + ghost update + owned-row SpMV); returns a dict."""
+    torch = env.torch
+    lo, hi = 2 * part.own_lo, 2 * part.own_hi
+    out = {"ok": True}
+    # (2) first: needs the unconstrained matrix
+    fem.assemble_matrix_nobc(A, form)
+    x = form.x
+    modes = {"tx": lambda: torch.stack([torch.ones_like(x[:, 0]), torch.zeros_like(x[:, 0])], dim=1),
+             "ty": lambda: torch.stack([torch.zeros_like(x[:, 0]), torch.ones_like(x[:, 0])], dim=1),
+             "rot": lambda: torch.stack([-x[:, 1], x[:, 0]], dim=1)}
+    nrm = torch.zeros(2, dtype=torch.float64, device="cuda")
+    fem.capi.call("femb200_matrix_norms", A.plan, fem._p(A.values), fem._p(nrm), fem._stream())
+    y = torch.empty(2 * x.shape[0], dtype=torch.float64, device="cuda")
+    worst = 0.0
+    for name, make in modes.items():
+        v = make().reshape(-1).contiguous()
+        v[:lo] = float("nan")
+        v[hi:] = float("nan")          # the ghosts must come through the transport
+        op.mult(v, y)
+        r = torch.stack([y[lo:hi].abs().max(), torch.zeros((), dtype=torch.float64, device="cuda")])
+        if env.world > 1:
+            env.td.all_reduce(r, op=env.td.ReduceOp.MAX)
+        worst = max(worst, float(r[0].item()))
+    # local Frobenius norm is enough for the scale (same order on every rank)
+    scale = float(np.sqrt(nrm[0].item()))
+    out["rigid_body_max_abs_over_fro"] = worst / scale
+    out["ok"] &= bool(np.isfinite(worst) and worst / scale < 1e-12)
+    # (1) the constrained matrix (left in A.values for the timed steps)
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    fem.assemble_matrix(A, form, norms_out=sums)
+    if part.world > 1 or part.own_lo != 0 or part.own_hi != A.nnodes:
+        # owned rows only: recompute on the owned value range
+        sums = owned_norms(torch, fem, A, part)
+    op.allreduce_sum(sums)
+    f2, tr = (float(v) for v in sums.tolist())
+    out["fro2"], out["trace"] = f2, tr
+    gold = None
+    if os.path.exists(GOLDEN) and rows == n:
+        with open(GOLDEN) as f:
+            gold = json.load(f).get(str(n))
+    if gold is not None:
+        out["fro2_rel_err"] = abs(f2 - gold["fro2"]) / gold["fro2"]
+        out["trace_rel_err"] = abs(tr - gold["trace"]) / abs(gold["trace"])
+        out["golden"] = "tests/golden/config_norms.json (oracle, strip by strip)"
+        out["ok"] &= out["fro2_rel_err"] < 1e-12 and out["trace_rel_err"] < 1e-12
+    else:
+        out["golden"] = None
+    return out
+
+
+def owned_norms(torch, fem, A, part):
+    """(|K|_F^2, trace K) over the owned rows of this rank (device; torch reductions on slices: checker code)."""
+    brp, _ = A.block_csr()
+    v0, v1 = 4 * int(brp[part.own_lo].item()), 4 * int(brp[part.own_hi].item())
+    f2 = torch.zeros((), dtype=torch.float64, device="cuda")
+    chunk = 1 << 28
+    for s in range(v0, v1, chunk):
+        seg = A.values[s:min(s + chunk, v1)]
+        f2 += torch.dot(seg, seg)
+    d = A.diagonal()[2 * part.own_lo:2 * part.own_hi]
+    return torch.stack([f2, d.sum()])
+
+
+def run_b200(args):
+    env = Env()
+    torch, td, world, rank = env.torch, env.td, env.world, env.rank
+    from femb200 import fem, dist
+    K, W, n = args.steps, max(args.warmup, 3), args.n
+    rows = args.rows if args.rows else n
+    if rows % world:
+        raise SystemExit(f"bench.py: {rows} cell rows do not split into {world} strips")
+    t0 = time.perf_counter()
+    part = dist.strip_partition_device(n, rows, rank, world, jitter_amp=0.2, seed=1234)
+    m = part.mesh
+    torch.cuda.synchronize()
+    mesh_s = time.perf_counter() - t0
+    form = fem.ElasticityForm(m, part.E, 0.3)
+    # load the library's CUDA module (lazy, one-off) outside the pattern-build timing
+    from femb200 import mesh as _fm
+    _tiny = _fm.structured_triangles(4, order=2)
+    fem.create_matrix(fem.ElasticityForm(_tiny, _fm.young_per_cell(_tiny.ncells), 0.3))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    A = fem.create_matrix(form)
+    A.set_bcs([fem.DirichletBC(part.bc, part.g)])
+    torch.cuda.synchronize()
+    pattern_ms = 1e3 * (time.perf_counter() - t0)
+    owned_nodes, owned_dofs = part.n_owned, 2 * part.n_owned
+    total_dofs, total_cells = env.sumi(owned_dofs), env.sumi(part.n_owned_cells)
+    lo, hi = 2 * part.own_lo, 2 * part.own_hi
+
+    op = dist.DistOperator(A, part, transport=args.transport)
+    bvec = torch.where(part.bc != 0, part.g, torch.ones_like(part.g))
+    parity = parity_checks(env, fem, dist, A, form, part, op, n, rows, bvec)
+    dcg = dist.DistCG(A, part, rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters, op=op, use_graph=not args.no_graph)
+    xsol = torch.zeros_like(bvec)
+    ytmp = torch.empty_like(bvec)
+    vtmp = bvec.clone()
+
+    def asm():
         fem.assemble_matrix(A, form)
+
+    def cg_run():
+        dcg.solve(bvec, xsol, fixed_iters=args.cg_iters)
+
+    def spmv_run():
+        op.mult(vtmp, ytmp)            # ghost update, then the owned rows
+
+    def step():
+        asm()
+        cg_run()
 
     for _ in range(W):
         step()
-    sampler = ClockSampler(local)
+    spmv_run()
+    sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
-    total_ms, per_call = timed(step, K)
-    asm_ms = total_ms / K
-    kernel_ms = float(np.mean(per_call))
-    total_dofs = sumint(owned_dofs)
-    total_cells = sumint(owned_cells)
-    value = total_dofs / (asm_ms * 1e-3) / 1e9
-
-    # ---- operator apply inside CG ------------------------------------------
-    if part is None:
-        bvec = fem.to_device(np.where(bc != 0, g, 1.0), np.float64)
-        cg = fem.CGSolver(rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters)
-        cg.SetOperator(A)
-        cg.SetPreconditioner("jacobi")
-        xsol = torch.empty_like(bvec)
-        ytmp = torch.empty_like(bvec)
-
-        def cg_run():
-            cg.Mult(bvec, xsol, fixed_iters=args.cg_iters)
-
-        def spmv_run():
-            A.mult(bvec, ytmp)
-    else:
-        from femb200 import dist
-        dcg = dist.DistCG(A, part, rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters)
-        bvec = fem.to_device(np.where(bc != 0, g, 1.0), np.float64)
-        xsol = torch.zeros_like(bvec)
-        ytmp = torch.empty_like(bvec)
-
-        def cg_run():
-            dcg.solve(bvec, xsol, fixed_iters=args.cg_iters)
-
-        def spmv_run():
-            dcg.mult(bvec, ytmp)     # halo exchange, then the owned rows
-
-    for _ in range(max(1, min(W, 2))):
-        cg_run()
-        spmv_run()
+    step_total, _ = env.timed(step, K)
+    step_ms = step_total / K
+    value = total_dofs / (step_ms * 1e-3) / 1e9
+    asm_total, asm_calls = env.timed(asm, K)
+    asm_ms = asm_total / K
     kc = max(1, min(K, 5))
-    cg_total, _ = timed(cg_run, kc)
-    # one PCG call = setup (init + first apply) + cg_iters iterations: count cg_iters + 1 applies
-    cg_iter_ms = cg_total / kc / (args.cg_iters + 1)
+    cg_total, _ = env.timed(cg_run, kc)
+    cg_iter_ms = cg_total / kc / (args.cg_iters + 1)      # one PCG call = setup (init + first apply) + cg_iters iterations
     ks = max(K, 10)
-    spmv_total, spmv_calls = timed(spmv_run, ks)
+    spmv_total, spmv_calls = env.timed(spmv_run, ks)
     spmv_ms = spmv_total / ks
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end: host buffers through the public API -------------------
-    gv = form.geometry_vertices                         # the geometry is P1: only its vertices are inputs
-    hx = torch.from_numpy(np.ascontiguousarray(m.x[gv])).pin_memory()
-    dxv = torch.empty(hx.shape, dtype=torch.float64, device="cuda")
-    hE = torch.from_numpy(np.ascontiguousarray(E)).pin_memory()
-    # Two steps in flight: a copy stream uploads the inputs of step k + 1 (double-buffered device
-    # inputs) while the compute stream assembles step k; every step's H2D copies, its assembly, its
-    # checksum and the D2H read of that checksum are inside the timed region, and the host reads the
-    # result of step k - 1 before it enqueues step k + 1.
-    copy_stream = torch.cuda.Stream()
-    comp = torch.cuda.current_stream()
-    dxv = [torch.empty(hx.shape, dtype=torch.float64, device="cuda") for _ in range(2)]
-    dE = [torch.empty(hE.shape, dtype=torch.float64, device="cuda") for _ in range(2)]
-    hout = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in range(2)]
-    dout = [torch.empty(2, dtype=torch.float64, device="cuda") for _ in range(2)]
-    ev_up = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    state = {"k": 0}
+    # PCG consistency (parity check 3): the recurrence residual of the last solve equals b - A x through the
+    # distributed operator, and (where the oracle's PCG state is committed) the 25-iteration iterate matches it
+    r_rec = op.vectors()[0][lo:hi].clone()
+    op.mult(xsol, ytmp)
+    chk = torch.stack([((bvec - ytmp)[lo:hi] - r_rec).pow(2).sum(), bvec[lo:hi].pow(2).sum(), xsol[lo:hi].pow(2).sum()])
+    op.allreduce_sum(chk)
+    parity["pcg_residual_consistency"] = float((chk[0] / chk[1]).sqrt().item())
+    parity["pcg_x_norm"] = float(chk[2].sqrt().item())
+    parity["pcg_final_norm"] = dcg.final_norm
+    parity["ok"] &= parity["pcg_residual_consistency"] < 1e-10
+    if os.path.exists(GOLDEN) and rows == n and args.cg_iters == 25:
+        with open(GOLDEN) as f:
+            gold = json.load(f).get(str(n), {}).get("pcg25")
+        if gold:
+            parity["pcg_x_norm_rel_err"] = abs(parity["pcg_x_norm"] - gold["x_norm"]) / gold["x_norm"]
+            parity["pcg_final_norm_rel_err"] = abs(dcg.final_norm - gold["final_norm"]) / gold["final_norm"]
+            parity["ok"] &= parity["pcg_x_norm_rel_err"] < 1e-10 and parity["pcg_final_norm_rel_err"] < 1e-8
 
-    def e2e_step():
-        k = state["k"]
-        b = k & 1
-        with torch.cuda.stream(copy_stream):
-            if k >= 2:
-                copy_stream.wait_event(ev_done[b])         # the buffers of step k - 2 are free
-            dxv[b].copy_(hx, non_blocking=True)            # H2D: vertex coordinates of this step
-            dE[b].copy_(hE, non_blocking=True)             # H2D: material field of this step
-            ev_up[b].record(copy_stream)
-        comp.wait_event(ev_up[b])
-        form.set_geometry(dxv[b])
-        form.set_E(dE[b])
-        fem.assemble_matrix(A, form, norms_out=dout[b])   # assembly + Dirichlet, (|K|_F^2, trace K) fused in
-        hout[b].copy_(dout[b], non_blocking=True)          # D2H: (|K|_F^2, trace K)
-        ev_done[b].record(comp)
-        if k >= 1:
-            ev_done[1 - b].synchronize()                   # the host consumes the result of step k - 1
-            state["last"] = (float(hout[1 - b][0]), float(hout[1 - b][1]))
-        state["k"] = k + 1
+    # transports side by side at N > 1: the NCCL baseline of the same iteration
+    comm = {"transport": op.transport, "graph": not args.no_graph}
+    if world > 1 and op.transport == "p2p" and not args.no_nccl_compare:
+        op.use("nccl")
+        for _ in range(2):
+            cg_run()
+        t_nccl, _ = env.timed(cg_run, kc)
+        comm["nccl_cg_iter_ms"] = t_nccl / kc / (args.cg_iters + 1)
+        comm["p2p_cg_iter_ms"] = cg_iter_ms
+        op.use("p2p")
 
-    def e2e_drain():
-        torch.cuda.synchronize()
-        b = (state["k"] - 1) & 1
-        state["last"] = (float(hout[b][0]), float(hout[b][1]))
+    # ---- end to end: one Newton linearisation through the public API, host buffers ------------------
+    e2e = e2e_newton(env, fem, dist, form, part, op, A, args, total_dofs)
 
-    for _ in range(max(1, min(W, 2))):
-        e2e_step()
-    e2e_drain()
-
-    def e2e_all():
-        for _ in range(K):
-            e2e_step()
-        e2e_drain()
-
-    e2e_total, _ = timed(e2e_all, 1)
-    e2e_ms = e2e_total / K
-    e2e_value = total_dofs / (e2e_ms * 1e-3) / 1e9
-    h2d = hx.numel() * 8 + hE.numel() * 8
-    fro, tr = float(np.sqrt(state["last"][0])), float(state["last"][1])
-
+    nnzb_owned = part.owned_nnz_blocks(A)
+    plan_bytes = A.plan_bytes
+    a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)            # this rank's launch (ghost cell row included)
+    s_bytes = spmv_bytes(nnzb_owned, owned_nodes)
+    c_bytes = cg_iter_bytes(nnzb_owned, owned_nodes)
     if rank != 0:
-        if world > 1:
-            td.destroy_process_group()
+        if world == 1:
+            pass
+        op.close()
+        env.close()
         return
 
     peak, peak_src = measured_peaks()
-    a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)
-    s_bytes = spmv_bytes(A.nnz_blocks if part is None else part.owned_nnz_blocks(A), owned_nodes)
-    c_bytes = cg_iter_bytes(A.nnz_blocks if part is None else part.owned_nnz_blocks(A), owned_nodes)
-    a_gbs = a_bytes / (kernel_ms * 1e-3) / 1e9
-    s_gbs = s_bytes / (float(np.mean(spmv_calls)) * 1e-3) / 1e9
-    c_gbs = c_bytes / (cg_iter_ms * 1e-3) / 1e9
-
+    a_ms = float(np.mean(asm_calls))
+    s_ms = float(np.mean(spmv_calls))
+    a_gbs, s_gbs, c_gbs = a_bytes / (a_ms * 1e-3) / 1e9, s_bytes / (s_ms * 1e-3) / 1e9, c_bytes / (cg_iter_ms * 1e-3) / 1e9
+    # PCG call: init, scalar, apply, scalar; cg_iters - 1 full iterations of 5 kernels; the last one 2; one ghost-update
+    # kernel per apply on the P2P transport
+    launches_pcg = 4 + 5 * (args.cg_iters - 1) + 2 + (args.cg_iters if (world > 1 and op.transport == "p2p") else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": asm_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"P2 triangles, structured n={n} per GPU ({m.ncells} local elements incl. ghost row), "
-                               "jittered, E = reference 200-value table, nu = 0.3; step = full CSR assembly + Dirichlet",
-                   "elements": total_cells, "dofs": total_dofs, "nnz_per_gpu": A.nnz,
-                   "l2": "inputs + outputs per step (3.5 GB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"strips x{world}" if world > 1 else "single GPU", "cg_iters": args.cg_iters,
-                   "pattern_build_ms": pattern_ms},
-        "roofline": {"kernel": "assemble_fast_kernel<P2> (+ cell_setup_kernel, dirichlet_kernel)", "bound": "hbm", "achieved": a_gbs,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": a_gbs / peak,
-                     "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": kernel_ms,
-                     "traffic": traffic_from_profile("assemble") if (n == 1448 and world == 1) else None},
-        "cg": {"spmv_ms": spmv_ms, "spmv_gbs": s_gbs, "spmv_frac": s_gbs / peak, "spmv_gdofs": owned_dofs * world / (spmv_ms * 1e-3) / 1e9,
-               "spmv_algorithmic_bytes": s_bytes, "spmv_traffic": traffic_from_profile("spmv") if (n == 1448 and world == 1) else None,
+        "config": {"workload": workload_text(n, rows), "step": f"full CSR assembly + Dirichlet, then {args.cg_iters} Jacobi-PCG "
+                   "iterations (ghost update + all-reduces inside at N > 1)", "elements": total_cells, "dofs": total_dofs,
+                   "nnz_rank0": A.nnz, "plan_bytes_rank0": plan_bytes,
+                   "l2": "values + vectors per step (>= 6 GB per GPU at N = 8) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"{world} strips of cell rows, one ghost cell row, owner = lowest rank" if world > 1 else "single GPU",
+                   "cg_iters": args.cg_iters, "pattern_build_ms": pattern_ms, "mesh_generation_s": mesh_s},
+        "parity": parity,
+        "roofline": {"kernel": "spmv_tma_kernel<DOT,64,2,4> (dominant: cg_iters + 1 launches per step)", "bound": "hbm",
+                     "achieved": s_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": s_gbs / peak,
+                     "algorithmic_bytes_per_launch": s_bytes, "kernel_ms": s_ms,
+                     "traffic": traffic_from_profile("spmv", n, world), "note": "rank 0's owned rows; timed alone over "
+                     f"{ks} launches (with the ghost update at N > 1)"},
+        "assembly": {"ms": asm_ms, "gdofs": total_dofs / (asm_ms * 1e-3) / 1e9,
+                     "roofline": {"kernel": "assemble_fast_kernel<P2> (+ cell_setup_kernel, dirichlet_kernel)", "bound": "hbm",
+                                  "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak,
+                                  "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": a_ms,
+                                  "traffic": traffic_from_profile("assemble", n, world)}},
+        "cg": {"spmv_ms": spmv_ms, "spmv_gbs": s_gbs, "spmv_frac": s_gbs / peak, "spmv_gdofs": total_dofs / (spmv_ms * 1e-3) / 1e9,
                "cg_iter_ms": cg_iter_ms, "cg_iter_gbs": c_gbs, "cg_iter_frac": c_gbs / peak,
-               "cg_iter_gdofs": total_dofs / (cg_iter_ms * 1e-3) / 1e9, "precond": "jacobi", "iters": args.cg_iters},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 16, "what": "per step: pinned host vertex coordinates + E -> device (copy stream, "
-                                                  "double-buffered, overlapping the previous step's assembly), set_geometry, "
-                                                  "assemble_matrix(A, form, bcs, norms_out) (Frobenius norm and trace fused into the assembly pass), 16-byte read back consumed by "
-                                                  "the host; K steps timed as a whole", "fro": fro, "trace": tr},
-        "gpu_launches": 3 * K,  # cell_setup + assemble + dirichlet per step
+               "cg_iter_gdofs": total_dofs / (cg_iter_ms * 1e-3) / 1e9, "precond": "jacobi", "iters": args.cg_iters,
+               "comm": comm},
+        "e2e": e2e,
+        "gpu_launches": K * (3 + launches_pcg),
         "clocks": clocks,
     }
-    if world == 1:
-        line["matrix_free"] = pa_probe(fem, form, bc, g, m, timed, peak)
-    if world == 1 and args.extras:
-        line["extras"] = extras(fem, timed, peak)
+    del dcg, xsol, ytmp, vtmp, bvec
+    op.close()
+    if world == 1 and not args.skip_extras:
+        del A, form, part, m, op
+        torch.cuda.empty_cache()
+        line["extras"] = extras(env, fem, peak, args)
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(args.cpu_n, 3, 1)
-        line["cpu_baseline"] = {"value": r["assembly_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                                "sample": r["sample"], "spmv_gbs": r["spmv_gbs"], "spmv_gdofs": r["spmv_gdofs"],
+        r = cpu_reference(args.cpu_baseline_n, 3, 1, args.cg_iters)
+        line["cpu_baseline"] = {"value": r["step_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                "sample": r["sample"], "assembly_gdofs": r["assembly_gdofs"], "spmv_gbs": r["spmv_gbs"],
+                                "spmv_gdofs": r["spmv_gdofs"], "one_thread": r["one_thread"],
                                 "reference_element_kernel": reference_element_kernel_rate()}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        td.destroy_process_group()
+    env.close()
+    if not parity["ok"]:
+        raise SystemExit("bench.py: in-run parity check FAILED: " + json.dumps(parity))
 
 
-def pa_probe(fem, form, bc, g, m, timed, peak):
-    """Matrix-free apply (AssemblePA / AddMultPA role) of the same operator on the same mesh."""
-    import torch
-    pa = fem.PAOperator(form, bcs=[fem.DirichletBC(bc, g)])
-    v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
-    y = torch.empty_like(v)
-    for _ in range(3):
-        pa.mult(v, y)
-    tot, _ = timed(lambda: pa.mult(v, y), 10)
-    ms = tot / 10
-    nbytes = m.nnodes * 32 + m.ncells * (8 * (2 * m.nv + 2) + 4 * m.nd + 4)
-    return {"pa_apply_ms": ms, "gdofs": m.ndofs / (ms * 1e-3) / 1e9, "gbs": nbytes / (ms * 1e-3) / 1e9,
-            "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": nbytes}
+def e2e_newton(env, fem, dist, form, part, op, A, args, total_dofs):
+    """The same step end to end through the public API with HOST buffers: per step the current iterate u goes up
+    from pinned host memory, NewtonSolver.residual (F(u) + lifting) and NewtonSolver.increment (tangent assembly +
+    Dirichlet + `cg_iters` PCG iterations) run, and the increment du comes back to pinned host memory.  Geometry,
+    materials and the pattern are resident (uploaded once: they do not change between Newton iterations)."""
+    torch = env.torch
+    K = max(1, min(args.steps, args.e2e_steps))
+    ns = fem.NewtonSolver.__new__(fem.NewtonSolver)          # reuse the bench's matrix / operator (no second 49 GB)
+    ns.form, ns.f, ns.A, ns.part = form, None, A, part
+    ns.rel_tol, ns.abs_tol, ns.max_iter, ns.convention = 1e-7, 5e-8, 10, "mfem"
+    ns.g = part.g
+    ns.cg = dist.DistCG(A, part, rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters, op=op, jacobi=False,
+                        use_graph=not args.no_graph)
+    ns._lo, ns._hi = 2 * part.own_lo, 2 * part.own_hi
+    ns._work = torch.empty(2 * A.ndofs, dtype=torch.float64, device="cuda")
+    ns._b = torch.empty(A.ndofs, dtype=torch.float64, device="cuda")
+    ns._du = torch.zeros(A.ndofs, dtype=torch.float64, device="cuda")
+    ns._nrm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ns._lifted, ns._tangent_ready = False, False
+    ns.residual_norms, ns.linear_iterations = [], []
+    nloc = A.ndofs
+    hu = torch.zeros(nloc, dtype=torch.float64).pin_memory()
+    hu.copy_(torch.from_numpy(1e-4 * np.cos(np.arange(nloc, dtype=np.float64) * 1e-3)))
+    hdu = torch.empty(ns._hi - ns._lo, dtype=torch.float64).pin_memory()
+    du_dev = torch.empty(nloc, dtype=torch.float64, device="cuda")
+
+    def e2e_step():
+        du_dev.copy_(hu, non_blocking=True)                       # H2D: the iterate (owned + ghost window)
+        ns._lifted = False
+        b = ns.residual(du_dev)                                   # F(u), unconstrained tangent, lifting
+        du = ns.increment(b, fixed_iters=args.cg_iters)           # Dirichlet rows/cols, Jacobi, PCG
+        hdu.copy_(du[ns._lo:ns._hi], non_blocking=True)           # D2H: the increment (owned dofs)
+        torch.cuda.current_stream().synchronize()                 # the host consumes du
+
+    for _ in range(2):
+        e2e_step()
+    tot, _ = env.timed(lambda: [e2e_step() for _ in range(K)], 1)
+    ms = tot / K
+    return {"value": total_dofs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": K,
+            "h2d_bytes_per_step": int(hu.numel() * 8), "d2h_bytes_per_step": int(hdu.numel() * 8),
+            "du_checksum": float(hdu.abs().sum().item()),
+            "what": "per step and per rank: pinned host u -> device, NewtonSolver.residual (F(u) + apply_lifting; this "
+                    "residual assembly and one extra SpMV are work the device-timed `value` does not contain), "
+                    "NewtonSolver.increment (tangent assembly + Dirichlet + Jacobi + PCG), owned du -> pinned host, "
+                    "host waits for it; geometry / materials / pattern resident (constant across Newton iterations)"}
 
 
-def extras(fem, timed, peak):
-    """Other BASELINE configs on one GPU (developer flag --extras): config 3 (Q2 quads, matrix-free,
-    16.8 M elements) and the config-5 workload (damaged-tangent reassembly, closed form and AD)."""
-    import torch
-    from femb200 import mesh as fm
+def extras(env, fem, peak, args):
+    """The other BASELINE configurations on one GPU, in the default run: configs[2] (Q2 quads, matrix-free CG,
+    16.8 M elements), configs[4] (damaged-tangent reassembly of 16.8 M P2 elements at 10 / 50 / 100 % damaged cells,
+    closed form and AD), and the FP64 roofline of the element kernels."""
+    torch = env.torch
+    from femb200 import mesh as fm, dist
+    capi = fem.capi
     out = {}
+    # ---- FP64 peak (measured) + element kernels -------------------------------------------------------
+    nb, fl = ctypes.c_int64(), ctypes.c_double()
+    capi.call("femb200_fp64_probe", 8, 4096, None, ctypes.byref(nb), ctypes.byref(fl), None)
+    buf = torch.empty(nb.value * 256, dtype=torch.float64, device="cuda")
+    probe = lambda: capi.call("femb200_fp64_probe", 8, 4096, fem._p(buf), ctypes.byref(nb), ctypes.byref(fl), fem._stream())
+    for _ in range(3):
+        probe()
+    tot, calls = env.timed(probe, 10)
+    fp64_peak = fl.value / (min(calls) * 1e-3) / 1e12
+    out["fp64"] = {"peak_tflops": fp64_peak, "how": "femb200_fp64_probe: 8 x 148 blocks x 256 threads x 8 independent DFMA "
+                   "chains x 4096 rounds, best of 10, CUDA events", "flops_per_launch": fl.value}
+    n = 1448
+    p = dist.strip_partition_device(n, n, 0, 1)
+    m = p.mesh
+    form = fem.ElasticityForm(m, p.E, 0.3)
+    Ae = torch.empty((m.ncells, 12, 12), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        fem.tabulate_tensor_batched(form, out=Ae)
+    tot, calls = env.timed(lambda: fem.tabulate_tensor_batched(form, out=Ae), 10)
+    ms = float(np.mean(calls))
+    FL_TAB = 36 * 3 * 38 + 3 * 70     # 36 block pairs x 3 points x bdb_block (38 flops) + 3 x point geometry (~70)
+    out["fp64"]["tabulate_kernel_p2"] = {
+        "ms": ms, "cells": m.ncells, "flops_per_element": FL_TAB, "tflops": FL_TAB * m.ncells / (ms * 1e-3) / 1e12,
+        "frac_fp64": FL_TAB * m.ncells / (ms * 1e-3) / 1e12 / fp64_peak, "bytes_written_per_element": 1152,
+        "frac_hbm": (1152 + 40) * m.ncells / (ms * 1e-3) / 1e9 / peak,
+        "what": "femb200_tabulate_tensor_batched (ufcx / AssembleElementGrad surface): all 12 x 12 element tangents to HBM"}
+    del Ae
+    A = fem.create_matrix(form)
+    for _ in range(3):
+        fem.assemble_matrix(A, form)
+    tot, calls = env.timed(lambda: fem.assemble_matrix(A, form), 10)
+    ms = float(np.mean(calls))
+    FL_FAST = 900
+    out["fp64"]["assemble_fast_kernel_p2"] = {
+        "ms": ms, "cells": m.ncells, "flops_per_element": FL_FAST, "tflops": FL_FAST * m.ncells / (ms * 1e-3) / 1e12,
+        "frac_fp64": FL_FAST * m.ncells / (ms * 1e-3) / 1e12 / fp64_peak,
+        "frac_hbm": assembly_bytes(A.nnz, m.ncells, m.nnodes) / (ms * 1e-3) / 1e9 / peak,
+        "what": "the fused element + gather kernel of the timed path at n = 1448 (closed-form P2 blocks: ~0.9 kflop per "
+                "element); HBM-bound, the FP64 pipe idles"}
+    out["config2_p2_n1448"] = {"assembly_ms": ms, "assembly_gdofs": m.ndofs / (ms * 1e-3) / 1e9,
+                               "assembly_frac_hbm": out["fp64"]["assemble_fast_kernel_p2"]["frac_hbm"]}
+    del A, form, p, m
+    torch.cuda.empty_cache()
+
+    # ---- config 3: Q2 matrix-free ----------------------------------------------------------------------
     n = 4096
     m = fm.jitter(fm.structured_quads_q2(n), 0.2, seed=1234)
     E = fm.young_per_cell(m.ncells)
     bc, g = fm.dirichlet_markers(m)
     form = fem.ElasticityForm(m, E, 0.3)
-    r = pa_probe(fem, form, bc, g, m, timed, peak)
     pa = fem.PAOperator(form, bcs=[fem.DirichletBC(bc, g)])
+    v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(v)
+    for _ in range(3):
+        pa.mult(v, y)
+    tot, calls = env.timed(lambda: pa.mult(v, y), 10)
+    ms = float(np.mean(calls))
+    nbytes = m.nnodes * 32 + m.ncells * (8 * (2 * m.nv + 2) + 4 * m.nd + 4)
+    r = {"workload": f"Q2 quads n={n}: {m.ncells} elements, {m.ndofs} dofs, 3x3 Gauss, sum-factorised (BASELINE configs[2])",
+         "pa_apply_ms": ms, "gdofs": m.ndofs / (ms * 1e-3) / 1e9, "gbs": nbytes / (ms * 1e-3) / 1e9,
+         "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": nbytes,
+         "bytes_per_element": nbytes / m.ncells, "survey_bytes_per_element": 596,
+         "frac_at_survey_bytes": 596 * m.ncells / (ms * 1e-3) / 1e9 / peak}
     cg = fem.CGSolver(rel_tol=0.0, max_iter=10)
     cg.SetOperator(pa)
     cg.SetPreconditioner("jacobi")
     b = torch.ones(m.ndofs, dtype=torch.float64, device="cuda")
     x = torch.empty_like(b)
     cg.Mult(b, x, fixed_iters=10)
-    tot, _ = timed(lambda: cg.Mult(b, x, fixed_iters=10), 3)
-    r.update({"workload": f"Q2 quads n={n}: {m.ncells} elements, {m.ndofs} dofs, 3x3 Gauss, sum-factorised",
-              "pa_cg_iter_ms": tot / 3 / 11, "pa_cg_iter_gdofs": m.ndofs / (tot / 3 / 11 * 1e-3) / 1e9,
-              "survey_bytes_per_element": 596, "frac_at_survey_bytes": 596 * m.ncells / (r["pa_apply_ms"] * 1e-3) / 1e9 / peak})
+    tot, _ = env.timed(lambda: cg.Mult(b, x, fixed_iters=10), 3)
+    r.update({"pa_cg_iter_ms": tot / 3 / 11, "pa_cg_iter_gdofs": m.ndofs / (tot / 3 / 11 * 1e-3) / 1e9})
     out["config3_q2_matrix_free"] = r
-    del pa, cg, form, b, x
+    del pa, cg, form, b, x, v, y
     torch.cuda.empty_cache()
-    n = 1448
-    m = fm.jitter(fm.structured_triangles(n, order=2), 0.2, seed=1234)
-    E = fm.young_per_cell(m.ncells)
-    d = fm.damage_band(m)
-    u = 1e-3 * np.random.default_rng(0).standard_normal(m.ndofs)
-    res = {"workload": f"P2 n={n}, damage band on {100 * float((d[m.xdofmap].mean(axis=1) > 0).mean()):.1f} % of the cells, "
-                       "values-only reassembly on a frozen pattern"}
-    for variant, name in ((0, "closed_form"), (1, "ad")):
-        form = fem.ElasticityForm(m, E, 0.3, d=d, u=u, variant=variant)
-        A = fem.create_matrix(form)
-        for _ in range(2):
-            fem.assemble_matrix(A, form)
-        tot, _ = timed(lambda: fem.assemble_matrix(A, form), 5)
-        res[name + "_ms"] = tot / 5
-        res[name + "_gdofs"] = m.ndofs / (tot / 5 * 1e-3) / 1e9
-        del A, form
-    out["config5_damaged_reassembly_1gpu"] = res
+
+    # ---- config 5: damaged reassembly ---------------------------------------------------------------------
+    n = 2896
+    p = dist.strip_partition_device(n, n, 0, 1)
+    m = p.mesh
+    xy = m.x
+    u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    res = {"workload": f"P2 n={n} ({m.ncells} elements, BASELINE configs[4] on one GPU), values-only reassembly on a frozen "
+                       "pattern, damage band of the stated width"}
+    form0 = fem.ElasticityForm(m, p.E, 0.3)
+    A = fem.create_matrix(form0)
+    for _ in range(2):
+        fem.assemble_matrix(A, form0)
+    tot, calls = env.timed(lambda: fem.assemble_matrix(A, form0), 5)
+    res["undamaged_ms"] = float(np.mean(calls))
+    a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)
+    for label, half_width in (("10pct", 0.05), ("50pct", 0.25), ("100pct", 10.0)):
+        d = torch.clamp(1.0 - (xy[:, 1] - 0.5 - 0.1 * torch.sin(6.0 * xy[:, 0])).abs() / half_width, min=0.0, max=0.95)
+        share = float((d[m.xdofmap.long()].max(dim=1).values > 0).double().mean().item())
+        rec = {"damaged_cell_share": share}
+        for variant, name in ((0, "closed_form"), (1, "ad")):
+            form = fem.ElasticityForm(m, p.E, 0.3, d=d, u=u, variant=variant)
+            for _ in range(2):
+                fem.assemble_matrix(A, form)
+            tot, calls = env.timed(lambda: fem.assemble_matrix(A, form), 5)
+            ms = float(np.mean(calls))
+            rec[name + "_ms"] = ms
+            rec[name + "_gdofs"] = m.ndofs / (ms * 1e-3) / 1e9
+            rec[name + "_frac_hbm"] = (a_bytes + 8 * m.nnodes + 16 * m.nnodes) / (ms * 1e-3) / 1e9 / peak
+            del form
+        rec["ad_over_closed"] = rec["ad_ms"] / rec["closed_form_ms"]
+        res[label] = rec
+    out["config5_damaged_reassembly"] = res
     return out
 
 
 def config5(args, rank, world, local):
-    """BASELINE config 5: repeated tangent reassembly (closed-form and AD tangents, M.cc:736-872 / 752-765) of
-    16 773 632 P2 elements on `world` GPUs: strips of the nx = 2896 mesh, a vertical damage band through
+    """BASELINE config 5 over the ranks: repeated tangent reassembly (closed-form and AD tangents, M.cc:736-872 /
+    752-765) of 16 773 632 P2 elements on `world` GPUs: strips of the nx = 2896 mesh, a vertical damage band through
     every strip, 10 reassemblies on the frozen pattern.  Assembly needs no communication (ghost cell row)."""
     import torch
     import torch.distributed as td
-    from femb200 import fem, dist, mesh as fm
+    from femb200 import fem, dist
     torch.cuda.set_device(local)
     if world > 1:
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx = 2896
-    if world == 1:
-        m = fm.jitter(fm.structured_triangles(nx, order=2), 0.2, seed=1234)
-        E, owned_dofs = fm.young_per_cell(m.ncells), m.ndofs
-    else:
-        part = dist.strip_partition(nx, nx - nx % world, order=2, rank=rank, world=world, jitter_amp=0.2, seed=1234)
-        m, E, owned_dofs = part.mesh, part.E, 2 * part.n_owned
+    part = dist.strip_partition_device(nx, nx - nx % world, rank, world, jitter_amp=0.2, seed=1234)
+    m, E, owned_dofs = part.mesh, part.E, 2 * part.n_owned
     x, y = m.x[:, 0], m.x[:, 1]
-    d = np.minimum(np.maximum(0.0, 1.0 - np.abs(x - 0.5 - 0.1 * np.sin(6.0 * y)) / 0.05), 0.95)
-    u = 1e-3 * np.random.default_rng(rank).standard_normal(m.ndofs)
-    share = float((d[m.xdofmap].mean(axis=1) > 0).mean())
+    d = torch.clamp(1.0 - (x - 0.5 - 0.1 * torch.sin(6.0 * y)).abs() / args.damage_half_width, min=0.0, max=0.95)
+    u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(rank))
+    share = float((d[m.xdofmap.long()].max(dim=1).values > 0).double().mean().item())
     reps = 10
 
     def sync():
@@ -567,7 +742,7 @@ def config5(args, rank, world, local):
                           "value": out["closed_form"]["gdofs"], "n_gpus": world, "reassemblies": reps,
                           "higher_is_better": True, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": f"P2 triangles nx = {nx}, strips over {world} GPU(s), vertical damage band "
-                                                 f"on {100 * share:.1f} % of the cells, values-only reassembly on a frozen "
+                                                 f"on {100 * share:.1f} % of rank 0's cells, values-only reassembly on a frozen "
                                                  "pattern", "elements_total": 2 * nx * (nx - nx % world)},
                           "closed_form": out["closed_form"], "ad": out["ad"],
                           "ad_over_closed": out["ad"]["ms_per_reassembly"] / out["closed_form"]["ms_per_reassembly"]}),
@@ -576,12 +751,16 @@ def config5(args, rank, world, local):
         td.destroy_process_group()
 
 
-def traffic_from_profile(which: str):
-    """dram bytes per launch from the committed ncu --set full summary, if present."""
+def traffic_from_profile(which: str, n: int, world: int):
+    """dram__bytes (read + write) per launch of the kernel from the committed `ncu --set full` capture of THIS workload
+    size on one GPU (profiles/traffic.json: {"<n>": {"assemble": ..., "spmv": ...}}); null when no capture of this size
+    is committed.  ncu cannot run inside the timed process: a number printed under a profiler is never a bench value."""
+    if world != 1:
+        return None
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(which)
+            return json.load(f).get(str(n), {}).get(which)
     except Exception:
         return None
 
@@ -589,19 +768,25 @@ def traffic_from_profile(which: str):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=1448, help="cells per side per GPU (1448 -> 4.19 M P2 triangles)")
+    ap.add_argument("--size", dest="n", type=int, default=5792, help="cells per side of the global mesh (5792 -> 67 M P2 triangles)")
+    ap.add_argument("--rows", type=int, default=0, help="cell rows of the global mesh (default: --size)")
     ap.add_argument("--cg-iters", type=int, default=25)
-    ap.add_argument("--cpu-n", type=int, default=512, help="cells per side of the CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=1448, help="cells per side of the CPU sample of --impl reference")
+    ap.add_argument("--cpu-baseline-n", type=int, default=1024, help="cells per side of the cpu_baseline leg of the default run")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-nccl-compare", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time config 3 (Q2 matrix-free) and config 5 (damage)")
+    ap.add_argument("--skip-extras", action="store_true", help="N = 1 only: skip configs 3 / 5 and the FP64 roofline")
     ap.add_argument("--config5", action="store_true",
-                    help="BASELINE config 5 instead of the headline step: repeated damaged-tangent reassembly "
-                         "(closed form and AD) of 16.8 M P2 elements split over the ranks (nx = 2896)")
+                    help="BASELINE config 5 over the ranks instead of the headline step: repeated damaged-tangent reassembly "
+                         "(closed form and AD) of 16.8 M P2 elements (nx = 2896)")
+    ap.add_argument("--damage-half-width", type=float, default=0.05)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     elif args.config5:

@@ -34,7 +34,7 @@
 //                          fan-edge columns carried in registers, L2 prefetch of the next wave's records;
 //                          damaged cells (d > 0) copy the row slices of per-cell element tangents
 //                          (cell_setup_damage_kernel + cell_tangent_kernel);
-//   assemble_kernel        the generic-record form: Q2 and FEMB200_FORCE_GENERIC (per-quadrature-point
+//   assemble_kernel        the generic-record form: Q2 and assembly_path = 2 (per-quadrature-point
 //                          integration per visit) and plans without fast records;
 //   dirichlet_kernel, fro / trace kernels, the fused-norm correction kernels.
 #include <algorithm>
@@ -985,8 +985,7 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    const size_t smem = 16 * (size_t)A.stage_units + 4 * (size_t)(2 * kAsmR + 1 + kAsmLevels) + 16;
    FEMB_CHECK(smem <= budget, "assemble: a %d-node tile needs %zu B of shared memory (> %zu)", kAsmR, smem, budget);
-   FEMB_CUDA(cudaFuncSetAttribute(assemble_kernel<ET, FAST, CH, TPN, DMG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+   if (int rc = ensure_dynamic_smem<assemble_kernel<ET, FAST, CH, TPN, DMG>>(smem)) return rc;
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
    assemble_kernel<ET, FAST, CH, TPN, DMG><<<grid, kAsmR * TPN, smem, st>>>(A);
    FEMB_LAUNCH_CHECK();
@@ -998,23 +997,20 @@ static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t s
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    A.flevels = p->flevels;
-   {
-      const char *env = getenv("FEMB200_ASM_PREFETCH");
-      A.prefetch_tiles = env ? atoi(env) : 8 * devinfo().sm_count;  // a good wave of resident CTAs ahead
-   }
+   A.prefetch_tiles = p->opt_prefetch_tiles >= 0 ? p->opt_prefetch_tiles : 8 * devinfo().sm_count;  // a good wave of resident CTAs ahead
    const size_t smem = 16 * (size_t)A.stage_units;
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
    if (d_norms)
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
-      FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, true>>(smem)) return rc;
       assemble_fast_kernel<ET, DMG, true><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
       norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
    }
    else
    {
-      FEMB_CUDA(cudaFuncSetAttribute(assemble_fast_kernel<ET, DMG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, false>>(smem)) return rc;
       assemble_fast_kernel<ET, DMG, false><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
    }
    FEMB_LAUNCH_CHECK();
@@ -1027,14 +1023,14 @@ static int launch_assemble(const femb200_plan *p, const AsmArgs &A, cudaStream_t
 {
    *fused = false;
    if (!FAST) return launch_assemble_ch<ET, FAST, 1, 1>(p, A, st);
-   if (ET != FEMB200_Q2 && A.frec && !getenv("FEMB200_ASM_OLD"))
+   if (ET != FEMB200_Q2 && A.frec && p->opt_assembly_path != 1)
    {
       constexpr int TRI = ET == FEMB200_Q2 ? FEMB200_P2 : ET;
       *fused = d_norms != nullptr;
       return A.celld ? launch_assemble_fast<TRI, true>(p, A, st, d_norms) : launch_assemble_fast<TRI, false>(p, A, st, d_norms);
    }
    // older record format (16-byte visit records, staging addresses computed per block): plans without
-   // fast records (a node in 16 cells, a staging image over 32 KB) and the FEMB200_ASM_OLD switch
+   // fast records (a node in 16 cells, a staging image over 32 KB) and plans with assembly_path = 1
    if (A.celld) return launch_assemble_ch<ET, FAST, 1, 2, true>(p, A, st);  // damaged cells present
    return launch_assemble_ch<ET, FAST, 1, 2>(p, A, st);
 }
@@ -1055,8 +1051,8 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
    A.dnod = d_dnod, A.u = d_u, A.variant = variant, A.values = d_values;
    cudaStream_t st = as_stream(stream);
    // triangles take the per-cell pre-pass + fast kernel (damaged cells through their own per-cell
-   // tangent records); Q2 and FEMB200_FORCE_GENERIC take the per-quadrature-point kernel
-   const bool linear = (p->etype != FEMB200_Q2) && !getenv("FEMB200_FORCE_GENERIC");
+   // tangent records); Q2 and plans with assembly_path = 2 take the per-quadrature-point kernel
+   const bool linear = (p->etype != FEMB200_Q2) && p->opt_assembly_path != 2;
    A.cellrec = nullptr, A.celld = nullptr;
    if (linear)
    {

@@ -22,13 +22,11 @@
 // CGSolver / KSP.
 #include <algorithm>
 
-#include "plan.cuh"
+#include "dist.cuh"
 #include "reduce.cuh"
 
 namespace femb {
 
-int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
-                double *d_dot_out, cudaStream_t st);
 int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
                     cudaStream_t st);
 
@@ -140,8 +138,20 @@ dot_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b
 }
 
 // phase 0: after init (nom)   phase 1: after spmv+dot (den)   phase 2: after update_xr (betanom)
-__global__ void cg_scalar_kernel(double *__restrict__ s, int phase)
+// One warp.  With a P2P communicator the all-reduce of the freshly written partial sum is fused in (lane p
+// exchanges with rank p, dist.cuh); every rank adds the partials in rank order, so the scalars -- and the
+// convergence decisions -- are bit-identical on all ranks.
+__global__ void __launch_bounds__(32) cg_scalar_kernel(double *__restrict__ s, int phase, RedArgs ra)
 {
+   const int idx = phase == 0 ? SC_RED_NOM : (phase == 1 ? SC_RED_DEN : SC_RED_BETA);
+   if (ra.hdr)
+   {
+      double v[1] = {s[idx]};
+      __syncwarp();
+      mailbox_allreduce<1>(ra, v);
+      if (threadIdx.x == 0) s[idx] = v[0];
+   }
+   if (threadIdx.x != 0) return;
    if (phase == 0)
    {
       const double nom = s[SC_RED_NOM];
@@ -149,7 +159,8 @@ __global__ void cg_scalar_kernel(double *__restrict__ s, int phase)
       s[SC_R0] = fmax(nom * s[SC_RTOL2], s[SC_ATOL2]);
       s[SC_FINAL] = nom;
       s[SC_ITERS] = 0.;
-      s[SC_FLAG] = (nom <= s[SC_R0]) ? 1. : 0.;
+      // <B r, r> < 0: the preconditioner is not positive definite (mfem::CGSolver::Mult returns unconverged)
+      s[SC_FLAG] = (nom < 0.) ? 2. : ((nom <= s[SC_R0]) ? 1. : 0.);
       return;
    }
    if (s[SC_FLAG] != 0.) return;
@@ -165,7 +176,9 @@ __global__ void cg_scalar_kernel(double *__restrict__ s, int phase)
       s[SC_BETANOM] = betanom;
       s[SC_ITERS] += 1.;
       s[SC_FINAL] = betanom;
-      if (betanom <= s[SC_R0])
+      if (betanom < 0.)
+         s[SC_FLAG] = 2.;
+      else if (betanom <= s[SC_R0])
          s[SC_FLAG] = 1.;
       else
       {
@@ -234,7 +247,7 @@ extern "C" int femb200_cg_init(int64_t n, const double *d_b, const double *d_din
 extern "C" int femb200_cg_scalar_step(double *d_scal, int phase, void *stream)
 {
    FEMB_CHECK(d_scal && phase >= 0 && phase <= 2, "cg_scalar_step: bad argument");
-   cg_scalar_kernel<<<1, 1, 0, as_stream(stream)>>>(d_scal, phase);
+   cg_scalar_kernel<<<1, 32, 0, as_stream(stream)>>>(d_scal, phase, RedArgs());
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -266,51 +279,119 @@ extern "C" int femb200_cg_update_dir(int64_t n, const double *d_scal, const doub
    return 0;
 }
 
-// z = A d with the fused partial <d, A d> into scal[SC_RED_DEN]; no-op once the flag is set
-extern "C" int femb200_cg_apply(const femb200_plan *plan, int op_kind, const void *op, const double *d_values,
-                                const double *d_dir, double *d_Ad, double *d_scal, void *stream)
+namespace femb {
+
+// z = A d on the owned rows with the fused partial <d, A d> into scal[SC_RED_DEN]; no-op once the flag is set
+static int cg_apply_rows(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const RowRange &rr,
+                         const double *d_dir, double *d_Ad, double *d_scal, cudaStream_t st)
 {
-   FEMB_CHECK(d_dir && d_Ad && d_scal, "cg_apply: null argument");
-   cudaStream_t st = as_stream(stream);
    if (op_kind == FEMB200_OP_CSR)
-   {
-      FEMB_CHECK(plan && d_values, "cg_apply: CSR operator needs a plan and values");
-      return spmv_launch(plan, d_values, d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st);
-   }
-   FEMB_CHECK(op_kind == FEMB200_OP_PA && op, "cg_apply: unknown operator kind %d", op_kind);
+      return spmv_launch(plan, rr, d_values, d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, false, st);
    return pa_apply_launch(static_cast<const femb200_pa *>(op), d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st);
 }
 
-extern "C" int femb200_pcg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values,
-                           const double *d_b, double *d_x, int64_t n, double rtol, double atol, int maxit,
-                           const double *d_dinv, int check_every, int fixed_iters, double *d_work, int *iters,
-                           double *final_norm, int *converged, void *stream)
+// The PCG loop of femb200_pcg and femb200_dist_pcg.  Vector kernels run on the owned dofs [2 own_lo,
+// 2 own_hi) of the local vectors; with a communicator the search direction gets its ghost update before
+// every operator apply and the three dot products are all-reduced (fused into the scalar kernels on the P2P
+// transport, ncclAllReduce on the NCCL transport).  With use_graph the full iteration (update_xr, scalar,
+// update_dir, ghost update, apply + dot, scalar) is captured once into a CUDA graph cached in the
+// communicator and replayed; everything it needs (scalars, sequence numbers) lives in device memory.
+int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, cudaStream_t st)
 {
-   FEMB_CHECK(d_b && d_x && d_work && n > 0 && (n & 1) == 0, "pcg: bad argument");
-   FEMB_CHECK(maxit >= 0, "pcg: negative maxit");
-   cudaStream_t st = as_stream(stream);
-   double *r = d_work, *dir = d_work + n, *z = d_work + 2 * n, *scal = d_work + 3 * n;
-   if (check_every <= 0) check_every = 25;
+   const int64_t o = 2 * P.own_lo, n = 2 * (P.own_hi - P.own_lo);
+   const double *dinv_o = P.dinv ? P.dinv + o : nullptr;
+   double *scal = P.scal;
+   RowRange rr{0, 0, {0, 0}};
+   if (P.op_kind == FEMB200_OP_CSR)
+   {
+      FEMB_CHECK(P.plan && P.values, "pcg: the CSR operator needs a plan and values");
+      if (int rc = plan_row_range(P.plan, P.own_lo, P.own_hi, &rr)) return rc;
+   }
+   else
+      FEMB_CHECK(P.op_kind == FEMB200_OP_PA && P.op, "pcg: unknown operator kind %d", P.op_kind);
+   const RedArgs ra = dist_red_args(P.comm);
+   const unsigned gv = vec_grid(n / 2), gi = vec_grid(n);
+   ReduceScratch red;
+   if (int rc = reduce_scratch(std::max(gv, gi), st, &red)) return rc;  // grown before any capture
    int rc;
-   if ((rc = femb200_cg_set_tolerances(scal, rtol, atol, stream))) return rc;
-   if ((rc = femb200_cg_init(n, d_b, d_dinv, d_x, r, dir, scal, stream))) return rc;
-   if ((rc = femb200_cg_scalar_step(scal, 0, stream))) return rc;
-   if ((rc = femb200_cg_apply(plan, op_kind, op, d_values, dir, z, scal, stream))) return rc;
-   if ((rc = femb200_cg_scalar_step(scal, 1, stream))) return rc;
-   const int nit = fixed_iters > 0 ? fixed_iters : maxit;
+   auto scalar = [&](int phase, int idx) -> int {
+      if (int e = dist_allreduce_pre(P.comm, scal + idx, 1, st)) return e;
+      cg_scalar_kernel<<<1, 32, 0, st>>>(scal, phase, ra);
+      FEMB_LAUNCH_CHECK();
+      return 0;
+   };
+   auto apply = [&]() -> int {
+      if (int e = dist_halo_arena(P.comm, st)) return e;
+      if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.d, P.z, scal, st)) return e;
+      return scalar(1, SC_RED_DEN);
+   };
+   auto update_xr = [&]() -> int {
+      cg_update_xr_kernel<<<gv, kVecThreads, 0, st>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.d + o),
+                                                      reinterpret_cast<const double2 *>(P.z + o),
+                                                      reinterpret_cast<const double2 *>(dinv_o),
+                                                      reinterpret_cast<double2 *>(P.x + o), reinterpret_cast<double2 *>(P.r + o),
+                                                      red, scal + SC_RED_BETA);
+      FEMB_LAUNCH_CHECK();
+      return scalar(2, SC_RED_BETA);
+   };
+   auto update_dir = [&]() -> int {
+      cg_update_dir_kernel<<<gv, kVecThreads, 0, st>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.r + o),
+                                                       reinterpret_cast<const double2 *>(dinv_o),
+                                                       reinterpret_cast<double2 *>(P.d + o));
+      FEMB_LAUNCH_CHECK();
+      return 0;
+   };
+   auto full_iteration = [&]() -> int {
+      if (int e = update_xr()) return e;
+      if (int e = update_dir()) return e;
+      return apply();
+   };
+
+   if ((rc = femb200_cg_set_tolerances(scal, P.rtol, P.atol, st))) return rc;
+   cg_init_kernel<<<gi, kVecThreads, 0, st>>>(n, P.b + o, dinv_o, P.x + o, P.r + o, P.d + o, red, scal + SC_RED_NOM);
+   FEMB_LAUNCH_CHECK();
+   if ((rc = scalar(0, SC_RED_NOM))) return rc;
+   if ((rc = apply())) return rc;
+
+   const int nit = P.fixed_iters > 0 ? P.fixed_iters : P.maxit;
+   const int check_every = P.check_every > 0 ? P.check_every : 25;
    double hs[SC_COUNT];
    bool stopped = false;
+   // iterations 1 .. nit - 1 are full ones; the last one stops after the residual update
+   IterGraph *G = (P.use_graph && P.comm && nit >= 4) ? dist_iter_graph(P.comm) : nullptr;
    for (int i = 1; i <= nit && !stopped; ++i)
    {
-      if ((rc = femb200_cg_update_xr(n, scal, dir, z, d_dinv, d_x, r, stream))) return rc;
-      if ((rc = femb200_cg_scalar_step(scal, 2, stream))) return rc;
-      if (i < nit)
+      if (i == nit)
       {
-         if ((rc = femb200_cg_update_dir(n, scal, r, d_dinv, dir, stream))) return rc;
-         if ((rc = femb200_cg_apply(plan, op_kind, op, d_values, dir, z, scal, stream))) return rc;
-         if ((rc = femb200_cg_scalar_step(scal, 1, stream))) return rc;
+         if ((rc = update_xr())) return rc;
       }
-      if (fixed_iters <= 0 && (i % check_every == 0) && i < nit)
+      else if (G && i >= 2)
+      {  // iteration 1 ran eagerly (warm kernels, NCCL connections); capture on first use, then replay
+         const void *key[8] = {P.plan, P.op, P.values, P.x, P.r, P.d, P.z, P.dinv};
+         const int64_t ikey[3] = {P.own_lo, P.own_hi, (int64_t)P.op_kind};
+         if (!G->exec || memcmp(G->key, key, sizeof(key)) || memcmp(G->ikey, ikey, sizeof(ikey)))
+         {
+            if (G->exec) cudaGraphExecDestroy(G->exec), G->exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            FEMB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int e = full_iteration();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (e || ce != cudaSuccess || !graph)
+            {
+               if (graph) cudaGraphDestroy(graph);
+               if (e) return e;
+               return set_error("pcg: capturing the iteration graph failed: %s", cudaGetErrorString(ce));
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&G->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            FEMB_CHECK(ie == cudaSuccess, "pcg: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            memcpy(G->key, key, sizeof(key)), memcpy(G->ikey, ikey, sizeof(ikey));
+         }
+         FEMB_CUDA(cudaGraphLaunch(G->exec, st));
+      }
+      else if ((rc = full_iteration()))
+         return rc;
+      if (P.fixed_iters <= 0 && (i % check_every == 0) && i < nit)
       {
          FEMB_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
          FEMB_CUDA(cudaStreamSynchronize(st));
@@ -319,11 +400,55 @@ extern "C" int femb200_pcg(const femb200_plan *plan, int op_kind, const void *op
    }
    FEMB_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
    FEMB_CUDA(cudaStreamSynchronize(st));
+   if ((rc = dist_check_error(P.comm, st))) return rc;
    const bool conv = hs[SC_FLAG] == 1.;
    if (converged) *converged = conv ? 1 : 0;
-   if (iters) *iters = conv ? (int)hs[SC_ITERS] : (fixed_iters > 0 ? (int)hs[SC_ITERS] : maxit);
+   // mfem::CGSolver: final_iter = the iteration it stopped in (convergence or breakdown), max_iter otherwise
+   if (iters) *iters = (conv || hs[SC_FLAG] == 2. || P.fixed_iters > 0) ? (int)hs[SC_ITERS] : P.maxit;
    if (final_norm) *final_norm = sqrt(hs[SC_FINAL] > 0. ? hs[SC_FINAL] : 0.);
    return 0;
+}
+
+}  // namespace femb
+
+// z = A d with the fused partial <d, A d> into scal[SC_RED_DEN]; no-op once the flag is set
+extern "C" int femb200_cg_apply(const femb200_plan *plan, int op_kind, const void *op, const double *d_values,
+                                const double *d_dir, double *d_Ad, double *d_scal, void *stream)
+{
+   FEMB_CHECK(d_dir && d_Ad && d_scal, "cg_apply: null argument");
+   RowRange rr{0, 0, {0, 0}};
+   if (op_kind == FEMB200_OP_CSR)
+   {
+      FEMB_CHECK(plan && d_values, "cg_apply: CSR operator needs a plan and values");
+      if (int rc = plan_row_range(plan, 0, plan->nnodes, &rr)) return rc;
+   }
+   else
+      FEMB_CHECK(op_kind == FEMB200_OP_PA && op, "cg_apply: unknown operator kind %d", op_kind);
+   return cg_apply_rows(plan, op_kind, op, d_values, rr, d_dir, d_Ad, d_scal, as_stream(stream));
+}
+
+int64_t pa_num_dofs(const femb200_pa *pa);
+
+extern "C" int femb200_pcg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values,
+                           const double *d_b, double *d_x, int64_t n, double rtol, double atol, int maxit,
+                           const double *d_dinv, int check_every, int fixed_iters, double *d_work, int *iters,
+                           double *final_norm, int *converged, void *stream)
+{
+   FEMB_CHECK(d_b && d_x && d_work && n > 0 && (n & 1) == 0, "pcg: bad argument");
+   FEMB_CHECK(maxit >= 0, "pcg: negative maxit");
+   if (op_kind == FEMB200_OP_CSR)
+      FEMB_CHECK(plan && n == 2 * plan->nnodes, "pcg: n = %lld does not match the operator (%lld dofs)", (long long)n,
+                 (long long)(plan ? 2 * plan->nnodes : 0));
+   else if (op_kind == FEMB200_OP_PA && op)
+      FEMB_CHECK(n == pa_num_dofs(static_cast<const femb200_pa *>(op)), "pcg: n = %lld does not match the matrix-free operator",
+                 (long long)n);
+   CgProblem P;
+   P.plan = plan, P.op_kind = op_kind, P.op = op, P.values = d_values;
+   P.own_lo = 0, P.own_hi = n / 2;
+   P.b = d_b, P.dinv = d_dinv, P.x = d_x;
+   P.r = d_work, P.d = d_work + n, P.z = d_work + 2 * n, P.scal = d_work + 3 * n;
+   P.rtol = rtol, P.atol = atol, P.maxit = maxit, P.check_every = check_every, P.fixed_iters = fixed_iters;
+   return cg_core(P, iters, final_norm, converged, as_stream(stream));
 }
 
 // dst[k] = src[idx[k]] over node pairs (16-byte items): packs the interface dofs

@@ -41,6 +41,19 @@ struct DevInfo
 };
 const DevInfo &devinfo();
 
+// opt-in dynamic shared memory of a kernel, set once per growth (not on every launch)
+template <auto Kernel>
+static inline int ensure_dynamic_smem(size_t smem)
+{
+   static size_t have = 0;
+   if (smem > have)
+   {
+      FEMB_CUDA(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      have = smem;
+   }
+   return 0;
+}
+
 // ---- element tables --------------------------------------------------------
 __host__ __device__ constexpr int elem_nd(int etype) { return etype == FEMB200_P1 ? 3 : (etype == FEMB200_P2 ? 6 : 9); }
 __host__ __device__ constexpr int elem_nv(int etype) { return etype == FEMB200_Q2 ? 4 : 3; }

@@ -1011,6 +1011,7 @@ extern "C" int femb200_pa_apply(const femb200_pa *pa, const double *d_x, double 
    return pa_apply_launch(pa, d_x, d_y, nullptr, nullptr, as_stream(stream));
 }
 
+int64_t pa_num_dofs(const femb200_pa *pa) { return pa ? 2 * pa->nnodes : 0; }
 extern "C" int femb200_pa_diagonal(const femb200_pa *pa, double *d_diag, void *stream)
 {
    FEMB_CHECK(pa && d_diag, "pa_diagonal: null argument");

@@ -16,6 +16,13 @@ namespace femb {
 
 constexpr int kMaxDeg = 96;  // block degree cap of the builder (thread-local scratch)
 
+// --- input validation: every dof / geometry index inside [0, nnodes) ----------------------------
+__global__ void k_check_range(int64_t n, const int32_t *__restrict__ idx, int32_t nnodes, int32_t *__restrict__ bad)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && (idx[i] < 0 || idx[i] >= nnodes)) atomicOr(bad, 1);
+}
+
 // --- node -> cell visit lists -------------------------------------------------
 __global__ void k_count_visits(int64_t nvis, const int32_t *__restrict__ dofmap, int32_t *__restrict__ cnt)
 {
@@ -519,7 +526,6 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
    femb200_plan *p = new femb200_plan();
    p->etype = etype, p->nd = nd, p->nv = elem_nv(etype);
    p->nnodes = nnodes, p->ncells = ncells, p->nvisits = nvis;
-   p->row_lo = 0, p->row_hi = nnodes;
    p->dofmap = d_dofmap, p->xdofmap = d_xdofmap;
 
    int32_t *cnt = nullptr, *deg = nullptr, *flags = nullptr;
@@ -542,6 +548,16 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
        cudaMemsetAsync(flags, 0, sizeof(int32_t) * (2 + kNumTileR), st) != cudaSuccess)
       return fail(set_error("plan_create: memset failed"));
 
+   // 0. the maps come across the C ABI: refuse indices outside [0, nnodes) instead of scattering out of bounds
+   k_check_range<<<(unsigned)cdiv(nvis, T), T, 0, st>>>(nvis, d_dofmap, (int32_t)nnodes, flags);
+   k_check_range<<<(unsigned)cdiv(ncells * p->nv, T), T, 0, st>>>(ncells * p->nv, d_xdofmap, (int32_t)nnodes, flags);
+   {
+      int32_t bad = 0;
+      if (cudaMemcpyAsync(&bad, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+         return fail(set_error("plan_create: index check failed: %s", cudaGetErrorString(cudaGetLastError())));
+      if (bad) return fail(set_error("plan_create: the dof map or the geometry map holds an index outside [0, %lld)", (long long)nnodes));
+   }
    // 1. node -> cell visit lists
    k_count_visits<<<(unsigned)cdiv(nvis, T), T, 0, st>>>(nvis, d_dofmap, cnt);
    if ((rc = exclusive_scan_i32_i32(cnt, p->nptr, nnodes, st))) return fail(rc);
@@ -594,7 +610,6 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
       return fail(set_error("plan_create: slot map build failed: %s", cudaGetErrorString(cudaGetLastError())));
 
-   p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
    // fast-path records: triangles whose kAsmR-row staging image is addressable with 15-bit byte offsets
    // and whose nodes belong to fewer than 16 cells
    if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 4) < 32768)
@@ -713,28 +728,58 @@ extern "C" int femb200_plan_set_dirichlet(femb200_plan *p, const uint8_t *d_bc, 
    return 0;
 }
 
-extern "C" int femb200_plan_set_row_range(femb200_plan *p, int64_t row_lo, int64_t row_hi)
+namespace femb {
+// SpMV tiling of the node rows [lo, hi): the bulk-copy staged kernel sizes its shared-memory stages for the
+// largest tile.  Ranges that start on a 64-row boundary share the plan's aligned tiles; any other range (the
+// owned rows of a rank) is measured once (synchronises the device) and cached in the plan.
+int plan_row_range(const femb200_plan *p, int64_t lo, int64_t hi, RowRange *out)
 {
-   FEMB_CHECK(p != nullptr, "plan_set_row_range: null plan");
-   FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "plan_set_row_range: bad range [%lld, %lld)",
-              (long long)row_lo, (long long)row_hi);
-   p->row_lo = row_lo, p->row_hi = row_hi;
-   p->row_tile_max[0] = p->tile_max_blocks[0], p->row_tile_max[1] = p->tile_max_blocks[1];
-   if (row_lo % 64 != 0 && row_hi > row_lo)
-   {  // the SpMV tiles no longer coincide with the plan's aligned tiles: measure them
+   FEMB_CHECK(p != nullptr, "row range: null plan");
+   FEMB_CHECK(0 <= lo && lo <= hi && hi <= p->nnodes, "row range: bad range [%lld, %lld) of %lld node rows", (long long)lo,
+              (long long)hi, (long long)p->nnodes);
+   out->lo = lo, out->hi = hi;
+   out->tile_max[0] = p->tile_max_blocks[0], out->tile_max[1] = p->tile_max_blocks[1];
+   if (lo % 64 == 0 || hi == lo) return 0;
+   femb200_plan *pm = const_cast<femb200_plan *>(p);
+   std::lock_guard<std::mutex> lock(pm->range_mtx);
+   auto it = pm->range_tile_max.find(std::make_pair(lo, hi));
+   if (it == pm->range_tile_max.end())
+   {
       int32_t *d = nullptr, h[2] = {0, 0};
       FEMB_CUDA(cudaMalloc(&d, 2 * sizeof(int32_t)));
       FEMB_CUDA(cudaMemset(d, 0, 2 * sizeof(int32_t)));
       for (int k = 0; k < 2; ++k)
       {
          const int R = 32 << k;
-         const int64_t nt = cdiv(row_hi - row_lo, R);
-         k_range_tile_max<<<(unsigned)cdiv(nt, 256), 256>>>(row_lo, row_hi, R, p->brp, d + k);
+         const int64_t nt = cdiv(hi - lo, R);
+         k_range_tile_max<<<(unsigned)cdiv(nt, 256), 256>>>(lo, hi, R, p->brp, d + k);
       }
       const cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
       cudaFree(d);
-      FEMB_CHECK(e == cudaSuccess, "plan_set_row_range: %s", cudaGetErrorString(e));
-      p->row_tile_max[0] = h[0], p->row_tile_max[1] = h[1];
+      FEMB_CHECK(e == cudaSuccess, "row range: %s", cudaGetErrorString(e));
+      it = pm->range_tile_max.emplace(std::make_pair(lo, hi), std::array<int32_t, 2>{h[0], h[1]}).first;
    }
+   out->tile_max[0] = it->second[0], out->tile_max[1] = it->second[1];
+   return 0;
+}
+}  // namespace femb
+
+extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int value)
+{
+   FEMB_CHECK(p && key, "plan_set_option: null argument");
+   if (!strcmp(key, "assembly_path"))
+   {
+      FEMB_CHECK(value >= 0 && value <= 2, "plan_set_option: assembly_path must be 0 (auto), 1 (visit records) or 2 (per point)");
+      p->opt_assembly_path = value;
+   }
+   else if (!strcmp(key, "spmv_path"))
+   {
+      FEMB_CHECK(value == 0 || value == 1, "plan_set_option: spmv_path must be 0 (auto) or 1 (direct)");
+      p->opt_spmv_path = value;
+   }
+   else if (!strcmp(key, "prefetch_tiles"))
+      p->opt_prefetch_tiles = value;
+   else
+      return set_error("plan_set_option: unknown key '%s'", key);
    return 0;
 }

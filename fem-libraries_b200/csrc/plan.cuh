@@ -1,6 +1,11 @@
 // plan.cuh -- the assembly plan: node->cell visit lists, node-block CSR pattern and
 // the per-visit slot map of the write-once gather assembly.
 #pragma once
+#include <array>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace femb {
@@ -116,6 +121,25 @@ struct femb200_plan
    double *celld = nullptr;    // damaged cells: [ncells][2nd x 2nd] element tangents (row-major, interleaved dofs), lazily allocated
    int32_t *celld_count = nullptr;  // [1 + ncells]: number of damaged cells, then their list
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
-   int64_t row_lo = 0, row_hi = 0;  // node rows applied by spmv (owned rows of this rank)
-   int32_t row_tile_max[2] = {0, 0};  // largest 32- / 64-row tile (in node blocks) of the tiling that starts at row_lo
+   // Kernel selection of this plan (femb200_plan_set_option): the fallback kernels that serve plans without
+   // fast records / oversized SpMV tiles can be forced, so that the tests cover them on any mesh.
+   int opt_assembly_path = 0;    // 0 auto; 1 visit-record kernel; 2 per-quadrature-point kernel
+   int opt_spmv_path = 0;        // 0 auto (bulk-copy staged, persistent); 1 direct kernel
+   int opt_prefetch_tiles = -1;  // record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count)
+   // largest 32- / 64-row SpMV tile (in node blocks) of the tiling that starts at row_lo, per row range
+   // [row_lo, row_hi) that has been applied (the owned rows of a rank; measured once, on first use)
+   std::map<std::pair<int64_t, int64_t>, std::array<int32_t, 2>> range_tile_max;
+   std::mutex range_mtx;
 };
+
+namespace femb {
+// [lo, hi) = node rows to apply; tile_max from plan_range_tile_max()
+struct RowRange
+{
+   int64_t lo, hi;
+   int32_t tile_max[2];
+};
+int plan_row_range(const femb200_plan *p, int64_t lo, int64_t hi, RowRange *out);
+int spmv_launch(const femb200_plan *p, const RowRange &rr, const double *d_values, const double *d_x, double *d_y,
+                const double *d_flag, double *d_dot_out, bool accumulate, cudaStream_t st);
+}  // namespace femb

@@ -100,7 +100,8 @@ template <bool DOT, int R, int kTmaStages, int L>
 __global__ void __launch_bounds__(kTmaThreads)
 spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
                 const double *__restrict__ values, const double *__restrict__ x, double *__restrict__ y,
-                const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out, SpmvTile cap, int ntiles)
+                const double *__restrict__ flag, ReduceScratch red, double *__restrict__ out, SpmvTile cap, int ntiles,
+                bool accumulate)
 {
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
@@ -215,7 +216,7 @@ spmv_tma_kernel(int64_t row_lo, int64_t row_hi, const int64_t *__restrict__ brp,
          if (lane == 0) mbar_arrive(&empty[s]);
       }
    }
-   if (DOT) block_reduce_finish<kTmaThreads>(part, red, out);
+   if (DOT) block_reduce_finish<kTmaThreads>(part, red, out, accumulate);
 }
 
 __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, const uint8_t *__restrict__ dslot,
@@ -231,14 +232,14 @@ __global__ void diag_kernel(int64_t nnodes, const int64_t *__restrict__ brp, con
 }
 
 template <bool DOT, int R, int S, int L>
-static int spmv_tma_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
-                           const double *d_flag, double *d_dot_out, cudaStream_t st)
+static int spmv_tma_launch(const femb200_plan *p, const RowRange &rr, const double *d_values, const double *d_x,
+                           double *d_y, const double *d_flag, double *d_dot_out, bool accumulate, cudaStream_t st)
 {
-   static_assert(R == 32 || R == 64, "plan->row_tile_max is measured for 32- and 64-row tiles");
+   static_assert(R == 32 || R == 64, "RowRange::tile_max is measured for 32- and 64-row tiles");
    static_assert(R * L % kTmaConsumers == 0, "a tile must be a whole number of consumer passes");
-   const int64_t nrows = p->row_hi - p->row_lo;
+   const int64_t nrows = rr.hi - rr.lo;
    const int ntiles = (int)cdiv(nrows, R);
-   const int maxb = p->row_tile_max[R == 32 ? 0 : 1];
+   const int maxb = rr.tile_max[R == 32 ? 0 : 1];
    SpmvTile cap;
    cap.vbytes = 32 * maxb;
    cap.cbytes = ((4 * (maxb + 4) + 15) & ~15);
@@ -246,54 +247,35 @@ static int spmv_tma_launch(const femb200_plan *p, const double *d_values, const 
    const size_t smem = (size_t)S * (cap.vbytes + cap.cbytes + cap.pbytes);
    const size_t budget = devinfo().smem_optin ? devinfo().smem_optin : 227 * 1024;
    if (smem > budget) return -1;  // caller falls back to the direct kernel
-   FEMB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<DOT, R, S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   if (int rc = ensure_dynamic_smem<spmv_tma_kernel<DOT, R, S, L>>(smem)) return rc;
    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(7, (budget + 1024) / (smem + 1024)));
    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)devinfo().sm_count * per_sm);
    ReduceScratch red{nullptr, nullptr};
    if (DOT)
       if (int rc = reduce_scratch(grid, st, &red)) return rc;
-   spmv_tma_kernel<DOT, R, S, L><<<grid, kTmaThreads, smem, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x,
-                                                                  d_y, d_flag, red, d_dot_out, cap, ntiles);
+   spmv_tma_kernel<DOT, R, S, L><<<grid, kTmaThreads, smem, st>>>(rr.lo, rr.hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag,
+                                                                  red, d_dot_out, cap, ntiles, accumulate);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
 
-template <bool DOT>
-static int spmv_tma_dispatch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
-                             const double *d_flag, double *d_dot_out, cudaStream_t st)
+// y = A x on the node rows of rr (+ d_dot_out (+)= <x, y> over those rows; no-op when *d_flag != 0).
+// Default: 64-row tiles, 2 stages (3 CTAs per SM), 4 lanes per row: 0.59 ms on the n = 1448 P2 matrix against
+// 0.99 ms with 3 stages and 8 lanes (profiles/r1_summary.md).  Tiles too large for shared memory, and plans
+// with spmv_path = 1, take the direct kernel.
+int spmv_launch(const femb200_plan *p, const RowRange &rr, const double *d_values, const double *d_x, double *d_y,
+                const double *d_flag, double *d_dot_out, bool accumulate, cudaStream_t st)
 {
-   // developer switch FEMB200_SPMV_CFG = <R><S><L>; default 6424 = 64-row tiles, 2 stages (3 CTAs per SM), 4 lanes
-   // per row: 0.59 ms on the n = 1448 P2 matrix against 0.99 ms for 6438 (profiles/r1_summary.md)
-   const char *env = getenv("FEMB200_SPMV_CFG");
-   const int cfg = env ? atoi(env) : 6424;
-   switch (cfg)
-   {
-      case 3228: return spmv_tma_launch<DOT, 32, 2, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 3238: return spmv_tma_launch<DOT, 32, 3, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 3248: return spmv_tma_launch<DOT, 32, 4, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 6434: return spmv_tma_launch<DOT, 64, 3, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 6444: return spmv_tma_launch<DOT, 64, 4, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 6428: return spmv_tma_launch<DOT, 64, 2, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 6448: return spmv_tma_launch<DOT, 64, 4, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      case 6438: return spmv_tma_launch<DOT, 64, 3, 8>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-      default: return spmv_tma_launch<DOT, 64, 2, 4>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
-   }
-}
-
-int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
-                double *d_dot_out, cudaStream_t st)
-{
-   const int64_t nrows = p->row_hi - p->row_lo;
+   const int64_t nrows = rr.hi - rr.lo;
    if (nrows <= 0)
    {
-      if (d_dot_out) FEMB_CUDA(cudaMemsetAsync(d_dot_out, 0, sizeof(double), st));
+      if (d_dot_out && !accumulate) FEMB_CUDA(cudaMemsetAsync(d_dot_out, 0, sizeof(double), st));
       return 0;
    }
-   const bool direct = getenv("FEMB200_SPMV_DIRECT") != nullptr;
-   if (!direct)
+   if (p->opt_spmv_path == 0)
    {
-      const int rc = d_dot_out ? spmv_tma_dispatch<true>(p, d_values, d_x, d_y, d_flag, d_dot_out, st)
-                               : spmv_tma_dispatch<false>(p, d_values, d_x, d_y, d_flag, d_dot_out, st);
+      const int rc = d_dot_out ? spmv_tma_launch<true, 64, 2, 4>(p, rr, d_values, d_x, d_y, d_flag, d_dot_out, accumulate, st)
+                               : spmv_tma_launch<false, 64, 2, 4>(p, rr, d_values, d_x, d_y, d_flag, d_dot_out, accumulate, st);
       if (rc >= 0) return rc;
    }
    const unsigned grid = (unsigned)cdiv(nrows * kSpmvLanes, kSpmvThreads);
@@ -301,12 +283,12 @@ int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red)) return rc;
-      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
-                                                        d_flag, red, d_dot_out);
+      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(rr.lo, rr.hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag, red,
+                                                        d_dot_out, accumulate);
    }
    else
-      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(p->row_lo, p->row_hi, p->brp, p->bcol, d_values, d_x, d_y,
-                                                         d_flag, ReduceScratch{nullptr, nullptr}, nullptr);
+      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(rr.lo, rr.hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag,
+                                                         ReduceScratch{nullptr, nullptr}, nullptr);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -319,7 +301,9 @@ extern "C" int femb200_spmv(const femb200_plan *p, const double *d_values, const
 {
    FEMB_CHECK(p && d_values && d_x && d_y, "spmv: null argument");
    FEMB_CHECK(d_x != d_y, "spmv: x and y must not alias");
-   return spmv_launch(p, d_values, d_x, d_y, nullptr, nullptr, as_stream(stream));
+   RowRange rr;
+   if (int rc = plan_row_range(p, 0, p->nnodes, &rr)) return rc;
+   return spmv_launch(p, rr, d_values, d_x, d_y, nullptr, nullptr, false, as_stream(stream));
 }
 
 extern "C" int femb200_spmv_dot(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
@@ -327,35 +311,24 @@ extern "C" int femb200_spmv_dot(const femb200_plan *p, const double *d_values, c
 {
    FEMB_CHECK(p && d_values && d_x && d_y && d_dot, "spmv_dot: null argument");
    FEMB_CHECK(d_x != d_y, "spmv_dot: x and y must not alias");
-   return spmv_launch(p, d_values, d_x, d_y, nullptr, d_dot, as_stream(stream));
+   RowRange rr;
+   if (int rc = plan_row_range(p, 0, p->nnodes, &rr)) return rc;
+   return spmv_launch(p, rr, d_values, d_x, d_y, nullptr, d_dot, false, as_stream(stream));
 }
 
-// y = A x on an arbitrary range of node rows (no tiling state needed: the plain kernel), optionally
-// d_dot (+)= <x, y> over those rows and gated by a convergence flag: the boundary rows of a rank, which
-// wait for the halo while the interior rows (femb200_spmv / cg_apply on the plan's row range) run.
+// y = A x on the node rows [row_lo, row_hi) (the rows a rank owns, or the rows next to its ghosts); rows
+// outside are left untouched.  d_dot (or NULL) receives <x, y> over those rows, added to its content when
+// `accumulate`; d_flag (or NULL): no-op when *d_flag != 0 (converged CG).  The first call with a range that
+// does not start on a 64-row boundary measures its tiling (synchronises the device once).
 extern "C" int femb200_spmv_rows(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y,
                                  int64_t row_lo, int64_t row_hi, double *d_dot, int accumulate, const double *d_flag,
                                  void *stream)
 {
    FEMB_CHECK(p && d_values && d_x && d_y, "spmv_rows: null argument");
    FEMB_CHECK(d_x != d_y, "spmv_rows: x and y must not alias");
-   FEMB_CHECK(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nnodes, "spmv_rows: bad range [%lld, %lld)",
-              (long long)row_lo, (long long)row_hi);
-   cudaStream_t st = as_stream(stream);
-   if (row_hi == row_lo) return 0;
-   const unsigned grid = (unsigned)cdiv((row_hi - row_lo) * kSpmvLanes, kSpmvThreads);
-   if (d_dot)
-   {
-      ReduceScratch red;
-      if (int rc = reduce_scratch(grid, st, &red)) return rc;
-      spmv_kernel<true><<<grid, kSpmvThreads, 0, st>>>(row_lo, row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag, red,
-                                                        d_dot, accumulate != 0);
-   }
-   else
-      spmv_kernel<false><<<grid, kSpmvThreads, 0, st>>>(row_lo, row_hi, p->brp, p->bcol, d_values, d_x, d_y, d_flag,
-                                                         ReduceScratch{nullptr, nullptr}, nullptr);
-   FEMB_LAUNCH_CHECK();
-   return 0;
+   RowRange rr;
+   if (int rc = plan_row_range(p, row_lo, row_hi, &rr)) return rc;
+   return spmv_launch(p, rr, d_values, d_x, d_y, d_flag, d_dot, accumulate != 0, as_stream(stream));
 }
 
 extern "C" int femb200_extract_diagonal(const femb200_plan *p, const double *d_values, double *d_diag, void *stream)

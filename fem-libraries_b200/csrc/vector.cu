@@ -156,12 +156,43 @@ __global__ void lift_b_kernel(int64_t n, const uint8_t *__restrict__ bc, const d
    if (i < n) b[i] = bc[i] ? scale * w[i] : b[i] - scale * y[i];
 }
 
-int spmv_launch(const femb200_plan *p, const double *d_values, const double *d_x, double *d_y, const double *d_flag,
-                double *d_dot_out, cudaStream_t st);
+// b = scale * (g - u) on the constrained dofs (dolfinx set_bc, F.cc:836); free dofs untouched
+__global__ void set_bc_kernel(int64_t n, const uint8_t *__restrict__ bc, const double *__restrict__ g,
+                              const double *__restrict__ u, double scale, double *__restrict__ b)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && bc[i]) b[i] = scale * (g[i] - u[i]);
+}
+
+__global__ void axpy_kernel(int64_t n, double alpha, const double *__restrict__ x, double *__restrict__ y)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) y[i] += alpha * x[i];
+}
 
 }  // namespace femb
 
 using namespace femb;
+
+extern "C" int femb200_set_bc(const femb200_plan *p, const double *d_g, const double *d_u, double scale, double *d_b,
+                              void *stream)
+{
+   FEMB_CHECK(p && d_g && d_u && d_b, "set_bc: null argument");
+   FEMB_CHECK(p->bc != nullptr, "set_bc: no Dirichlet dofs set on the plan");
+   const int64_t n = 2 * p->nnodes;
+   set_bc_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(n, p->bc, d_g, d_u, scale, d_b);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
+extern "C" int femb200_axpy(int64_t n, double alpha, const double *d_x, double *d_y, void *stream)
+{
+   FEMB_CHECK(n >= 0 && (n == 0 || (d_x && d_y)), "axpy: bad argument");
+   if (n == 0) return 0;
+   axpy_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(n, alpha, d_x, d_y);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
 
 extern "C" int femb200_assemble_vector(const femb200_plan *p, const double *d_x, int x_stride, const double *d_E,
                                        double nu, const double *d_dnod, const double *d_u, const double *d_fnod,
@@ -196,7 +227,11 @@ extern "C" int femb200_apply_lifting(const femb200_plan *p, const double *d_valu
    const unsigned grid = (unsigned)cdiv(n, 256);
    lift_w_kernel<<<grid, 256, 0, st>>>(n, p->bc, d_g, d_u, w);
    FEMB_LAUNCH_CHECK();
-   if (int rc = spmv_launch(p, d_values_nobc, w, y, nullptr, nullptr, st)) return rc;
+   // every local row (a rank's ghost rows included: their b entries are never used), whatever row ranges
+   // other callers apply on this plan
+   RowRange rr;
+   if (int rc = plan_row_range(p, 0, p->nnodes, &rr)) return rc;
+   if (int rc = spmv_launch(p, rr, d_values_nobc, w, y, nullptr, nullptr, false, st)) return rc;
    lift_b_kernel<<<grid, 256, 0, st>>>(n, p->bc, w, y, scale, d_b);
    FEMB_LAUNCH_CHECK();
    return 0;

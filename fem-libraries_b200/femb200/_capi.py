@@ -16,6 +16,7 @@ P1, P2, Q2 = 0, 1, 2
 ROWMAJOR_INTERLEAVED, COLMAJOR_BYNODES = 0, 1
 TANGENT_CLOSED, TANGENT_AD = 0, 1
 OP_CSR, OP_PA = 0, 1
+DIST_NCCL, DIST_P2P, DIST_BLOB_BYTES = 1, 2, 256
 SC_FLAG, SC_ITERS, SC_FINAL, SC_RED_NOM, SC_RED_DEN, SC_RED_BETA, SC_COUNT = 4, 5, 6, 9, 10, 11, 16
 
 vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -23,6 +24,7 @@ vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
 # name -> argtypes; every function returns int (0 = ok) unless listed in _SPECIAL
 SIGNATURES = {
     "femb200_device_info": [C.POINTER(C.c_int)] * 3,
+    "femb200_fp64_probe": [i32, i32, vp, C.POINTER(i64), C.POINTER(f64), vp],
     "femb200_tabulate_tensor_batched": [i32, i64, vp, vp, i32, vp, vp, vp, f64, vp, vp, i32, i32, vp],
     "femb200_plan_create": [i32, i64, i64, vp, vp, vp, C.POINTER(vp)],
     "femb200_plan_sizes": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32),
@@ -34,6 +36,8 @@ SIGNATURES = {
     "femb200_assemble_matrix_nobc": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp],
     "femb200_assemble_vector": [vp, vp, i32, vp, f64, vp, vp, vp, vp, vp],
     "femb200_apply_lifting": [vp, vp, vp, vp, f64, vp, vp, vp],
+    "femb200_set_bc": [vp, vp, vp, f64, vp, vp],
+    "femb200_axpy": [i64, f64, vp, vp, vp],
     "femb200_plan_set_dirichlet": [vp, vp, vp],
     "femb200_apply_dirichlet": [vp, vp, f64, vp],
     "femb200_matrix_norms": [vp, vp, vp, vp],
@@ -57,7 +61,21 @@ SIGNATURES = {
     "femb200_pa_diagonal": [vp, vp, vp],
     "femb200_gather": [i64, vp, vp, vp, vp],
     "femb200_scatter_rows": [i64, i32, vp, vp, vp, vp],
-    "femb200_plan_set_row_range": [vp, i64, i64],
+    "femb200_plan_set_option": [vp, C.c_char_p, i32],
+    "femb200_dist_create": [vp, i32, i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, C.POINTER(vp)],
+    "femb200_dist_nccl_unique_id": [vp],
+    "femb200_dist_nccl_comm_create": [vp, i32, i32, C.POINTER(vp)],
+    "femb200_dist_nccl_comm_destroy": [vp],
+    "femb200_dist_attach_nccl": [vp, vp],
+    "femb200_dist_p2p_export": [vp, vp],
+    "femb200_dist_p2p_attach": [vp, vp],
+    "femb200_dist_set_transport": [vp, i32],
+    "femb200_dist_allreduce_sum": [vp, vp, i32, vp],
+    "femb200_dist_halo": [vp, vp, vp],
+    "femb200_dist_mult": [vp, vp, vp, vp, vp],
+    "femb200_dist_pcg": [vp, i32, vp, vp, vp, vp, f64, f64, i32, vp, i32, i32, i32, C.POINTER(C.c_int),
+                         C.POINTER(C.c_double), C.POINTER(C.c_int), vp],
+    "femb200_dist_vectors": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "femb200_assemble_matrix_norms": [vp, vp, i32, vp, f64, vp, vp, i32, vp, vp, vp],
     "femb200_create_pattern": [i32, i64, i64, vp, vp, vp, C.POINTER(vp)],
     "femb200_element_grad_batched": [i32, i64, vp, vp, i32, vp, vp, vp, f64, vp, vp, i32, vp],
@@ -72,6 +90,8 @@ _SPECIAL = {
     "femb200_version": ([], C.c_int),
     "femb200_last_error": ([], C.c_char_p),
     "femb200_plan_destroy": ([vp], None),
+    "femb200_dist_destroy": ([vp], None),
+    "femb200_dist_transport": ([vp], C.c_int),
     "femb200_pa_destroy": ([vp], None),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))

@@ -126,6 +126,87 @@ def strip_partition(nx: int, ny_total: int, order: int, rank: int, world: int, j
     return part
 
 
+def strip_partition_device(nx: int, ny_total: int, rank: int, world: int, jitter_amp: float = 0.2, seed: int = 1234,
+                           device=None) -> StripPartition:
+    """strip_partition for large meshes: the same rank-local P2 strip, generated with torch on `device`
+    (lattice slicing instead of per-cell fancy indexing; 67 M cells in about a second).  Every array is
+    bit-identical to the numpy version (same IEEE operations: linspace as index * step, the per-lattice-row
+    Philox jitter drawn on the host, edge nodes as 0.5 * (a + b) of their two vertices); the fields of
+    part.mesh / E / bc / g are torch tensors.  Checked against strip_partition in tests/test_dist_cpu.py."""
+    if ny_total % world:
+        raise ValueError("strip_partition: ny_total must be a multiple of the number of ranks")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    rows = ny_total // world
+    r0, r1 = rank * rows, (rank + 1) * rows
+    r1g = min(r1 + 1, ny_total)
+    ny = r1g - r0
+    mx, my = 2 * nx + 1, 2 * ny + 1
+    f64, i32, i64 = torch.float64, torch.int32, torch.int64
+    # numpy.linspace(0, stop, num): arange(num) * (stop / (num - 1)), last entry = stop
+    xs = torch.arange(mx, dtype=f64, device=dev) * (1.0 / (mx - 1))
+    xs[-1] = 1.0
+    tot = 2 * ny_total + 1
+    ys = torch.arange(2 * r0, 2 * r1g + 1, dtype=f64, device=dev) * ((ny_total / nx) / (tot - 1))
+    if 2 * r1g == tot - 1:
+        ys[-1] = ny_total / nx
+    x = torch.empty((my, mx, 2), dtype=f64, device=dev)
+    x[:, :, 0] = xs[None, :]
+    x[:, :, 1] = ys[:, None]
+    if jitter_amp != 0.0:
+        h = 1.0 / nx
+        vrows = [lr for lr in range(0, my, 2) if 0 < 2 * r0 + lr < tot - 1]
+        if vrows:
+            J = np.empty((len(vrows), nx + 1, 2))
+            for k, lr in enumerate(vrows):
+                d = np.random.default_rng([seed, 2 * r0 + lr]).uniform(-jitter_amp * h, jitter_amp * h, size=(nx + 1, 2))
+                d[0] = d[-1] = 0.0
+                J[k] = d
+            Jd = torch.from_numpy(J).to(dev)
+            idx = torch.tensor(vrows, dtype=i64, device=dev)
+            x[idx, 0::2] += Jd
+            del Jd, J
+    # edge nodes: midpoint of their two vertices (horizontal, vertical, right diagonal)
+    x[0::2, 1::2] = 0.5 * (x[0::2, 0:-1:2] + x[0::2, 2::2])
+    x[1::2, 0::2] = 0.5 * (x[0:-1:2, 0::2] + x[2::2, 0::2])
+    x[1::2, 1::2] = 0.5 * (x[0:-1:2, 0:-1:2] + x[2::2, 2::2])
+    x = x.view(my * mx, 2)
+    cx = torch.arange(nx, dtype=i64, device=dev)[None, :]
+    cy = torch.arange(ny, dtype=i64, device=dev)[:, None]
+    v0 = ((2 * cx) + mx * (2 * cy)).reshape(-1)
+    v1, v2, v3 = v0 + 2, v0 + 2 * mx, v0 + 2 * mx + 2
+    dm = torch.empty((2 * nx * ny, 6), dtype=i32, device=dev)
+    for k, (a, b, c) in enumerate(((v0, v1, v3), (v0, v2, v3))):
+        dm[k::2, 0], dm[k::2, 1], dm[k::2, 2] = a.to(i32), b.to(i32), c.to(i32)
+        dm[k::2, 3], dm[k::2, 4], dm[k::2, 5] = ((b + c) // 2).to(i32), ((a + c) // 2).to(i32), ((a + b) // 2).to(i32)
+    del v0, v1, v2, v3
+    tri = dm[:, :3].contiguous()
+    cell_offset = 2 * nx * r0
+    tab = torch.from_numpy(fm.young_table()).to(dev)
+    E = tab[torch.arange(cell_offset, cell_offset + dm.shape[0], dtype=i64, device=dev) % 200]
+    bc = torch.zeros((my, mx, 2), dtype=torch.uint8, device=dev)
+    bc[:, 0, :] = 1
+    bc[:, -1, :] = 1
+    g = torch.zeros((my, mx, 2), dtype=f64, device=dev)
+    g[:, -1, 0] = 0.01
+    m = fm.Mesh(fm.P2, x, tri, dm, nx, ny, {"kind": "structured-tri-right", "order": 2, "jitter": jitter_amp})
+    own_row_lo = 0 if rank == 0 else 1
+    own_row_hi = 2 * rows + 1
+    part = StripPartition(rank, world, nx, ny_total, m, E, bc.view(-1), g.view(-1), own_row_lo * mx, own_row_hi * mx,
+                          2 * nx * rows, 2 * r0 * mx, cell_offset)
+    if rank > 0:
+        part.sends[rank - 1] = (1 * mx, 3 * mx)
+        part.recvs[rank - 1] = (0, mx)
+    if rank < world - 1:
+        part.sends[rank + 1] = ((2 * rows) * mx, (2 * rows + 1) * mx)
+        part.recvs[rank + 1] = ((2 * rows + 1) * mx, (2 * rows + 3) * mx)
+    return part
+
+
+def trivial_partition(mesh: fm.Mesh) -> StripPartition:
+    """The whole mesh as the one partition of a single rank (no neighbours, every node owned)."""
+    return StripPartition(0, 1, mesh.nx, mesh.ny, mesh, None, None, None, 0, mesh.nnodes, mesh.ncells, 0, 0)
+
+
 class Halo:
     """Forward ghost update of a local dof vector (2 dofs per node, blocked).  Works on
     CUDA tensors (NCCL) and on CPU tensors (gloo, used by the CPU tests of the host
@@ -163,131 +244,171 @@ def _p(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _off(t: torch.Tensor, n_doubles: int):
-    return C.c_void_p(t.data_ptr() + 8 * n_doubles)
+class DistOperator:
+    """The rank-local piece of the distributed operator: a femb200_dist communicator (C, csrc/dist.cu) over the
+    plan of `A` with the partition's owned range and neighbour table, plus its transport.
+
+    transport = "p2p":  NVLink peer memory (CUDA IPC): halo = one kernel storing into the neighbours' ghost
+                        rows, dot-product all-reduce fused into the CG's scalar kernel -- no collective launches;
+                "nccl": grouped ncclSend/ncclRecv + ncclAllReduce on a communicator the library creates from a
+                        unique id broadcast through torch.distributed;
+                "auto": p2p when every rank can map every peer, else nccl.
+    torch.distributed (any backend) is only the bootstrap: it carries the 128-byte NCCL id and the 256-byte
+    IPC blobs.  All ranks must construct, use and close the operator in the same order."""
+
+    def __init__(self, A, part: StripPartition, transport: str = "auto", group=None):
+        self.A, self.part, self.group = A, part, group
+        self._d = C.c_void_p()
+        self._comm = C.c_void_p()
+        nb = sorted(part.sends)
+        if sorted(part.recvs) != nb:
+            raise ValueError("DistOperator: sends and receives must name the same neighbours")
+        peers = np.array(nb, dtype=np.int32)
+        sl = np.array([part.sends[p][0] for p in nb], dtype=np.int64)
+        sh = np.array([part.sends[p][1] for p in nb], dtype=np.int64)
+        rl = np.array([part.recvs[p][0] for p in nb], dtype=np.int64)
+        rh = np.array([part.recvs[p][1] for p in nb], dtype=np.int64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        capi.call("femb200_dist_create", A.plan, part.rank, part.world, part.own_lo, part.own_hi, len(nb), ptr(peers),
+                  ptr(sl), ptr(sh), ptr(rl), ptr(rh), _st(), C.byref(self._d))
+        self.transport = "none"
+        if part.world > 1:
+            if transport in ("auto", "p2p"):
+                ok = self._attach_p2p()
+                if not ok and transport == "p2p":
+                    raise RuntimeError("DistOperator: peer memory could not be mapped on every rank")
+            if self.transport == "none":
+                self._attach_nccl()
+
+    # -- bootstrap ---------------------------------------------------------------------------
+    def _attach_p2p(self) -> bool:
+        blob = (C.c_ubyte * capi.DIST_BLOB_BYTES)()
+        capi.call("femb200_dist_p2p_export", self._d, blob)
+        blobs = [None] * self.part.world
+        td.all_gather_object(blobs, bytes(blob), group=self.group)
+        buf = (C.c_ubyte * (capi.DIST_BLOB_BYTES * self.part.world)).from_buffer_copy(b"".join(blobs))
+        rc = capi.lib().femb200_dist_p2p_attach(self._d, buf)
+        self.p2p_error = None if rc == 0 else capi.lib().femb200_last_error().decode(errors="replace")
+        oks = [None] * self.part.world
+        td.all_gather_object(oks, rc == 0, group=self.group)
+        if all(oks):
+            self.transport = "p2p"
+            return True
+        return False
+
+    def _attach_nccl(self):
+        idb = (C.c_ubyte * 128)()
+        if self.part.rank == 0:
+            capi.call("femb200_dist_nccl_unique_id", idb)
+        box = [bytes(idb)]
+        td.broadcast_object_list(box, src=0, group=self.group)
+        idb = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        capi.call("femb200_dist_nccl_comm_create", idb, self.part.rank, self.part.world, C.byref(self._comm))
+        capi.call("femb200_dist_attach_nccl", self._d, self._comm)
+        capi.call("femb200_dist_set_transport", self._d, capi.DIST_NCCL)
+        self.transport = "nccl"
+
+    def use(self, transport: str):
+        """Switch between attached transports ("p2p" / "nccl"); attaches NCCL on first use."""
+        if transport == "nccl" and not self._comm.value:
+            self._attach_nccl()
+            return
+        capi.call("femb200_dist_set_transport", self._d, capi.DIST_P2P if transport == "p2p" else capi.DIST_NCCL)
+        self.transport = transport
+
+    def close(self):
+        if getattr(self, "_d", None) is not None and self._d.value:
+            torch.cuda.synchronize()
+            if self.part.world > 1:
+                td.barrier(group=self.group)          # nobody stores into an arena that is about to go
+            capi.lib().femb200_dist_destroy(self._d)
+            self._d = C.c_void_p()
+            if self._comm.value:
+                capi.lib().femb200_dist_nccl_comm_destroy(self._comm)
+                self._comm = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_d", None) is not None and self._d.value and self.part.world == 1:
+                capi.lib().femb200_dist_destroy(self._d)
+                self._d = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._d
+
+    # -- collectives / operator -----------------------------------------------------------------
+    def allreduce_sum(self, v: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of a device vector of at most 3 doubles."""
+        capi.call("femb200_dist_allreduce_sum", self._d, _p(v), v.numel(), _st())
+        return v
+
+    def halo(self, v: torch.Tensor) -> torch.Tensor:
+        capi.call("femb200_dist_halo", self._d, _p(v), _st())
+        return v
+
+    def mult(self, v: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """y[owned] = (A v)[owned] with the ghost update of v."""
+        capi.call("femb200_dist_mult", self._d, _p(self.A.values), _p(v), _p(y), _st())
+        return y
+
+    def vectors(self):
+        """(r, d, z, scal) of the last solve as torch views of the communicator's device memory."""
+        ps = [C.c_void_p() for _ in range(4)]
+        capi.call("femb200_dist_vectors", self._d, *[C.byref(p) for p in ps])
+        n = 2 * self.part.mesh.nnodes
+        return tuple(_view(p.value, k) for p, k in zip(ps, (n, n, n, capi.SC_COUNT)))
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _view(ptr: int, n: int) -> torch.Tensor:
+    """float64 device tensor over memory owned by the C library (no copy; valid while the owner lives)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device="cuda")
 
 
 class DistCG:
-    """(Jacobi-)PCG over the strips with mfem::CGSolver semantics (M.cc:1502,1525-1528):
-    the single-GPU kernels of libfemb200 on the owned rows + halo exchange of the
-    search direction + all-reduce of the three dot products."""
+    """(Jacobi-)PCG over the ranks with mfem::CGSolver semantics (M.cc:1502,1525-1528): femb200_dist_pcg, the
+    single-GPU kernels on the owned rows + ghost update of the search direction + all-reduce of the three dot
+    products, the whole loop in C (one CUDA graph per iteration).  world = 1 works without a process group."""
 
     def __init__(self, A, part: StripPartition, rel_tol=1e-12, abs_tol=0.0, max_iter=2000, check_every=25,
-                 jacobi=True, group=None, overlap: bool = False):
+                 jacobi=True, group=None, transport: str = "auto", use_graph: bool = True, op: DistOperator | None = None):
         self.A, self.part = A, part
         self.rel_tol, self.abs_tol, self.max_iter, self.check_every = rel_tol, abs_tol, max_iter, check_every
-        self.halo = Halo(part, group)
-        self.group = group
-        # Owned rows that read ghost values (strip layout: the two lattice rows above the bottom ghost row, the
-        # lattice row below the top ghost rows) are applied after the halo exchange; all the other owned rows --
-        # the plan's row range -- run while the exchange is in flight on a second stream.
-        mx = 2 * part.nx + 1
-        self.bottom = (part.own_lo, min(part.own_lo + 2 * mx, part.own_hi)) if part.rank > 0 else (part.own_lo, part.own_lo)
-        self.top = (max(part.own_hi - mx, self.bottom[1]), part.own_hi) if part.rank < part.world - 1 else (part.own_hi, part.own_hi)
-        # (measured at 2 GPUs: 0.854 ms per iteration with the overlap, 0.848 ms without -- the communication
-        # cost of an iteration is the latency of its three all-reduces, not the 93 KB halo -- hence off by default)
-        self.overlap = bool(overlap) and part.world > 1 and A.values.is_cuda
-        if self.overlap:
-            A.set_row_range(self.bottom[1], self.top[0])
-            self.side = torch.cuda.Stream()
-            self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
-        else:
-            A.set_row_range(part.own_lo, part.own_hi)
-        nl = 2 * part.mesh.nnodes
-        dev = A.values.device
-        self.r = torch.zeros(nl, dtype=torch.float64, device=dev)
-        self.d = torch.zeros(nl, dtype=torch.float64, device=dev)
-        self.z = torch.zeros(nl, dtype=torch.float64, device=dev)
-        self.scal = torch.zeros(capi.SC_COUNT, dtype=torch.float64, device=dev)
+        self.op = DistOperator(A, part, transport, group) if op is None else op
+        self.use_graph = use_graph
         self.dinv = None
         if jacobi:
-            diag = A.diagonal()
-            self.dinv = torch.empty_like(diag)
-            capi.call("femb200_jacobi_setup", diag.numel(), _p(diag), _p(self.dinv), self._st())
+            self.update_preconditioner()
         self.iterations, self.final_norm, self.converged = 0, 0.0, False
 
-    @staticmethod
-    def _st():
-        return torch.cuda.current_stream().cuda_stream
-
-    def _allreduce(self, idx: int):
-        if self.part.world > 1:
-            td.all_reduce(self.scal[idx:idx + 1], group=self.group)
+    def update_preconditioner(self):
+        diag = self.A.diagonal()
+        self.dinv = torch.empty_like(diag)
+        capi.call("femb200_jacobi_setup", diag.numel(), _p(diag), _p(self.dinv), _st())
 
     def mult(self, v: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        """y[owned] = (A v)[owned] with the ghost update of v: halo exchange on the second stream while the
-        interior rows run, then the rows next to the ghosts (the operator apply of one CG iteration)."""
-        A, st = self.A, self._st
-        if not self.overlap:
-            self.halo.forward(v)
-            capi.call("femb200_spmv", A.plan, _p(A.values), _p(v), _p(y), st())
-            return y
-        main = torch.cuda.current_stream()
-        self.ev_ready.record(main)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(self.ev_ready)
-            self.halo.forward(v)
-            self.ev_halo.record(self.side)
-        capi.call("femb200_spmv", A.plan, _p(A.values), _p(v), _p(y), st())
-        main.wait_event(self.ev_halo)
-        for lo, hi in (self.bottom, self.top):
-            if hi > lo:
-                capi.call("femb200_spmv_rows", A.plan, _p(A.values), _p(v), _p(y), lo, hi, None, 0, None, st())
-        return y
+        return self.op.mult(v, y)
 
     def solve(self, b: torch.Tensor, x: torch.Tensor, fixed_iters: int = 0) -> torch.Tensor:
-        p = self.part
-        o, n = 2 * p.own_lo, 2 * p.n_owned
-        st = self._st
-        A, scal = self.A, self.scal
-        dinv_o = None if self.dinv is None else _off(self.dinv, o)
-        capi.call("femb200_cg_set_tolerances", _p(scal), self.rel_tol, self.abs_tol, st())
-        capi.call("femb200_cg_init", n, _off(b, o), dinv_o, _off(x, o), _off(self.r, o), _off(self.d, o), _p(scal), st())
-        self._allreduce(capi.SC_RED_NOM)
-        capi.call("femb200_cg_scalar_step", _p(scal), 0, st())
-
-        def apply():
-            if not self.overlap:
-                self.halo.forward(self.d)
-                capi.call("femb200_cg_apply", A.plan, capi.OP_CSR, None, _p(A.values), _p(self.d), _p(self.z), _p(scal), st())
-            else:
-                main = torch.cuda.current_stream()
-                self.ev_ready.record(main)                       # the search direction is final
-                with torch.cuda.stream(self.side):
-                    self.side.wait_event(self.ev_ready)
-                    self.halo.forward(self.d)                    # NCCL send/recv of the interface rows
-                    self.ev_halo.record(self.side)
-                # interior rows: Ad and the partial <d, A d>, while the halo is in flight
-                capi.call("femb200_cg_apply", A.plan, capi.OP_CSR, None, _p(A.values), _p(self.d), _p(self.z), _p(scal), st())
-                main.wait_event(self.ev_halo)
-                flag = _off(scal, capi.SC_FLAG)
-                for lo, hi in (self.bottom, self.top):           # rows that read ghost values; dot accumulated
-                    if hi > lo:
-                        capi.call("femb200_spmv_rows", A.plan, _p(A.values), _p(self.d), _p(self.z), lo, hi,
-                                  _off(scal, capi.SC_RED_DEN), 1, flag, st())
-            self._allreduce(capi.SC_RED_DEN)
-            capi.call("femb200_cg_scalar_step", _p(scal), 1, st())
-
-        apply()
-        nit = fixed_iters if fixed_iters > 0 else self.max_iter
-        stopped = False
-        i = 0
-        while i < nit and not stopped:
-            i += 1
-            capi.call("femb200_cg_update_xr", n, _p(scal), _off(self.d, o), _off(self.z, o), dinv_o, _off(x, o),
-                      _off(self.r, o), st())
-            self._allreduce(capi.SC_RED_BETA)
-            capi.call("femb200_cg_scalar_step", _p(scal), 2, st())
-            if i < nit:
-                capi.call("femb200_cg_update_dir", n, _p(scal), _off(self.r, o), dinv_o, _off(self.d, o), st())
-                apply()
-            if fixed_iters <= 0 and i % self.check_every == 0 and i < nit:
-                stopped = scal[capi.SC_FLAG].item() != 0.0
-        hs = scal.cpu().numpy()
-        self.converged = hs[capi.SC_FLAG] == 1.0
-        self.iterations = int(hs[capi.SC_ITERS]) if (self.converged or fixed_iters > 0) else self.max_iter
-        self.final_norm = float(np.sqrt(max(hs[capi.SC_FINAL], 0.0)))
+        it, fn, cv = C.c_int(), C.c_double(), C.c_int()
+        capi.call("femb200_dist_pcg", self.op.handle, capi.OP_CSR, None, _p(self.A.values), _p(b), _p(x), self.rel_tol,
+                  self.abs_tol, self.max_iter, _p(self.dinv), self.check_every, int(fixed_iters), int(self.use_graph),
+                  C.byref(it), C.byref(fn), C.byref(cv), _st())
+        self.iterations, self.final_norm, self.converged = it.value, fn.value, bool(cv.value)
         return x
+
+    def close(self):
+        self.op.close()
 
 
 def gather_owned(part: StripPartition, v_local: torch.Tensor, group=None) -> np.ndarray | None:

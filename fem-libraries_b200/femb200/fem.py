@@ -207,6 +207,13 @@ class Matrix:
         return brp, bcol
 
     def set_bcs(self, bcs):
+        one = bcs[0] if isinstance(bcs, (list, tuple)) and len(bcs) == 1 else bcs
+        if isinstance(one, DirichletBC) and isinstance(one.marker, torch.Tensor) and one.marker.is_cuda:
+            # a single marker already on the device (large meshes): no round trip through the host
+            self.bc_dev = (one.marker != 0).to(torch.uint8).contiguous()
+            capi.call("femb200_plan_set_dirichlet", self._plan, _p(self.bc_dev), _stream())
+            self._bc_marker = None
+            return
         m = merge_bcs(bcs, self.ndofs)
         if m is None:
             capi.call("femb200_plan_set_dirichlet", self._plan, None, _stream())
@@ -216,8 +223,16 @@ class Matrix:
             capi.call("femb200_plan_set_dirichlet", self._plan, _p(self.bc_dev), _stream())
         self._bc_marker = m
 
-    def set_row_range(self, lo: int, hi: int):
-        capi.call("femb200_plan_set_row_range", self._plan, int(lo), int(hi))
+    def set_option(self, key: str, value: int):
+        """Kernel selection of the plan (femb200_plan_set_option): "assembly_path", "spmv_path", "prefetch_tiles"."""
+        capi.call("femb200_plan_set_option", self._plan, key.encode(), int(value))
+
+    def mult_rows(self, x: torch.Tensor, y: torch.Tensor, lo: int, hi: int, dot: torch.Tensor | None = None,
+                  accumulate: bool = False) -> torch.Tensor:
+        """y = A x on the node rows [lo, hi) only (the rows a rank owns); `dot` (1 device double) gets <x, y>."""
+        capi.call("femb200_spmv_rows", self._plan, _p(self.values), _p(x), _p(y), int(lo), int(hi), _p(dot),
+                  int(accumulate), None, _stream())
+        return y
 
     # --- operator interface (mfem::Operator::Mult / PETSc MatMult) -------------
     def mult(self, x: torch.Tensor, y: torch.Tensor | None = None) -> torch.Tensor:
@@ -307,43 +322,121 @@ def apply_lifting(A: Matrix, b: torch.Tensor, g: torch.Tensor, u: torch.Tensor, 
 
 
 class NewtonSolver:
-    """The Newton loop around the hot path (mfem::NewtonSolver, M.cc:1531-1549; dolfinx NewtonSolver,
-    F.cc:705-714,869-907): per iteration residual F(u) (+ lifting), tangent J(u), Jacobi-PCG solve,
-    u <- u - du.  Convergence as MFEM: |b| <= max(rel_tol |b_0|, abs_tol) (M.cc:1535-1541)."""
+    """The Newton loop around the hot path (mfem::NewtonSolver, M.cc:1531-1549; dolfinx nls::petsc::NewtonSolver,
+    F.cc:705-714,869-907).  Per iteration: residual b = F(u) with the Dirichlet lifting (setF, F.cc:817-845), tangent
+    J(u) with Dirichlet rows/columns (setJ, F.cc:847-862), Jacobi-PCG solve J du = b, u <- u - du.
+
+    Both convergence conventions of the reference (doc.tex:2065-2068):
+      convention="mfem"     |b| <= max(rel_tol |b_0|, abs_tol), b_0 = the first residual (M.cc:1535-1541);
+      convention="dolfinx"  |b| / r_0 < rel_tol or |b| < abs_tol with r_0 = |du_0|, the norm of the FIRST
+                            SOLUTION INCREMENT (set after the first update; before it only the absolute test
+                            can stop the loop) -- the reason FEniCSx iterates twice more than MFEM.
+    `part` (a dist.StripPartition) runs the same loop on one partition per rank: owned-row norms are all-reduced,
+    u gets its ghost update after every increment (newton_solver.set_form, F.cc:865-866) and the linear solve is
+    femb200_dist_pcg; without it the solver works on the whole mesh (a one-rank partition).
+    The tangent is assembled only when an increment is actually computed (after the convergence test), and once
+    u carries the boundary values (every iteration after the first) the lifting reduces to set_bc."""
 
     def __init__(self, form: ElasticityForm, bcs, f=None, rel_tol=1e-7, abs_tol=5e-8, max_iter=10, cg_rel_tol=1e-12,
-                 cg_max_iter=2000):
+                 cg_max_iter=2000, convention: str = "mfem", part=None, transport: str = "auto", group=None):
+        from . import dist
+        if convention not in ("mfem", "dolfinx"):
+            raise ValueError("convention must be 'mfem' or 'dolfinx'")
         self.form, self.f = form, to_device(f, np.float64)
-        self.rel_tol, self.abs_tol, self.max_iter = rel_tol, abs_tol, max_iter
+        self.rel_tol, self.abs_tol, self.max_iter, self.convention = rel_tol, abs_tol, max_iter, convention
         self.A = create_matrix(form)
         self.A.set_bcs(bcs)
-        gv = np.zeros(self.A.ndofs)
-        for bc in ([bcs] if isinstance(bcs, DirichletBC) else bcs):
-            if bc.values is not None:
-                m = np.asarray(bc.marker) != 0
-                gv[m] = np.asarray(bc.values)[m]
-        self.g = to_device(gv, np.float64)
-        self.cg = CGSolver(rel_tol=cg_rel_tol, max_iter=cg_max_iter)
+        one = bcs[0] if isinstance(bcs, (list, tuple)) and len(bcs) == 1 else bcs
+        if isinstance(one, DirichletBC) and isinstance(one.values, torch.Tensor) and one.values.is_cuda:
+            self.g = one.values.to(torch.float64).contiguous()
+        else:
+            gv = np.zeros(self.A.ndofs)
+            for bc in ([bcs] if isinstance(bcs, DirichletBC) else bcs):
+                if bc.values is not None:
+                    m = np.asarray(bc.marker) != 0
+                    gv[m] = np.asarray(bc.values)[m]
+            self.g = to_device(gv, np.float64)
+        self.part = dist.trivial_partition(form.mesh) if part is None else part
+        self.cg = dist.DistCG(self.A, self.part, rel_tol=cg_rel_tol, max_iter=cg_max_iter, jacobi=False,
+                              transport=transport, group=group)
+        self._lo, self._hi = 2 * self.part.own_lo, 2 * self.part.own_hi
+        self._work = torch.empty(2 * self.A.ndofs, dtype=torch.float64, device="cuda")
+        self._b = torch.empty(self.A.ndofs, dtype=torch.float64, device="cuda")
+        self._du = torch.zeros(self.A.ndofs, dtype=torch.float64, device="cuda")
+        self._nrm = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self._lifted = False          # does u carry the boundary values already?
+        self._tangent_ready = False   # A.values holds the unconstrained tangent of the current u
         self.residual_norms, self.linear_iterations = [], []
 
-    def solve(self, u0=None) -> torch.Tensor:
-        form, A = self.form, self.A
-        u = torch.zeros(A.ndofs, dtype=torch.float64, device="cuda") if u0 is None else to_device(u0, np.float64).clone()
-        self.residual_norms, self.linear_iterations = [], []
-        for it in range(self.max_iter + 1):
-            form.u = u
-            b = assemble_vector(A, form, self.f)
+    def close(self):
+        self.cg.close()
+
+    # -- building blocks (one Newton linearisation = residual() + increment()) -----------------
+    def residual(self, u: torch.Tensor) -> torch.Tensor:
+        """b = F(u) with apply_lifting + set_bc (scale -1), setF lambda F.cc:817-845."""
+        form, A, b = self.form, self.A, self._b
+        form.u = u
+        assemble_vector(A, form, self.f, out=b)
+        self._tangent_ready = False
+        if self._lifted:
+            capi.call("femb200_set_bc", A.plan, _p(self.g), _p(u), -1.0, _p(b), _stream())
+        else:
             assemble_matrix_nobc(A, form)
-            apply_lifting(A, b, self.g, u, -1.0)
-            self.residual_norms.append(float(b.norm().item()))
-            if self.residual_norms[-1] <= max(self.rel_tol * self.residual_norms[0], self.abs_tol) or it == self.max_iter:
-                break
+            self._tangent_ready = True
+            capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(self.g), _p(u), -1.0, _p(b), _p(self._work), _stream())
+        return b
+
+    def norm(self, v: torch.Tensor) -> float:
+        """l2 norm over the owned dofs of every rank (one 8-byte read back: the convergence decision is the host's)."""
+        n = self._hi - self._lo
+        off = C.c_void_p(v.data_ptr() + 8 * self._lo)
+        capi.call("femb200_dot", n, off, off, _p(self._nrm), _stream())
+        self.cg.op.allreduce_sum(self._nrm)
+        return float(np.sqrt(self._nrm.item()))
+
+    def increment(self, b: torch.Tensor, fixed_iters: int = 0) -> torch.Tensor:
+        """du = J(u)^-1 b: tangent with Dirichlet rows/columns (setJ lambda F.cc:847-862) + Jacobi-PCG."""
+        form, A = self.form, self.A
+        if self._tangent_ready:
             capi.call("femb200_apply_dirichlet", A.plan, _p(A.values), 1.0, _stream())
-            self.cg.SetOperator(A)
-            self.cg.SetPreconditioner("jacobi")
-            du = self.cg.Mult(b)
-            self.linear_iterations.append(self.cg.GetNumIterations())
-            u = u - du
+        else:
+            assemble_matrix(A, form)
+        self._tangent_ready = False
+        self.cg.update_preconditioner()
+        self.cg.solve(b, self._du, fixed_iters=fixed_iters)
+        self.linear_iterations.append(self.cg.iterations)
+        return self._du
+
+    def update(self, u: torch.Tensor, du: torch.Tensor) -> torch.Tensor:
+        """u <- u - du on the owned dofs, then the ghost update of u (F.cc:865-866)."""
+        n = self._hi - self._lo
+        capi.call("femb200_axpy", n, -1.0, C.c_void_p(du.data_ptr() + 8 * self._lo), C.c_void_p(u.data_ptr() + 8 * self._lo),
+                  _stream())
+        self.cg.op.halo(u)
+        self._lifted = True
+        return u
+
+    def solve(self, u0=None) -> torch.Tensor:
+        A = self.A
+        u = torch.zeros(A.ndofs, dtype=torch.float64, device="cuda") if u0 is None else to_device(u0, np.float64).clone()
+        self.residual_norms, self.linear_iterations, self.increment_norms = [], [], []
+        self._lifted = False
+        self.converged = False
+        r0 = None
+        for it in range(self.max_iter + 1):
+            nrm = self.norm(self.residual(u))
+            self.residual_norms.append(nrm)
+            if self.convention == "mfem":
+                self.converged = nrm <= max(self.rel_tol * self.residual_norms[0], self.abs_tol)
+            else:
+                self.converged = nrm < self.abs_tol or (r0 is not None and nrm / r0 < self.rel_tol)
+            if self.converged or it == self.max_iter:
+                break
+            du = self.increment(self._b)
+            if it == 0:
+                r0 = self.norm(du)
+            self.increment_norms.append(r0 if it == 0 else None)
+            self.update(u, du)
         self.iterations = len(self.residual_norms) - 1
         return u
 

@@ -63,6 +63,10 @@ int femb200_version(void);
 const char *femb200_last_error(void);
 /* host scalars: SM count and compute capability of the current device */
 int femb200_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* FP64 FMA throughput probe (the measured denominator of the FP64 roofline of the element kernels): one launch
+ * of blocks_per_sm * SM count blocks x 256 threads x iters x 8 independent FMA chains on `stream`; the caller
+ * times it.  *flops = operations of the launch (FMA = 2); d_out: *blocks_out * 256 doubles (NULL: size query). */
+int femb200_fp64_probe(int blocks_per_sm, int iters, double *d_out, int64_t *blocks_out, double *flops, void *stream);
 
 /* ------------------------------------------------------------------------
  * Element kernel.
@@ -147,6 +151,11 @@ int femb200_assemble_vector(const femb200_plan *plan, const double *d_x, int x_s
                             const double *d_dnod, const double *d_u, const double *d_fnod, double *d_b, void *stream);
 int femb200_apply_lifting(const femb200_plan *plan, const double *d_values_nobc, const double *d_g, const double *d_u,
                           double scale, double *d_b, double *d_work, void *stream);
+/* set_bc alone (F.cc:836): b[bc] = scale * (g - u)[bc]; what the lifting reduces to once u carries the
+ * boundary values (every Newton iteration after the first) */
+int femb200_set_bc(const femb200_plan *plan, const double *d_g, const double *d_u, double scale, double *d_b, void *stream);
+/* y += alpha x (the Newton update u <- u - du, M.cc:1546 / F.cc:894) */
+int femb200_axpy(int64_t n, double alpha, const double *d_x, double *d_y, void *stream);
 
 /* ------------------------------------------------------------------------
  * Assembled operator apply.
@@ -158,9 +167,10 @@ int femb200_spmv(const femb200_plan *plan, const double *d_values, const double 
 /* y = A x and d_dot[0] = <x, y> in the same pass (deterministic reduction) */
 int femb200_spmv_dot(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, double *d_dot,
                      void *stream);
-/* y = A x on the node rows [row_lo, row_hi) only (any range); d_dot (or NULL) receives <x, y> over those rows,
- * added to its content when `accumulate`; d_flag (or NULL): no-op when *d_flag != 0 (converged CG).  For the
- * boundary rows of a rank, which wait for the halo while the interior rows run. */
+/* y = A x on the node rows [row_lo, row_hi) only (any range: the rows a rank owns); rows outside are left
+ * untouched.  d_dot (or NULL) receives <x, y> over those rows, added to its content when `accumulate`; d_flag
+ * (or NULL): no-op when *d_flag != 0 (converged CG).  The first call with a range that does not start on a
+ * 64-row boundary measures its tiling once (synchronises the device). */
 int femb200_spmv_rows(const femb200_plan *plan, const double *d_values, const double *d_x, double *d_y, int64_t row_lo,
                       int64_t row_hi, double *d_dot, int accumulate, const double *d_flag, void *stream);
 int femb200_extract_diagonal(const femb200_plan *plan, const double *d_values, double *d_diag, void *stream);
@@ -223,9 +233,72 @@ int femb200_gather(int64_t nnodes_out, const int32_t *d_node_idx, const double *
 /* d_dst[d_idx[k]] = d_src[k] over rows of `width` doubles: refreshes the coordinates of the geometry
  * vertices only (dolfinx mesh.geometry.x holds the P1 geometry, F.cc:213) */
 int femb200_scatter_rows(int64_t n, int width, const int32_t *d_idx, const double *d_src, double *d_dst, void *stream);
-/* restrict femb200_spmv / femb200_cg_apply to the node rows [row_lo, row_hi)
- * (the rows this rank owns); rows outside are left untouched */
-int femb200_plan_set_row_range(femb200_plan *plan, int64_t row_lo, int64_t row_hi);
+/* Kernel selection of a plan.  The write-once assembly and the SpMV each have a fallback kernel for
+ * patterns the fast one does not cover (a node in 16 or more cells, a 64-row tile beyond the shared-memory
+ * budget); these options force a path so that tests exercise the fallbacks on any mesh.  Read at launch
+ * from the plan, no environment variables.
+ *   "assembly_path"  0 auto | 1 visit-record kernel | 2 per-quadrature-point kernel
+ *   "spmv_path"      0 auto (bulk-copy staged) | 1 direct kernel
+ *   "prefetch_tiles" record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count, 0: off) */
+int femb200_plan_set_option(femb200_plan *plan, const char *key, int value);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: one mesh partition per rank (one process per GPU).
+ * Replaces: the MPI layer under the linear solve of both drivers -- the forward
+ * ghost update before an operator apply (VecGhostUpdate(INSERT, FORWARD),
+ * F.cc:865-866; the halo inside HypreParMatrix::Mult) and the MPI_Allreduce of
+ * the CG dot products inside mfem::CGSolver / PETSc KSP cg (M.cc:1502-1528,
+ * F.cc:718-722); partition = element blocks, ownership = lowest rank
+ * (doc.tex:444-464, F.cc:159).
+ * Local numbering: owned nodes are ONE contiguous range [own_lo, own_hi) of the
+ * plan's nodes, ghost nodes around it; the rank's mesh holds every cell touching
+ * an owned node, so assembly needs no communication and owned rows are complete.
+ * Per neighbour k: peers[k], owned nodes [send_lo[k], send_hi[k]) to send, ghost
+ * nodes [recv_lo[k], recv_hi[k]) to receive (contiguous ranges).
+ * Transports (attach one or both, pick with set_transport; the last attached is
+ * active):
+ *   NCCL  any ncclComm_t (void*) of `world` ranks: ncclSend/ncclRecv halo,
+ *         ncclAllReduce of the dot products, on the caller's stream;
+ *   P2P   NVLink peer memory on one box: every rank exports its arena with
+ *         p2p_export (FEMB200_DIST_BLOB_BYTES bytes), the host all-gathers the
+ *         blobs (rank order) and hands them to p2p_attach.  The halo is then one
+ *         kernel storing straight into the neighbours' ghost rows, the all-reduce
+ *         is fused into the scalar kernel of the CG (no collective launches).
+ * All ranks must issue the same sequence of dist calls.
+ * ------------------------------------------------------------------------ */
+typedef struct femb200_dist femb200_dist;
+#define FEMB200_DIST_NCCL 1
+#define FEMB200_DIST_P2P 2
+#define FEMB200_DIST_BLOB_BYTES 256
+int femb200_dist_create(const femb200_plan *plan, int rank, int world, int64_t own_lo, int64_t own_hi, int nneigh,
+                        const int32_t *peers, const int64_t *send_lo, const int64_t *send_hi, const int64_t *recv_lo,
+                        const int64_t *recv_hi, void *stream, femb200_dist **out);
+void femb200_dist_destroy(femb200_dist *dist);
+/* helpers for hosts without a communicator of their own: id on rank 0 (128 bytes, broadcast it), then
+ * comm_create on every rank (ncclCommInitRank) */
+int femb200_dist_nccl_unique_id(unsigned char *id128);
+int femb200_dist_nccl_comm_create(const unsigned char *id128, int rank, int world, void **nccl_comm_out);
+int femb200_dist_nccl_comm_destroy(void *nccl_comm);
+int femb200_dist_attach_nccl(femb200_dist *dist, void *nccl_comm);
+int femb200_dist_p2p_export(femb200_dist *dist, unsigned char *blob);
+int femb200_dist_p2p_attach(femb200_dist *dist, const unsigned char *blobs_of_all_ranks);
+int femb200_dist_set_transport(femb200_dist *dist, int transport);
+int femb200_dist_transport(const femb200_dist *dist);
+/* sum of d_vals[0..count) (count <= 3) over the ranks, in place, identical on every rank */
+int femb200_dist_allreduce_sum(femb200_dist *dist, double *d_vals, int count, void *stream);
+/* forward ghost update of a local dof vector (2 * plan nodes) */
+int femb200_dist_halo(femb200_dist *dist, double *d_v, void *stream);
+/* y[owned] = (A v)[owned] after the ghost update of v */
+int femb200_dist_mult(femb200_dist *dist, const double *d_values, double *d_v, double *d_y, void *stream);
+/* femb200_pcg over the ranks: d_b, d_x, d_dinv are local vectors (ghosts included, only owned entries are
+ * read / written); `use_graph` replays one captured CUDA graph per iteration; host scalars are identical on
+ * every rank; synchronises the stream.  world = 1 needs no transport. */
+int femb200_dist_pcg(femb200_dist *dist, int op_kind, const void *op, const double *d_values, const double *d_b,
+                     double *d_x, double rtol, double atol, int maxit, const double *d_dinv, int check_every,
+                     int fixed_iters, int use_graph, int *iters, double *final_norm, int *converged, void *stream);
+/* work vectors of the communicator after a solve (device pointers, local length): recurrence residual r,
+ * search direction, A d, and the 16 CG scalars */
+int femb200_dist_vectors(femb200_dist *dist, double **d_r, double **d_dir, double **d_z, double **d_scal);
 
 /* ------------------------------------------------------------------------
  * Partial assembly (matrix-free).

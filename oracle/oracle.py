@@ -156,17 +156,20 @@ def assemble_vector(etype, x, xdofmap, dofmap, E, nu, u, dnod=None, fnod=None) -
 
 
 def newton(etype, x, xdofmap, dofmap, E, nu, bc, g, dnod=None, fnod=None, variant=TANGENT_CLOSED, rel_tol=1e-7,
-           abs_tol=5e-8, max_iter=10, cg_rtol=1e-12, cg_maxit=4000):
+           abs_tol=5e-8, max_iter=10, cg_rtol=1e-12, cg_maxit=4000, convention="mfem"):
     """Newton loop of the reference (tolerances M.cc:1531-1543; BC treatment F.cc:817-862):
     b = F(u); b -= (-1) J[:, bc] (g - u)_bc; b[bc] = -(g - u)_bc; J with BC rows/cols zeroed and unit diagonal;
-    solve J du = b with Jacobi-PCG; u <- u - du.  MFEM convergence: |b| <= max(rel_tol |b0|, abs_tol).
-    Returns u, iterations, residual norms."""
+    solve J du = b with Jacobi-PCG; u <- u - du.  Convergence, convention "mfem": |b| <= max(rel_tol |b0|, abs_tol)
+    (M.cc:1535-1541); "dolfinx": |b| < abs_tol or |b| / r0 < rel_tol with r0 = |du_0|, the norm of the first
+    increment, known after the first update only (dolfinx 0.8 NewtonSolver as driven by F.cc:869-891;
+    doc.tex:2065-2068).  Returns u, iterations, residual norms."""
     x = _f64(x)
     nn = x.shape[0]
     rowptr, colidx = build_pattern(nn, dofmap)
     u = np.zeros(2 * nn)
     c = np.asarray(bc) != 0
     norms = []
+    r0 = None
     for it in range(max_iter + 1):
         b = assemble_vector(etype, x, xdofmap, dofmap, E, nu, u, dnod, fnod)
         full = assemble_matrix(etype, x, xdofmap, dofmap, E, nu, rowptr, colidx, dnod=dnod, u=u, variant=variant)
@@ -174,10 +177,16 @@ def newton(etype, x, xdofmap, dofmap, E, nu, bc, g, dnod=None, fnod=None, varian
         b = b + spmv(rowptr, colidx, full, w)
         b[c] = -(g - u)[c]
         norms.append(float(np.linalg.norm(b)))
-        if norms[-1] <= max(rel_tol * norms[0], abs_tol) or it == max_iter:
+        if convention == "mfem":
+            done = norms[-1] <= max(rel_tol * norms[0], abs_tol)
+        else:
+            done = norms[-1] < abs_tol or (r0 is not None and norms[-1] / r0 < rel_tol)
+        if done or it == max_iter:
             break
         vals = assemble_matrix(etype, x, xdofmap, dofmap, E, nu, rowptr, colidx, dnod=dnod, u=u, variant=variant, bc=bc)
         du, _, _, conv = pcg(rowptr, colidx, vals, b, rtol=cg_rtol, maxit=cg_maxit, jacobi=True)
+        if it == 0:
+            r0 = float(np.linalg.norm(du))
         u = u - du
     return u, len(norms) - 1, norms
 

@@ -4,7 +4,9 @@
   device; the halo is applied by hand (slice copies), the kernels run with their
   owned-row ranges: the concatenated owned CSR rows must equal the single-GPU CSR
   bit for bit, values included, and the distributed SpMV the global one;
-* >= 2 GPUs (gpurun --gpus 2): real NCCL ranks, DistCG against the oracle PCG.
+* >= 2 GPUs (gpurun --gpus 2): real ranks, both transports of csrc/dist.cu (NVLink peer memory and NCCL),
+  the distributed operator and DistCG against the oracle's global SpMV / PCG;
+* one GPU: the communicator with world = 1 (the path bench.py takes at N = 1) against the oracle.
 """
 import os
 import socket
@@ -53,9 +55,8 @@ def test_strips_match_global_on_one_gpu(world):
         # halo by hand: the local vector is a window of the global one
         v = vg[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)].clone()
         y = torch.full_like(v, float("nan"))
-        A.set_row_range(p.own_lo, p.own_hi)
         out = torch.zeros(1, dtype=torch.float64, device="cuda")
-        fem.capi.call("femb200_spmv_dot", A.plan, fem._p(A.values), fem._p(v), fem._p(y), fem._p(out), fem._stream())
+        A.mult_rows(v, y, p.own_lo, p.own_hi, dot=out)
         yh = y.cpu().numpy()
         assert np.isnan(yh[:lo]).all() and np.isnan(yh[hi:]).all()
         got[go:go + hi - lo] = yh[lo:hi]
@@ -82,6 +83,9 @@ def _nccl_worker(rank, world, port, out):
     try:
         from femb200 import dist, fem
         p = dist.strip_partition(NX, ROWS * world, 2, rank, world)
+        pd = dist.strip_partition_device(NX, ROWS * world, rank, world)      # the generator bench.py uses
+        assert np.array_equal(pd.mesh.x.cpu().numpy(), p.mesh.x) and np.array_equal(pd.mesh.dofmap.cpu().numpy(), p.mesh.dofmap)
+        assert np.array_equal(pd.E.cpu().numpy(), p.E) and np.array_equal(pd.bc.cpu().numpy(), p.bc)
         f = fem.ElasticityForm(p.mesh, p.E)
         A = fem.create_matrix(f)
         fem.assemble_matrix(A, f, bcs=[fem.DirichletBC(p.bc, p.g)])
@@ -94,34 +98,59 @@ def _nccl_worker(rank, world, port, out):
         vals = oracle.assemble_matrix(mg.etype, mg.x, mg.xdofmap, mg.dofmap, Eg, 0.3, rowptr, colidx, bc=bcg)
         b = -oracle.spmv(rowptr, colidx, full, gg)
         b[bcg != 0] = gg[bcg != 0]
+        lo, hi = 2 * p.own_lo, 2 * p.own_hi
+        glo = 2 * (p.node_offset + p.own_lo)
         bl = fem.to_device(b[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)], np.float64)
-        x = torch.zeros_like(bl)
-        cg0 = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000)            # plain: halo, then all owned rows
-        x0 = torch.zeros_like(bl)
-        cg0.solve(bl, x0)
-        cg = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000, overlap=True)
-        # the overlapped operator apply (interior rows during the halo exchange, then the rows next to the
-        # ghosts) against the oracle's global product on the owned rows
+        want, it, _, conv = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=4000, jacobi=True)
         vg = np.random.default_rng(3).standard_normal(mg.ndofs)
-        vl = fem.to_device(vg[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)].copy(), np.float64)
-        vl[:2 * p.own_lo] = float("nan")
-        vl[2 * p.own_hi:] = float("nan")                      # ghosts must come from the neighbours
-        yl = torch.full_like(vl, float("nan"))
-        cg.mult(vl, yl)
-        torch.cuda.synchronize()
-        wantl = oracle.spmv(rowptr, colidx, vals, vg)[2 * (p.node_offset + p.own_lo):2 * (p.node_offset + p.own_hi)]
-        gotl = yl[2 * p.own_lo:2 * p.own_hi].cpu().numpy()
-        assert np.isfinite(gotl).all() and np.linalg.norm(gotl - wantl) <= 1e-12 * np.linalg.norm(wantl)
-        cg.solve(bl, x)
-        assert cg0.converged and abs(cg0.iterations - cg.iterations) <= 1
-        assert ((x0 - x)[2 * p.own_lo:2 * p.own_hi].norm() / x[2 * p.own_lo:2 * p.own_hi].norm()).item() < 1e-10
-        xs = dist.gather_owned(p, x)
-        if rank == 0:
-            want, it, _, conv = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=4000, jacobi=True)
-            err = np.linalg.norm(xs - want) / np.linalg.norm(want)
-            assert cg.converged and conv and err < 1e-10, f"err {err} its {cg.iterations} vs {it}"
-            assert abs(cg.iterations - it) <= max(3, it // 50)
-        out.put((rank, "ok"))
+        want_mult = oracle.spmv(rowptr, colidx, vals, vg)[glo:glo + hi - lo]
+        op = dist.DistOperator(A, p, transport="auto")
+        transports = [op.transport] + (["nccl"] if op.transport == "p2p" else [])
+        sols = {}
+        for tr in transports:
+            op.use(tr)
+            # the operator apply with ghosts that must come from the neighbours, against the oracle's global product
+            vl = fem.to_device(vg[2 * p.node_offset:2 * (p.node_offset + p.mesh.nnodes)].copy(), np.float64)
+            vl[:lo] = float("nan")
+            vl[hi:] = float("nan")
+            yl = torch.full_like(vl, float("nan"))
+            op.mult(vl, yl)
+            torch.cuda.synchronize()
+            gotl = yl[lo:hi].cpu().numpy()
+            assert np.isfinite(gotl).all() and np.linalg.norm(gotl - want_mult) <= 1e-12 * np.linalg.norm(want_mult), tr
+            # sum over the ranks of a device vector
+            s = torch.tensor([rank + 1.0, 0.5, -2.0 * rank], dtype=torch.float64, device="cuda")
+            op.allreduce_sum(s)
+            assert s.tolist() == [world * (world + 1) / 2, 0.5 * world, -world * (world - 1.0)], (tr, s.tolist())
+            for graph in (False, True):
+                cg = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000, op=op, use_graph=graph)
+                x = torch.zeros_like(bl)
+                cg.solve(bl, x)
+                xs = dist.gather_owned(p, x)
+                sols[(tr, graph)] = (x[lo:hi].clone(), cg.iterations)
+                assert cg.converged, (tr, graph)
+                if rank == 0:
+                    err = np.linalg.norm(xs - want) / np.linalg.norm(want)
+                    assert conv and err < 1e-10, f"{tr} graph={graph}: err {err} its {cg.iterations} vs {it}"
+                    assert abs(cg.iterations - it) <= max(3, it // 50)
+            # the captured graph replays the same kernels: same bits, same iteration count
+            assert sols[(tr, True)][1] == sols[(tr, False)][1] and torch.equal(sols[(tr, True)][0], sols[(tr, False)][0]), tr
+            # fixed-iteration mode (bench): recurrence residual == true residual b - A x
+            cg = dist.DistCG(A, p, rel_tol=0.0, max_iter=25, op=op)
+            x = torch.zeros_like(bl)
+            cg.solve(bl, x, fixed_iters=25)
+            r = op.vectors()[0][lo:hi].clone()
+            ax = torch.zeros_like(bl)
+            op.mult(x, ax)
+            num = torch.tensor([((bl - ax)[lo:hi] - r).pow(2).sum().item(), bl[lo:hi].pow(2).sum().item()],
+                               dtype=torch.float64, device="cuda")
+            op.allreduce_sum(num)
+            assert (num[0] / num[1]).sqrt().item() < 1e-12, (tr, num.tolist())
+        if len(transports) == 2:   # both transports solve the same system: same iterates up to the all-reduce order
+            a, c = sols[("p2p", True)], sols[("nccl", True)]
+            assert abs(a[1] - c[1]) <= 1 and ((a[0] - c[0]).norm() / c[0].norm()).item() < 1e-10
+        op.close()
+        out.put((rank, "ok " + "+".join(transports)))
     except Exception:  # noqa: BLE001
         import traceback
         out.put((rank, traceback.format_exc()))
@@ -146,4 +175,34 @@ def test_dist_cg_nccl():
     for pr in procs:
         pr.join(timeout=60)
     for rank, msg in results:
-        assert msg == "ok", f"rank {rank}: {msg}"
+        assert msg.startswith("ok"), f"rank {rank}: {msg}"
+    print("transports exercised:", results[0][1])
+
+
+def test_dist_world1_matches_oracle():
+    """femb200_dist_pcg with a single rank (no transport): graph replay and eager launches give the same bits,
+    the solution matches the oracle PCG, and the per-call row range leaves the plan's other users alone."""
+    import torch
+    from femb200 import dist, fem
+    p = dist.strip_partition_device(NX, ROWS, 0, 1)
+    f = fem.ElasticityForm(p.mesh, p.E)
+    A = fem.create_matrix(f)
+    fem.assemble_matrix(A, f, bcs=[fem.DirichletBC(p.bc, p.g)])
+    mg = global_mesh(1)
+    np.testing.assert_array_equal(p.mesh.x.cpu().numpy(), mg.x)
+    Eg = fm.young_per_cell(mg.ncells)
+    bcg, gg = fm.dirichlet_markers(mg)
+    rowptr, colidx = oracle.build_pattern(mg.nnodes, mg.dofmap)
+    vals = oracle.assemble_matrix(mg.etype, mg.x, mg.xdofmap, mg.dofmap, Eg, 0.3, rowptr, colidx, bc=bcg)
+    b = np.where(bcg != 0, gg, 1.0)
+    want, it, _, conv = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=4000, jacobi=True)
+    bl = fem.to_device(b, np.float64)
+    xs = []
+    for graph in (False, True):
+        cg = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000, use_graph=graph)
+        x = torch.zeros_like(bl)
+        cg.solve(bl, x)
+        assert cg.converged and abs(cg.iterations - it) <= max(3, it // 50)
+        assert np.linalg.norm(x.cpu().numpy() - want) / np.linalg.norm(want) < 1e-10
+        xs.append(x)
+    assert torch.equal(xs[0], xs[1])

@@ -187,9 +187,7 @@ def test_assembly_random_orientation(kind, n, old, square, monkeypatch):
     """The fast kernel carries fan-edge columns in registers along a rotational walk of every vertex fan,
     flipping vertex labels where the orientation demands it: meshes with random cell order and random
     per-cell vertex labelling (and the clockwise square.msh) against the oracle; the older record format
-    (FEMB200_ASM_OLD) on the same meshes."""
-    if old:
-        monkeypatch.setenv("FEMB200_ASM_OLD", "1")
+    (plan option assembly_path = 1) on the same meshes."""
     f = fem()
     rng = np.random.default_rng(17 + n)
     meshes = [relabel_cells(make_mesh(kind, n, ny=n + 2), rng)[0]]
@@ -201,6 +199,8 @@ def test_assembly_random_orientation(kind, n, old, square, monkeypatch):
         rowptr, colidx, want = oracle_assemble(m, E, bc=bc)
         form = f.ElasticityForm(m, E)
         A = f.create_matrix(form)
+        if old:
+            A.set_option("assembly_path", 1)
         np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
         np.testing.assert_array_equal(A.colidx.cpu().numpy(), colidx)
         A.values.fill_(float("nan"))
@@ -313,15 +313,11 @@ def test_assembly_linear(kind, n, with_bc, monkeypatch):
     if kind in ("P1", "P2"):
         # the older record format of the fast kernel and the generic per-quadrature-point path
         # must give the same matrix
-        monkeypatch.setenv("FEMB200_ASM_OLD", "1")
-        A.values.fill_(float("nan"))
-        f.assemble_matrix(A, form)
-        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
-        monkeypatch.delenv("FEMB200_ASM_OLD")
-        monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
-        A.values.fill_(float("nan"))
-        f.assemble_matrix(A, form)
-        assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
+        for path in (1, 2):
+            A.set_option("assembly_path", path)
+            A.values.fill_(float("nan"))
+            f.assemble_matrix(A, form)
+            assert relfro(A.values.cpu().numpy(), want) < TOL_VALUES
 
 
 @pytest.mark.parametrize("kind", ["P1", "P2", "Q2"])
@@ -333,7 +329,6 @@ def test_assembly_damaged_tangent(kind, variant, generic, monkeypatch):
     if generic:
         if kind == "Q2":
             pytest.skip("Q2 always takes the per-quadrature-point path")
-        monkeypatch.setenv("FEMB200_FORCE_GENERIC", "1")
     m = make_mesh(kind, 12)
     E = fm.young_per_cell(m.ncells)
     d = fm.damage_band(m)
@@ -341,6 +336,8 @@ def test_assembly_damaged_tangent(kind, variant, generic, monkeypatch):
     f = fem()
     form = f.ElasticityForm(m, E, 0.3, d=d, variant=variant)
     A = f.create_matrix(form)
+    if generic:
+        A.set_option("assembly_path", 2)
     bc = fm.dirichlet_markers(m)[0]
     A.set_bcs([f.DirichletBC(bc)])
     for it in range(3):  # repeated reassembly with a new iterate
@@ -409,30 +406,31 @@ def test_spmv_and_pa_apply(kind, n):
 def test_spmv_variants_and_row_ranges(direct, monkeypatch):
     """TMA-staged and direct kernels; owned-row ranges (multi-GPU) incl. odd and ragged bounds."""
     import torch
-    if direct:
-        monkeypatch.setenv("FEMB200_SPMV_DIRECT", "1")
     m = make_mesh("P2", 40, ny=23)
     E = fm.young_per_cell(m.ncells)
     f = fem()
     form = f.ElasticityForm(m, E)
     A = f.assemble_matrix(f.create_matrix(form), form)
+    if direct:
+        A.set_option("spmv_path", 1)
     rowptr, colidx, vals = oracle_assemble(m, E)
     rng = np.random.default_rng(3)
     v = rng.standard_normal(m.ndofs)
     want = oracle.spmv(rowptr, colidx, vals, v)
     vd = f.to_device(v, np.float64)
     for lo, hi in ((0, m.nnodes), (1, m.nnodes - 1), (81, 81 + 64), (163, 1000), (m.nnodes - 5, m.nnodes), (7, 7)):
-        A.set_row_range(lo, hi)
         y = torch.full((m.ndofs,), -7.0, dtype=torch.float64, device="cuda")
         out = torch.full((1,), -1.0, dtype=torch.float64, device="cuda")
-        f.capi.call("femb200_spmv_dot", A.plan, f._p(A.values), f._p(vd), f._p(y), f._p(out), f._stream())
+        A.mult_rows(vd, y, lo, hi, dot=out)
         yh = y.cpu().numpy()
         assert relfro(yh[2 * lo:2 * hi], want[2 * lo:2 * hi]) < 1e-13 if hi > lo else True
         np.testing.assert_array_equal(yh[:2 * lo], -7.0)
         np.testing.assert_array_equal(yh[2 * hi:], -7.0)
         ref = v[2 * lo:2 * hi] @ want[2 * lo:2 * hi]
         assert abs(out.item() - ref) <= 1e-12 * max(1.0, np.abs(v[2 * lo:2 * hi] * want[2 * lo:2 * hi]).sum())
-    A.set_row_range(0, m.nnodes)
+    # the whole-matrix entry points are not affected by the ranges applied before (ADVICE r1: no persistent state)
+    y = A.mult(vd)
+    assert relfro(y.cpu().numpy(), want) < 1e-13
 
 
 # ---------------------------------------------------------------------------
@@ -684,6 +682,29 @@ def test_config1_square_msh_newton(square):
     assert ns.iterations == it_o
     assert relfro(u, want) < 1e-9
     assert ns.residual_norms[-1] <= max(1e-7 * ns.residual_norms[0], 5e-8)
+
+
+def test_newton_both_convergence_conventions(square):
+    """SURVEY.md 8f rank 2 / doc.tex:2065-2068: MFEM tests |b| against rel_tol |b_0|, FEniCSx divides by the norm of
+    the first increment |du_0| (F.cc:869-891), which is smaller here, so it iterates longer on the same damaged
+    problem.  Both rules against the oracle's loop, on the reference's mesh."""
+    m = square_mesh(square)
+    E = oracle.E_table()[square["tag"] % 200]
+    bc, g = fm.dirichlet_markers(m)
+    d = fm.damage_band(m)
+    fnod = fm.body_force(m)
+    f = fem()
+    its = {}
+    for conv in ("mfem", "dolfinx"):
+        want, it_o, norms_o = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, bc, g, dnod=d, fnod=fnod.ravel(),
+                                            convention=conv, max_iter=20)
+        ns = f.NewtonSolver(f.ElasticityForm(m, E, 0.3, d=d), [f.DirichletBC(bc, g)], f=fnod, convention=conv, max_iter=20)
+        u = ns.solve().cpu().numpy()
+        assert ns.converged and ns.iterations == it_o, (conv, ns.iterations, it_o)
+        assert relfro(u, want) < 1e-9
+        np.testing.assert_allclose(ns.residual_norms, norms_o, rtol=1e-6, atol=1e-9)
+        its[conv] = ns.iterations
+    assert its["dolfinx"] > its["mfem"], its   # r_0 = |du_0| is smaller than |b_0| on this problem
 
 
 def test_set_geometry_vertices_only():
