@@ -314,44 +314,46 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
    ReduceScratch red;
    if (int rc = reduce_scratch(std::max(gv, gi), st, &red)) return rc;  // grown before any capture
    int rc;
-   auto scalar = [&](int phase, int idx) -> int {
-      if (int e = dist_allreduce_pre(P.comm, scal + idx, 1, st)) return e;
-      cg_scalar_kernel<<<1, 32, 0, st>>>(scal, phase, ra);
+   auto scalar = [&](int phase, int idx, cudaStream_t s) -> int {
+      if (int e = dist_allreduce_pre(P.comm, scal + idx, 1, s)) return e;
+      cg_scalar_kernel<<<1, 32, 0, s>>>(scal, phase, ra);
       FEMB_LAUNCH_CHECK();
       return 0;
    };
-   auto apply = [&]() -> int {
-      if (int e = dist_halo_arena(P.comm, st)) return e;
-      if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.d, P.z, scal, st)) return e;
-      return scalar(1, SC_RED_DEN);
+   auto apply = [&](cudaStream_t s) -> int {
+      if (int e = dist_halo_arena(P.comm, s)) return e;
+      if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.d, P.z, scal, s)) return e;
+      return scalar(1, SC_RED_DEN, s);
    };
-   auto update_xr = [&]() -> int {
-      cg_update_xr_kernel<<<gv, kVecThreads, 0, st>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.d + o),
-                                                      reinterpret_cast<const double2 *>(P.z + o),
+   auto update_xr = [&](cudaStream_t s) -> int {
+      ReduceScratch rs;
+      if (int e = reduce_scratch(gv, s, &rs)) return e;
+      cg_update_xr_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.d + o),
+                                                     reinterpret_cast<const double2 *>(P.z + o),
+                                                     reinterpret_cast<const double2 *>(dinv_o),
+                                                     reinterpret_cast<double2 *>(P.x + o), reinterpret_cast<double2 *>(P.r + o),
+                                                     rs, scal + SC_RED_BETA);
+      FEMB_LAUNCH_CHECK();
+      return scalar(2, SC_RED_BETA, s);
+   };
+   auto update_dir = [&](cudaStream_t s) -> int {
+      cg_update_dir_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.r + o),
                                                       reinterpret_cast<const double2 *>(dinv_o),
-                                                      reinterpret_cast<double2 *>(P.x + o), reinterpret_cast<double2 *>(P.r + o),
-                                                      red, scal + SC_RED_BETA);
-      FEMB_LAUNCH_CHECK();
-      return scalar(2, SC_RED_BETA);
-   };
-   auto update_dir = [&]() -> int {
-      cg_update_dir_kernel<<<gv, kVecThreads, 0, st>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.r + o),
-                                                       reinterpret_cast<const double2 *>(dinv_o),
-                                                       reinterpret_cast<double2 *>(P.d + o));
+                                                      reinterpret_cast<double2 *>(P.d + o));
       FEMB_LAUNCH_CHECK();
       return 0;
    };
-   auto full_iteration = [&]() -> int {
-      if (int e = update_xr()) return e;
-      if (int e = update_dir()) return e;
-      return apply();
+   auto full_iteration = [&](cudaStream_t s) -> int {
+      if (int e = update_xr(s)) return e;
+      if (int e = update_dir(s)) return e;
+      return apply(s);
    };
 
    if ((rc = femb200_cg_set_tolerances(scal, P.rtol, P.atol, st))) return rc;
    cg_init_kernel<<<gi, kVecThreads, 0, st>>>(n, P.b + o, dinv_o, P.x + o, P.r + o, P.d + o, red, scal + SC_RED_NOM);
    FEMB_LAUNCH_CHECK();
-   if ((rc = scalar(0, SC_RED_NOM))) return rc;
-   if ((rc = apply())) return rc;
+   if ((rc = scalar(0, SC_RED_NOM, st))) return rc;
+   if ((rc = apply(st))) return rc;
 
    const int nit = P.fixed_iters > 0 ? P.fixed_iters : P.maxit;
    const int check_every = P.check_every > 0 ? P.check_every : 25;
@@ -363,7 +365,7 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
    {
       if (i == nit)
       {
-         if ((rc = update_xr())) return rc;
+         if ((rc = update_xr(st))) return rc;
       }
       else if (G && i >= 2)
       {  // iteration 1 ran eagerly (warm kernels, NCCL connections); capture on first use, then replay
@@ -372,10 +374,17 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
          if (!G->exec || memcmp(G->key, key, sizeof(key)) || memcmp(G->ikey, ikey, sizeof(ikey)))
          {
             if (G->exec) cudaGraphExecDestroy(G->exec), G->exec = nullptr;
+            // captured on the communicator's own stream (the caller's may be the legacy default stream, which
+            // cannot be captured); the fused-reduction scratch of that stream is created before the capture
+            cudaStream_t cs = dist_capture_stream(P.comm);
+            FEMB_CHECK(cs != nullptr, "pcg: no capture stream");
+            ReduceScratch warm;
+            if (int e = reduce_scratch(4096, cs, &warm)) return e;
+            FEMB_CUDA(cudaStreamSynchronize(cs));
             cudaGraph_t graph = nullptr;
-            FEMB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int e = full_iteration();
-            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            FEMB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            const int e = full_iteration(cs);
+            const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
             if (e || ce != cudaSuccess || !graph)
             {
                if (graph) cudaGraphDestroy(graph);
@@ -389,7 +398,7 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
          }
          FEMB_CUDA(cudaGraphLaunch(G->exec, st));
       }
-      else if ((rc = full_iteration()))
+      else if ((rc = full_iteration(st)))
          return rc;
       if (P.fixed_iters <= 0 && (i % check_every == 0) && i < nit)
       {

@@ -110,6 +110,7 @@ struct femb200_dist
    unsigned char *peer_arena[femb::kMaxWorld] = {};   // IPC mappings (self: arena)
    int64_t peer_recv_lo[femb::kMaxNeigh] = {};        // first node (neighbour's numbering) of my message there
    femb::IterGraph graph;
+   cudaStream_t capture_stream = nullptr;  // iteration graphs are captured here and launched on the caller's stream
 };
 
 namespace femb {
@@ -286,6 +287,13 @@ int dist_check_error(femb200_dist *D, cudaStream_t st)
 
 IterGraph *dist_iter_graph(femb200_dist *D) { return D ? &D->graph : nullptr; }
 
+cudaStream_t dist_capture_stream(femb200_dist *D)
+{
+   if (!D) return nullptr;
+   if (!D->capture_stream && cudaStreamCreateWithFlags(&D->capture_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+   return D->capture_stream;
+}
+
 }  // namespace femb
 
 using namespace femb;
@@ -294,6 +302,7 @@ extern "C" void femb200_dist_destroy(femb200_dist *D)
 {
    if (!D) return;
    if (D->graph.exec) cudaGraphExecDestroy(D->graph.exec);
+   if (D->capture_stream) cudaStreamDestroy(D->capture_stream);
    for (int p = 0; p < D->world && p < kMaxWorld; ++p)
       if (D->peer_arena[p] && D->peer_arena[p] != D->arena) cudaIpcCloseMemHandle(D->peer_arena[p]);
    cudaFree(D->arena);
@@ -509,6 +518,10 @@ extern "C" int femb200_dist_halo(femb200_dist *D, double *d_v, void *stream)
    for (int k = 0; k < D->nneigh; ++k) A.lo[k] = D->recv_lo[k], A.cnt[k] = D->recv_cnt[k], total += D->recv_cnt[k];
    A.src = reinterpret_cast<const double2 *>(D->d), A.dst = reinterpret_cast<double2 *>(d_v);
    range_copy_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(total, 256), 64)), 256, 0, st>>>(A);
+   FEMB_LAUNCH_CHECK();
+   // Barrier: a neighbour that runs ahead must not store the NEXT message into the arena's ghost rows while this
+   // rank is still copying the current one out (inside the PCG the all-reduce of <d, A d> plays this role).
+   allreduce_kernel<<<1, 32, 0, st>>>(D->scal + 13, 1, dist_red_args(D));
    FEMB_LAUNCH_CHECK();
    return 0;
 }

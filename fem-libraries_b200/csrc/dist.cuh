@@ -92,6 +92,7 @@ struct IterGraph
    int64_t ikey[3] = {};
 };
 IterGraph *dist_iter_graph(femb200_dist *D);
+cudaStream_t dist_capture_stream(femb200_dist *D);
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {

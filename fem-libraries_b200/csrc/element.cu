@@ -124,3 +124,73 @@ extern "C" int femb200_tabulate_tensor_batched(int etype, int64_t ncells, double
    FEMB_LAUNCH_CHECK();
    return 0;
 }
+
+// ---- the ufcx kernel signature -----------------------------------------------------------------
+// `ufcx_tabulate_tensor_float64` (ufcx.h of ffcx 0.8, un-vendored; corroborated by the generated-kernel patch
+// FEniCSx/mechanic2d/addprofile:6-9 and by the form look-ups F.cc:31-67): what a dolfinx Form holds as its cell
+// kernel for the bilinear form J of manual.py:102 and calls once per cell.  Batch of one with the device staging
+// inside: A (6 x 6 row-major, interleaved dofs, caller-owned, pre-zeroed by the caller) is ACCUMULATED into, as
+// ffcx kernels do; no return value (ufcx has no error channel: on a CUDA failure A is left untouched and the
+// message is in femb200_last_error()).  Coefficient packing as the form file creates them (manual.py:19,22,30):
+//   w = [d0, d1, d2,  E,  u0x, u0y, u1x, u1y, u2x, u2y],  c = [nu],  coordinate_dofs = 3 x (x, y, z).
+// Re-entrant: the device scratch is per host thread.  This is the parity surface of the FEniCSx side; the fast path
+// is femb200_tabulate_tensor_batched / femb200_assemble_matrix.
+namespace femb {
+struct UfcxScratch
+{
+   double *d = nullptr;   // x[9] | E[1] | dnod[3] | u[6] | A[36]
+   int32_t *map = nullptr;
+};
+static UfcxScratch *ufcx_scratch()
+{
+   static thread_local UfcxScratch s;
+   if (!s.d)
+   {
+      const int32_t id[3] = {0, 1, 2};
+      if (cudaMalloc(&s.d, sizeof(double) * 55) != cudaSuccess || cudaMalloc(&s.map, sizeof(id)) != cudaSuccess ||
+          cudaMemcpy(s.map, id, sizeof(id), cudaMemcpyHostToDevice) != cudaSuccess)
+      {
+         set_error("tabulate_tensor_ufcx: device scratch: %s", cudaGetErrorString(cudaGetLastError()));
+         cudaFree(s.d), cudaFree(s.map);
+         s.d = nullptr, s.map = nullptr;
+         return nullptr;
+      }
+   }
+   return &s;
+}
+}  // namespace femb
+
+extern "C" void femb200_tabulate_tensor_ufcx(double *A, const double *w, const double *c, const double *coordinate_dofs,
+                                             const int *entity_local_index, const uint8_t *quadrature_permutation)
+{
+   (void)entity_local_index, (void)quadrature_permutation;  // cell integrals use neither
+   if (!A || !w || !c || !coordinate_dofs)
+   {
+      set_error("tabulate_tensor_ufcx: null argument");
+      return;
+   }
+   UfcxScratch *s = ufcx_scratch();
+   if (!s) return;
+   double h[19];
+   for (int i = 0; i < 9; ++i) h[i] = coordinate_dofs[i];
+   h[9] = w[3];
+   for (int i = 0; i < 3; ++i) h[10 + i] = w[i];
+   for (int i = 0; i < 6; ++i) h[13 + i] = w[4 + i];
+   const bool damaged = w[0] != 0. || w[1] != 0. || w[2] != 0.;
+   if (cudaMemcpy(s->d, h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess)
+   {
+      set_error("tabulate_tensor_ufcx: H2D: %s", cudaGetErrorString(cudaGetLastError()));
+      return;
+   }
+   if (femb200_tabulate_tensor_batched(FEMB200_P1, 1, s->d + 19, s->d, 3, s->map, s->map, s->d + 9, c[0],
+                                       damaged ? s->d + 10 : nullptr, s->d + 13, FEMB200_TANGENT_CLOSED,
+                                       FEMB200_ROWMAJOR_INTERLEAVED, nullptr))
+      return;
+   double out[36];
+   if (cudaMemcpy(out, s->d + 19, sizeof(out), cudaMemcpyDeviceToHost) != cudaSuccess)
+   {
+      set_error("tabulate_tensor_ufcx: D2H: %s", cudaGetErrorString(cudaGetLastError()));
+      return;
+   }
+   for (int i = 0; i < 36; ++i) A[i] += out[i];
+}

@@ -90,6 +90,8 @@ _SPECIAL = {
     "femb200_version": ([], C.c_int),
     "femb200_last_error": ([], C.c_char_p),
     "femb200_plan_destroy": ([vp], None),
+    "femb200_tabulate_tensor_ufcx": ([C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_uint8)], None),
     "femb200_dist_destroy": ([vp], None),
     "femb200_dist_transport": ([vp], C.c_int),
     "femb200_pa_destroy": ([vp], None),

@@ -86,6 +86,15 @@ int femb200_tabulate_tensor_batched(int etype, int64_t ncells, double *d_A, cons
                                     const int32_t *d_xdofmap, const int32_t *d_dofmap, const double *d_E, double nu,
                                     const double *d_dnod, const double *d_u, int variant, int layout, void *stream);
 
+/* The ufcx cell-kernel signature itself (ufcx_tabulate_tensor_float64 of ffcx 0.8; FEniCSx/mechanic2d/
+ * addprofile:6-9, F.cc:31-67): the symbol a dolfinx Form can hold as the kernel of the P1 form J.  Batch of one
+ * with the device staging inside; A (6 x 6 row-major, interleaved dofs) is caller-owned, pre-zeroed by the
+ * caller and ACCUMULATED into; host pointers; no return value (errors: A untouched, femb200_last_error()).
+ *   w = [d0, d1, d2, E, u0x, u0y, u1x, u1y, u2x, u2y] (manual.py:19,22,30), c = [nu] (manual.py:23),
+ *   coordinate_dofs = 3 x (x, y, z) (F.cc:213).  Parity surface; the batched entry point above is the fast one. */
+void femb200_tabulate_tensor_ufcx(double *A, const double *w, const double *c, const double *coordinate_dofs,
+                                  const int *entity_local_index, const uint8_t *quadrature_permutation);
+
 /* ------------------------------------------------------------------------
  * Sparsity pattern + gather maps.
  * Replaces: dolfinx::fem::petsc::create_matrix(*J_form) (F.cc:688).

@@ -29,6 +29,62 @@ def test_library_exports_every_declared_symbol():
     assert capi.lib().femb200_version() == 100
 
 
+def header_prototypes():
+    """name -> (return kind, [argument kinds]) parsed from include/femb200.h; kinds: i32, i64, f64, ptr, void."""
+    src = open(os.path.join(ROOT, "include", "femb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+
+    def kind(t):
+        t = t.strip()
+        if "*" in t:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned)\b", "", t).split()
+        base = base[0] if base else ""
+        return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "double": "f64", "void": "void"}[base]
+
+    out = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(femb200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        argl = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        # drop the parameter name (last identifier) unless the declaration is a bare type
+        kinds = []
+        for a in argl:
+            m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)?$", a)
+            kinds.append(kind(m.group(1) if m.group(1).strip() else a))
+        out[name] = (kind(ret), kinds)
+    return out
+
+
+def ctypes_kind(t):
+    if t is None:
+        return "void"
+    if t in (ctypes.c_int, ctypes.c_int32):
+        return "i32"
+    if t is ctypes.c_int64:
+        return "i64"
+    if t is ctypes.c_double:
+        return "f64"
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_") and issubclass(t, ctypes._Pointer):
+        return "ptr"
+    raise AssertionError(f"unmapped ctypes type {t}")
+
+
+def test_ctypes_table_matches_header_prototypes():
+    """The binding table of femb200/_capi.py against the PARSED prototypes of include/femb200.h: same functions,
+    same arity, and every argument / return value of the same kind (32-bit int, 64-bit int, double, pointer)."""
+    from femb200 import capi
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(capi.ALL_SYMBOLS)
+    for name, args in capi.SIGNATURES.items():
+        ret, kinds = protos[name]
+        assert ret == "i32", f"{name}: returns {ret} in the header, the table assumes an int status"
+        assert [ctypes_kind(a) for a in args] == kinds, f"{name}: ctypes {[ctypes_kind(a) for a in args]} vs header {kinds}"
+    for name, (args, res) in capi._SPECIAL.items():
+        ret, kinds = protos[name]
+        assert ctypes_kind(res) == ret, f"{name}: return {ctypes_kind(res)} vs header {ret}"
+        assert [ctypes_kind(a) for a in args] == kinds, f"{name}: ctypes {[ctypes_kind(a) for a in args]} vs header {kinds}"
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -125,6 +125,30 @@ def test_tabulate_tensor_ufcx_shim(square):
         assert relfro(A.ravel(), want) < TOL_VALUES
 
 
+def test_tabulate_tensor_ufcx_c_symbol(square):
+    """The C symbol with the exact ufcx argument list (what a dolfinx Form would hold as its kernel pointer): host
+    pointers, batch of one, A accumulated; against the oracle's ufcx-signature kernel and the Python shim."""
+    import ctypes as C
+    L = fem().capi.lib()
+    dp = C.POINTER(C.c_double)
+    x, tri = square["x"], square["tri"]
+    rng = np.random.default_rng(5)
+    for e in (3, 42, 96):
+        cd = np.zeros((3, 3))
+        cd[:, :2] = x[tri[e]]
+        w = np.concatenate([[0.2, 0.0, 0.5] if e == 42 else np.zeros(3), [4.2e7], 1e-3 * rng.standard_normal(6)])
+        c = np.array([0.3])
+        A = np.full(36, -1.25)
+        L.femb200_tabulate_tensor_ufcx(A.ctypes.data_as(dp), w.ctypes.data_as(dp), c.ctypes.data_as(dp),
+                                       cd.ctypes.data_as(dp), None, None)
+        want = np.full(36, -1.25)
+        oracle.tabulate_tensor_J_p1(w, c, cd, A=want)
+        assert relfro(A, want) < TOL_VALUES
+        shim = np.full((6, 6), -1.25)
+        fem().tabulate_tensor(shim, w, c, cd)
+        np.testing.assert_array_equal(shim.ravel(), A)
+
+
 def test_element_grad_mfem_layout(square):
     """elmat column-major, byNODES (M.cc:647,673) against the two MFEM-style oracle paths."""
     m = square_mesh(square)
