@@ -33,7 +33,7 @@
 //                          per (visit, scalar row) with every address resolved at plan time, diagonal and
 //                          fan-edge columns carried in registers, L2 prefetch of the next wave's records;
 //                          damaged cells (d > 0) copy the row slices of per-cell element tangents
-//                          (cell_setup_damage_kernel + cell_tangent_kernel);
+//                          (cell_setup_damage_kernel);
 //   assemble_kernel        the generic-record form: Q2 and assembly_path = 2 (per-quadrature-point
 //                          integration per visit) and plans without fast records;
 //   dirichlet_kernel, fro / trace kernels, the fused-norm correction kernels.
@@ -138,12 +138,21 @@ __global__ void cell_setup_kernel(int64_t ncells, const int32_t *__restrict__ xd
 __device__ __forceinline__ int stored_position(int b, int a, int nd);
 
 // ---- damaged cells (d > 0 at some quadrature point): per-cell pre-pass ------------------
-// The tangent D_q (M.cc:736-872 closed form, or the dual-number Hessian M.cc:752-765) depends on
-// the cell only, but the gather assembly visits every cell once per node and scalar row: this
-// pre-pass classifies the cells (cell_setup_damage_kernel: undamaged cells keep the 32-byte
-// fast-path record, damaged ones get {NaN, index} and go on a compact list) and integrates the full
-// element tangent of every damaged cell once (cell_tangent_kernel); a damaged visit then copies its
-// row slice.
+// The tangent D_q (M.cc:736-872 closed form, or the dual-number Hessian M.cc:752-765) depends on the cell
+// only, but the gather assembly visits every cell once per node and scalar row.  The pre-pass
+// (cell_setup_damage_kernel) classifies the cells: undamaged ones keep the 32-byte fast-path record, damaged
+// ones get a NaN marker there and a DAMAGE RECORD at celld[cell] (indexed by the cell id: no compaction):
+//     [0..3]            grad lambda_1, grad lambda_2 (plain)
+//     [4 + 8 q .. + 5]  upper triangle (00, 01, 02, 11, 12, 22) of w_q |det J| D_q, for the nq points of the rule
+// (P1: 16 doubles, P2: 32 doubles = 256 B against the 1152 B of a full element tangent; D_q is symmetric to
+// rounding, its upper triangle is kept).  The constitutive evaluation -- the expensive, branchy part -- happens
+// once per cell; a visit rebuilds its 2 x 2nd row slice from the record with ~90 FMAs: on a straight-sided
+// triangle the P2 basis gradients at the points of the 3-point rule are fixed combinations of the grad lambda_c
+// (L_k = 2/3 at point k, 1/6 elsewhere), so with c_q = row h of B_a(q) D_q (three numbers per point),
+// C = sum_q c_q and S_v = sum_q 4 L_v(q) c_q = 2/3 C + 2 c_v:
+//     vertex column v        (S_v - C)   contracted with grad lambda_v
+//     edge column (p, r)      S_p contracted with grad lambda_r  +  S_r contracted with grad lambda_p
+// (K[(a,h), (b,.)] = sum_q c_q B_b(q)^t, M.cc:699-704, 885-887).
 template <int ET>
 __device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *phi, double &w2)
 {  // reference gradients, vertex basis and 2 * weight at point q of the rule of element.cuh
@@ -155,68 +164,66 @@ __device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *ph
 }
 
 template <int ET>
-__global__ void cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap,
-                                         const double *__restrict__ x, int xs, const double *__restrict__ E,
-                                         const double *__restrict__ dnod, double *__restrict__ rec,
-                                         int32_t *__restrict__ dlist, int32_t *__restrict__ count)
+__host__ __device__ constexpr int dmg_rec_doubles()
 {
-   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq;
+   return ET == FEMB200_P1 ? 16 : 32;
+}
+
+// One thread per cell.  The damage records leave through a per-warp shared-memory stage as whole 32-byte
+// sectors (a thread storing its own 256-byte record would touch 8 lines per store instruction).
+template <int ET>
+__global__ void __launch_bounds__(128)
+cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, const int32_t *__restrict__ dofmap,
+                         const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
+                         const double *__restrict__ dnod, const double *__restrict__ u, int variant,
+                         double *__restrict__ rec, double *__restrict__ celld)
+{
+   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, RS = dmg_rec_doubles<ET>(), STRIDE = RS + 2;
+   __shared__ __align__(16) double stage[4][32 * STRIDE];
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (e >= ncells) return;
-   const int64_t v0 = xdofmap[3 * e], v1 = xdofmap[3 * e + 1], v2 = xdofmap[3 * e + 2];
+   const bool active = e < ncells;
+   const int64_t ec = active ? e : ncells - 1;
+   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + 32 * warp;
+   const int64_t v0 = xdofmap[3 * ec], v1 = xdofmap[3 * ec + 1], v2 = xdofmap[3 * ec + 2];
    const double dv[3] = {dnod[v0], dnod[v1], dnod[v2]};
+   const double xv[3][2] = {{x[v0 * xs], x[v0 * xs + 1]}, {x[v1 * xs], x[v1 * xs + 1]}, {x[v2 * xs], x[v2 * xs + 1]}};
+   const double det = (xv[1][0] - xv[0][0]) * (xv[2][1] - xv[0][1]) - (xv[2][0] - xv[0][0]) * (xv[1][1] - xv[0][1]);
+   const double id = 1. / det;
+   double dq[nq];
    bool damaged = false;
 #pragma unroll
    for (int q = 0; q < nq; ++q)
    {
       double dN[nd][2], phi[3], w2;
       tri_ref_grads<ET>(q, dN, phi, w2);
-      damaged = damaged || (phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2]) > 0.;
+      dq[q] = phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2];
+      damaged = damaged || dq[q] > 0.;
    }
-   double2 *r = reinterpret_cast<double2 *>(rec + 4 * e);
-   if (damaged)
-   {  // NaN marker + index of the cell's tangent record (filled by cell_tangent_kernel)
-      const int idx = atomicAdd(count, 1);
-      dlist[idx] = (int32_t)e;
-      r[0] = make_double2(__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double((long long)idx));
-      r[1] = make_double2(0., 0.);
-      return;
-   }
-   const double x0 = x[v0 * xs], y0 = x[v0 * xs + 1];
-   const double x1 = x[v1 * xs], y1 = x[v1 * xs + 1];
-   const double x2 = x[v2 * xs], y2 = x[v2 * xs + 1];
-   const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
-   const double sc = sqrt(0.5 * fabs(det) * E[e]) / det;
-   r[0] = make_double2((y2 - y0) * sc, -(x2 - x0) * sc);
-   r[1] = make_double2(-(y1 - y0) * sc, (x1 - x0) * sc);
-}
-
-// Element tangent K_e = sum_q w_q |det J| B_q D_q B_q^t of every damaged cell (closed-form tangent
-// M.cc:736-872 or the dual-number Hessian M.cc:752-765; M.cc:699-704, 885-887 for B D B^t), row-major
-// 2nd x 2nd with interleaved dofs: the gather kernel then copies the row slices it needs instead of
-// integrating them once per visit.  Grid-stride over the compact list of damaged cells.
-template <int ET>
-__global__ void __launch_bounds__(128)
-cell_tangent_kernel(const int32_t *__restrict__ dlist, const int32_t *__restrict__ count,
-                    const int32_t *__restrict__ xdofmap, const int32_t *__restrict__ dofmap,
-                    const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
-                    const double *__restrict__ dnod, const double *__restrict__ u, int variant,
-                    double *__restrict__ celld)
-{
-   constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq;
-   const int n = *count;
-   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+   damaged = damaged && active;
+   const double g1x = (xv[2][1] - xv[0][1]) * id, g1y = -(xv[2][0] - xv[0][0]) * id;
+   const double g2x = -(xv[1][1] - xv[0][1]) * id, g2y = (xv[1][0] - xv[0][0]) * id;
+   const double Ee = E[ec];
+   if (active)
    {
-      const int64_t e = dlist[idx];
-      double xv[nv][2], dv[nv];
-#pragma unroll
-      for (int v = 0; v < nv; ++v)
-      {
-         const int64_t g = xdofmap[e * nv + v];
-         xv[v][0] = x[g * xs], xv[v][1] = x[g * xs + 1];
-         dv[v] = dnod[g];
+      double2 *r = reinterpret_cast<double2 *>(rec + 4 * e);
+      if (!damaged)
+      {  // the fast-path record of cell_setup_kernel
+         const double sc = sqrt(0.5 * fabs(det) * Ee);
+         r[0] = make_double2(g1x * sc, g1y * sc);
+         r[1] = make_double2(g2x * sc, g2y * sc);
       }
-      const double lam = E[e] * lc.c2, mu = E[e] * lc.c3;
+      else
+      {  // NaN marker: the damage record of this cell is celld[e]
+         r[0] = make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.);
+         r[1] = make_double2(0., 0.);
+      }
+   }
+   double *R = stage[warp] + lane * STRIDE;
+   if (damaged)
+   {
+      R[0] = g1x, R[1] = g1y, R[2] = g2x, R[3] = g2y;
+      const double lam = Ee * lc.c2, mu = Ee * lc.c3;
       double ue[nd][2];
 #pragma unroll
       for (int b = 0; b < nd; ++b)
@@ -224,62 +231,131 @@ cell_tangent_kernel(const int32_t *__restrict__ dlist, const int32_t *__restrict
          const int64_t gd = 2 * (int64_t)dofmap[e * nd + b];
          ue[b][0] = u ? u[gd] : 0., ue[b][1] = u ? u[gd + 1] : 0.;
       }
-      double G[nq][nd][2], D[nq][9];
-#pragma unroll
+#pragma unroll 1
       for (int q = 0; q < nq; ++q)
       {
-         double phi[nv];
-         const double w = qp_geometry<ET>(xv, q, G[q], phi);
-         double d = 0.;
-#pragma unroll
-         for (int v = 0; v < nv; ++v) d += phi[v] * dv[v];
-         if (d > 0.)
+         double G[nd][2], phi[3], D[9];
+         const double w = qp_geometry<ET>(xv, q, G, phi);
+         if (dq[q] > 0.)
          {
             double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
 #pragma unroll
             for (int b = 0; b < nd; ++b)
             {
-               g00 += ue[b][0] * G[q][b][0], g01 += ue[b][0] * G[q][b][1];
-               g10 += ue[b][1] * G[q][b][0], g11 += ue[b][1] * G[q][b][1];
+               g00 += ue[b][0] * G[b][0], g01 += ue[b][0] * G[b][1];
+               g10 += ue[b][1] * G[b][0], g11 += ue[b][1] * G[b][1];
             }
             const double sh = 0.5 * (g01 + g10);
             const double eps[4] = {g00, sh, sh, g11};
-            tangent(variant, lam, mu, d, eps, D[q]);
+            tangent(variant, lam, mu, dq[q], eps, D);
          }
          else
-            hooke_scaled(lam, mu, 1., D[q]);
-#pragma unroll
-         for (int k = 0; k < 9; ++k) D[q][k] *= w;
+            hooke_scaled(lam, mu, 1., D);
+         double *Rq = R + 4 + 8 * q;
+         Rq[0] = D[0] * w, Rq[1] = D[1] * w, Rq[2] = D[2] * w, Rq[3] = D[4] * w, Rq[4] = D[5] * w, Rq[5] = D[8] * w;
+         Rq[6] = Rq[7] = 0.;
       }
-      double *K = celld + (int64_t)idx * (4 * nd * nd);
+      if (RS > 4 + 8 * nq)
 #pragma unroll
-      for (int a = 0; a < nd; ++a)
-#pragma unroll
-         for (int b = 0; b < nd; ++b)
-         {
-            double k[4] = {0., 0., 0., 0.};
-#pragma unroll
-            for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], 1., k);
-            reinterpret_cast<double2 *>(K + (2 * a) * (2 * nd) + 2 * b)[0] = make_double2(k[0], k[1]);
-            reinterpret_cast<double2 *>(K + (2 * a + 1) * (2 * nd) + 2 * b)[0] = make_double2(k[2], k[3]);
-         }
+         for (int k = 4 + 8 * nq; k < RS; ++k) R[k] = 0.;
+   }
+   const unsigned mask = __ballot_sync(0xffffffffu, damaged);
+   __syncwarp();
+   constexpr int UPC = RS / 2;  // 16-byte units per record
+   for (int t = lane; t < 32 * UPC; t += 32)
+   {
+      const int c = t / UPC, k = t - c * UPC;
+      if ((mask >> c) & 1u)
+         reinterpret_cast<double2 *>(celld + (e0 + c) * RS)[k] = reinterpret_cast<const double2 *>(stage[warp] + c * STRIDE)[k];
    }
 }
 
-// row slice of a damaged cell: scalar row h of local row a, copied from the cell's tangent record
+// symmetric D of one point from a damage record (two 256-bit loads)
+struct SymD
+{
+   double d00, d01, d02, d11, d12, d22;
+};
+__device__ __forceinline__ SymD ld_symd(const double *p)
+{
+   SymD D;
+   double pad0, pad1;
+   ld_d4(p, D.d00, D.d01, D.d02, D.d11);
+   ld_d4(p + 4, D.d12, D.d22, pad0, pad1);
+   return D;
+}
+// row h of B_a D with B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]  (M.cc:699-704)
+__device__ __forceinline__ void bd_row(const SymD &D, double gx, double gy, int h, double *c)
+{
+   const double p0 = h ? gy : gx, p2 = h ? gx : gy;  // multiply D row h and D row 2
+   c[0] = p0 * (h ? D.d01 : D.d00) + p2 * D.d02;
+   c[1] = p0 * (h ? D.d11 : D.d01) + p2 * D.d12;
+   c[2] = p0 * (h ? D.d12 : D.d02) + p2 * D.d22;
+}
+// (K[(a,h),(b,0)], K[(a,h),(b,1)]) += c contracted with B_b, gradient (gx, gy)
+__device__ __forceinline__ void cb_add(const double *c, double gx, double gy, double &k0, double &k1)
+{
+   k0 += c[0] * gx + c[2] * gy;
+   k1 += c[1] * gy + c[2] * gx;
+}
+
+// Row (a, h) of the element tangent of a damaged cell from its damage record, natural local numbering:
+// k[b] = (K[(a,h), (b,0)], K[(a,h), (b,1)]).  The plain per-point form (fallback kernels).
 template <int ET>
-__device__ __forceinline__ void damaged_compute_stage(const AsmArgs &A, const Visit &r, int idx, double2 *sv, int rbase,
-                                                      int h)
+__device__ __forceinline__ void damaged_row_slice(const double *__restrict__ R, int a, int h, double (*k)[2])
+{
+   constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq;
+   double g[3][2];
+   ld_d4(R, g[1][0], g[1][1], g[2][0], g[2][1]);
+   g[0][0] = -g[1][0] - g[2][0], g[0][1] = -g[1][1] - g[2][1];
+#pragma unroll
+   for (int b = 0; b < nd; ++b) k[b][0] = k[b][1] = 0.;
+#pragma unroll
+   for (int q = 0; q < nq; ++q)
+   {
+      const SymD D = ld_symd(R + 4 + 8 * q);
+      double G[nd][2];
+      if (ET == FEMB200_P1)
+      {
+#pragma unroll
+         for (int v = 0; v < 3; ++v) G[v][0] = g[v][0], G[v][1] = g[v][1];
+      }
+      else
+      {  // P2 at point q of the 3-point rule: L_q = 2/3, the other two 1/6 (element.cuh)
+#pragma unroll
+         for (int v = 0; v < 3; ++v)
+         {
+            const double cv = (v == q) ? 5. / 3. : -1. / 3.;  // 4 L_v - 1
+            G[v][0] = cv * g[v][0], G[v][1] = cv * g[v][1];
+            const int p = (v + 1) % 3, r = (v + 2) % 3;         // the edge opposite v joins p and r
+            const double Lp = (p == q) ? 2. / 3. : 1. / 6., Lr = (r == q) ? 2. / 3. : 1. / 6.;
+            G[3 + v][0] = 4. * (Lp * g[r][0] + Lr * g[p][0]);
+            G[3 + v][1] = 4. * (Lp * g[r][1] + Lr * g[p][1]);
+         }
+      }
+      double gax = 0., gay = 0.;
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+         if (b == a) gax = G[b][0], gay = G[b][1];
+      double c[3];
+      bd_row(D, gax, gay, h, c);
+#pragma unroll
+      for (int b = 0; b < nd; ++b) cb_add(c, G[b][0], G[b][1], k[b][0], k[b][1]);
+   }
+}
+
+// row slice of a damaged cell staged by the visit-record kernel: scalar row h of local row a
+template <int ET>
+__device__ __forceinline__ void damaged_compute_stage(const AsmArgs &A, const Visit &r, double2 *sv, int rbase, int h)
 {
    constexpr int nd = Elem<ET>::nd;
    const int a = r.a;
-   const double2 *K = reinterpret_cast<const double2 *>(A.celld + (int64_t)idx * (4 * nd * nd) + (2 * a + h) * (2 * nd));
+   double k[nd][2];
+   damaged_row_slice<ET>(A.celld + (int64_t)r.e * dmg_rec_doubles<ET>(), a, h, k);
 #pragma unroll
    for (int b = 0; b < nd; ++b)
    {
-      const double2 kv = K[b];
       const int t = stored_position(b, a, nd);
-      stage_put(sv, rbase + r.slot(t), kv.x, kv.y, r.is_first(t));
+      stage_put(sv, rbase + r.slot(t), k[b][0], k[b][1], r.is_first(t));
    }
 }
 
@@ -446,21 +522,65 @@ __device__ __forceinline__ void fast_values(const AsmArgs &A, const uint4 raw, c
    }
 }
 
-// The same slice for a damaged cell: copied from the cell's tangent record (cell_tangent_kernel).
-template <int ET>
-__device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw, int idx, int h, double (*v)[2])
+// The same slice for a damaged cell, rebuilt from the cell's damage record in the record's own frame: positions
+// 0', 1', 2' are the local vertices i0, i1, i2 (i0 = the row's vertex, or the vertex opposite to the row's edge),
+// positions 3..5 the edges opposite to them; the point of the rule that sits next to vertex i_t is "point t".
+template <int ET, bool EDGE>
+__device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw, int h, double (*v)[2])
 {
-   constexpr int nd = Elem<ET>::nd;
+   const double *R = A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
    const int i1 = (int)(raw.w & 3u), i2 = (int)((raw.w >> 2) & 3u), i0 = 3 - i1 - i2;
-   const int a = ((raw.z >> 2) & 1u) ? 3 + i0 : i0;  // local dof of the row
-   const double2 *K = reinterpret_cast<const double2 *>(A.celld + (int64_t)idx * (4 * nd * nd) + (2 * a + h) * (2 * nd));
-#pragma unroll
-   for (int t = 0; t < nd; ++t)
-   {
-      const int b = (t >= 3 ? 3 : 0) + (t % 3 == 0 ? i0 : (t % 3 == 1 ? i1 : i2));  // local dof at position t
-      const double2 kv = K[b];
-      v[t][0] = h ? kv.y : kv.x, v[t][1] = h ? kv.x : kv.y;  // exchanged frame
+   double g1x, g1y, g2x, g2y;
+   ld_d4(R, g1x, g1y, g2x, g2y);
+   const double h0x = -g1x - g2x, h0y = -g1y - g2y;
+   // gradients of lambda at positions 1', 2', 0'
+   const double p1x = i1 == 0 ? h0x : (i1 == 1 ? g1x : g2x), p1y = i1 == 0 ? h0y : (i1 == 1 ? g1y : g2y);
+   const double p2x = i2 == 0 ? h0x : (i2 == 1 ? g1x : g2x), p2y = i2 == 0 ? h0y : (i2 == 1 ? g1y : g2y);
+   const double p0x = -p1x - p2x, p0y = -p1y - p2y;
+   auto out = [&](int t, double k0, double k1) { v[t][0] = h ? k1 : k0, v[t][1] = h ? k0 : k1; };  // exchanged frame
+   if (ET == FEMB200_P1)
+   {  // one point, constant gradients: K_ab = (row h of B_a D) B_b^t
+      const SymD D = ld_symd(R + 4);
+      double c[3];
+      bd_row(D, p0x, p0y, h, c);
+      double k0, k1;
+      k0 = k1 = 0., cb_add(c, p0x, p0y, k0, k1), out(0, k0, k1);
+      k0 = k1 = 0., cb_add(c, p1x, p1y, k0, k1), out(1, k0, k1);
+      k0 = k1 = 0., cb_add(c, p2x, p2y, k0, k1), out(2, k0, k1);
+      return;
    }
+   // D at the points next to 0', 1', 2' (point index = local vertex number)
+   const SymD D0 = ld_symd(R + 4 + 8 * i0), D1 = ld_symd(R + 4 + 8 * i1), D2 = ld_symd(R + 4 + 8 * i2);
+   // c_t = row h of B_a(point t) D_t: gradient of the row's own basis function at the three points
+   double c0[3], c1[3], c2[3];
+   if (!EDGE)
+   {  // vertex 0': (4 L_0 - 1) grad lambda_0 = 5/3, -1/3, -1/3
+      bd_row(D0, (5. / 3.) * p0x, (5. / 3.) * p0y, h, c0);
+      bd_row(D1, (-1. / 3.) * p0x, (-1. / 3.) * p0y, h, c1);
+      bd_row(D2, (-1. / 3.) * p0x, (-1. / 3.) * p0y, h, c2);
+   }
+   else
+   {  // edge (1', 2'): 4 (L_1 grad lambda_2 + L_2 grad lambda_1)
+      bd_row(D0, (-2. / 3.) * p0x, (-2. / 3.) * p0y, h, c0);
+      bd_row(D1, (8. / 3.) * p2x + (2. / 3.) * p1x, (8. / 3.) * p2y + (2. / 3.) * p1y, h, c1);
+      bd_row(D2, (2. / 3.) * p2x + (8. / 3.) * p1x, (2. / 3.) * p2y + (8. / 3.) * p1y, h, c2);
+   }
+   double S0[3], S1[3], S2[3], P0[3], P1[3], P2[3];
+#pragma unroll
+   for (int j = 0; j < 3; ++j)
+   {
+      const double C = c0[j] + c1[j] + c2[j];
+      S0[j] = (2. / 3.) * C + 2. * c0[j], S1[j] = (2. / 3.) * C + 2. * c1[j], S2[j] = (2. / 3.) * C + 2. * c2[j];
+      P0[j] = S0[j] - C, P1[j] = S1[j] - C, P2[j] = S2[j] - C;
+   }
+   double k0, k1;
+   k0 = k1 = 0., cb_add(P0, p0x, p0y, k0, k1), out(0, k0, k1);
+   k0 = k1 = 0., cb_add(P1, p1x, p1y, k0, k1), out(1, k0, k1);
+   k0 = k1 = 0., cb_add(P2, p2x, p2y, k0, k1), out(2, k0, k1);
+   // edge opposite t joins the other two positions
+   k0 = k1 = 0., cb_add(S1, p2x, p2y, k0, k1), cb_add(S2, p1x, p1y, k0, k1), out(3, k0, k1);
+   k0 = k1 = 0., cb_add(S0, p2x, p2y, k0, k1), cb_add(S2, p0x, p0y, k0, k1), out(4, k0, k1);
+   k0 = k1 = 0., cb_add(S0, p1x, p1y, k0, k1), cb_add(S1, p0x, p0y, k0, k1), out(5, k0, k1);
 }
 
 // Accumulates / carries / stages the slice: the diagonal block goes to registers (C.dg); the carry
@@ -532,8 +652,8 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
 // depend on the block and thread index only: the dependent chain of a tile is record -> cell record
 // -> first put (the tile header is needed by the stream-out only), with the cell record one visit
 // and the record two visits ahead.
-template <int ET, bool DMG, bool NORMS>
-__global__ void __launch_bounds__(kAsmR * 2, DMG ? 6 : 7)
+template <int ET, bool DMG, bool NORMS, int MINB = (DMG ? 5 : 7)>
+__global__ void __launch_bounds__(kAsmR * 2, MINB)
 assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out)
 {
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
@@ -575,15 +695,14 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          raw = raw1, geo = geo1, raw1 = raw2;
          if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
          raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
-         // damaged cell: NaN marker + index of its per-cell tangent record
+         // damaged cell: NaN marker, its damage record is celld[cell]
          const bool dam = DMG && geo.g1x != geo.g1x;
-         const int didx = dam ? (int)__double_as_longlong(geo.g1y) : 0;
          if (!((raw.z >> 2) & 1u))
          {  // vertex row
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET>(A, raw, didx, half, v);
+               damaged_values<ET, false>(A, raw, half, v);
                emit_row_slice<ET, false>(raw, img, half, C, v);
             }
             else
@@ -597,7 +716,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET>(A, raw, didx, half, v);
+               damaged_values<ET, true>(A, raw, half, v);
                emit_row_slice<ET, true>(raw, img, half, C, v);
             }
             else
@@ -850,14 +969,13 @@ __global__ void __launch_bounds__(kAsmR * TPN) assemble_kernel(AsmArgs A)
                if (c + j < cnt)
                {
                   if (DMG && geo[j].g1x != geo[j].g1x)
-                  {  // damaged cell: NaN marker + index of its per-cell tangent record
-                     const int idx = (int)__double_as_longlong(geo[j].g1y);
+                  {  // damaged cell: NaN marker, its damage record is celld[cell]
                      if (TPN == 2)
-                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, half ? r1 : r0, half);
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), sv, half ? r1 : r0, half);
                      else
                      {
-                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, r0, 0);
-                        damaged_compute_stage<ET>(A, Visit(raw[j]), idx, sv, r1, 1);
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), sv, r0, 0);
+                        damaged_compute_stage<ET>(A, Visit(raw[j]), sv, r1, 1);
                      }
                   }
                   else if (TPN == 2)
@@ -992,8 +1110,8 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    return 0;
 }
 
-template <int ET, bool DMG>
-static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
+template <int ET, bool DMG, int MINB>
+static int launch_assemble_fast_m(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
    A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
    A.flevels = p->flevels;
@@ -1004,17 +1122,25 @@ static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t s
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
-      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, true>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, true><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
+      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, true, MINB>>(smem)) return rc;
+      assemble_fast_kernel<ET, DMG, true, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
       norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
    }
    else
    {
-      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, false>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, false><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
+      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, false, MINB>>(smem)) return rc;
+      assemble_fast_kernel<ET, DMG, false, MINB><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
    }
    FEMB_LAUNCH_CHECK();
    return 0;
+}
+
+// the damaged variant is compiled for 5 resident CTAs per SM (96 registers, no spills): 4 (107 registers) and 6
+// (80 registers, spills in the damaged branch) measured 2 % and 24 % slower at 100 % damaged cells
+template <int ET, bool DMG>
+static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
+{
+   return launch_assemble_fast_m<ET, DMG, DMG ? 5 : 7>(p, A, st, d_norms);
 }
 
 // *fused: in: the caller wants (|K|_F^2, trace K) in d_norms; out: whether the kernel produced them
@@ -1059,36 +1185,32 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
       femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan
       if (!pm->cellrec)
       {
-         FEMB_CUDA(cudaMalloc(&pm->cellrec, sizeof(double) * 4 * (size_t)p->ncells));
-         pm->bytes += sizeof(double) * 4 * (size_t)p->ncells;
+         std::lock_guard<std::mutex> lock(pm->range_mtx);
+         if (!pm->cellrec)
+         {
+            FEMB_CUDA(cudaMalloc(&pm->cellrec, sizeof(double) * 4 * (size_t)p->ncells));
+            pm->bytes += sizeof(double) * 4 * (size_t)p->ncells;
+         }
       }
       const unsigned grid = (unsigned)cdiv(p->ncells, 128);
       if (d_dnod)
       {
-         const size_t W = 4 * (size_t)p->nd * p->nd;  // one element tangent per damaged cell (worst case: all)
+         const size_t W = p->etype == FEMB200_P1 ? dmg_rec_doubles<FEMB200_P1>() : dmg_rec_doubles<FEMB200_P2>();
          if (!pm->celld)
-         {
-            FEMB_CUDA(cudaMalloc(&pm->celld, sizeof(double) * W * (size_t)p->ncells));
-            FEMB_CUDA(cudaMalloc(&pm->celld_count, sizeof(int32_t) * (1 + (size_t)p->ncells)));
-            pm->bytes += (sizeof(double) * W + sizeof(int32_t)) * (size_t)p->ncells;
+         {  // one damage record per cell at worst (256 B for P2); allocated on the first damaged assembly
+            std::lock_guard<std::mutex> lock(pm->range_mtx);
+            if (!pm->celld)
+            {
+               FEMB_CUDA(cudaMalloc(&pm->celld, sizeof(double) * W * (size_t)p->ncells));
+               pm->bytes += sizeof(double) * W * (size_t)p->ncells;
+            }
          }
-         int32_t *dlist = pm->celld_count + 1;
-         FEMB_CUDA(cudaMemsetAsync(pm->celld_count, 0, sizeof(int32_t), st));
-         const unsigned g2 = (unsigned)std::min<int64_t>(cdiv(p->ncells, 128), (int64_t)devinfo().sm_count * 16);
          if (p->etype == FEMB200_P1)
-         {
-            cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, d_dnod,
-                                                                       pm->cellrec, dlist, pm->celld_count);
-            cell_tangent_kernel<FEMB200_P1><<<g2, 128, 0, st>>>(dlist, pm->celld_count, p->xdofmap, p->dofmap, d_x, x_stride,
-                                                                d_E, A.lc, d_dnod, d_u, variant, pm->celld);
-         }
+            cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld);
          else
-         {
-            cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, d_x, x_stride, d_E, d_dnod,
-                                                                       pm->cellrec, dlist, pm->celld_count);
-            cell_tangent_kernel<FEMB200_P2><<<g2, 128, 0, st>>>(dlist, pm->celld_count, p->xdofmap, p->dofmap, d_x, x_stride,
-                                                                d_E, A.lc, d_dnod, d_u, variant, pm->celld);
-         }
+            cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld);
          A.celld = pm->celld;
       }
       else

@@ -8,26 +8,36 @@
 
 namespace femb {
 
-template <int ET>
+// One thread integrates one cell; the 2 x n slabs of the element matrix (a row pair in the ufcx layout, a column
+// pair in the MFEM layout) go through a per-warp shared-memory stage (padded: conflict-free 16-byte accesses) and
+// leave as contiguous n-double chunks, 12 lanes per 96-byte chunk for P2: every 32-byte sector written whole,
+// instead of 32 lanes storing 1152 bytes apart (5.1 -> ~0.9 ms for 4.19 M P2 cells).
+template <int ET, bool ROWMAJOR>
 __global__ void __launch_bounds__(128)
 tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict__ x, int xs,
                 const int32_t *__restrict__ xdofmap, const int32_t *__restrict__ dofmap, const double *__restrict__ E,
-                LameCoef lc, const double *__restrict__ dnod, const double *__restrict__ u, int variant, int layout)
+                LameCoef lc, const double *__restrict__ dnod, const double *__restrict__ u, int variant)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq, n = 2 * nd;
+   constexpr int STRIDE = 2 * n + 2;  // doubles per lane in the stage
+   __shared__ __align__(16) double stage[4][32 * STRIDE];
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (e >= ncells) return;
+   const bool active = e < ncells;
+   const int64_t ec = active ? e : ncells - 1;  // idle lanes of the last warp repeat the last cell, store nothing
+   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + 32 * warp;  // first cell of this warp
+   const int nwarp = (int)max((int64_t)0, min((int64_t)32, ncells - e0));
 
    double xv[nv][2], dv[nv];
 #pragma unroll
    for (int v = 0; v < nv; ++v)
    {
-      const int64_t g = xdofmap[e * nv + v];
+      const int64_t g = xdofmap[ec * nv + v];
       xv[v][0] = x[g * xs];
       xv[v][1] = x[g * xs + 1];
       dv[v] = dnod ? dnod[g] : 0.;
    }
-   const double Ee = E[e];
+   const double Ee = E[ec];
    const double lam = Ee * lc.c2, mu = Ee * lc.c3;  // M.cc:1093-1098
 
    double G[nq][nd][2], w[nq], D[nq][9];
@@ -46,7 +56,7 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
 #pragma unroll
             for (int a = 0; a < nd; ++a)
             {
-               const int64_t gd = 2 * (int64_t)dofmap[e * nd + a];
+               const int64_t gd = 2 * (int64_t)dofmap[ec * nd + a];
                const double ux = u[gd], uy = u[gd + 1];
                g00 += ux * G[q][a][0];
                g01 += ux * G[q][a][1];
@@ -61,31 +71,41 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
          hooke_scaled(lam, mu, 1., D[q]);
    }
 
-   double *Ae = A + e * (int64_t)(n * n);
+   constexpr bool rowmajor = ROWMAJOR;
+   double *st = stage[warp] + lane * STRIDE;
+   constexpr int UNR = 1;  // rolled loops (G indexed in local memory, L1 hits): 154 registers for P2 against 254 unrolled
 #pragma unroll 1
-   for (int a = 0; a < nd; ++a)
-   {
-#pragma unroll 1
-      for (int b = 0; b < nd; ++b)
+   for (int o = 0; o < nd; ++o)
+   {  // slab o: rows (2o, 2o+1) of the ufcx layout / columns (o, nd + o) of the MFEM layout
+#pragma unroll UNR
+      for (int i = 0; i < nd; ++i)
       {
+         const int a = rowmajor ? o : i, b = rowmajor ? i : o;
          double k[4] = {0., 0., 0., 0.};
 #pragma unroll
          for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], w[q], k);
-         if (layout == FEMB200_ROWMAJOR_INTERLEAVED)
-         {
-            Ae[(2 * a) * n + 2 * b] = k[0];
-            Ae[(2 * a) * n + 2 * b + 1] = k[1];
-            Ae[(2 * a + 1) * n + 2 * b] = k[2];
-            Ae[(2 * a + 1) * n + 2 * b + 1] = k[3];
+         if (rowmajor)
+         {  // chunk r = row 2a + r: entries (2b, 2b + 1)
+            reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
+            reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
          }
          else
-         {
-            Ae[a + b * n] = k[0];
-            Ae[a + (nd + b) * n] = k[1];
-            Ae[(nd + a) + b * n] = k[2];
-            Ae[(nd + a) + (nd + b) * n] = k[3];
+         {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
+            st[a] = k[0], st[nd + a] = k[2];
+            st[n + a] = k[1], st[n + nd + a] = k[3];
          }
       }
+      __syncwarp();
+      // 2 chunks of n doubles per cell, n double2 units per cell
+      for (int t = lane; t < nwarp * n; t += 32)
+      {
+         const int c = t / n, r = t - c * n;       // cell of the warp, unit in its slab
+         const int ch = r / nd, j = r - ch * nd;   // chunk, double2 inside the chunk
+         const double2 val = reinterpret_cast<const double2 *>(stage[warp] + c * STRIDE + ch * n)[j];
+         double *dst = A + (e0 + c) * (int64_t)(n * n) + (rowmajor ? (int64_t)(2 * o + ch) * n : (int64_t)(ch * nd + o) * n);
+         reinterpret_cast<double2 *>(dst)[j] = val;
+      }
+      __syncwarp();
    }
 }
 
@@ -101,26 +121,28 @@ extern "C" int femb200_tabulate_tensor_batched(int etype, int64_t ncells, double
    FEMB_CHECK(etype >= FEMB200_P1 && etype <= FEMB200_Q2, "tabulate: unknown element family %d", etype);
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "tabulate: x_stride must be 2 or 3, got %d", x_stride);
    FEMB_CHECK(d_A && d_x && d_xdofmap && d_dofmap && d_E, "tabulate: null pointer argument");
+   FEMB_CHECK((reinterpret_cast<uintptr_t>(d_A) & 15) == 0, "tabulate: d_A must be 16-byte aligned");
    FEMB_CHECK(layout == FEMB200_ROWMAJOR_INTERLEAVED || layout == FEMB200_COLMAJOR_BYNODES, "tabulate: bad layout %d",
               layout);
    if (ncells <= 0) return 0;
    const LameCoef lc = lame_coef(nu);
    const unsigned grid = (unsigned)cdiv(ncells, 128);
    cudaStream_t st = as_stream(stream);
+   const bool rm = layout == FEMB200_ROWMAJOR_INTERLEAVED;
+#define FEMB_TAB(ET)                                                                                                     \
+   if (rm)                                                                                                               \
+      tabulate_kernel<ET, true><<<grid, 128, 0, st>>>(ncells, d_A, d_x, x_stride, d_xdofmap, d_dofmap, d_E, lc, d_dnod,  \
+                                                      d_u, variant);                                                     \
+   else                                                                                                                  \
+      tabulate_kernel<ET, false><<<grid, 128, 0, st>>>(ncells, d_A, d_x, x_stride, d_xdofmap, d_dofmap, d_E, lc, d_dnod, \
+                                                       d_u, variant)
    switch (etype)
    {
-      case FEMB200_P1:
-         tabulate_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(ncells, d_A, d_x, x_stride, d_xdofmap, d_dofmap, d_E, lc,
-                                                         d_dnod, d_u, variant, layout);
-         break;
-      case FEMB200_P2:
-         tabulate_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(ncells, d_A, d_x, x_stride, d_xdofmap, d_dofmap, d_E, lc,
-                                                         d_dnod, d_u, variant, layout);
-         break;
-      default:
-         tabulate_kernel<FEMB200_Q2><<<grid, 128, 0, st>>>(ncells, d_A, d_x, x_stride, d_xdofmap, d_dofmap, d_E, lc,
-                                                         d_dnod, d_u, variant, layout);
+      case FEMB200_P1: FEMB_TAB(FEMB200_P1); break;
+      case FEMB200_P2: FEMB_TAB(FEMB200_P2); break;
+      default: FEMB_TAB(FEMB200_Q2);
    }
+#undef FEMB_TAB
    FEMB_LAUNCH_CHECK();
    return 0;
 }
@@ -138,7 +160,7 @@ extern "C" int femb200_tabulate_tensor_batched(int etype, int64_t ncells, double
 namespace femb {
 struct UfcxScratch
 {
-   double *d = nullptr;   // x[9] | E[1] | dnod[3] | u[6] | A[36]
+   double *d = nullptr;   // x[9] | E[1] | dnod[3] | u[6] | pad | A[36] (16-byte aligned)
    int32_t *map = nullptr;
 };
 static UfcxScratch *ufcx_scratch()
@@ -147,7 +169,7 @@ static UfcxScratch *ufcx_scratch()
    if (!s.d)
    {
       const int32_t id[3] = {0, 1, 2};
-      if (cudaMalloc(&s.d, sizeof(double) * 55) != cudaSuccess || cudaMalloc(&s.map, sizeof(id)) != cudaSuccess ||
+      if (cudaMalloc(&s.d, sizeof(double) * 56) != cudaSuccess || cudaMalloc(&s.map, sizeof(id)) != cudaSuccess ||
           cudaMemcpy(s.map, id, sizeof(id), cudaMemcpyHostToDevice) != cudaSuccess)
       {
          set_error("tabulate_tensor_ufcx: device scratch: %s", cudaGetErrorString(cudaGetLastError()));
@@ -182,12 +204,12 @@ extern "C" void femb200_tabulate_tensor_ufcx(double *A, const double *w, const d
       set_error("tabulate_tensor_ufcx: H2D: %s", cudaGetErrorString(cudaGetLastError()));
       return;
    }
-   if (femb200_tabulate_tensor_batched(FEMB200_P1, 1, s->d + 19, s->d, 3, s->map, s->map, s->d + 9, c[0],
+   if (femb200_tabulate_tensor_batched(FEMB200_P1, 1, s->d + 20, s->d, 3, s->map, s->map, s->d + 9, c[0],
                                        damaged ? s->d + 10 : nullptr, s->d + 13, FEMB200_TANGENT_CLOSED,
                                        FEMB200_ROWMAJOR_INTERLEAVED, nullptr))
       return;
    double out[36];
-   if (cudaMemcpy(out, s->d + 19, sizeof(out), cudaMemcpyDeviceToHost) != cudaSuccess)
+   if (cudaMemcpy(out, s->d + 20, sizeof(out), cudaMemcpyDeviceToHost) != cudaSuccess)
    {
       set_error("tabulate_tensor_ufcx: D2H: %s", cudaGetErrorString(cudaGetLastError()));
       return;

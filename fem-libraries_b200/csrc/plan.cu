@@ -779,6 +779,7 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
    }
    else if (!strcmp(key, "prefetch_tiles"))
       p->opt_prefetch_tiles = value;
+
    else
       return set_error("plan_set_option: unknown key '%s'", key);
    return 0;

@@ -74,7 +74,7 @@ int femb200_fp64_probe(int blocks_per_sm, int iters, double *d_out, int64_t *blo
  * (manual.py:102; ufcx signature, FEniCSx/mechanic2d/addprofile:6-9) called once
  * per cell by dolfinx, and mfem `damIntegrator::AssembleElementGrad`
  * (M.cc:639-916) called once per element by ParNonlinearForm::GetGradient.
- * One launch tabulates `ncells` cells; d_A is ncells x (2nd)^2, overwritten.
+ * One launch tabulates `ncells` cells; d_A is ncells x (2nd)^2, overwritten (16-byte aligned).
  *   d_x        nnodes x x_stride coordinates (x_stride 2, or 3 for xyz-padded
  *              dolfinx geometry, F.cc:213)
  *   d_xdofmap  ncells x nv geometry vertices;  d_dofmap ncells x nd scalar dofs

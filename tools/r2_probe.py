@@ -1,0 +1,75 @@
+"""Developer probe (round 2): times the kernels under work on one GPU.  python tools/r2_probe.py [what ...]
+what: tab (tabulate P2), dmg (damaged reassembly n=1448), asm (linear assembly n=1448), pa (Q2 apply n=2048)"""
+import os
+import sys
+import json
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "fem-libraries_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+from femb200 import fem, dist, mesh as fm
+
+PEAK = 6451.2
+
+
+def timed(fn, k=10, w=3):
+    for _ in range(w):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+    for a, b in evs:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    t = [a.elapsed_time(b) for a, b in evs]
+    return float(np.mean(t)), float(np.min(t))
+
+
+def main():
+    what = sys.argv[1:] or ["tab", "dmg", "asm"]
+    out = {}
+    n = 1448
+    p = dist.strip_partition_device(n, n, 0, 1)
+    m = p.mesh
+    form = fem.ElasticityForm(m, p.E, 0.3)
+    if "tab" in what:
+        Ae = torch.empty((m.ncells, 12, 12), dtype=torch.float64, device="cuda")
+        for lay in (0, 1):
+            ms, mn = timed(lambda: fem.tabulate_tensor_batched(form, layout=lay, out=Ae))
+            out[f"tabulate_p2_layout{lay}"] = {"ms": ms, "min": mn, "frac_hbm": 1192 * m.ncells / (ms * 1e-3) / 1e9 / PEAK,
+                                               "tflops": 4314 * m.ncells / (ms * 1e-3) / 1e12}
+        del Ae
+    A = fem.create_matrix(form)
+    abytes = 8 * A.nnz + m.ncells * 32 + m.nnodes * 16
+    if "asm" in what:
+        ms, mn = timed(lambda: fem.assemble_matrix(A, form))
+        out["assemble_p2"] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+    if "dmg" in what or "dmg100" in what:
+        xy = m.x
+        u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+        levels = (("100pct", 10.0),) if "dmg100" in what else (("10pct", 0.05), ("50pct", 0.25), ("100pct", 10.0))
+        for label, hw in levels:
+            d = torch.clamp(1.0 - (xy[:, 1] - 0.5 - 0.1 * torch.sin(6.0 * xy[:, 0])).abs() / hw, min=0.0, max=0.95)
+            for variant, name in ((0, "closed"), (1, "ad")):
+                f2 = fem.ElasticityForm(m, p.E, 0.3, d=d, u=u, variant=variant)
+                ms, mn = timed(lambda: fem.assemble_matrix(A, f2), k=5, w=2)
+                out[f"dmg_{label}_{name}"] = {"ms": ms, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+    if "pa" in what:
+        del A
+        nq = 2048
+        mq = fm.jitter(fm.structured_quads_q2(nq), 0.2, seed=1234)
+        Eq = fm.young_per_cell(mq.ncells)
+        bc, g = fm.dirichlet_markers(mq)
+        fq = fem.ElasticityForm(mq, Eq, 0.3)
+        pa = fem.PAOperator(fq, bcs=[fem.DirichletBC(bc, g)])
+        v = torch.randn(mq.ndofs, dtype=torch.float64, device="cuda")
+        y = torch.empty_like(v)
+        ms, mn = timed(lambda: pa.mult(v, y))
+        nbytes = mq.nnodes * 32 + mq.ncells * (8 * (2 * mq.nv + 2) + 4 * mq.nd + 4)
+        out["pa_q2_n2048"] = {"ms": ms, "min": mn, "frac": nbytes / (ms * 1e-3) / 1e9 / PEAK, "gdofs": mq.ndofs / ms / 1e6}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
