@@ -235,6 +235,26 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity) so that the pinned host buffers of the
+    end-to-end leg are first-touched on that GPU's NUMA node: eight ranks sharing one node's memory controller was
+    the round-1 e2e bottleneck (torchrun does not bind its workers).  Returns the number of cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class Env:
     """rank / world, barrier, max-over-ranks timing."""
 
@@ -248,6 +268,8 @@ class Env:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
         torch.cuda.set_device(self.local)
+        self.orig_affinity = os.sched_getaffinity(0)
+        self.cpu_binding = bind_to_gpu_numa(self.local)
         if self.world > 1:
             td.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
@@ -513,6 +535,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
         line["extras"] = extras(env, fem, peak, args)
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, env.orig_affinity)      # the CPU arm gets every core of the box back
         r = cpu_reference(args.cpu_baseline_n, 3, 1, args.cg_iters)
         line["cpu_baseline"] = {"value": r["step_gdofs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                 "sample": r["sample"], "assembly_gdofs": r["assembly_gdofs"], "spmv_gbs": r["spmv_gbs"],
@@ -564,6 +587,7 @@ def e2e_newton(env, fem, dist, form, part, op, A, args, total_dofs):
     ms = tot / K
     return {"value": total_dofs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": K,
             "h2d_bytes_per_step": int(hu.numel() * 8), "d2h_bytes_per_step": int(hdu.numel() * 8),
+            "cpu_cores_bound_to_gpu_numa_node": env.cpu_binding,
             "du_checksum": float(hdu.abs().sum().item()),
             "what": "per step and per rank: pinned host u -> device, NewtonSolver.residual (F(u) + apply_lifting; this "
                     "residual assembly and one extra SpMV are work the device-timed `value` does not contain), "

@@ -3,12 +3,36 @@
 // plan / pa / pcg functions for callers that bind the reference-side names directly.
 #include "plan.cuh"
 
+#include <map>
+#include <mutex>
+
 namespace femb {
 
-__global__ void axpy1_kernel(int64_t n, const double *__restrict__ t, double *__restrict__ y)
+// scratch of femb200_cg: one buffer per device, grown on demand, kept for the life of the process (a solver
+// called once per Newton iteration must not pay a cudaMalloc / cudaFree pair every time)
+static int cg_scratch(size_t doubles, double **out)
 {
-   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) y[i] += t[i];
+   struct Slot
+   {
+      double *p = nullptr;
+      size_t cap = 0;
+   };
+   static std::map<int, Slot> slots;
+   static std::mutex mtx;
+   std::lock_guard<std::mutex> lock(mtx);
+   int dev = 0;
+   FEMB_CUDA(cudaGetDevice(&dev));
+   Slot &s = slots[dev];
+   if (doubles > s.cap)
+   {
+      FEMB_CUDA(cudaDeviceSynchronize());
+      cudaFree(s.p);
+      s.p = nullptr, s.cap = 0;
+      FEMB_CUDA(cudaMalloc(&s.p, sizeof(double) * doubles));
+      s.cap = doubles;
+   }
+   *out = s.p;
+   return 0;
 }
 
 }  // namespace femb
@@ -39,20 +63,9 @@ extern "C" int femb200_assemble_pa(int etype, int64_t nnodes, int64_t ncells, co
    return femb200_pa_create(etype, nnodes, ncells, d_dofmap, d_xdofmap, d_x, x_stride, d_E, nu, stream, out);
 }
 
-// BilinearFormIntegrator::AddMultPA(x, y): y += A x.  d_work: 2 * nnodes doubles of scratch.
-extern "C" int femb200_add_mult_pa(const femb200_pa *pa, int64_t ndofs, const double *d_x, double *d_y, double *d_work,
-                                   void *stream)
-{
-   FEMB_CHECK(pa && d_x && d_y && d_work, "add_mult_pa: null argument");
-   FEMB_CHECK(d_work != d_x && d_work != d_y, "add_mult_pa: the scratch vector must not alias x or y");
-   if (int rc = femb200_pa_apply(pa, d_x, d_work, stream)) return rc;
-   axpy1_kernel<<<(unsigned)cdiv(ndofs, 256), 256, 0, as_stream(stream)>>>(ndofs, d_work, d_y);
-   FEMB_LAUNCH_CHECK();
-   return 0;
-}
-
 // CGSolver::Mult / KSPSolve with the tolerances of M.cc:1525-1528, F.cc:718-722; precond NONE or JACOBI.
-// Allocates and frees its own scratch (4 n + 64 doubles); synchronises the stream.
+// Its scratch (4 n + 64 doubles) comes from a per-device buffer that is grown on demand and kept; synchronises the
+// stream.  Not re-entrant on one device (one solve at a time, as the reference's Newton loop).
 extern "C" int femb200_cg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const double *d_b,
                           double *d_x, int64_t n, double rtol, double atol, int maxit, int precond, int *iters,
                           double *final_res, int *converged, void *stream)
@@ -61,7 +74,7 @@ extern "C" int femb200_cg(const femb200_plan *plan, int op_kind, const void *op,
    FEMB_CHECK(n > 0 && d_b && d_x, "cg: null argument");
    cudaStream_t st = as_stream(stream);
    double *work = nullptr;
-   FEMB_CUDA(cudaMalloc(&work, sizeof(double) * (4 * (size_t)n + 64)));
+   if (int rc0 = cg_scratch(4 * (size_t)n + 64, &work)) return rc0;
    double *dinv = nullptr;
    int rc = 0;
    if (precond == FEMB200_PRECOND_JACOBI)
@@ -76,7 +89,6 @@ extern "C" int femb200_cg(const femb200_plan *plan, int op_kind, const void *op,
    if (!rc)
       rc = femb200_pcg(plan, op_kind, op, d_values, d_b, d_x, n, rtol, atol, maxit, dinv, 25, 0, work, &it, &fin, &conv, stream);
    cudaStreamSynchronize(st);
-   cudaFree(work);
    if (iters) *iters = it;
    if (final_res) *final_res = fin;
    if (converged) *converged = conv;

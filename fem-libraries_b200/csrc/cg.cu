@@ -28,7 +28,7 @@
 namespace femb {
 
 int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
-                    cudaStream_t st);
+                    cudaStream_t st, bool accumulate);
 
 enum
 {
@@ -287,7 +287,7 @@ static int cg_apply_rows(const femb200_plan *plan, int op_kind, const void *op, 
 {
    if (op_kind == FEMB200_OP_CSR)
       return spmv_launch(plan, rr, d_values, d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, false, st);
-   return pa_apply_launch(static_cast<const femb200_pa *>(op), d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st);
+   return pa_apply_launch(static_cast<const femb200_pa *>(op), d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st, false);
 }
 
 // The PCG loop of femb200_pcg and femb200_dist_pcg.  Vector kernels run on the owned dofs [2 own_lo,

@@ -449,6 +449,7 @@ struct PaArgs
    double *y;
    const double *flag;
    PaLayout L;
+   int accumulate;  // y += A x (AddMultPA) instead of y = A x
 };
 
 __global__ void pa_zero_shared_kernel(int n, const int32_t *__restrict__ list, double *__restrict__ y,
@@ -655,6 +656,12 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
                red_add_f64(yp, acc[j].x);
                red_add_f64(yp + 1, acc[j].y);
             }
+            else if (A.accumulate)
+            {
+               double2 o = y2[id];
+               o.x += acc[j].x, o.y += acc[j].y;
+               y2[id] = o;
+            }
             else
                y2[id] = acc[j];
          }
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
 // y[bc] = diag x[bc]; adds diag x[bc]^2 to the fused dot.  One CTA.
 __global__ void __launch_bounds__(256)
 pa_bc_fix_kernel(int nbc, const int32_t *__restrict__ list, double diag, const double *__restrict__ x,
-                 double *__restrict__ y, const double *__restrict__ flag, double *__restrict__ out)
+                 double *__restrict__ y, const double *__restrict__ flag, double *__restrict__ out, bool accumulate)
 {
    __shared__ double sh[8];
    if (flag && *flag != 0.) return;
@@ -676,7 +683,7 @@ pa_bc_fix_kernel(int nbc, const int32_t *__restrict__ list, double diag, const d
    {
       const int64_t i = list[k];
       const double xi = x[i];
-      y[i] = diag * xi;
+      y[i] = accumulate ? y[i] + diag * xi : diag * xi;  // the element products left nothing on constrained dofs
       part += diag * xi * xi;
    }
    if (out)
@@ -757,7 +764,7 @@ static PaLayout pa_layout(const femb200_pa *pa)
 
 template <int ET>
 static int pa_apply_t(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
-                      cudaStream_t st)
+                      cudaStream_t st, bool accumulate)
 {
    const PaLayout L = pa_layout(pa);
    const size_t smem = (size_t)L.ye + sizeof(double2) * (size_t)kPaThreads * Elem<ET>::nd;
@@ -776,7 +783,8 @@ static int pa_apply_t(const femb200_pa *pa, const double *d_x, double *d_y, cons
    else
       FEMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pa_tile_kernel<ET, false>, kPaThreads, smem));
    const unsigned grid = (unsigned)std::min<int64_t>(pa->ntiles, (int64_t)devinfo().sm_count * std::max(1, per_sm));
-   PaArgs A{pa->ncells, (int)pa->ntiles, pa->tnodes, pa->tptr, pa->trefs, pa->lidx, pa->geo, pa->cmask, d_x, d_y, d_flag, L};
+   PaArgs A{pa->ncells, (int)pa->ntiles, pa->tnodes, pa->tptr, pa->trefs, pa->lidx, pa->geo, pa->cmask, d_x, d_y, d_flag, L,
+            accumulate ? 1 : 0};
    if (d_dot_out)
    {
       ReduceScratch red;
@@ -790,10 +798,11 @@ static int pa_apply_t(const femb200_pa *pa, const double *d_x, double *d_y, cons
 }
 
 int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
-                    cudaStream_t st)
+                    cudaStream_t st, bool accumulate)
 {
-   // only the nodes shared between tiles are accumulated with reductions: zero those
-   if (pa->nshared > 0)
+   // only the nodes shared between tiles are accumulated with reductions: zero those (y = A x); with
+   // accumulate (y += A x) the reductions add to what y holds and interior nodes read-modify-write
+   if (pa->nshared > 0 && !accumulate)
    {
       pa_zero_shared_kernel<<<(unsigned)cdiv(pa->nshared, 256), 256, 0, st>>>(pa->nshared, pa->shared_nodes, d_y, d_flag);
       FEMB_LAUNCH_CHECK();
@@ -801,14 +810,14 @@ int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const 
    int rc;
    switch (pa->etype)
    {
-      case FEMB200_P1: rc = pa_apply_t<FEMB200_P1>(pa, d_x, d_y, d_flag, d_dot_out, st); break;
-      case FEMB200_P2: rc = pa_apply_t<FEMB200_P2>(pa, d_x, d_y, d_flag, d_dot_out, st); break;
-      default: rc = pa_apply_t<FEMB200_Q2>(pa, d_x, d_y, d_flag, d_dot_out, st);
+      case FEMB200_P1: rc = pa_apply_t<FEMB200_P1>(pa, d_x, d_y, d_flag, d_dot_out, st, accumulate); break;
+      case FEMB200_P2: rc = pa_apply_t<FEMB200_P2>(pa, d_x, d_y, d_flag, d_dot_out, st, accumulate); break;
+      default: rc = pa_apply_t<FEMB200_Q2>(pa, d_x, d_y, d_flag, d_dot_out, st, accumulate);
    }
    if (rc) return rc;
    if (pa->nbc > 0)
    {
-      pa_bc_fix_kernel<<<1, 256, 0, st>>>(pa->nbc, pa->bc_dofs, pa->diag, d_x, d_y, d_flag, d_dot_out);
+      pa_bc_fix_kernel<<<1, 256, 0, st>>>(pa->nbc, pa->bc_dofs, pa->diag, d_x, d_y, d_flag, d_dot_out, accumulate);
       FEMB_LAUNCH_CHECK();
    }
    return 0;
@@ -936,10 +945,10 @@ extern "C" int femb200_pa_create(int etype, int64_t nnodes, int64_t ncells, cons
    FEMB_CHECK(nnodes > 0 && ncells > 0, "pa_create: empty mesh");
    FEMB_CHECK(d_dofmap && d_xdofmap && d_x && d_E, "pa_create: null argument");
    FEMB_CHECK(x_stride == 2 || x_stride == 3, "pa_create: x_stride must be 2 or 3, got %d", x_stride);
+   FEMB_CHECK(ncells < (int64_t)1 << 31 && nnodes < (int64_t)1 << 31, "pa_create: mesh too large for 32-bit local indices");
    femb200_pa *pa = new femb200_pa();
    pa->etype = etype, pa->nd = elem_nd(etype), pa->nv = elem_nv(etype);
    pa->nnodes = nnodes, pa->ncells = ncells, pa->dofmap = d_dofmap;
-   FEMB_CHECK(ncells < (int64_t)1 << 31 && nnodes < (int64_t)1 << 31, "pa_create: mesh too large for 32-bit local indices");
    cudaStream_t st = as_stream(stream);
    if (pa_build_tiles(pa, d_xdofmap, d_x, x_stride, st))
    {
@@ -977,24 +986,29 @@ extern "C" int femb200_pa_set_dirichlet(femb200_pa *pa, const uint8_t *d_bc, dou
    pa->diag = diag;
    if (!d_bc) return 0;
    const int64_t nd = 2 * pa->nnodes;
-   FEMB_CUDA(cudaMalloc(&pa->bc, (size_t)nd));
-   FEMB_CUDA(cudaMalloc(&pa->cmask, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads));
-   FEMB_CUDA(cudaMemsetAsync(pa->cmask, 0, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads, st));
-   FEMB_CUDA(cudaMemcpyAsync(pa->bc, d_bc, (size_t)nd, cudaMemcpyDeviceToDevice, st));
+   int32_t *count = nullptr;
+   // every failure below leaves the operator unconstrained and owns nothing
+   auto fail = [&](const char *what) {
+      cudaFree(count);
+      cudaFree(pa->cmask), cudaFree(pa->bc), cudaFree(pa->bc_dofs);
+      pa->cmask = nullptr, pa->bc = nullptr, pa->bc_dofs = nullptr, pa->nbc = 0;
+      return set_error("pa_set_dirichlet: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+   };
+   if (cudaMalloc(&pa->bc, (size_t)nd) != cudaSuccess ||
+       cudaMalloc(&pa->cmask, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads) != cudaSuccess ||
+       cudaMalloc(&count, sizeof(int32_t)) != cudaSuccess)
+      return fail("cudaMalloc");
+   if (cudaMemsetAsync(pa->cmask, 0, sizeof(uint32_t) * (size_t)pa->ntiles * kPaThreads, st) != cudaSuccess ||
+       cudaMemcpyAsync(pa->bc, d_bc, (size_t)nd, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+       cudaMemsetAsync(count, 0, sizeof(int32_t), st) != cudaSuccess)
+      return fail("copy");
    pa_cmask_kernel<<<(unsigned)cdiv(pa->ncells, 256), 256, 0, st>>>(pa->ncells, pa->nd, pa->cperm, pa->dofmap, pa->bc,
                                                                     pa->cmask);
-   int32_t *count = nullptr;
-   FEMB_CUDA(cudaMalloc(&count, sizeof(int32_t)));
-   FEMB_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
    pa_bc_list_kernel<<<(unsigned)cdiv(nd, 256), 256, 0, st>>>(nd, pa->bc, nullptr, count);
    int32_t n = 0;
    cudaMemcpyAsync(&n, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-   if (cudaStreamSynchronize(st) != cudaSuccess)
-   {
-      cudaFree(count);
-      return set_error("pa_set_dirichlet: %s", cudaGetErrorString(cudaGetLastError()));
-   }
-   cudaMalloc(&pa->bc_dofs, sizeof(int32_t) * (size_t)(n ? n : 1));
+   if (cudaStreamSynchronize(st) != cudaSuccess) return fail("constrained-dof count");
+   if (cudaMalloc(&pa->bc_dofs, sizeof(int32_t) * (size_t)(n ? n : 1)) != cudaSuccess) return fail("cudaMalloc");
    cudaMemsetAsync(count, 0, sizeof(int32_t), st);
    pa_bc_list_kernel<<<(unsigned)cdiv(nd, 256), 256, 0, st>>>(nd, pa->bc, pa->bc_dofs, count);
    cudaStreamSynchronize(st);
@@ -1008,10 +1022,23 @@ extern "C" int femb200_pa_apply(const femb200_pa *pa, const double *d_x, double 
 {
    FEMB_CHECK(pa && d_x && d_y, "pa_apply: null argument");
    FEMB_CHECK(d_x != d_y, "pa_apply: x and y must not alias");
-   return pa_apply_launch(pa, d_x, d_y, nullptr, nullptr, as_stream(stream));
+   return pa_apply_launch(pa, d_x, d_y, nullptr, nullptr, as_stream(stream), false);
 }
 
 int64_t pa_num_dofs(const femb200_pa *pa) { return pa ? 2 * pa->nnodes : 0; }
+// BilinearFormIntegrator::AddMultPA(x, y): y += A x, accumulated in the node phase of the apply kernel (no scratch
+// vector, no extra pass); d_work is unused and may be NULL (kept for the round-1 signature)
+extern "C" int femb200_add_mult_pa(const femb200_pa *pa, int64_t ndofs, const double *d_x, double *d_y, double *d_work,
+                                   void *stream)
+{
+   (void)d_work;
+   FEMB_CHECK(pa && d_x && d_y, "add_mult_pa: null argument");
+   FEMB_CHECK(d_x != d_y, "add_mult_pa: x and y must not alias");
+   FEMB_CHECK(ndofs == 2 * pa->nnodes, "add_mult_pa: ndofs = %lld, the operator has %lld", (long long)ndofs,
+              (long long)(2 * pa->nnodes));
+   return pa_apply_launch(pa, d_x, d_y, nullptr, nullptr, as_stream(stream), true);
+}
+
 extern "C" int femb200_pa_diagonal(const femb200_pa *pa, double *d_diag, void *stream)
 {
    FEMB_CHECK(pa && d_diag, "pa_diagonal: null argument");

@@ -351,7 +351,7 @@ int femb200_cell_strain_stress(int etype, int64_t ncells, const int32_t *d_xdofm
  *   element_grad_batched = tabulate_tensor_batched in the MFEM layout: elmat column-major,
  *                          dofs byNODES (damIntegrator::AssembleElementGrad, M.cc:639,673)
  *   assemble_pa          = pa_create          (BilinearFormIntegrator::AssemblePA)
- *   add_mult_pa          : y += A x           (AddMultPA; d_work: ndofs doubles of scratch)
+ *   add_mult_pa          : y += A x           (AddMultPA; accumulated inside the apply kernel, d_work unused: may be NULL)
  *   cg                   = pcg with its own scratch and Jacobi set-up (CGSolver::Mult /
  *                          KSPSolve; precond FEMB200_PRECOND_NONE | _JACOBI); synchronises
  * ------------------------------------------------------------------------ */

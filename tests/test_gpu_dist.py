@@ -66,6 +66,15 @@ def test_strips_match_global_on_one_gpu(world):
     assert abs(dots - ref) <= 1e-12 * np.abs(vg.cpu().numpy() * want).sum()
 
 
+def assert_norms_match(got, want, noise=1e-7):
+    """Residual histories agree to 6 digits; entries at the rounding-noise floor of the converged state only in size."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    big = want > noise
+    np.testing.assert_allclose(got[big], want[big], rtol=1e-6)
+    assert (got[~big] <= noise).all()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -150,6 +159,21 @@ def _nccl_worker(rank, world, port, out):
             a, c = sols[("p2p", True)], sols[("nccl", True)]
             assert abs(a[1] - c[1]) <= 1 and ((a[0] - c[0]).norm() / c[0].norm()).item() < 1e-10
         op.close()
+        # distributed Newton (residual + lifting + tangent + PCG on strips, ghost update of u after every increment,
+        # all-reduced norms) against the oracle's Newton loop on the global mesh, both convergence conventions
+        dg, fg = fm.damage_band(mg), fm.body_force(mg)
+        for conv_rule in ("mfem", "dolfinx"):
+            wantu, it_o, norms_o = oracle.newton(mg.etype, mg.x, mg.xdofmap, mg.dofmap, Eg, 0.3, bcg, gg, dnod=dg,
+                                                 fnod=fg.ravel(), convention=conv_rule, max_iter=20)
+            ns = fem.NewtonSolver(fem.ElasticityForm(p.mesh, p.E, 0.3, d=fm.damage_band(p.mesh)), [fem.DirichletBC(p.bc, p.g)],
+                                  f=fm.body_force(p.mesh), convention=conv_rule, max_iter=20, part=p)
+            ul = ns.solve()
+            us = dist.gather_owned(p, ul)
+            assert ns.converged and ns.iterations == it_o, (conv_rule, ns.iterations, it_o)
+            assert_norms_match(ns.residual_norms, norms_o)
+            if rank == 0:
+                assert np.linalg.norm(us - wantu) / np.linalg.norm(wantu) < 1e-9
+            ns.close()
         out.put((rank, "ok " + "+".join(transports)))
     except Exception:  # noqa: BLE001
         import traceback
