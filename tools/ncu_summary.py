@@ -70,7 +70,7 @@ def main():
             v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu], 1.0)
             agg.setdefault(r[kn].split("(")[0].replace("void ", "").replace("femb::", "")[:58], []).append(v)
         tot = sum(sum(v) for v in agg.values())
-        lines += ["## Launch list (`bench.py --steps 2 --cg-iters 3 --no-cpu-baseline`)", "",
+        lines += ["## Launch list (`bench.py --steps 2 --warmup 3 --skip-extras --no-cpu-baseline --e2e-steps 1`, first 420 launches)", "",
                   "| kernel | launches | mean µs | share of GPU time |", "|---|---:|---:|---:|"]
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             lines.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f} % |")
@@ -100,9 +100,14 @@ def main():
             lines += [f"{p:5.1f}%  {why:<15s} {s}" for p, why, s in src] + ["```", ""]
     with open(os.path.join(PROF, f"{tag}_summary.md"), "w") as f:
         f.write("\n".join(lines))
+    # profiles/traffic.json: {"<n>": {"assemble": bytes, "spmv": bytes}} -- names of the form <kernel>@<n> are recorded
     tj = os.path.join(PROF, "traffic.json")
     old = json.load(open(tj)) if os.path.exists(tj) else {}
-    old.update(traffic)
+    old = {k: v for k, v in old.items() if isinstance(v, dict)}
+    for name, b in traffic.items():
+        if "@" in name:
+            kern, n = name.split("@")
+            old.setdefault(n, {})[kern] = b
     json.dump(old, open(tj, "w"), indent=1)
     print("\n".join(lines[:60]))
 
