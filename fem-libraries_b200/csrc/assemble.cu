@@ -734,16 +734,29 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       }
    }
    __syncthreads();
-   // stream the finished tile out: one contiguous byte range of the CSR values
-   double *dst = A.values + 4 * b0;
-   const int padded = (units + 7) & ~7;
-   for (int k = tid; k < padded; k += THREADS)
+   // stream the finished tile out: one contiguous byte range of the CSR values.  The swizzle key of unit k depends on
+   // (k >> 3) & 7, which the stride of THREADS = 16 groups leaves alone: per thread the swizzle is one constant XOR.
+   // The full rounds (every thread in range, swizzle partner included) run unrolled without bounds checks.
+   static_assert(THREADS % 64 == 0, "the stream-out stride must keep (k >> 3) & 7");
+   double2 *dst = reinterpret_cast<double2 *>(A.values + 4 * b0);
+   const int kx = swz(tid) ^ tid;
+   const int full = units & ~7;  // units below this bound have their whole 8-unit group inside the tile
+   int k = tid;
+#pragma unroll 4
+   for (; k + 0 < full - (full % THREADS); k += THREADS)
    {
-      const int u = swz(k);
+      const double2 val = sv[k];
+      st_stream_d2(reinterpret_cast<double *>(dst + (k ^ kx)), val);
+      if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
+   }
+   const int padded = (units + 7) & ~7;
+   for (; k < padded; k += THREADS)
+   {
+      const int u = k ^ kx;
       if (u < units)
       {
          const double2 val = sv[k];
-         st_stream_d2(dst + 2 * (int64_t)u, val);
+         st_stream_d2(reinterpret_cast<double *>(dst + u), val);
          if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
       }
    }

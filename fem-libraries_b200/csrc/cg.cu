@@ -29,6 +29,9 @@ namespace femb {
 
 int pa_apply_launch(const femb200_pa *pa, const double *d_x, double *d_y, const double *d_flag, double *d_dot_out,
                     cudaStream_t st, bool accumulate);
+}  // namespace femb
+int64_t pa_num_dofs(const femb200_pa *pa);
+namespace femb {
 
 enum
 {
@@ -129,8 +132,9 @@ __global__ void dinv_kernel(int64_t n, const double *__restrict__ diag, double *
 
 __global__ void __launch_bounds__(kVecThreads)
 dot_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, ReduceScratch red,
-           double *__restrict__ out)
+           double *__restrict__ out, const double *__restrict__ flag = nullptr)
 {
+   if (flag && *flag != 0.) return;  // converged CG: keep the previous value
    double part = 0.;
    const int64_t stride = (int64_t)gridDim.x * kVecThreads;
    for (int64_t i = (int64_t)blockIdx.x * kVecThreads + threadIdx.x; i < n; i += stride) part += a[i] * b[i];
@@ -282,12 +286,25 @@ extern "C" int femb200_cg_update_dir(int64_t n, const double *d_scal, const doub
 namespace femb {
 
 // z = A d on the owned rows with the fused partial <d, A d> into scal[SC_RED_DEN]; no-op once the flag is set
+// The matrix-free operator of a rank works on its whole local mesh (owned + ghost cells): the rows of the owned
+// nodes are complete, those of ghost nodes are partial and ignored, so with a partition the fused <d, A d> of the
+// apply kernel (a sum over every local node) is replaced by a dot product over the owned dofs.
 static int cg_apply_rows(const femb200_plan *plan, int op_kind, const void *op, const double *d_values, const RowRange &rr,
-                         const double *d_dir, double *d_Ad, double *d_scal, cudaStream_t st)
+                         int64_t own_lo, int64_t own_hi, const double *d_dir, double *d_Ad, double *d_scal, cudaStream_t st)
 {
    if (op_kind == FEMB200_OP_CSR)
       return spmv_launch(plan, rr, d_values, d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, false, st);
-   return pa_apply_launch(static_cast<const femb200_pa *>(op), d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st, false);
+   const femb200_pa *pa = static_cast<const femb200_pa *>(op);
+   if (own_lo == 0 && 2 * own_hi == pa_num_dofs(pa))
+      return pa_apply_launch(pa, d_dir, d_Ad, d_scal + SC_FLAG, d_scal + SC_RED_DEN, st, false);
+   if (int rc = pa_apply_launch(pa, d_dir, d_Ad, d_scal + SC_FLAG, nullptr, st, false)) return rc;
+   const int64_t n = 2 * (own_hi - own_lo);
+   const unsigned grid = vec_grid(n);
+   ReduceScratch red;
+   if (int rc = reduce_scratch(grid, st, &red)) return rc;
+   dot_kernel<<<grid, kVecThreads, 0, st>>>(n, d_dir + 2 * own_lo, d_Ad + 2 * own_lo, red, d_scal + SC_RED_DEN, d_scal + SC_FLAG);
+   FEMB_LAUNCH_CHECK();
+   return 0;
 }
 
 // The PCG loop of femb200_pcg and femb200_dist_pcg.  Vector kernels run on the owned dofs [2 own_lo,
@@ -322,7 +339,7 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
    };
    auto apply = [&](cudaStream_t s) -> int {
       if (int e = dist_halo_arena(P.comm, s)) return e;
-      if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.d, P.z, scal, s)) return e;
+      if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.own_lo, P.own_hi, P.d, P.z, scal, s)) return e;
       return scalar(1, SC_RED_DEN, s);
    };
    auto update_xr = [&](cudaStream_t s) -> int {
@@ -433,10 +450,9 @@ extern "C" int femb200_cg_apply(const femb200_plan *plan, int op_kind, const voi
    }
    else
       FEMB_CHECK(op_kind == FEMB200_OP_PA && op, "cg_apply: unknown operator kind %d", op_kind);
-   return cg_apply_rows(plan, op_kind, op, d_values, rr, d_dir, d_Ad, d_scal, as_stream(stream));
+   return cg_apply_rows(plan, op_kind, op, d_values, rr, 0, op_kind == FEMB200_OP_CSR ? plan->nnodes : pa_num_dofs(static_cast<const femb200_pa *>(op)) / 2,
+                        d_dir, d_Ad, d_scal, as_stream(stream));
 }
-
-int64_t pa_num_dofs(const femb200_pa *pa);
 
 extern "C" int femb200_pcg(const femb200_plan *plan, int op_kind, const void *op, const double *d_values,
                            const double *d_b, double *d_x, int64_t n, double rtol, double atol, int maxit,

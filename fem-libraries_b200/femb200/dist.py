@@ -381,8 +381,11 @@ class DistCG:
     products, the whole loop in C (one CUDA graph per iteration).  world = 1 works without a process group."""
 
     def __init__(self, A, part: StripPartition, rel_tol=1e-12, abs_tol=0.0, max_iter=2000, check_every=25,
-                 jacobi=True, group=None, transport: str = "auto", use_graph: bool = True, op: DistOperator | None = None):
-        self.A, self.part = A, part
+                 jacobi=True, group=None, transport: str = "auto", use_graph: bool = True, op: DistOperator | None = None,
+                 pa=None):
+        """`pa` (a fem.PAOperator built on the rank's local mesh, Dirichlet included) switches the operator of the
+        solve from the assembled CSR of `A` to the matrix-free apply; `A` still provides the plan of the communicator."""
+        self.A, self.part, self.pa = A, part, pa
         self.rel_tol, self.abs_tol, self.max_iter, self.check_every = rel_tol, abs_tol, max_iter, check_every
         self.op = DistOperator(A, part, transport, group) if op is None else op
         self.use_graph = use_graph
@@ -392,7 +395,7 @@ class DistCG:
         self.iterations, self.final_norm, self.converged = 0, 0.0, False
 
     def update_preconditioner(self):
-        diag = self.A.diagonal()
+        diag = self.A.diagonal() if self.pa is None else self.pa.diagonal()
         self.dinv = torch.empty_like(diag)
         capi.call("femb200_jacobi_setup", diag.numel(), _p(diag), _p(self.dinv), _st())
 
@@ -401,7 +404,8 @@ class DistCG:
 
     def solve(self, b: torch.Tensor, x: torch.Tensor, fixed_iters: int = 0) -> torch.Tensor:
         it, fn, cv = C.c_int(), C.c_double(), C.c_int()
-        capi.call("femb200_dist_pcg", self.op.handle, capi.OP_CSR, None, _p(self.A.values), _p(b), _p(x), self.rel_tol,
+        kind, opp, vals = (capi.OP_CSR, None, _p(self.A.values)) if self.pa is None else (capi.OP_PA, self.pa.handle, None)
+        capi.call("femb200_dist_pcg", self.op.handle, kind, opp, vals, _p(b), _p(x), self.rel_tol,
                   self.abs_tol, self.max_iter, _p(self.dinv), self.check_every, int(fixed_iters), int(self.use_graph),
                   C.byref(it), C.byref(fn), C.byref(cv), _st())
         self.iterations, self.final_norm, self.converged = it.value, fn.value, bool(cv.value)

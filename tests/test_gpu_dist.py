@@ -155,6 +155,15 @@ def _nccl_worker(rank, world, port, out):
                                dtype=torch.float64, device="cuda")
             op.allreduce_sum(num)
             assert (num[0] / num[1]).sqrt().item() < 1e-12, (tr, num.tolist())
+        # matrix-free operator over the ranks (each rank applies its local cells, owned rows complete, owned-dof dot)
+        pa = fem.PAOperator(f, bcs=[fem.DirichletBC(p.bc, p.g)])
+        cgp = dist.DistCG(A, p, rel_tol=1e-12, max_iter=4000, op=op, pa=pa)
+        xp = torch.zeros_like(bl)
+        cgp.solve(bl, xp)
+        xsp = dist.gather_owned(p, xp)
+        assert cgp.converged and abs(cgp.iterations - it) <= max(3, it // 50)
+        if rank == 0:
+            assert np.linalg.norm(xsp - want) / np.linalg.norm(want) < 1e-10
         if len(transports) == 2:   # both transports solve the same system: same iterates up to the all-reduce order
             a, c = sols[("p2p", True)], sols[("nccl", True)]
             assert abs(a[1] - c[1]) <= 1 and ((a[0] - c[0]).norm() / c[0].norm()).item() < 1e-10

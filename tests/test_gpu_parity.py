@@ -555,6 +555,130 @@ def test_error_behaviour():
 
 
 # ---------------------------------------------------------------------------
+# full-size parity: the WHOLE matrix, not a window
+# ---------------------------------------------------------------------------
+def _golden_norms(n):
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_norms.json")) as f:
+        return json.load(f).get(str(n))
+
+
+@pytest.mark.skipif(os.environ.get("FEMB200_SKIP_LARGE") == "1", reason="large case disabled")
+def test_full_size_whole_matrix_against_oracle():
+    """BASELINE config 2 at full size (P2 n = 1448, 385 886 212 non-zeros): EVERY value of the constrained tangent
+    against the oracle (all host threads), structure bit-exact, then 25 Jacobi-PCG iterations against the oracle's
+    committed state (tests/golden/config_norms.json)."""
+    import torch
+    from femb200 import dist
+    n = 1448
+    p = dist.strip_partition(n, n, 2, 0, 1)
+    m = p.mesh
+    f = fem()
+    form = f.ElasticityForm(m, p.E)
+    A = f.create_matrix(form)
+    f.assemble_matrix(A, form, bcs=[f.DirichletBC(p.bc, p.g)])
+    rowptr, colidx = oracle.build_pattern(m.nnodes, m.dofmap)
+    nt = len(os.sched_getaffinity(0))
+    want = oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, p.E, 0.3, rowptr, colidx, bc=p.bc, nthreads=nt)
+    assert A.nnz == 385886212 == rowptr[-1]
+    np.testing.assert_array_equal(A.rowptr.cpu().numpy(), rowptr)
+    assert torch.equal(A.colidx.cpu(), torch.from_numpy(colidx))
+    got = A.values.cpu().numpy()
+    assert relfro(got, want) < TOL_VALUES
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()     # no single entry off either
+    gold = _golden_norms(n)
+    assert abs(float((got * got).sum()) - gold["fro2"]) < 1e-12 * gold["fro2"]
+    del got, want, colidx
+    b = np.where(p.bc != 0, p.g, 1.0)
+    cg = f.CGSolver(rel_tol=0.0, max_iter=25)
+    cg.SetOperator(A)
+    cg.SetPreconditioner("jacobi")
+    x = cg.Mult(f.to_device(b, np.float64), fixed_iters=25)
+    assert abs(x.norm().item() - gold["pcg25"]["x_norm"]) < 1e-10 * gold["pcg25"]["x_norm"]
+    assert abs(cg.GetFinalNorm() - gold["pcg25"]["final_norm"]) < 1e-8 * gold["pcg25"]["final_norm"]
+
+
+@pytest.mark.skipif(os.environ.get("FEMB200_SKIP_LARGE") == "1", reason="large case disabled")
+def test_plan_beyond_2_31_nonzeros_on_one_rank():
+    """A single-rank plan with more than 2^31 non-zeros (P2 n = 3424: 2 157 393 924): structural count, (|K|_F^2,
+    trace K) of the constrained matrix against the oracle's strip-by-strip golden sums, the last rows against the oracle
+    on a window (their value offsets are beyond 2^31), SpMV rigid-body modes."""
+    import torch
+    from femb200 import dist
+    n = 3424
+    gold = _golden_norms(n)
+    assert gold is not None and gold["nnz"] == 2157393924 > 2 ** 31
+    p = dist.strip_partition_device(n, n, 0, 1)
+    m = p.mesh
+    f = fem()
+    form = f.ElasticityForm(m, p.E)
+    A = f.create_matrix(form)
+    assert A.nnz == gold["nnz"]
+    A.set_bcs([f.DirichletBC(p.bc, p.g)])
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    f.assemble_matrix(A, form, norms_out=sums)
+    f2, tr = sums.tolist()
+    assert abs(f2 - gold["fro2"]) < 1e-12 * gold["fro2"] and abs(tr - gold["trace"]) < 1e-12 * abs(gold["trace"])
+    # the same sums by the separate kernels (different code path, 64-bit offsets everywhere)
+    fro, tr2 = A.norms()
+    assert abs(fro * fro - gold["fro2"]) < 1e-12 * gold["fro2"] and abs(tr2 - gold["trace"]) < 1e-12 * abs(gold["trace"])
+    # window: the last 5 cell rows with the oracle (unconstrained), compared on the rows of the top 9 lattice rows
+    f.assemble_matrix_nobc(A, form)
+    mx = 2 * n + 1
+    rows0 = 2 * (n - 5)                                   # first lattice row of the window
+    lo_node = rows0 * mx
+    xw = m.x[lo_node:].cpu().numpy()
+    cells0 = 2 * n * (n - 5)
+    dmw = m.dofmap[cells0:].cpu().numpy() - lo_node
+    sub = fm.Mesh(fm.P2, xw, np.ascontiguousarray(dmw[:, :3]), np.ascontiguousarray(dmw))
+    Ew = p.E[cells0:].cpu().numpy()
+    rowptr, colidx, want = oracle_assemble(sub, Ew)
+    first = 2 * mx                                        # skip the window's two bottom lattice rows (incomplete)
+    brp, _ = A.block_csr()
+    g0 = 4 * int(brp[lo_node + first].item())
+    assert g0 > 2 ** 31
+    w0 = int(rowptr[2 * first])
+    got = A.values[g0:].cpu().numpy()
+    assert got.size == want.size - w0
+    assert relfro(got, want[w0:]) < TOL_VALUES
+    # rigid-body modes of the unconstrained operator
+    x = m.x
+    ones, zeros = torch.ones_like(x[:, 0]), torch.zeros_like(x[:, 0])
+    for t in (torch.stack([ones, zeros], 1), torch.stack([zeros, ones], 1), torch.stack([-x[:, 1], x[:, 0]], 1)):
+        y = A.mult(t.reshape(-1).contiguous())
+        assert y.abs().max().item() < 1e-12 * fro
+
+
+@pytest.mark.skipif(os.environ.get("FEMB200_SKIP_LARGE") == "1", reason="large case disabled")
+def test_full_size_q2_matrix_free_strip_against_oracle():
+    """BASELINE config 3 at full size (Q2 n = 4096, 16 777 216 cells, 134 M dofs): the matrix-free apply against the
+    oracle's matrix-free apply on a strip of cell rows in the middle of the mesh (the oracle is serial: 8 cell rows)."""
+    import torch
+    n = 4096
+    m = fm.jitter(fm.structured_quads_q2(n), 0.2, seed=1234)
+    assert m.ncells == 16777216
+    E = fm.young_per_cell(m.ncells)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    pa = f.PAOperator(form)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    v = torch.randn(m.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    y = pa.mult(v).cpu().numpy()
+    mx = 2 * n + 1
+    r0, nr = n // 2, 8                                     # cell rows [r0, r0 + nr)
+    lo_node, hi_node = 2 * r0 * mx, (2 * (r0 + nr) + 1) * mx
+    cells = slice(n * r0, n * (r0 + nr))
+    dmw = m.dofmap[cells] - lo_node
+    sub = fm.Mesh(fm.Q2, m.x[lo_node:hi_node], np.ascontiguousarray(dmw[:, [0, 2, 6, 8]]), np.ascontiguousarray(dmw))
+    vw = v[2 * lo_node:2 * hi_node].cpu().numpy()
+    want = oracle.apply_matrix_free(sub.etype, sub.x, sub.xdofmap, sub.dofmap, E[cells], 0.3, vw)
+    # rows strictly inside the strip are complete in the window: lattice rows 1 .. 2 nr - 1
+    a, b = 2 * mx, 2 * (2 * nr) * mx
+    got = y[2 * lo_node + a:2 * lo_node + b]
+    assert relfro(got, want[a:b]) < TOL_VALUES
+
+
+# ---------------------------------------------------------------------------
 # full-size properties (BASELINE config 2: P2, n = 1448, 4.19 M elements)
 # ---------------------------------------------------------------------------
 @pytest.mark.skipif(os.environ.get("FEMB200_SKIP_LARGE") == "1", reason="large case disabled")
