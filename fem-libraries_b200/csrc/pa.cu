@@ -211,16 +211,16 @@ __global__ void pa_setup_kernel(int64_t ncells, const int32_t *__restrict__ cper
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= ncells) return;
    const int64_t src = cperm[e];
-   double *g = geo + e * W;
+   // tile-major, then structure of arrays: pair k of cell t of a tile at ((tile * W/2 + k) * CT + t): the apply
+   // kernel reads its W/2 pairs with coalesced 16-byte loads (no shared-memory stage for the geometry)
+   double2 *g = reinterpret_cast<double2 *>(geo) + (e / kPaThreads) * (W / 2) * kPaThreads + (e % kPaThreads);
 #pragma unroll
    for (int v = 0; v < nv; ++v)
    {
       const int64_t n = xdofmap[src * nv + v];
-      g[2 * v] = x[n * xs];
-      g[2 * v + 1] = x[n * xs + 1];
+      g[v * kPaThreads] = make_double2(x[n * xs], x[n * xs + 1]);
    }
-   g[2 * nv] = E[src] * lc.c2;      // lambda, M.cc:1093-1098
-   g[2 * nv + 1] = E[src] * lc.c3;  // mu
+   g[nv * kPaThreads] = make_double2(E[src] * lc.c2, E[src] * lc.c3);  // lambda, mu (M.cc:1093-1098)
 }
 
 __global__ void pa_cmask_kernel(int64_t ncells, int nd, const int32_t *__restrict__ cperm,
@@ -428,10 +428,10 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
 // byte offsets of the CTA's shared-memory buffers (from the host) and the bulk-copy sizes
 struct PaLayout
 {
-   int geo, li, cm;      // per-cell inputs of the current tile (one buffer)
+   int li, cm;           // per-cell inputs of the current tile (one buffer)
    int nb, nb_bytes;     // 3 buffers of {tn, tp}: node ids and node -> refs offsets
    int tp;               // offset of tp inside one of them
-   int tr, tr_bytes;     // 2 buffers of trefs
+   int tr, tr_bytes;     // trefs of the current tile
    int xs, xs_bytes;     // x values of the current tile
    int ye;               // element results
    int b_tn, b_tp;       // bytes copied per tile for tn / tp
@@ -465,12 +465,14 @@ __global__ void pa_zero_shared_kernel(int n, const int32_t *__restrict__ list, d
 // values of tile i+1 are gathered with 16-byte cp.async (into the buffer tile i has just emptied into
 // registers) while tile i is computed, so no thread waits on DRAM in steady state.  Per tile: inputs -> registers | element products -> ye |
 // one thread per tile node sums its contributions and stores (interior) or reduces (tile boundary).
+// 4 CTAs per SM (128 registers, no spills): compiled for 5 (96 registers, 136 bytes of spills) the Q2 apply is 9 %
+// slower although the shared-memory footprint (45 KB) would allow it (profiles/r2_experiments.md)
 template <int ET, bool DOT>
 __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, ReduceScratch red, double *__restrict__ out)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, W = 2 * nv + 2, CT = kPaThreads, S = CT * nd;
    extern __shared__ __align__(128) unsigned char pa_sm[];
-   __shared__ uint64_t fullG, fullN[3], fullT[2];
+   __shared__ uint64_t fullG, fullN[3], fullT;
    if (A.flag && *A.flag != 0.) return;
    const int tid = threadIdx.x;
    const PaLayout &L = A.L;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
       mbar_init(&fullG, 1);
 #pragma unroll
       for (int s = 0; s < 3; ++s) mbar_init(&fullN[s], 1);
-      mbar_init(&fullT[0], 1), mbar_init(&fullT[1], 1);
+      mbar_init(&fullT, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncthreads();
@@ -495,15 +497,14 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
       bulk_g2s(dst, A.tnodes + tile * S, (uint32_t)L.b_tn, &fullN[it % 3]);
       bulk_g2s(dst + L.tp, A.tptr + tile * (S + 8), (uint32_t)L.b_tp, &fullN[it % 3]);
    };
-   auto load_T = [&](int it) {
-      mbar_expect_tx(&fullT[it & 1], S * 2);
-      bulk_g2s(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes, A.trefs + tile_of(it) * S, S * 2, &fullT[it & 1]);
+   auto load_T = [&](int it) {  // one buffer: reloaded after the scatter of the previous tile (barrier B2)
+      mbar_expect_tx(&fullT, S * 2);
+      bulk_g2s(pa_sm + L.tr, A.trefs + tile_of(it) * S, S * 2, &fullT);
    };
    auto load_G = [&](int it) {
       const int64_t tile = tile_of(it);
-      mbar_expect_tx(&fullG, CT * W * 8 + S * 2 + b_cm);
+      mbar_expect_tx(&fullG, S * 2 + b_cm);
       bulk_g2s(pa_sm + L.li, A.lidx + tile * S, S * 2, &fullG);
-      bulk_g2s(pa_sm + L.geo, A.geo + tile * (CT * W), CT * W * 8, &fullG);
       if (b_cm) bulk_g2s(pa_sm + L.cm, A.cmask + tile * CT, b_cm, &fullG);
    };
    const double2 *x2 = reinterpret_cast<const double2 *>(A.x);
@@ -533,29 +534,29 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
    cp_async_commit();
    for (int it = 0; it < nmine; ++it)
    {
+      // per-cell geometry + Lame pair straight from global memory (coalesced 16-byte loads, issued before the waits)
+      double g[W];
+      {
+         const double2 *g2 = reinterpret_cast<const double2 *>(A.geo) + tile_of(it) * (W / 2) * CT + tid;
+#pragma unroll
+         for (int k = 0; k < W / 2; ++k)
+         {
+            const double2 v = ld_stream_d2(reinterpret_cast<const double *>(g2 + k * CT));
+            g[2 * k] = v.x, g[2 * k + 1] = v.y;
+         }
+      }
       cp_async_wait<0>();
       __syncthreads();  // A: x of tile it visible; every thread is done with tile it - 1
-      if (tid == 0)
-      {
-         if (it + 2 < nmine) load_N(it + 2);
-         if (it + 1 < nmine) load_T(it + 1);
-      }
+      if (tid == 0 && it + 2 < nmine) load_N(it + 2);
       const int64_t e = tile_of(it) * CT + tid;
       const bool valid = e < A.ncells;
       const double2 *xs = reinterpret_cast<const double2 *>(pa_sm + L.xs);
       mbar_wait(&fullG, it & 1);
       uint32_t m = 0u;
-      double g[W], ux[nd], uy[nd];
+      double ux[nd], uy[nd];
       {
          const uint16_t *lp = reinterpret_cast<const uint16_t *>(pa_sm + L.li) + tid;
          if (A.cmask) m = reinterpret_cast<const uint32_t *>(pa_sm + L.cm)[tid];
-         const double2 *g2 = reinterpret_cast<const double2 *>(pa_sm + L.geo) + tid * (W / 2);
-#pragma unroll
-         for (int k = 0; k < W / 2; ++k)
-         {
-            const double2 v = g2[k];
-            g[2 * k] = v.x, g[2 * k + 1] = v.y;
-         }
 #pragma unroll
          for (int a = 0; a < nd; ++a)
          {
@@ -602,12 +603,13 @@ __global__ void __launch_bounds__(kPaThreads, 4) pa_tile_kernel(PaArgs A, Reduce
             }
          }
          // contributions go to their node-sorted positions
-         const uint16_t *pp = reinterpret_cast<const uint16_t *>(pa_sm + L.tr + (size_t)(it & 1) * L.tr_bytes) + tid;
-         mbar_wait(&fullT[it & 1], (it >> 1) & 1);
+         const uint16_t *pp = reinterpret_cast<const uint16_t *>(pa_sm + L.tr) + tid;
+         mbar_wait(&fullT, it & 1);
 #pragma unroll
          for (int a = 0; a < nd; ++a) ye[pp[a * CT]] = make_double2(yx[a], yy[a]);
       }
-      __syncthreads();  // B2: ye complete
+      __syncthreads();  // B2: ye complete, the scatter map of this tile is free
+      if (tid == 0 && it + 1 < nmine) load_T(it + 1);
       // one thread per tile node: sum its (contiguous) contributions in a fixed order; KU nodes in flight
       const unsigned char *nb = pa_sm + L.nb + (size_t)(it % 3) * L.nb_bytes;
       const int32_t *tn = reinterpret_cast<const int32_t *>(nb);
@@ -701,12 +703,17 @@ pa_diag_kernel(int64_t ncells, const int32_t *__restrict__ cperm, const int32_t 
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq, W = 2 * nv + 2;
    const int64_t e = (int64_t)blockIdx.x * kPaThreads + threadIdx.x;
    if (e >= ncells) return;
-   const double *g = geo + e * W;
+   const double2 *g = reinterpret_cast<const double2 *>(geo) + (e / kPaThreads) * (W / 2) * kPaThreads + (e % kPaThreads);
    double xv[nv][2];
 #pragma unroll
-   for (int v = 0; v < nv; ++v) xv[v][0] = g[2 * v], xv[v][1] = g[2 * v + 1];
+   for (int v = 0; v < nv; ++v)
+   {
+      const double2 p = g[v * kPaThreads];
+      xv[v][0] = p.x, xv[v][1] = p.y;
+   }
    double D[9];
-   hooke_scaled(g[2 * nv], g[2 * nv + 1], 1., D);
+   const double2 lm = g[nv * kPaThreads];
+   hooke_scaled(lm.x, lm.y, 1., D);
    double kd[nd][2];
 #pragma unroll
    for (int a = 0; a < nd; ++a) kd[a][0] = kd[a][1] = 0.;
@@ -742,11 +749,10 @@ __global__ void pa_diag_bc_kernel(int nbc, const int32_t *__restrict__ list, dou
 
 static PaLayout pa_layout(const femb200_pa *pa)
 {
-   const int CT = kPaThreads, S = CT * pa->nd, W = 2 * pa->nv + 2;
+   const int CT = kPaThreads, S = CT * pa->nd;
    auto up = [](int v) { return (v + 127) & ~127; };
    PaLayout L;
    int o = 0;
-   L.geo = o, o += up(CT * W * 8);
    L.li = o, o += up(S * 2);
    L.cm = o, o += up(CT * 4);
    L.b_tn = ((pa->max_uniq + 3) & ~3) * 4;
@@ -755,7 +761,7 @@ static PaLayout pa_layout(const femb200_pa *pa)
    L.nb_bytes = L.tp + up(L.b_tp);
    L.nb = o, o += 3 * L.nb_bytes;
    L.tr_bytes = up(S * 2);
-   L.tr = o, o += 2 * L.tr_bytes;
+   L.tr = o, o += L.tr_bytes;
    L.xs_bytes = up(pa->max_uniq * 16);
    L.xs = o, o += L.xs_bytes;
    L.ye = o;
