@@ -480,6 +480,9 @@ def run_b200(args):
     # ---- end to end: one Newton linearisation through the public API, host buffers ------------------
     e2e = e2e_newton(env, fem, dist, form, part, op, A, args, total_dofs)
 
+    # BASELINE configs[4] over the ranks (N > 1; at N = 1 it is part of `extras`)
+    c5 = config5_ranks(env, fem, dist, assembly_bytes) if (world > 1 and not args.skip_extras) else None
+
     nnzb_owned = part.owned_nnz_blocks(A)
     plan_bytes = A.plan_bytes
     a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)            # this rank's launch (ghost cell row included)
@@ -528,6 +531,8 @@ def run_b200(args):
         "gpu_launches": K * (3 + launches_pcg),
         "clocks": clocks,
     }
+    if c5 is not None:
+        line["config5_over_ranks"] = c5
     del dcg, xsol, ytmp, vtmp, bvec
     op.close()
     if world == 1 and not args.skip_extras:
@@ -710,6 +715,40 @@ def extras(env, fem, peak, args):
         rec["ad_over_closed"] = rec["ad_ms"] / rec["closed_form_ms"]
         res[label] = rec
     out["config5_damaged_reassembly"] = res
+    return out
+
+
+def config5_ranks(env, fem, dist, abytes):
+    """BASELINE configs[4] ("repeated tangent reassembly on 16 M P2 elements, 8 B200") inside the default multi-GPU run:
+    the nx = 2896 mesh in `world` strips, a vertical damage band of 10 % / 100 % of the cells through every strip,
+    values-only reassembly on the frozen pattern (no communication: ghost cell row), closed form and AD."""
+    torch = env.torch
+    nx = 2896
+    rows = nx - nx % env.world
+    part = dist.strip_partition_device(nx, rows, env.rank, env.world, jitter_amp=0.2, seed=1234)
+    m = part.mesh
+    x, y = m.x[:, 0], m.x[:, 1]
+    u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(env.rank))
+    form0 = fem.ElasticityForm(m, part.E, 0.3)
+    A = fem.create_matrix(form0)
+    dofs = env.sumi(2 * part.n_owned)
+    peak, _ = measured_peaks()
+    out = {"workload": f"P2 nx = {nx}, {rows} cell rows in {env.world} strips ({2 * nx * rows} elements), vertical damage band, "
+                       "values-only reassembly on a frozen pattern, no communication", "dofs": dofs}
+    for label, hw in (("10pct", 0.05), ("100pct", 10.0)):
+        d = torch.clamp(1.0 - (x - 0.5 - 0.1 * torch.sin(6.0 * y)).abs() / hw, min=0.0, max=0.95)
+        rec = {}
+        for variant, name in ((0, "closed_form"), (1, "ad")):
+            form = fem.ElasticityForm(m, part.E, 0.3, d=d, u=u, variant=variant)
+            for _ in range(3):
+                fem.assemble_matrix(A, form)
+            tot, calls = env.timed(lambda: fem.assemble_matrix(A, form), 10)
+            ms = tot / 10
+            rec[name + "_ms"] = ms
+            rec[name + "_gdofs"] = dofs / (ms * 1e-3) / 1e9
+            rec[name + "_frac_hbm_rank0"] = abytes(A.nnz, m.ncells, m.nnodes) / (float(np.mean(calls)) * 1e-3) / 1e9 / peak
+        rec["ad_over_closed"] = rec["ad_ms"] / rec["closed_form_ms"]
+        out[label] = rec
     return out
 
 
