@@ -37,14 +37,69 @@
 //   assemble_kernel        the generic-record form: Q2 and assembly_path = 2 (per-quadrature-point
 //                          integration per visit) and plans without fast records;
 //   dirichlet_kernel, fro / trace kernels, the fused-norm correction kernels.
+#include <cuda.h>  // CUtensorMap (type and enums only: cuTensorMapEncodeTiled is fetched through the runtime)
+
 #include <algorithm>
 
 #include "constitutive.cuh"
 #include "element.cuh"
 #include "plan.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 
 namespace femb {
+
+// ---- tensor maps of the value array (host) -----------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query: libfemb200.so does not link
+// libcuda.  The value array is described as rows of 128 bytes (16 doubles); a box is `rows` such lines, SWIZZLE_128B.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+   static EncodeTiledFn fn = nullptr;
+   static bool tried = false;
+   if (!tried)
+   {
+      tried = true;
+      void *p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+          q == cudaDriverEntryPointSuccess)
+         fn = reinterpret_cast<EncodeTiledFn>(p);
+      else
+         cudaGetLastError();
+   }
+   return fn;
+}
+
+// fills plan->tmap8 / tmap1 for this value array; false when tensor bulk stores cannot be used (the caller falls back
+// to the store loop): no driver entry point, or a value array that does not start on a 128-byte line
+static bool values_tensor_maps(femb200_plan *pm, double *d_values)
+{
+   if (pm->tmap_values == d_values) return true;
+   EncodeTiledFn enc = encode_tiled();
+   if (!enc || (reinterpret_cast<uintptr_t>(d_values) & 127) != 0) return false;
+   const cuuint64_t lines = (cuuint64_t)((4 * pm->nnzb + 15) / 16);  // 128-byte lines of the value array
+   if (lines == 0 || lines >= ((cuuint64_t)1 << 31)) return false;   // line coordinates are 32-bit
+   const cuuint64_t gdim[2] = {16, lines};
+   const cuuint64_t gstride[1] = {128};
+   const cuuint32_t estride[2] = {1, 1};
+   std::lock_guard<std::mutex> lock(pm->range_mtx);
+   for (int k = 0; k < 2; ++k)
+   {
+      const cuuint32_t box[2] = {16, k == 0 ? 8u : 1u};
+      CUtensorMap *tm = reinterpret_cast<CUtensorMap *>(k == 0 ? pm->tmap8 : pm->tmap1);
+      if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_values, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      {
+         pm->tmap_values = nullptr;
+         return false;
+      }
+   }
+   pm->tmap_values = d_values;
+   return true;
+}
 
 __device__ __forceinline__ void stage_put(double2 *sv, int unit, double a, double b, bool first)
 {
@@ -101,6 +156,7 @@ struct AsmArgs
    int variant;
    double *values;
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
+   int use_tma;      // fast kernel: the finished tile leaves with tensor bulk stores
 };
 
 // ---- fast path: straight-sided P1 / P2 triangle, linear elasticity --------------
@@ -654,10 +710,11 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
 // and the record two visits ahead.
 template <int ET, bool DMG, bool NORMS, int MINB = (DMG ? 5 : 7)>
 __global__ void __launch_bounds__(kAsmR * 2, MINB)
-assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out)
+assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out, const __grid_constant__ CUtensorMap tm8,
+                     const __grid_constant__ CUtensorMap tm1)
 {
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
-   extern __shared__ double2 sv[];
+   extern __shared__ __align__(1024) double2 sv[];
    const int tid = threadIdx.x;
    const TileHdr *hdr = A.thdr + blockIdx.x;
    const int64_t b0 = hdr->b0;
@@ -734,30 +791,56 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       }
    }
    __syncthreads();
-   // stream the finished tile out: one contiguous byte range of the CSR values.  The swizzle key of unit k depends on
-   // (k >> 3) & 7, which the stride of THREADS = 16 groups leaves alone: per thread the swizzle is one constant XOR.
-   // The full rounds (every thread in range, swizzle partner included) run unrolled without bounds checks.
-   static_assert(THREADS % 64 == 0, "the stream-out stride must keep (k >> 3) & 7");
-   double2 *dst = reinterpret_cast<double2 *>(A.values + 4 * b0);
-   const int kx = swz(tid) ^ tid;
-   const int full = units & ~7;  // units below this bound have their whole 8-unit group inside the tile
-   int k = tid;
-#pragma unroll 4
-   for (; k + 0 < full - (full % THREADS); k += THREADS)
+   // Stream the finished tile out: one contiguous byte range of the CSR values.  Image position p holds the unit
+   // (first unit of the tile - shift) + p of the value array, chunk-swizzled inside its 128-byte line (swz_tma).
+   const int shift = (int)((2 * b0) & 7);
+   const int end = shift + units;                                  // positions [shift, end) are this tile's
+   double2 *dst = reinterpret_cast<double2 *>(A.values) + (2 * b0 - shift);  // position p <-> dst[p]
+   if (!NORMS && A.use_tma)
    {
-      const double2 val = sv[k];
-      st_stream_d2(reinterpret_cast<double *>(dst + (k ^ kx)), val);
-      if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
-   }
-   const int padded = (units + 7) & ~7;
-   for (; k < padded; k += THREADS)
-   {
-      const int u = k ^ kx;
-      if (u < units)
+      // full lines [lf, ll) by the TMA unit (it reads shared memory itself and undoes the swizzle: no LDS, no STG,
+      // no per-thread loop); the partial first / last line by 16 threads
+      const int lf = shift ? 1 : 0, ll = end >> 3;
+      if (tid == 0)
       {
-         const double2 val = sv[k];
-         st_stream_d2(reinterpret_cast<double *>(dst + u), val);
-         if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the image was written by ordinary stores
+         const int gl0 = (int)((2 * b0 - shift) >> 3);                 // 128-byte line of the value array of image line 0
+         int l = lf;
+         for (; l + 8 <= ll; l += 8)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tm8), "r"(0),
+                         "r"(gl0 + l), "r"(smem_u32(sv + 8 * l))
+                         : "memory");
+         for (; l < ll; ++l)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tm1), "r"(0),
+                         "r"(gl0 + l), "r"(smem_u32(sv + 8 * l))
+                         : "memory");
+         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      else if (tid >= 32 && tid < 48)
+      {
+         const int c = tid & 7, l = (tid < 40) ? 0 : ll;              // chunk, image line (first / last)
+         const int p = 8 * l + (c ^ (l & 7));
+         const bool mine = (tid < 40) ? (shift != 0 && ll > 0) : ((end & 7) != 0);
+         if (mine && p >= shift && p < end) st_stream_d2(reinterpret_cast<double *>(dst + p), sv[8 * l + c]);
+      }
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the image must outlive the reads
+   }
+   else
+   {
+      // store loop.  The swizzle key of position q is (q >> 3) & 7, which the stride of THREADS = 16 lines leaves
+      // alone: per thread the swizzle is one constant XOR.
+      static_assert(THREADS % 64 == 0, "the stream-out stride must keep (q >> 3) & 7");
+      const int kx = (tid >> 3) & 7;
+      const int padded = (end + 7) & ~7;
+      for (int q = tid; q < padded; q += THREADS)
+      {
+         const int p = q ^ kx;
+         if (p >= shift && p < end)
+         {
+            const double2 val = sv[q];
+            st_stream_d2(reinterpret_cast<double *>(dst + p), val);
+            if (NORMS) nrm[0] += val.x * val.x + val.y * val.y;
+         }
       }
    }
    // fused (|K|_F^2, trace K) of the unconstrained matrix: one partial pair per CTA, summed in a fixed
@@ -1126,23 +1209,27 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
 template <int ET, bool DMG, int MINB>
 static int launch_assemble_fast_m(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
-   A.stage_units = (2 * p->tile_max_blocks[1] + 7) & ~7;
+   // the image starts at the tile's offset inside its 128-byte line (up to 6 units) and is whole lines
+   A.stage_units = (2 * p->tile_max_blocks[1] + 6 + 7) & ~7;
    A.flevels = p->flevels;
    A.prefetch_tiles = p->opt_prefetch_tiles >= 0 ? p->opt_prefetch_tiles : 8 * devinfo().sm_count;  // a good wave of resident CTAs ahead
    const size_t smem = 16 * (size_t)A.stage_units;
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
+   femb200_plan *pm = const_cast<femb200_plan *>(p);
+   A.use_tma = (!d_norms && p->opt_stream_out == 0 && values_tensor_maps(pm, A.values)) ? 1 : 0;
+   const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap8), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap1);
    if (d_norms)
    {
       ReduceScratch red;
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
       if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, true, MINB>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, true, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms);
+      assemble_fast_kernel<ET, DMG, true, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
       norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
    }
    else
    {
       if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, false, MINB>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, false, MINB><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr);
+      assemble_fast_kernel<ET, DMG, false, MINB><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr, tm8, tm1);
    }
    FEMB_LAUNCH_CHECK();
    return 0;

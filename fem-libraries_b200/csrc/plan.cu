@@ -309,7 +309,8 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
    const int cnt = nptr[node + 1] - nptr[node];
    tcnt[n0 + rank] = (uint8_t)cnt;
    const int deg = (int)(brp[node + 1] - brp[node]);
-   const int r0 = 2 * (int)(brp[node] - brp[n0]);  // first 16-byte unit of scalar row 0 in the tile image
+   // first 16-byte unit of scalar row 0 in the tile image: the image starts at the tile's offset inside its 128-byte line
+   const int r0 = (int)((2 * brp[n0]) & 7) + 2 * (int)(brp[node] - brp[n0]);
    const int32_t vbase = nptr[n0];
    const uint16_t *vo = voff + (int64_t)blockIdx.x * kAsmLevels;
    uint32_t touched[(kMaxDeg + 31) / 32];
@@ -380,7 +381,7 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
       for (int h = 0; h < 2; ++h)
       {
          uint32_t ent[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz(r0 + h * deg + sl[t]);
+         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz_tma(r0 + h * deg + sl[t]);
          frec[(((int64_t)blockIdx.x * flevels + j) * kAsmR + rank) * 2 + h] =
             make_uint4(r.e | ((uint32_t)cnt << 28), ent[0] | (first & 0xfu) | (ent[1] << 16),
                        ent[2] | ((first >> 4) & 0x1u) | (cout ? 2u : 0u) | (vert ? 0u : 4u) | (ent[3] << 16),
@@ -612,7 +613,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
 
    // fast-path records: triangles whose kAsmR-row staging image is addressable with 15-bit byte offsets
    // and whose nodes belong to fewer than 16 cells
-   if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 4) < 32768)
+   if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 8) < 32768)
    {
       const int64_t ntiles = cdiv(nnodes, kAsmR);
       if (dev_alloc(&p->thdr, (size_t)ntiles, &p->bytes)) return fail(1);
@@ -779,6 +780,11 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
    }
    else if (!strcmp(key, "prefetch_tiles"))
       p->opt_prefetch_tiles = value;
+   else if (!strcmp(key, "stream_out"))
+   {
+      FEMB_CHECK(value == 0 || value == 1, "plan_set_option: stream_out must be 0 (auto: tensor bulk stores) or 1 (store loop)");
+      p->opt_stream_out = value;
+   }
 
    else
       return set_error("plan_set_option: unknown key '%s'", key);

@@ -59,11 +59,20 @@ __host__ __device__ __forceinline__ int swz(int u)
    return u ^ (((g & 1) << 2) | (g & 2) | ((g >> 2) & 1));
 }
 
+// Staging layout of the FAST kernel (round 2).  Position p = (first 16-byte unit of the tile in the value array mod 8)
+// + tile-local unit: the 128-byte lines of the image coincide with the 128-byte lines of the value array, and the
+// 16-byte chunk inside a line is XORed with the line index mod 8.  That is the TMA SWIZZLE_128B pattern (byte address
+// bits [4:6] ^= bits [7:9], image base 1024-byte aligned): the finished tile leaves with tensor bulk stores
+// (cp.async.bulk.tensor, UTMASTG) which undo the swizzle on the way out, instead of an LDS + STG loop over 30 KB.
+// (The simulated conflict factor of this key is 1.56 against 1.34 for the bit-reversed one of swz(): about 4 % more
+// staging wavefronts, against a quarter of the kernel's LSU wavefronts saved.)
+__host__ __device__ __forceinline__ int swz_tma(int p) { return p ^ ((p >> 3) & 7); }
+
 // Fast-path record of one (visit, scalar row h) pair, triangles only: everything the row thread
 // needs in one 16-byte load, with the staging addresses resolved at plan time:
 //   x        cell id e
 //   y, z, w  six 16-bit entries (positions t = 0..5, rotated order as in VisitRec): BYTE offset of the
-//            16-byte staging unit of column t in the tile image (already swizzled; a multiple of 16
+//            16-byte staging unit of column t in the tile image (swz_tma layout above; a multiple of 16
 //            below 32768).  The free low nibbles of the even entries carry
 //              y: first-touch bits of the first four puts;
 //              z: first-touch bit of the fifth put (bit 0), carry-out (bit 1), edge row (bit 2);
@@ -121,6 +130,10 @@ struct femb200_plan
    double *celld = nullptr;    // damaged cells: [ncells][2nd x 2nd] element tangents (row-major, interleaved dofs), lazily allocated
    int32_t *celld_count = nullptr;  // [1 + ncells]: number of damaged cells, then their list
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
+   // tensor maps of the value array the fast kernel last wrote (boxes of 8 lines and of 1 line of 128 bytes)
+   alignas(64) unsigned char tmap8[128] = {}, tmap1[128] = {};
+   const void *tmap_values = nullptr;
+   int opt_stream_out = 0;  // 0 auto (tensor bulk stores when available), 1 LDS + STG loop
    // Kernel selection of this plan (femb200_plan_set_option): the fallback kernels that serve plans without
    // fast records / oversized SpMV tiles can be forced, so that the tests cover them on any mesh.
    int opt_assembly_path = 0;    // 0 auto; 1 visit-record kernel; 2 per-quadrature-point kernel

@@ -43,8 +43,10 @@ def main():
     A = fem.create_matrix(form)
     abytes = 8 * A.nnz + m.ncells * 32 + m.nnodes * 16
     if "asm" in what:
-        ms, mn = timed(lambda: fem.assemble_matrix(A, form))
-        out["assemble_p2"] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+        for so in (1, 0):
+            A.set_option("stream_out", so)
+            ms, mn = timed(lambda: fem.assemble_matrix(A, form))
+            out[f"assemble_p2_stream_out{so}"] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
     if "dmg" in what or "dmg100" in what:
         xy = m.x
         u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
