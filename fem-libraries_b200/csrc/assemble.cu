@@ -525,6 +525,23 @@ struct FastCarry
    double dg[2], cv[2], ce[2];
 };
 
+// fields of a fast-path record (plan.cuh): ONE record per visit, shared by the two scalar-row threads of the node
+__device__ __forceinline__ int rec_i1(const uint4 r) { return (int)((r.y >> 29) & 3u); }
+__device__ __forceinline__ int rec_i2(const uint4 r) { return (int)((r.z >> 29) & 3u); }
+__device__ __forceinline__ bool rec_edge(const uint4 r) { return (r.y >> 28) & 1u; }
+__device__ __forceinline__ bool rec_cout(const uint4 r) { return (r.y >> 27) & 1u; }
+__device__ __forceinline__ bool rec_first(const uint4 r, int b) { return (r.y >> (22 + b)) & 1u; }
+// units between the two scalar rows of the node in the image (its block degree), times h
+__device__ __forceinline__ uint32_t rec_hdeg(const uint4 r, int h) { return h ? ((r.z >> 22) & 0x7fu) : 0u; }
+// byte offset in the tile image of column t (position t of the record) of scalar row h: position of row 0 + h deg,
+// chunk-swizzled inside its 128-byte line (swz_tma)
+__device__ __forceinline__ uint32_t rec_off(const uint4 r, int t, uint32_t hdeg)
+{
+   const uint32_t w = t < 2 ? r.y : (t < 4 ? r.z : r.w);
+   const uint32_t p = (((t & 1) ? (w >> 11) : w) & 0x7ffu) + hdeg;
+   return (p ^ ((p >> 3) & 7u)) << 4;
+}
+
 // Values of the row slice of one visit, positions t = 0..5 of the record's numbering (0', 1', 2', then
 // the edges opposite to them), for scalar row h, in the EXCHANGED frame of row h: for h = 1 the two
 // entries of every pair are swapped (row 1 of the closed form is row 0 with x and y exchanged in every
@@ -534,7 +551,7 @@ __device__ __forceinline__ void fast_values(const AsmArgs &A, const uint4 raw, c
 {
    // gradients of the visit's vertices 1' and 2' (local numbers from the record; 0' is the row's own
    // vertex, or the vertex opposite to the row's own edge)
-   const int i1 = (int)(raw.w & 3u), i2 = (int)((raw.w >> 2) & 3u);
+   const int i1 = rec_i1(raw), i2 = rec_i2(raw);
    const double h0x = -g.g1x - g.g2x, h0y = -g.g1y - g.g2y;
    const double a1x = i1 == 0 ? h0x : (i1 == 1 ? g.g1x : g.g2x), a1y = i1 == 0 ? h0y : (i1 == 1 ? g.g1y : g.g2y);
    const double a2x = i2 == 0 ? h0x : (i2 == 1 ? g.g1x : g.g2x), a2y = i2 == 0 ? h0y : (i2 == 1 ? g.g1y : g.g2y);
@@ -585,7 +602,7 @@ template <int ET, bool EDGE>
 __device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw, int h, double (*v)[2])
 {
    const double *R = A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
-   const int i1 = (int)(raw.w & 3u), i2 = (int)((raw.w >> 2) & 3u), i0 = 3 - i1 - i2;
+   const int i1 = rec_i1(raw), i2 = rec_i2(raw), i0 = 3 - i1 - i2;
    double g1x, g1y, g2x, g2y;
    ld_d4(R, g1x, g1y, g2x, g2y);
    const double h0x = -g1x - g2x, h0y = -g1y - g2y;
@@ -645,12 +662,12 @@ template <int ET, bool EDGE>
 __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *sv, int h, FastCarry &C,
                                                const double (*v)[2])
 {
-   const bool cout = (raw.z >> 1) & 1u;
+   const bool cout = rec_cout(raw);
+   const uint32_t hdeg = rec_hdeg(raw, h);
    // t = position (address entry), b = index of the put (first-touch bit)
    auto put = [&](int t, int b, double k0, double k1) {
-      const uint32_t w = t < 2 ? raw.y : (t < 4 ? raw.z : raw.w);
-      const uint32_t off = (t & 1) ? (w >> 16) : (w & 0x7ff0u);
-      const bool first = b < 4 ? ((raw.y >> b) & 1u) : (raw.z & 1u);
+      const uint32_t off = rec_off(raw, t, hdeg);
+      const bool first = rec_first(raw, b);
       double2 *p = reinterpret_cast<double2 *>(sv + off);
       const double va = h ? k1 : k0, vb = h ? k0 : k1;
       if (first)
@@ -723,8 +740,8 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    const int half = (tid >> 4) & 1;
    double nrm[2] = {0., 0.};  // NORMS: this thread's share of sum v^2 and of the trace
    {
-      const uint4 *rec = A.frec + ((int64_t)blockIdx.x * A.flevels * R + rank) * 2 + half;
-      constexpr int LS = 2 * R;  // records per level
+      const uint4 *rec = A.frec + ((int64_t)blockIdx.x * A.flevels * R + rank);  // shared by the node's two row threads
+      constexpr int LS = R;  // records per level
       unsigned char *img = reinterpret_cast<unsigned char *>(sv);
       const uint4 none = make_uint4(0u, 0u, 0u, 0u);
       uint4 raw = none, raw1, raw2;
@@ -739,8 +756,8 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       raw1 = rec[0];
       raw2 = A.flevels > 1 ? rec[LS] : none;
       const int cnt = (int)(raw1.x >> 28);  // visits of this row (0: padding)
-      if (cfut > 0)
-      {
+      if (cfut > 0 && (tid & 23) == 0)
+      {  // one lane per 128-byte line of records (8 ranks; the first of them has the largest visit count)
          const uint4 *nx = rec + (int64_t)A.prefetch_tiles * A.flevels * LS;
 #pragma unroll
          for (int j = 0; j < 8; ++j)
@@ -754,7 +771,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
          // damaged cell: NaN marker, its damage record is celld[cell]
          const bool dam = DMG && geo.g1x != geo.g1x;
-         if (!((raw.z >> 2) & 1u))
+         if (!rec_edge(raw))
          {  // vertex row
             double v[Elem<ET>::nd][2];
             if (dam)
@@ -785,7 +802,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       }
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
-         const uint32_t off = (raw.z & 4u) ? (raw.z >> 16) : (raw.y & 0x7ff0u);
+         const uint32_t off = rec_off(raw, rec_edge(raw) ? 3 : 0, rec_hdeg(raw, half));
          *reinterpret_cast<double2 *>(img + off) = make_double2(half ? C.dg[1] : C.dg[0], half ? C.dg[0] : C.dg[1]);
          nrm[1] = C.dg[0];  // the diagonal entry of this scalar row (exchanged frame: first of the pair)
       }

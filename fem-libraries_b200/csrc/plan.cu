@@ -378,15 +378,13 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
          }
          ++bit;
       }
-      for (int h = 0; h < 2; ++h)
-      {
-         uint32_t ent[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-         for (int t = 0; t < nd && t < 6; ++t) ent[t] = 16u * (uint32_t)swz_tma(r0 + h * deg + sl[t]);
-         frec[(((int64_t)blockIdx.x * flevels + j) * kAsmR + rank) * 2 + h] =
-            make_uint4(r.e | ((uint32_t)cnt << 28), ent[0] | (first & 0xfu) | (ent[1] << 16),
-                       ent[2] | ((first >> 4) & 0x1u) | (cout ? 2u : 0u) | (vert ? 0u : 4u) | (ent[3] << 16),
-                       ent[4] | (uint32_t)i1 | ((uint32_t)i2 << 2) | (ent[5] << 16));
-      }
+      // one record per visit (plan.cuh): positions of row 0, the row-1 thread adds the block degree
+      uint32_t pos[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+      for (int t = 0; t < nd && t < 6; ++t) pos[t] = (uint32_t)(r0 + sl[t]);
+      frec[((int64_t)blockIdx.x * flevels + j) * kAsmR + rank] =
+         make_uint4(r.e | ((uint32_t)cnt << 28),
+                    pos[0] | (pos[1] << 11) | ((first & 0x1fu) << 22) | (cout ? 1u << 27 : 0u) | (vert ? 0u : 1u << 28) | ((uint32_t)i1 << 29),
+                    pos[2] | (pos[3] << 11) | ((uint32_t)deg << 22) | ((uint32_t)i2 << 29), pos[4] | (pos[5] << 11));
       cin = cout;
       if (cout) carry_v = vert ? sl[2] : sl[1], carry_e = vert ? (p2 ? sl[4] : -1) : sl[2];
    }
@@ -613,7 +611,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
 
    // fast-path records: triangles whose kAsmR-row staging image is addressable with 15-bit byte offsets
    // and whose nodes belong to fewer than 16 cells
-   if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 8) < 32768)
+   if (etype != FEMB200_Q2 && 32 * ((int64_t)p->tile_max_blocks[1] + 8) < 32768 && p->max_deg < 128)
    {
       const int64_t ntiles = cdiv(nnodes, kAsmR);
       if (dev_alloc(&p->thdr, (size_t)ntiles, &p->bytes)) return fail(1);
@@ -626,7 +624,7 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       if (maxcnt >= 1 && maxcnt < 16)
       {
          p->flevels = maxcnt;
-         const size_t nrec = (size_t)ntiles * (size_t)maxcnt * kAsmR * 2;
+         const size_t nrec = (size_t)ntiles * (size_t)maxcnt * kAsmR;
          if (dev_alloc(&p->frec, nrec, &p->bytes) || dev_alloc(&p->tcnt, (size_t)ntiles * kAsmR, &p->bytes)) return fail(1);
          cudaMemsetAsync(p->frec, 0, sizeof(uint4) * nrec, st);
          cudaMemsetAsync(p->tcnt, 0, (size_t)ntiles * kAsmR, st);

@@ -68,22 +68,22 @@ __host__ __device__ __forceinline__ int swz(int u)
 // staging wavefronts, against a quarter of the kernel's LSU wavefronts saved.)
 __host__ __device__ __forceinline__ int swz_tma(int p) { return p ^ ((p >> 3) & 7); }
 
-// Fast-path record of one (visit, scalar row h) pair, triangles only: everything the row thread
-// needs in one 16-byte load, with the staging addresses resolved at plan time:
-//   x        cell id e
-//   y, z, w  six 16-bit entries (positions t = 0..5, rotated order as in VisitRec): BYTE offset of the
-//            16-byte staging unit of column t in the tile image (swz_tma layout above; a multiple of 16
-//            below 32768).  The free low nibbles of the even entries carry
-//              y: first-touch bits of the first four puts;
-//              z: first-touch bit of the fifth put (bit 0), carry-out (bit 1), edge row (bit 2);
-//              w: local vertex numbers of the visit's vertices 1' (bits 0-1) and 2' (bits 2-3).
-//            The five puts are positions 1..5 of a vertex row, 0, 1, 2, 4, 5 of an edge row (the diagonal
-//            block never goes through the image).  Put / carry / flip semantics: k_fast_records.
-//   The top four bits of x hold the number of visits of the row (cells are numbered below 2^28).
-// Storage: fixed stride, record (tile, level j, rank r, h) at ((tile * flevels + j) * kAsmR + r) * 2 + h
-// with flevels = the largest visit count of the mesh (zero padding where a row has fewer visits):
-// the address depends on the block and thread index only, and the 32 lanes of a warp (16 ranks x
-// 2 rows) read 512 contiguous bytes.
+// Fast-path record of one visit, triangles only: everything the two row threads of the node (scalar rows h = 0, 1)
+// need in one 16-byte load (both load the same address), with the staging positions resolved at plan time:
+//   x   cell id e (bits 0-27) | number of visits of the row (bits 28-31; cells are numbered below 2^28)
+//   y   position of column 0 (bits 0-10) | column 1 (11-21) | first-touch bits of the five puts (22-26) | carry-out (27)
+//       | edge row (28) | local vertex number of the visit's vertex 1' (29-30)
+//   z   position of column 2 (0-10) | column 3 (11-21) | block degree of the node (22-28) | local vertex number of 2' (29-30)
+//   w   position of column 4 (0-10) | column 5 (11-21)
+// "Position" = 16-byte unit of the column in the tile image for scalar row 0, BEFORE the chunk swizzle (swz_tma above),
+// columns in rotated order as in VisitRec (t = 0..5); the row-1 thread adds the block degree (its row follows row 0 in
+// the CSR) and both apply the swizzle (three integer operations).  The five puts are positions 1..5 of a vertex row,
+// 0, 1, 2, 4, 5 of an edge row (the diagonal block never goes through the image before its final store).  Put / carry /
+// flip semantics: k_fast_records.  One record per visit instead of one per (visit, scalar row) halves the largest
+// read stream of the kernel (0.8 -> 0.4 GB at n = 1448).
+// Storage: fixed stride, record (tile, level j, rank r) at (tile * flevels + j) * kAsmR + r with flevels = the largest
+// visit count of the mesh (zero padding where a row has fewer visits): the address depends on the block and thread index
+// only, and the 16 ranks of a warp read 256 contiguous bytes.
 // Per-tile header of the streaming assembly kernel: everything a CTA needs to know about a tile in
 // one 64-byte bulk copy.
 struct __align__(64) TileHdr
@@ -111,7 +111,7 @@ struct femb200_plan
    const int32_t *dofmap = nullptr, *xdofmap = nullptr;  // borrowed
    int32_t *nptr = nullptr;                               // [nnodes+1]
    femb::VisitRec *vrec = nullptr;                        // [nvisits], tile-sorted (see above)
-   uint4 *frec = nullptr;                                 // [2 nvisits] fast-path records (triangles) or null
+   uint4 *frec = nullptr;                                 // [ntiles * flevels * kAsmR] fast-path records (triangles) or null
    uint8_t *tcnt = nullptr;                               // [ntiles * kAsmR] visit count of (tile, rank) (with frec)
    femb::TileHdr *thdr = nullptr;                         // [ntiles] tile headers (with frec)
    int32_t flevels = 0;                                   // levels of the fixed-stride frec layout (max visits per node)
