@@ -153,6 +153,10 @@ struct AsmArgs
    const double *dnod, *u;
    const double *cellrec;
    const double *celld;  // records of the damaged cells (see cell_setup_damage_kernel)
+   const int32_t *tdam;  // [ntiles][dmg_stage_cap]: cell whose damage record goes to slot s of the tile's stage, -1: none
+                         // (written by cell_setup_damage_kernel on every assembly through the plan's cell -> slot map)
+   const uint8_t *tflag;  // [ntiles] or null: 1 where a tile has a damaged cell in this assembly (pre-pass)
+   int tflag_want;        // with tflag: the CTA works only when its tile's flag equals this (two-kernel split)
    int variant;
    double *values;
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
@@ -199,9 +203,9 @@ __device__ __forceinline__ int stored_position(int b, int a, int nd);
 // (cell_setup_damage_kernel) classifies the cells: undamaged ones keep the 32-byte fast-path record, damaged
 // ones get a NaN marker there and a DAMAGE RECORD at celld[cell] (indexed by the cell id: no compaction):
 //     [0..3]            grad lambda_1, grad lambda_2 (plain)
-//     [4 + 8 q .. + 5]  upper triangle (00, 01, 02, 11, 12, 22) of w_q |det J| D_q, for the nq points of the rule
-// (P1: 16 doubles, P2: 32 doubles = 256 B against the 1152 B of a full element tangent; D_q is symmetric to
-// rounding, its upper triangle is kept).  The constitutive evaluation -- the expensive, branchy part -- happens
+//     [4 + 6 q .. + 5]  upper triangle (00, 01, 02, 11, 12, 22) of w_q |det J| D_q, for the nq points of the rule
+// (P1: 10 doubles in a 96-byte slot, P2: 22 doubles = 176 B in a 192-byte slot, against the 1152 B of a full element
+// tangent; D_q is symmetric to rounding, its upper triangle is kept).  The constitutive evaluation -- the expensive, branchy part -- happens
 // once per cell; a visit rebuilds its 2 x 2nd row slice from the record with ~90 FMAs: on a straight-sided
 // triangle the P2 basis gradients at the points of the 3-point rule are fixed combinations of the grad lambda_c
 // (L_k = 2/3 at point k, 1/6 elsewhere), so with c_q = row h of B_a(q) D_q (three numbers per point),
@@ -219,10 +223,24 @@ __device__ __forceinline__ void tri_ref_grads(int q, double (*dN)[2], double *ph
    w2 = 2. * w;
 }
 
+// global stride of a damage record in doubles (whole 32-byte sectors) and the bytes of it that carry data (what a
+// tile stages in shared memory: an odd number of 16-byte units, so records at consecutive slots start in different
+// bank groups)
 template <int ET>
 __host__ __device__ constexpr int dmg_rec_doubles()
 {
-   return ET == FEMB200_P1 ? 16 : 32;
+   return ET == FEMB200_P1 ? 12 : 24;
+}
+template <int ET>
+__host__ __device__ constexpr int dmg_rec_bytes()
+{
+   return ET == FEMB200_P1 ? 80 : 176;
+}
+constexpr int kDmgStageBytes = 144 * 176;  // record stage of a tile: 144 P2 records / 316 P1 records
+template <int ET>
+__host__ __device__ constexpr int dmg_stage_cap()
+{
+   return kDmgStageBytes / dmg_rec_bytes<ET>();
 }
 
 // One thread per cell.  The damage records leave through a per-warp shared-memory stage as whole 32-byte
@@ -232,7 +250,8 @@ __global__ void __launch_bounds__(128)
 cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, const int32_t *__restrict__ dofmap,
                          const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
                          const double *__restrict__ dnod, const double *__restrict__ u, int variant,
-                         double *__restrict__ rec, double *__restrict__ celld)
+                         double *__restrict__ rec, double *__restrict__ celld, const uint4 *__restrict__ cref,
+                         int32_t *__restrict__ tdam, uint8_t *__restrict__ tflag, int cap)
 {
    constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, RS = dmg_rec_doubles<ET>(), STRIDE = RS + 2;
    __shared__ __align__(16) double stage[4][32 * STRIDE];
@@ -275,6 +294,20 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
          r[1] = make_double2(0., 0.);
       }
    }
+   if (active && cref)
+   {  // tell every tile that visits this cell (plan: tile << 10 | slot; slot 0x3ff: not staged) whether the slot
+      // holds a damaged cell this time, and flag the tiles with a damaged cell (tflag was cleared before the launch)
+      const uint4 ra = cref[2 * e], rb = cref[2 * e + 1];
+      const uint32_t ref[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+         if (ref[k] != 0xffffffffu)
+         {
+            const uint32_t tile = ref[k] >> 10, sl = ref[k] & 0x3ffu;
+            if (sl != 0x3ffu) tdam[(int64_t)tile * cap + sl] = damaged ? (int32_t)e : -1;
+            if (damaged) tflag[tile] = 1;
+         }
+   }
    double *R = stage[warp] + lane * STRIDE;
    if (damaged)
    {
@@ -307,13 +340,11 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
          }
          else
             hooke_scaled(lam, mu, 1., D);
-         double *Rq = R + 4 + 8 * q;
+         double *Rq = R + 4 + 6 * q;
          Rq[0] = D[0] * w, Rq[1] = D[1] * w, Rq[2] = D[2] * w, Rq[3] = D[4] * w, Rq[4] = D[5] * w, Rq[5] = D[8] * w;
-         Rq[6] = Rq[7] = 0.;
       }
-      if (RS > 4 + 8 * nq)
 #pragma unroll
-         for (int k = 4 + 8 * nq; k < RS; ++k) R[k] = 0.;
+      for (int k = 4 + 6 * nq; k < RS; ++k) R[k] = 0.;
    }
    const unsigned mask = __ballot_sync(0xffffffffu, damaged);
    __syncwarp();
@@ -326,18 +357,23 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
    }
 }
 
-// symmetric D of one point from a damage record (two 256-bit loads)
+// symmetric D of one point from a damage record
 struct SymD
 {
    double d00, d01, d02, d11, d12, d22;
 };
 __device__ __forceinline__ SymD ld_symd(const double *p)
-{
+{  // three 16-byte loads; p may point into the tile's record stage (shared) or into celld (global)
+   const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2),
+                 c = *reinterpret_cast<const double2 *>(p + 4);
    SymD D;
-   double pad0, pad1;
-   ld_d4(p, D.d00, D.d01, D.d02, D.d11);
-   ld_d4(p + 4, D.d12, D.d22, pad0, pad1);
+   D.d00 = a.x, D.d01 = a.y, D.d02 = b.x, D.d11 = b.y, D.d12 = c.x, D.d22 = c.y;
    return D;
+}
+__device__ __forceinline__ void ld_grads(const double *p, double &g1x, double &g1y, double &g2x, double &g2y)
+{
+   const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+   g1x = a.x, g1y = a.y, g2x = b.x, g2y = b.y;
 }
 // row h of B_a D with B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]  (M.cc:699-704)
 __device__ __forceinline__ void bd_row(const SymD &D, double gx, double gy, int h, double *c)
@@ -361,14 +397,14 @@ __device__ __forceinline__ void damaged_row_slice(const double *__restrict__ R, 
 {
    constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq;
    double g[3][2];
-   ld_d4(R, g[1][0], g[1][1], g[2][0], g[2][1]);
+   ld_grads(R, g[1][0], g[1][1], g[2][0], g[2][1]);
    g[0][0] = -g[1][0] - g[2][0], g[0][1] = -g[1][1] - g[2][1];
 #pragma unroll
    for (int b = 0; b < nd; ++b) k[b][0] = k[b][1] = 0.;
 #pragma unroll
    for (int q = 0; q < nq; ++q)
    {
-      const SymD D = ld_symd(R + 4 + 8 * q);
+      const SymD D = ld_symd(R + 4 + 6 * q);
       double G[nd][2];
       if (ET == FEMB200_P1)
       {
@@ -599,12 +635,11 @@ __device__ __forceinline__ void fast_values(const AsmArgs &A, const uint4 raw, c
 // 0', 1', 2' are the local vertices i0, i1, i2 (i0 = the row's vertex, or the vertex opposite to the row's edge),
 // positions 3..5 the edges opposite to them; the point of the rule that sits next to vertex i_t is "point t".
 template <int ET, bool EDGE>
-__device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw, int h, double (*v)[2])
+__device__ __forceinline__ void damaged_values(const double *R, const uint4 raw, int h, double (*v)[2])
 {
-   const double *R = A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
    const int i1 = rec_i1(raw), i2 = rec_i2(raw), i0 = 3 - i1 - i2;
    double g1x, g1y, g2x, g2y;
-   ld_d4(R, g1x, g1y, g2x, g2y);
+   ld_grads(R, g1x, g1y, g2x, g2y);
    const double h0x = -g1x - g2x, h0y = -g1y - g2y;
    // gradients of lambda at positions 1', 2', 0'
    const double p1x = i1 == 0 ? h0x : (i1 == 1 ? g1x : g2x), p1y = i1 == 0 ? h0y : (i1 == 1 ? g1y : g2y);
@@ -623,7 +658,7 @@ __device__ __forceinline__ void damaged_values(const AsmArgs &A, const uint4 raw
       return;
    }
    // D at the points next to 0', 1', 2' (point index = local vertex number)
-   const SymD D0 = ld_symd(R + 4 + 8 * i0), D1 = ld_symd(R + 4 + 8 * i1), D2 = ld_symd(R + 4 + 8 * i2);
+   const SymD D0 = ld_symd(R + 4 + 6 * i0), D1 = ld_symd(R + 4 + 6 * i1), D2 = ld_symd(R + 4 + 6 * i2);
    // c_t = row h of B_a(point t) D_t: gradient of the row's own basis function at the three points
    double c0[3], c1[3], c2[3];
    if (!EDGE)
@@ -725,7 +760,7 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
 // depend on the block and thread index only: the dependent chain of a tile is record -> cell record
 // -> first put (the tile header is needed by the stream-out only), with the cell record one visit
 // and the record two visits ahead.
-template <int ET, bool DMG, bool NORMS, int MINB = (DMG ? 5 : 7)>
+template <int ET, bool DMG, bool NORMS, int MINB>
 __global__ void __launch_bounds__(kAsmR * 2, MINB)
 assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out, const __grid_constant__ CUtensorMap tm8,
                      const __grid_constant__ CUtensorMap tm1)
@@ -733,14 +768,57 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
    extern __shared__ __align__(1024) double2 sv[];
    const int tid = threadIdx.x;
-   const TileHdr *hdr = A.thdr + blockIdx.x;
+   // damaged assembly = two launches over the same grid: this kernel without the record stage (7 CTAs per SM) for the
+   // tiles that hold no damaged cell, the DMG variant for the others (tflag, written by the pre-pass); a CTA of the
+   // wrong kind leaves at once.  (CTAs striding over 8 tiles each, to save the launches of the idle ones, lost: 12 %
+   // slower at 100 % damaged cells, 5 % on the linear path.)
+   if (A.tflag && (int)A.tflag[blockIdx.x] != A.tflag_want) return;
+   const int64_t tile = blockIdx.x, ntiles = gridDim.x;
+   unsigned char *dstage = reinterpret_cast<unsigned char *>(sv) + 16 * (size_t)A.stage_units;
+   uint64_t *dbar = reinterpret_cast<uint64_t *>(dstage + kDmgStageBytes);
+   if (DMG)
+   {
+      if (tid == 0)
+      {
+         mbar_init(dbar, THREADS);
+         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();  // the barrier is initialised (nothing is in flight yet: all warps arrive at once)
+   }
+   const TileHdr *hdr = A.thdr + tile;
    const int64_t b0 = hdr->b0;
    const int units = hdr->units;  // 16-byte units of this tile
    const int rank = ((tid >> 5) << 4) + (tid & 15);
    const int half = (tid >> 4) & 1;
    double nrm[2] = {0., 0.};  // NORMS: this thread's share of sum v^2 and of the trace
+   // DMG: the damage records of the tile's cells (plan list tcell, slot number in the fast records) are staged behind
+   // the image with one bulk copy per damaged cell (no LSU instruction, no register): a visit then reads its record
+   // with 16-byte shared-memory loads (the two row threads of a node read the same addresses: broadcast) instead of
+   // pulling 176 bytes through L1 as scattered 32-byte sectors.
+   // Fill of the stage: the tile's row of tdam says which slots hold a damaged cell this time; one 16-byte LDGSTS per
+   // (slot, unit of the record), completion on the mbarrier.  The records of the tile `prefetch_tiles` ahead are
+   // pulled into L2 (thread = (slot, 128-byte line)), its tdam row was prefetched by the tile that far behind.
+   constexpr int DCAP = dmg_stage_cap<ET>(), DUPR = dmg_rec_bytes<ET>() / 16, DRS = dmg_rec_doubles<ET>();
+   constexpr int DNR = DMG ? (DCAP + THREADS - 1) / THREADS : 1;                 // row entries per thread
+   constexpr int DNF = DMG ? (DCAP * DUPR + THREADS - 1) / THREADS : 1;          // fill units per thread
+   constexpr int DLPR = (DRS * 8 + 127) / 128;                                   // 128-byte lines per record
+   const bool dstg = DMG && A.tdam != nullptr;
+   const bool dpf = dstg && A.prefetch_tiles > 0 && (int64_t)tile + A.prefetch_tiles < ntiles;
+   int32_t *drow = reinterpret_cast<int32_t *>(dstage + kDmgStageBytes + 16);    // [DCAP] this tile's row of tdam
+   int32_t rcell[DNR], fcell[DNR];
+   if (DMG)
    {
-      const uint4 *rec = A.frec + ((int64_t)blockIdx.x * A.flevels * R + rank);  // shared by the node's two row threads
+#pragma unroll
+      for (int k = 0; k < DNR; ++k)
+      {
+         const int i = tid + k * THREADS;
+         rcell[k] = (dstg && i < DCAP) ? A.tdam[(int64_t)tile * DCAP + i] : -1;
+         fcell[k] = (dpf && i < DCAP) ? A.tdam[((int64_t)tile + A.prefetch_tiles) * DCAP + i] : -1;
+      }
+   }
+   bool staged = !DMG;  // DMG: whether this thread has waited for the record stage
+   {
+      const uint4 *rec = A.frec + ((int64_t)tile * A.flevels * R + rank);  // shared by the node's two row threads
       constexpr int LS = R;  // records per level
       unsigned char *img = reinterpret_cast<unsigned char *>(sv);
       const uint4 none = make_uint4(0u, 0u, 0u, 0u);
@@ -751,8 +829,8 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       // The records are read once, from DRAM, at the head of every tile's dependent chain: the records of the
       // tile `prefetch_tiles` ahead (1.5 - 2 waves of resident CTAs) are pulled into L2; that tile's visit
       // count for this rank comes from the plan's byte table, loaded together with the first record.
-      const bool pf = A.prefetch_tiles > 0 && (int64_t)blockIdx.x + A.prefetch_tiles < (int64_t)gridDim.x;
-      const int cfut = pf ? (int)A.tcnt[((int64_t)blockIdx.x + A.prefetch_tiles) * R + rank] : 0;
+      const bool pf = A.prefetch_tiles > 0 && (int64_t)tile + A.prefetch_tiles < ntiles;
+      const int cfut = pf ? (int)A.tcnt[((int64_t)tile + A.prefetch_tiles) * R + rank] : 0;
       raw1 = rec[0];
       raw2 = A.flevels > 1 ? rec[LS] : none;
       const int cnt = (int)(raw1.x >> 28);  // visits of this row (0: padding)
@@ -764,19 +842,50 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             if (j < cfut) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + j * LS));
       }
       if (0 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
+      if (DMG)
+      {  // issue the stage fill behind the first loads of the visit pipeline: the row goes through shared memory (one
+         // global load per thread instead of one per fill unit; measured 4 % faster than per-thread row loads)
+#pragma unroll
+         for (int k = 0; k < DNR; ++k)
+            if (tid + k * THREADS < DCAP) drow[tid + k * THREADS] = rcell[k];
+         __syncthreads();
+#pragma unroll
+         for (int k = 0; k < DNF; ++k)
+         {
+            const int i = tid + k * THREADS;
+            if (i < DCAP * DUPR)
+            {
+               const int sl = i / DUPR;
+               const int32_t cc = drow[sl];
+               if (cc >= 0) cp_async16(dstage + 16 * i, A.celld + (int64_t)cc * DRS + 2 * (i - sl * DUPR));
+            }
+         }
+         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(dbar)) : "memory");
+         if (dpf && (int64_t)tile + 2 * A.prefetch_tiles < ntiles && tid < (DCAP * 4 + 127) / 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A.tdam + ((int64_t)tile + 2 * A.prefetch_tiles) * DCAP) + 128 * tid));
+      }
       for (int c = 0; c < cnt; ++c)
       {
          raw = raw1, geo = geo1, raw1 = raw2;
          if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
          raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
-         // damaged cell: NaN marker, its damage record is celld[cell]
+         // damaged cell: NaN marker; its damage record is in the tile's stage (slot in the record), or, where the tile
+         // has more cells than the stage holds (slot 0x3ff), at celld[cell]
          const bool dam = DMG && geo.g1x != geo.g1x;
+         const double *drec = nullptr;
+         if (dam)
+         {
+            if (!staged) mbar_wait(dbar, 0), staged = true;
+            const uint32_t slot = raw.w >> 22;
+            drec = slot != 0x3ffu ? reinterpret_cast<const double *>(dstage + slot * dmg_rec_bytes<ET>())
+                                  : A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
+         }
          if (!rec_edge(raw))
          {  // vertex row
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET, false>(A, raw, half, v);
+               damaged_values<ET, false>(drec, raw, half, v);
                emit_row_slice<ET, false>(raw, img, half, C, v);
             }
             else
@@ -790,7 +899,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET, true>(A, raw, half, v);
+               damaged_values<ET, true>(drec, raw, half, v);
                emit_row_slice<ET, true>(raw, img, half, C, v);
             }
             else
@@ -799,6 +908,17 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
                emit_row_slice<ET, true>(raw, img, half, C, v);
             }
          }
+      }
+      if (DMG)
+      {  // L2 prefetch of the damage records of the future tile
+#pragma unroll
+         for (int k = 0; k < DNR; ++k)
+            if (fcell[k] >= 0)
+            {
+               const char *q = reinterpret_cast<const char *>(A.celld + (int64_t)fcell[k] * DRS);
+#pragma unroll
+               for (int l = 0; l < DLPR; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * l));
+            }
       }
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
@@ -866,7 +986,27 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    {
       __shared__ double sh[THREADS / 32];
       const double f2 = block_sum<THREADS>(nrm[0], sh), tr = block_sum<THREADS>(nrm[1], sh);
-      if (tid == 0) red.partials[blockIdx.x] = f2, red.partials[(size_t)gridDim.x + blockIdx.x] = tr;
+      if (tid == 0) red.partials[tile] = f2, red.partials[(size_t)ntiles + tile] = tr;
+   }
+}
+
+// number of flagged tiles of a damaged assembly -> host-mapped word (read, without synchronisation, by the NEXT damaged
+// assembly on this plan to choose between one launch and two)
+__global__ void __launch_bounds__(1024) tile_flag_count_kernel(const uint8_t *__restrict__ tflag, int64_t ntiles, int *__restrict__ out)
+{
+   __shared__ int sh[32];
+   int c = 0;
+   for (int64_t i = threadIdx.x; i < ntiles; i += 1024) c += tflag[i];
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+   __syncthreads();
+   if (threadIdx.x < 32)
+   {
+      c = sh[threadIdx.x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (threadIdx.x == 0) *out = c;
    }
 }
 
@@ -1223,41 +1363,64 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    return 0;
 }
 
-template <int ET, bool DMG, int MINB>
-static int launch_assemble_fast_m(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
+template <int ET, bool DMG, bool NORMS, int MINB>
+static int launch_fast_kernel(const femb200_plan *p, AsmArgs A, const ReduceScratch &red, double *d_norms, cudaStream_t st)
+{
+   femb200_plan *pm = const_cast<femb200_plan *>(p);
+   const size_t smem = 16 * (size_t)A.stage_units + (DMG ? kDmgStageBytes + 16 + 4 * dmg_stage_cap<ET>() : 0);
+   const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
+   const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap8), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap1);
+   if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, NORMS, MINB>>(smem)) return rc;
+   assemble_fast_kernel<ET, DMG, NORMS, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
+   FEMB_LAUNCH_CHECK();
+   return 0;
+}
+
+// DMG: the pre-pass has flagged the tiles with a damaged cell; those go through the variant that holds the damage-record
+// stage next to the image (P2: 55 KB, P1: 40 KB per CTA, compiled for the 4 / 5 CTAs per SM that fit), the others
+// through the plain kernel at 7 CTAs per SM
+template <int ET, bool DMG, bool NORMS>
+static int launch_assemble_fast_n(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
    // the image starts at the tile's offset inside its 128-byte line (up to 6 units) and is whole lines
    A.stage_units = (2 * p->tile_max_blocks[1] + 6 + 7) & ~7;
    A.flevels = p->flevels;
    A.prefetch_tiles = p->opt_prefetch_tiles >= 0 ? p->opt_prefetch_tiles : 8 * devinfo().sm_count;  // a good wave of resident CTAs ahead
-   const size_t smem = 16 * (size_t)A.stage_units;
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
    femb200_plan *pm = const_cast<femb200_plan *>(p);
-   A.use_tma = (!d_norms && p->opt_stream_out == 0 && values_tensor_maps(pm, A.values)) ? 1 : 0;
-   const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap8), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap1);
-   if (d_norms)
-   {
-      ReduceScratch red;
+   A.use_tma = (!NORMS && p->opt_stream_out == 0 && values_tensor_maps(pm, A.values)) ? 1 : 0;
+   ReduceScratch red{nullptr, nullptr};
+   if (NORMS)
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
-      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, true, MINB>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, true, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
-      norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
-   }
-   else
+   A.tflag = nullptr, A.tflag_want = 0;
+   if (DMG)
    {
-      if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, false, MINB>>(smem)) return rc;
-      assemble_fast_kernel<ET, DMG, false, MINB><<<grid, kAsmR * 2, smem, st>>>(A, ReduceScratch{nullptr, nullptr}, nullptr, tm8, tm1);
+      A.tdam = pm->tdam;  // built by plan_tile_cells, written by the pre-pass
+      // One launch or two.  Two: the DMG variant for the flagged tiles, the plain kernel (7 CTAs per SM) for the others;
+      // the CTAs of the wrong kind leave at once, but 131 K idle CTAs still cost ~0.1 ms.  When most tiles were flagged
+      // in the PREVIOUS damaged assembly on this plan (count left in host-mapped memory, read without synchronisation:
+      // the choice affects speed only, either way every tile is assembled) the DMG variant takes all tiles.
+      const int64_t ntiles = grid;
+      const bool split = pm->tflag_count && (int64_t)*static_cast<volatile int *>(pm->tflag_count) * 4 < ntiles * 3;
+      tile_flag_count_kernel<<<1, 1024, 0, st>>>(pm->tflag, ntiles, pm->tflag_count_dev);
+      if (split) A.tflag = pm->tflag, A.tflag_want = 1;
+      if (int rc = launch_fast_kernel<ET, true, NORMS, ET == FEMB200_P1 ? 5 : 4>(p, A, red, d_norms, st)) return rc;
+      A.tflag_want = 0;
+      if (!split) return 0;
    }
-   FEMB_LAUNCH_CHECK();
+   if (int rc = launch_fast_kernel<ET, false, NORMS, 7>(p, A, red, d_norms, st)) return rc;
+   if (NORMS)
+   {
+      norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
+      FEMB_LAUNCH_CHECK();
+   }
    return 0;
 }
 
-// the damaged variant is compiled for 5 resident CTAs per SM (96 registers, no spills): 4 (107 registers) and 6
-// (80 registers, spills in the damaged branch) measured 2 % and 24 % slower at 100 % damaged cells
 template <int ET, bool DMG>
 static int launch_assemble_fast(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
-   return launch_assemble_fast_m<ET, DMG, DMG ? 5 : 7>(p, A, st, d_norms);
+   return d_norms ? launch_assemble_fast_n<ET, DMG, true>(p, A, st, d_norms) : launch_assemble_fast_n<ET, DMG, false>(p, A, st, d_norms);
 }
 
 // *fused: in: the caller wants (|K|_F^2, trace K) in d_norms; out: whether the kernel produced them
@@ -1296,7 +1459,7 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
    // triangles take the per-cell pre-pass + fast kernel (damaged cells through their own per-cell
    // tangent records); Q2 and plans with assembly_path = 2 take the per-quadrature-point kernel
    const bool linear = (p->etype != FEMB200_Q2) && p->opt_assembly_path != 2;
-   A.cellrec = nullptr, A.celld = nullptr;
+   A.cellrec = nullptr, A.celld = nullptr, A.tdam = nullptr, A.tflag = nullptr, A.tflag_want = 0;
    if (linear)
    {
       femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan
@@ -1322,12 +1485,20 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
                pm->bytes += sizeof(double) * W * (size_t)p->ncells;
             }
          }
+         // the fast kernel stages the damage records of a tile's cells in shared memory: slot map (plan, built on
+         // the first damaged assembly) + the per-assembly row of damaged cells the pre-pass writes through it
+         const bool fastk = p->frec && p->opt_assembly_path != 1;
+         const int cap = p->etype == FEMB200_P1 ? dmg_stage_cap<FEMB200_P1>() : dmg_stage_cap<FEMB200_P2>();
+         if (fastk)
+            if (int rc = plan_tile_cells(pm, cap, st)) return rc;
+         const uint4 *cref = (fastk && pm->tdam_refs) ? reinterpret_cast<const uint4 *>(pm->cref) : nullptr;
+         if (fastk) FEMB_CUDA(cudaMemsetAsync(pm->tflag, cref ? 0 : 1, (size_t)cdiv(p->nnodes, kAsmR), st));
          if (p->etype == FEMB200_P1)
             cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
-                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld);
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, pm->tflag, cap);
          else
             cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
-                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld);
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, pm->tflag, cap);
          A.celld = pm->celld;
       }
       else

@@ -390,6 +390,60 @@ k_fast_records(int64_t nnodes, int nd, const int32_t *__restrict__ nptr, const i
    }
 }
 
+// --- slot map of the damage-record stage of the fast kernel ----------------------------------
+// one CTA of kAsmR threads per tile, thread = rank: the distinct cells of the tile's visits get slot numbers
+// 0, 1, .. (shared hash table, first come first served: the numbering only decides where a record sits in the stage);
+// the slot goes into the tile's fast records and, as (tile << 10 | slot), into the cell's reference list cref.  Cells
+// beyond the capacity of the stage keep slot 0x3ff and are read from global memory by their visits.
+__global__ void __launch_bounds__(kAsmR)
+k_tile_cells(int64_t nnodes, int flevels, int cap, uint4 *__restrict__ frec, const uint8_t *__restrict__ tcnt,
+             uint32_t *__restrict__ cref, int32_t *__restrict__ crefcnt)
+{
+   constexpr int H = 2048;  // >= 2 x the visits of a tile (kAsmR rows x 15 levels)
+   __shared__ int32_t key[H], val[H];
+   __shared__ int next;
+   const int rank = threadIdx.x;
+   const int64_t n0 = (int64_t)blockIdx.x * kAsmR;
+   for (int t = rank; t < H; t += kAsmR) key[t] = -1;
+   if (rank == 0) next = 0;
+   __syncthreads();
+   const int cnt = n0 + rank < nnodes ? (int)tcnt[n0 + rank] : 0;
+   uint4 *rec = frec + ((int64_t)blockIdx.x * flevels) * kAsmR + rank;
+   for (int j = 0; j < cnt; ++j)
+   {
+      const int32_t e = (int32_t)(rec[(int64_t)j * kAsmR].x & 0x0fffffffu);
+      unsigned h = ((unsigned)e * 2654435761u) >> 21;  // 11 bits
+      for (;;)
+      {
+         const int32_t prev = atomicCAS(&key[h], -1, e);
+         if (prev == -1)
+         {  // this thread inserted the cell: it hands out the slot
+            const int s = atomicAdd(&next, 1);
+            const int v = s < cap ? s : 0x3ff;
+            if (cap > 0)
+            {
+               const int k = atomicAdd(&crefcnt[e], 1);  // a triangle has at most 6 nodes, hence at most 6 tiles
+               if (k < 6) cref[8 * (int64_t)e + k] = ((uint32_t)blockIdx.x << 10) | (uint32_t)v;
+            }
+            val[h] = v;
+            break;
+         }
+         if (prev == e) break;
+         h = (h + 1) & (H - 1);
+      }
+   }
+   __syncthreads();
+   for (int j = 0; j < cnt; ++j)
+   {
+      uint4 r = rec[(int64_t)j * kAsmR];
+      const int32_t e = (int32_t)(r.x & 0x0fffffffu);
+      unsigned h = ((unsigned)e * 2654435761u) >> 21;
+      while (key[h] != e) h = (h + 1) & (H - 1);
+      r.w = (r.w & 0x003fffffu) | ((uint32_t)val[h] << 22);
+      rec[(int64_t)j * kAsmR] = r;
+   }
+}
+
 __global__ void k_tile_hdr(int64_t nnodes, int64_t ntiles, const int32_t *__restrict__ nptr,
                            const int64_t *__restrict__ brp, const uint16_t *__restrict__ voff, TileHdr *__restrict__ hdr,
                            int32_t *__restrict__ maxcnt)
@@ -502,6 +556,10 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->bc_nodes);
    cudaFree(p->norm_partials);
    cudaFree(p->cellrec);
+   cudaFree(p->cref);
+   cudaFree(p->tdam);
+   cudaFree(p->tflag);
+   if (p->tflag_count) cudaFreeHost(p->tflag_count);
    cudaFree(p->celld);
    cudaFree(p->celld_count);
    delete p;
@@ -640,6 +698,38 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
    cudaFree(flags);
    cudaFree(tmpvis);
    *out = p;
+   return 0;
+}
+
+int femb::plan_tile_cells(femb200_plan *p, int cap, cudaStream_t st)
+{
+   FEMB_CHECK(p && p->frec && cap > 0 && cap < 0x3ff, "plan_tile_cells: plan without fast records or bad capacity %d", cap);
+   if (p->tdam_cap == cap) return 0;
+   std::lock_guard<std::mutex> lock(p->range_mtx);
+   if (p->tdam_cap == cap) return 0;
+   FEMB_CHECK(p->tdam_cap == 0, "plan_tile_cells: the stage capacity of a plan cannot change");
+   const int64_t ntiles = cdiv(p->nnodes, kAsmR);
+   // tile numbers are stored in 22 bits: larger plans run without the stage (every slot = 0x3ff, no references: the
+   // pre-pass flags nothing and every tile takes the damaged kernel)
+   const int use_cap = ntiles < (int64_t(1) << 22) ? cap : 0;
+   int32_t *crefcnt = nullptr;
+   FEMB_CUDA(cudaMalloc(&p->cref, sizeof(uint32_t) * 8 * (size_t)p->ncells));
+   FEMB_CUDA(cudaMalloc(&p->tdam, sizeof(int32_t) * (size_t)ntiles * (size_t)cap));
+   FEMB_CUDA(cudaMalloc(&p->tflag, (size_t)ntiles));
+   FEMB_CUDA(cudaHostAlloc(&p->tflag_count, sizeof(int), cudaHostAllocMapped));
+   *p->tflag_count = 0;
+   FEMB_CUDA(cudaHostGetDevicePointer(&p->tflag_count_dev, p->tflag_count, 0));
+   FEMB_CUDA(cudaMalloc(&crefcnt, sizeof(int32_t) * (size_t)p->ncells));
+   p->bytes += sizeof(uint32_t) * 8 * (size_t)p->ncells + sizeof(int32_t) * (size_t)ntiles * (size_t)cap;
+   FEMB_CUDA(cudaMemsetAsync(p->cref, 0xff, sizeof(uint32_t) * 8 * (size_t)p->ncells, st));
+   FEMB_CUDA(cudaMemsetAsync(p->tdam, 0xff, sizeof(int32_t) * (size_t)ntiles * (size_t)cap, st));
+   FEMB_CUDA(cudaMemsetAsync(crefcnt, 0, sizeof(int32_t) * (size_t)p->ncells, st));
+   k_tile_cells<<<(unsigned)ntiles, kAsmR, 0, st>>>(p->nnodes, p->flevels, use_cap, p->frec, p->tcnt, p->cref, crefcnt);
+   const cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(st);
+   cudaFree(crefcnt);
+   FEMB_CHECK(e1 == cudaSuccess && e2 == cudaSuccess, "plan_tile_cells: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+   p->tdam_cap = cap;
+   p->tdam_refs = use_cap > 0;
    return 0;
 }
 

@@ -74,7 +74,8 @@ __host__ __device__ __forceinline__ int swz_tma(int p) { return p ^ ((p >> 3) & 
 //   y   position of column 0 (bits 0-10) | column 1 (11-21) | first-touch bits of the five puts (22-26) | carry-out (27)
 //       | edge row (28) | local vertex number of the visit's vertex 1' (29-30)
 //   z   position of column 2 (0-10) | column 3 (11-21) | block degree of the node (22-28) | local vertex number of 2' (29-30)
-//   w   position of column 4 (0-10) | column 5 (11-21)
+//   w   position of column 4 (0-10) | column 5 (11-21) | slot of the cell in the tile's damage-record stage (22-31;
+//       0x3ff: not staged; written by plan_tile_cells on the first damaged assembly)
 // "Position" = 16-byte unit of the column in the tile image for scalar row 0, BEFORE the chunk swizzle (swz_tma above),
 // columns in rotated order as in VisitRec (t = 0..5); the row-1 thread adds the block degree (its row follows row 0 in
 // the CSR) and both apply the swizzle (three integer operations).  The five puts are positions 1..5 of a vertex row,
@@ -127,8 +128,17 @@ struct femb200_plan
    int32_t nbc = 0;
    double *norm_partials = nullptr;  // [3 nbc] scratch of femb200_assemble_matrix_norms
    size_t bytes = 0;
-   double *celld = nullptr;    // damaged cells: [ncells][2nd x 2nd] element tangents (row-major, interleaved dofs), lazily allocated
+   double *celld = nullptr;    // damage records of the cells (assemble.cu, cell_setup_damage_kernel), lazily allocated
    int32_t *celld_count = nullptr;  // [1 + ncells]: number of damaged cells, then their list
+   // damage-record stage of the fast kernel (plan_tile_cells, built on the first damaged assembly): every distinct cell
+   // of a tile has a slot in the tile's stage (number in the fast records); cref[cell] = up to 6 x (tile << 10 | slot),
+   // slot 0x3ff: visited but not staged, 0xffffffff: unused; tdam[tile][slot] = the cell when it is damaged in the current assembly, else -1
+   uint32_t *cref = nullptr;   // [ncells][8]
+   int32_t *tdam = nullptr;    // [ntiles][tdam_cap]
+   uint8_t *tflag = nullptr;   // [ntiles] 1: the tile has a damaged cell in the current assembly
+   int *tflag_count = nullptr, *tflag_count_dev = nullptr;  // host-mapped word: flagged tiles of the last damaged assembly
+   int32_t tdam_cap = 0;
+   bool tdam_refs = false;     // cref is filled (false: more than 2^22 tiles, no stage)
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
    // tensor maps of the value array the fast kernel last wrote (boxes of 8 lines and of 1 line of 128 bytes)
    alignas(64) unsigned char tmap8[128] = {}, tmap1[128] = {};
@@ -152,6 +162,9 @@ struct RowRange
    int64_t lo, hi;
    int32_t tile_max[2];
 };
+// builds p->cref / allocates p->tdam for a record stage of `cap` cells per tile and writes the slot numbers into the
+// fast records
+int plan_tile_cells(femb200_plan *p, int cap, cudaStream_t st);
 int plan_row_range(const femb200_plan *p, int64_t lo, int64_t hi, RowRange *out);
 int spmv_launch(const femb200_plan *p, const RowRange &rr, const double *d_values, const double *d_x, double *d_y,
                 const double *d_flag, double *d_dot_out, bool accumulate, cudaStream_t st);

@@ -57,6 +57,18 @@ def main():
                 f2 = fem.ElasticityForm(m, p.E, 0.3, d=d, u=u, variant=variant)
                 ms, mn = timed(lambda: fem.assemble_matrix(A, f2), k=5, w=2)
                 out[f"dmg_{label}_{name}"] = {"ms": ms, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+    if "p1" in what:
+        n1 = 2896
+        m1 = fm.jitter(fm.structured_triangles(n1, order=1), 0.2, seed=1234)
+        f1 = fem.ElasticityForm(m1, fm.young_per_cell(m1.ncells), 0.3)
+        A1 = fem.create_matrix(f1)
+        b1 = 8 * A1.nnz + m1.ncells * (3 * 4 + 8) + m1.nnodes * 16
+        for so in (1, 0):
+            A1.set_option("stream_out", so)
+            ms, mn = timed(lambda: fem.assemble_matrix(A1, f1))
+            out[f"assemble_p1_n{n1}_stream_out{so}"] = {"ms": ms, "min": mn, "frac": b1 / (ms * 1e-3) / 1e9 / PEAK,
+                                                        "gdofs": m1.ndofs / ms / 1e6, "nnz": A1.nnz}
+        del A1, f1, m1
     if "pa" in what:
         del A
         nq = 2048
