@@ -73,25 +73,41 @@ static EncodeTiledFn encode_tiled()
    return fn;
 }
 
-// fills plan->tmap8 / tmap1 for this value array; false when tensor bulk stores cannot be used (the caller falls back
-// to the store loop): no driver entry point, or a value array that does not start on a 128-byte line
+// Swizzle of the tile image (16-byte chunk index ^= 128-byte line index & mask): the TMA pattern that gives the fewest
+// bank conflicts for the staging stores of the element family (tools/swizzle_sim.py): P2 rows (19 / 9 blocks) want
+// SWIZZLE_128B (mask 7: 1.56 x the ideal wavefronts; 64B: 1.83, 32B: 2.97), P1 rows (7 blocks = 14 units per node, which
+// SWIZZLE_128B folds onto two bank groups: 3.3 x) want SWIZZLE_32B (mask 1: 1.0 x).
+template <int ET>
+__host__ __device__ constexpr uint32_t image_swizzle_mask()
+{
+   return ET == FEMB200_P1 ? 1u : 7u;
+}
+
+// fills the plan's tensor maps for this value array (boxes of 8 lines and of 1 line of 128 bytes; 64-line boxes were
+// measured 3 % slower on P2); false when tensor bulk
+// stores cannot be used (the caller falls back to the store loop): no driver entry point, or a value array that does
+// not start on a 128-byte line.  SWIZZLE_128B: the array as rows of 16 doubles; SWIZZLE_32B: as rows of 4 doubles (a
+// 128-byte line = 4 rows).
 static bool values_tensor_maps(femb200_plan *pm, double *d_values)
 {
    if (pm->tmap_values == d_values) return true;
    EncodeTiledFn enc = encode_tiled();
    if (!enc || (reinterpret_cast<uintptr_t>(d_values) & 127) != 0) return false;
+   const bool narrow = pm->etype == FEMB200_P1;                      // 32-byte rows
+   const cuuint32_t rowd = narrow ? 4u : 16u, rpl = narrow ? 4u : 1u;  // doubles per row, rows per 128-byte line
    const cuuint64_t lines = (cuuint64_t)((4 * pm->nnzb + 15) / 16);  // 128-byte lines of the value array
-   if (lines == 0 || lines >= ((cuuint64_t)1 << 31)) return false;   // line coordinates are 32-bit
-   const cuuint64_t gdim[2] = {16, lines};
-   const cuuint64_t gstride[1] = {128};
+   if (lines == 0 || lines * rpl >= ((cuuint64_t)1 << 31)) return false;  // row coordinates are 32-bit
+   const cuuint64_t gdim[2] = {rowd, lines * rpl};
+   const cuuint64_t gstride[1] = {rowd * 8};
    const cuuint32_t estride[2] = {1, 1};
    std::lock_guard<std::mutex> lock(pm->range_mtx);
    for (int k = 0; k < 2; ++k)
    {
-      const cuuint32_t box[2] = {16, k == 0 ? 8u : 1u};
-      CUtensorMap *tm = reinterpret_cast<CUtensorMap *>(k == 0 ? pm->tmap8 : pm->tmap1);
+      const cuuint32_t box[2] = {rowd, (k == 0 ? 8u : 1u) * rpl};
+      CUtensorMap *tm = reinterpret_cast<CUtensorMap *>(pm->tmap[k]);
       if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_values, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+              narrow ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       {
          pm->tmap_values = nullptr;
          return false;
@@ -571,11 +587,12 @@ __device__ __forceinline__ bool rec_first(const uint4 r, int b) { return (r.y >>
 __device__ __forceinline__ uint32_t rec_hdeg(const uint4 r, int h) { return h ? ((r.z >> 22) & 0x7fu) : 0u; }
 // byte offset in the tile image of column t (position t of the record) of scalar row h: position of row 0 + h deg,
 // chunk-swizzled inside its 128-byte line (swz_tma)
+template <uint32_t MASK>
 __device__ __forceinline__ uint32_t rec_off(const uint4 r, int t, uint32_t hdeg)
 {
    const uint32_t w = t < 2 ? r.y : (t < 4 ? r.z : r.w);
    const uint32_t p = (((t & 1) ? (w >> 11) : w) & 0x7ffu) + hdeg;
-   return (p ^ ((p >> 3) & 7u)) << 4;
+   return (p ^ ((p >> 3) & MASK)) << 4;
 }
 
 // Values of the row slice of one visit, positions t = 0..5 of the record's numbering (0', 1', 2', then
@@ -701,7 +718,7 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
    const uint32_t hdeg = rec_hdeg(raw, h);
    // t = position (address entry), b = index of the put (first-touch bit)
    auto put = [&](int t, int b, double k0, double k1) {
-      const uint32_t off = rec_off(raw, t, hdeg);
+      const uint32_t off = rec_off<image_swizzle_mask<ET>()>(raw, t, hdeg);
       const bool first = rec_first(raw, b);
       double2 *p = reinterpret_cast<double2 *>(sv + off);
       const double va = h ? k1 : k0, vb = h ? k0 : k1;
@@ -922,7 +939,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       }
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
-         const uint32_t off = rec_off(raw, rec_edge(raw) ? 3 : 0, rec_hdeg(raw, half));
+         const uint32_t off = rec_off<image_swizzle_mask<ET>()>(raw, rec_edge(raw) ? 3 : 0, rec_hdeg(raw, half));
          *reinterpret_cast<double2 *>(img + off) = make_double2(half ? C.dg[1] : C.dg[0], half ? C.dg[0] : C.dg[1]);
          nrm[1] = C.dg[0];  // the diagonal entry of this scalar row (exchanged frame: first of the pair)
       }
@@ -938,6 +955,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       // full lines [lf, ll) by the TMA unit (it reads shared memory itself and undoes the swizzle: no LDS, no STG,
       // no per-thread loop); the partial first / last line by 16 threads
       const int lf = shift ? 1 : 0, ll = end >> 3;
+      constexpr int RPL = ET == FEMB200_P1 ? 4 : 1;  // tensor rows per 128-byte line (SWIZZLE_32B: 32-byte rows)
       if (tid == 0)
       {
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the image was written by ordinary stores
@@ -945,18 +963,18 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          int l = lf;
          for (; l + 8 <= ll; l += 8)
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tm8), "r"(0),
-                         "r"(gl0 + l), "r"(smem_u32(sv + 8 * l))
+                         "r"((gl0 + l) * RPL), "r"(smem_u32(sv + 8 * l))
                          : "memory");
          for (; l < ll; ++l)
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tm1), "r"(0),
-                         "r"(gl0 + l), "r"(smem_u32(sv + 8 * l))
+                         "r"((gl0 + l) * RPL), "r"(smem_u32(sv + 8 * l))
                          : "memory");
          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       else if (tid >= 32 && tid < 48)
       {
          const int c = tid & 7, l = (tid < 40) ? 0 : ll;              // chunk, image line (first / last)
-         const int p = 8 * l + (c ^ (l & 7));
+         const int p = 8 * l + (c ^ (l & (int)image_swizzle_mask<ET>()));
          const bool mine = (tid < 40) ? (shift != 0 && ll > 0) : ((end & 7) != 0);
          if (mine && p >= shift && p < end) st_stream_d2(reinterpret_cast<double *>(dst + p), sv[8 * l + c]);
       }
@@ -967,7 +985,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       // store loop.  The swizzle key of position q is (q >> 3) & 7, which the stride of THREADS = 16 lines leaves
       // alone: per thread the swizzle is one constant XOR.
       static_assert(THREADS % 64 == 0, "the stream-out stride must keep (q >> 3) & 7");
-      const int kx = (tid >> 3) & 7;
+      const int kx = (tid >> 3) & (int)image_swizzle_mask<ET>();
       const int padded = (end + 7) & ~7;
       for (int q = tid; q < padded; q += THREADS)
       {
@@ -1369,7 +1387,7 @@ static int launch_fast_kernel(const femb200_plan *p, AsmArgs A, const ReduceScra
    femb200_plan *pm = const_cast<femb200_plan *>(p);
    const size_t smem = 16 * (size_t)A.stage_units + (DMG ? kDmgStageBytes + 16 + 4 * dmg_stage_cap<ET>() : 0);
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
-   const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap8), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap1);
+   const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap[0]), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap[1]);
    if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, NORMS, MINB>>(smem)) return rc;
    assemble_fast_kernel<ET, DMG, NORMS, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
    FEMB_LAUNCH_CHECK();
@@ -1408,7 +1426,7 @@ static int launch_assemble_fast_n(const femb200_plan *p, AsmArgs A, cudaStream_t
       A.tflag_want = 0;
       if (!split) return 0;
    }
-   if (int rc = launch_fast_kernel<ET, false, NORMS, 7>(p, A, red, d_norms, st)) return rc;
+   if (int rc = launch_fast_kernel<ET, false, NORMS, ET == FEMB200_P1 ? 8 : 7>(p, A, red, d_norms, st)) return rc;
    if (NORMS)
    {
       norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);

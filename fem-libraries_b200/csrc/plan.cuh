@@ -141,7 +141,7 @@ struct femb200_plan
    bool tdam_refs = false;     // cref is filled (false: more than 2^22 tiles, no stage)
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated
    // tensor maps of the value array the fast kernel last wrote (boxes of 8 lines and of 1 line of 128 bytes)
-   alignas(64) unsigned char tmap8[128] = {}, tmap1[128] = {};
+   alignas(64) unsigned char tmap[2][128] = {};
    const void *tmap_values = nullptr;
    int opt_stream_out = 0;  // 0 auto (tensor bulk stores when available), 1 LDS + STG loop
    // Kernel selection of this plan (femb200_plan_set_option): the fallback kernels that serve plans without
