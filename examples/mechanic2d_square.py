@@ -52,6 +52,7 @@ def fixture_msh(path: str) -> None:
 
 def run(msh_path: str, max_refine: int = 0, damaged_facet_tags=(4,), verbose: bool = True):
     mesh = fm.read_gmsh22(msh_path)                                          # 1
+    mesh = fm.refine_uniform(mesh, max_refine)                               # 1: the -r loop (M.cc:1037-1038, F.cc:166-185)
     E = fm.young_from_tags(mesh.meta["cell_tags"])                           # 4.1
     d0 = fm.damage_seed(mesh, list(damaged_facet_tags), max_dam=1.0)         # 4.2
     d = fem.DamageSmoother(mesh).smooth(d0, niter=8 * (max_refine + 1))
@@ -74,7 +75,8 @@ def run(msh_path: str, max_refine: int = 0, damaged_facet_tags=(4,), verbose: bo
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        out = run(sys.argv[1])
+        refine = int(os.environ.get("MAX_REFINE", "0"))                      # the reference's -r / MAX_REFINE
+        out = run(sys.argv[1], max_refine=refine)
         if len(sys.argv) > 2:                                                # IN_COMP (M.cc:1689-1725)
             l2x, l2y = compare.compare_disp_file(sys.argv[2], out["mesh"].x, out["u"].cpu().numpy())
             print(f"Error L2 x:{l2x}\nError L2 y:{l2y}")

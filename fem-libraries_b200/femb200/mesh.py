@@ -256,6 +256,46 @@ def read_gmsh22(path: str) -> Mesh:
     return Mesh(P1, x, tri, tri.copy(), 0, 0, meta)
 
 
+def refine_uniform(mesh: Mesh, levels: int = 1) -> Mesh:
+    """Uniform refinement of a P1 triangulation, `levels` times: the role of `pmesh->UniformRefinement(0)` in the
+    `-r` loop (M.cc:1037-1038) and of `plaza::refine` + `transfer_cell_meshtag` / `transfer_facet_meshtag`
+    (F.cc:166-185).  Every triangle (v0, v1, v2) becomes (v0, m01, m20), (m01, v1, m12), (m20, m12, v2) and
+    (m12, m20, m01) with m_ab the midpoint of edge (a, b): children keep the orientation of the parent, child c of
+    cell k is cell 4 k + c, the new vertices follow the old ones in the order of the sorted unique (min, max) edges.
+    Cell tags are inherited, every tagged facet becomes its two halves with the same tag (what the tag transfer of
+    both libraries does).  The vertex / cell NUMBERING the two libraries produce is theirs (un-vendored: unpinned);
+    the refined geometry, tags and everything computed from them do not depend on it."""
+    if mesh.etype != P1:
+        raise ValueError("refine_uniform: P1 triangulations only (refine before building the P2 space)")
+    for _ in range(int(levels)):
+        tri = mesh.xdofmap.astype(np.int64)
+        nv = mesh.nnodes
+        ea = np.stack([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]], axis=1).reshape(-1, 2)   # (3 ncells, 2)
+        key = np.minimum(ea[:, 0], ea[:, 1]) * nv + np.maximum(ea[:, 0], ea[:, 1])
+        ukey, inv = np.unique(key, return_inverse=True)
+        mid = (nv + inv).reshape(-1, 3)                                     # m01, m12, m20 of every cell
+        x = np.vstack([mesh.x, 0.5 * (mesh.x[ukey // nv] + mesh.x[ukey % nv])])
+        v0, v1, v2 = tri[:, 0], tri[:, 1], tri[:, 2]
+        m01, m12, m20 = mid[:, 0], mid[:, 1], mid[:, 2]
+        child = np.stack([np.stack([v0, m01, m20], 1), np.stack([m01, v1, m12], 1), np.stack([m20, m12, v2], 1),
+                          np.stack([m12, m20, m01], 1)], axis=1).reshape(-1, 3).astype(np.int32)
+        meta = dict(mesh.meta)
+        if "cell_tags" in meta:
+            meta["cell_tags"] = np.repeat(np.asarray(meta["cell_tags"]), 4)
+        if "facets" in meta and len(meta["facets"]):
+            f = np.asarray(meta["facets"], dtype=np.int64)
+            fk = np.minimum(f[:, 0], f[:, 1]) * nv + np.maximum(f[:, 0], f[:, 1])
+            pos = np.searchsorted(ukey, fk)
+            if np.any(pos >= len(ukey)) or np.any(ukey[np.minimum(pos, len(ukey) - 1)] != fk):
+                raise ValueError("refine_uniform: a tagged facet is not an edge of the triangulation")
+            fm_ = nv + pos
+            meta["facets"] = np.stack([np.stack([f[:, 0], fm_], 1), np.stack([fm_, f[:, 1]], 1)], axis=1).reshape(-1, 2).astype(np.int32)
+            meta["facet_tags"] = np.repeat(np.asarray(meta["facet_tags"]), 2)
+        meta["refined"] = int(meta.get("refined", 0)) + 1
+        mesh = Mesh(P1, np.ascontiguousarray(x), child, child.copy(), 0, 0, meta)
+    return mesh
+
+
 def young_from_tags(cell_tags: np.ndarray) -> np.ndarray:
     """E per cell from the physical tag: E_range[tag % 200] (M.cc:1580-1583, F.py:221)."""
     return young_table()[np.asarray(cell_tags, dtype=np.int64) % 200].copy()

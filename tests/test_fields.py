@@ -148,8 +148,9 @@ def test_gpu_strain_stress(kind, n):
 
 
 @pytest.mark.gpu
-def test_gpu_reference_driver_sequence(square, tmp_path):
-    """BASELINE config 1 end to end: the reference driver's stages (mesh file, materials by tag, damage seed +
+@pytest.mark.parametrize("refine", [0, 1])
+def test_gpu_reference_driver_sequence(square, tmp_path, refine):
+    """BASELINE config 1 end to end (refine = 1: with one level of the -r / MAX_REFINE loop, 8 (r + 1) smoothing sweeps): the reference driver's stages (mesh file, materials by tag, damage seed +
     smoothing, BCs, load, Newton, strain/stress) through examples/mechanic2d_square.py against the same
     sequence written with the oracle."""
     import importlib.util
@@ -159,10 +160,11 @@ def test_gpu_reference_driver_sequence(square, tmp_path):
     spec.loader.exec_module(ex)
     p = os.path.join(str(tmp_path), "square.msh")
     ex.fixture_msh(p)
-    out = ex.run(p, verbose=False)
+    out = ex.run(p, max_refine=refine, verbose=False)
     m = out["mesh"]
-    np.testing.assert_array_equal(m.x, square["x"])
-    d = oracle.smooth_damage(m.nnodes, m.xdofmap, out["d0"], niter=8)
+    np.testing.assert_array_equal(m.x[:len(square["x"])], square["x"])
+    assert m.ncells == len(square["tri"]) * 4 ** refine
+    d = oracle.smooth_damage(m.nnodes, m.xdofmap, out["d0"], niter=8 * (refine + 1))
     np.testing.assert_array_equal(out["d"].cpu().numpy(), d)
     assert (d > 0).sum() > (out["d0"] > 0).sum() and d.max() == 1.0 and d.min() >= 0.0
     want, it_o, norms_o = oracle.newton(m.etype, m.x, m.xdofmap, m.dofmap, out["E"], 0.3, out["bc"], out["g"], dnod=d,
@@ -226,3 +228,60 @@ def test_gmsh_reader_errors_and_sparse_ids(tmp_path):
         f.write("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n0\n$EndNodes\n$Elements\n0\n$EndElements\n")
     with pytest.raises(ValueError, match="2.x"):
         fm.read_gmsh22(r)
+
+
+def _areas(m):
+    t = m.xdofmap.astype(np.int64)
+    a, b, c = m.x[t[:, 0]], m.x[t[:, 1]], m.x[t[:, 2]]
+    return 0.5 * ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]))
+
+
+def test_refine_uniform_square_mesh(square, tmp_path):
+    """The -r / MAX_REFINE stage (M.cc:1037-1038, F.cc:166-185) on the reference's mesh: 4 children per cell, one new
+    vertex per edge, conforming, same area, orientation kept, cell and facet tags inherited; two levels."""
+    m0 = square_as_mesh(square, str(tmp_path))
+    area0 = _areas(m0)
+    m1 = fm.refine_uniform(m0)
+    tri = m0.xdofmap.astype(np.int64)
+    edges = np.unique(np.sort(np.stack([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]], 1).reshape(-1, 2), axis=1), axis=0)
+    assert m1.ncells == 4 * m0.ncells and m1.nnodes == m0.nnodes + len(edges)
+    a1 = _areas(m1)
+    np.testing.assert_allclose(a1.reshape(-1, 4).sum(1), area0, rtol=1e-13)
+    np.testing.assert_allclose(a1, np.repeat(area0 / 4, 4), rtol=1e-12)          # signed: orientation kept
+    np.testing.assert_array_equal(m1.meta["cell_tags"], np.repeat(m0.meta["cell_tags"], 4))
+    # conformity: every edge belongs to one (boundary) or two cells, and the tagged facets (boundary or interior
+    # lines) are edges of the refined triangulation
+    t1 = m1.xdofmap.astype(np.int64)
+    e1 = np.sort(np.stack([t1[:, [0, 1]], t1[:, [1, 2]], t1[:, [2, 0]]], 1).reshape(-1, 2), axis=1)
+    ue, cnt = np.unique(e1, axis=0, return_counts=True)
+    assert set(cnt.tolist()) <= {1, 2}
+    alle = {tuple(e) for e in ue.tolist()}
+    f1 = np.sort(m1.meta["facets"].astype(np.int64), axis=1)
+    assert len(f1) == 2 * len(m0.meta["facets"]) and all(tuple(e) in alle for e in f1.tolist())
+    np.testing.assert_array_equal(m1.meta["facet_tags"], np.repeat(m0.meta["facet_tags"], 2))
+    # the two halves of a facet meet at the midpoint of the parent facet
+    f0 = m0.meta["facets"].astype(np.int64)
+    np.testing.assert_allclose(m1.x[m1.meta["facets"][0::2, 1]], 0.5 * (m0.x[f0[:, 0]] + m0.x[f0[:, 1]]), rtol=0, atol=1e-15)
+    # the seeded damage of the refined mesh covers the seeded nodes of the coarse one plus the facet midpoints
+    d0, d1 = fm.damage_seed(m0, [4]), fm.damage_seed(m1, [4])
+    assert np.all(d1[:m0.nnodes] == d0) and d1.sum() == d0.sum() + (m0.meta["facet_tags"] == 4).sum()
+    m2 = fm.refine_uniform(m0, 2)
+    assert m2.ncells == 16 * m0.ncells and m2.meta["refined"] == 2
+    np.testing.assert_allclose(_areas(m2).sum(), area0.sum(), rtol=1e-13)
+    with pytest.raises(ValueError, match="P1"):
+        fm.refine_uniform(fm.structured_triangles(2, order=2))
+
+
+def test_refined_mesh_operator_properties(square, tmp_path):
+    """The oracle's tangent on the refined reference mesh: rigid-body modes in the null space, symmetric."""
+    m = fm.refine_uniform(square_as_mesh(square, str(tmp_path)))
+    E = fm.young_from_tags(m.meta["cell_tags"])
+    rp, ci = oracle.build_pattern(m.nnodes, m.dofmap)
+    K = oracle.assemble_matrix(m.etype, m.x, m.xdofmap, m.dofmap, E, 0.3, rp, ci)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((K, ci, rp), shape=(m.ndofs, m.ndofs))
+    fro = np.sqrt((K * K).sum())
+    x, y = m.x[:, 0], m.x[:, 1]
+    for mode in (np.stack([np.ones_like(x), 0 * x], 1), np.stack([0 * x, np.ones_like(x)], 1), np.stack([-y, x], 1)):
+        assert np.abs(A @ mode.ravel()).max() <= 1e-12 * fro
+    assert abs(A - A.T).max() <= 1e-12 * fro
