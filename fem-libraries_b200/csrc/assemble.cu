@@ -848,6 +848,11 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
       // count for this rank comes from the plan's byte table, loaded together with the first record.
       const bool pf = A.prefetch_tiles > 0 && (int64_t)tile + A.prefetch_tiles < ntiles;
       const int cfut = pf ? (int)A.tcnt[((int64_t)tile + A.prefetch_tiles) * R + rank] : 0;
+      // ... and half that distance ahead the records are in L2 already: the first record of that tile is read (one row
+      // thread per node) and the cell record of its first visit, the second link of that tile's chain, prefetched
+      const int ph = A.prefetch_tiles >> 1;  // measured: 0.683 -> 0.673 ms at n = 1448
+      uint32_t rfut = 0u;
+      if (ph > 0 && half == 0 && (int64_t)tile + ph < ntiles) rfut = reinterpret_cast<const uint32_t *>(rec + (int64_t)ph * A.flevels * LS)[0];
       raw1 = rec[0];
       raw2 = A.flevels > 1 ? rec[LS] : none;
       const int cnt = (int)(raw1.x >> 28);  // visits of this row (0: padding)
@@ -937,6 +942,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
                for (int l = 0; l < DLPR; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * l));
             }
       }
+      if ((rfut >> 28) != 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cellrec + 4 * (int64_t)(rfut & 0x0fffffffu)));
       if (cnt > 0)
       {  // the diagonal block, written once: position 0 of a vertex row, 3 of an edge row
          const uint32_t off = rec_off<image_swizzle_mask<ET>()>(raw, rec_edge(raw) ? 3 : 0, rec_hdeg(raw, half));
