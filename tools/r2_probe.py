@@ -42,12 +42,6 @@ def main():
         del Ae
     A = fem.create_matrix(form)
     abytes = 8 * A.nnz + m.ncells * 32 + m.nnodes * 16
-    if "pfx" in what:
-        for rep in range(3):
-            for pt in (1185, 1184):
-                A.set_option("prefetch_tiles", pt)
-                ms, mn = timed(lambda: fem.assemble_matrix(A, form))
-                out[f"assemble_p2_pf{pt}_{rep}"] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
     if "asm" in what:
         for so in (1, 0):
             A.set_option("stream_out", so)
