@@ -171,8 +171,6 @@ struct AsmArgs
    const double *celld;  // records of the damaged cells (see cell_setup_damage_kernel)
    const int32_t *tdam;  // [ntiles][dmg_stage_cap]: cell whose damage record goes to slot s of the tile's stage, -1: none
                          // (written by cell_setup_damage_kernel on every assembly through the plan's cell -> slot map)
-   const uint8_t *tflag;  // [ntiles] or null: 1 where a tile has a damaged cell in this assembly (pre-pass)
-   int tflag_want;        // with tflag: the CTA works only when its tile's flag equals this (two-kernel split)
    int variant;
    double *values;
    int stage_units;  // capacity of the staging image in 16-byte units (multiple of 8)
@@ -267,7 +265,7 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
                          const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
                          const double *__restrict__ dnod, const double *__restrict__ u, int variant,
                          double *__restrict__ rec, double *__restrict__ celld, const uint4 *__restrict__ cref,
-                         int32_t *__restrict__ tdam, uint8_t *__restrict__ tflag, int cap)
+                         int32_t *__restrict__ tdam, int cap, int *__restrict__ dmg_counter)
 {
    constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, RS = dmg_rec_doubles<ET>(), STRIDE = RS + 2;
    __shared__ __align__(16) double stage[4][32 * STRIDE];
@@ -311,18 +309,14 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
       }
    }
    if (active && cref)
-   {  // tell every tile that visits this cell (plan: tile << 10 | slot; slot 0x3ff: not staged) whether the slot
-      // holds a damaged cell this time, and flag the tiles with a damaged cell (tflag was cleared before the launch)
+   {  // tell every tile that stages this cell (plan: tile << 10 | slot; slot 0x3ff: visited, not staged) whether the slot
+      // holds a damaged cell this time
       const uint4 ra = cref[2 * e], rb = cref[2 * e + 1];
       const uint32_t ref[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
 #pragma unroll
       for (int k = 0; k < 6; ++k)
-         if (ref[k] != 0xffffffffu)
-         {
-            const uint32_t tile = ref[k] >> 10, sl = ref[k] & 0x3ffu;
-            if (sl != 0x3ffu) tdam[(int64_t)tile * cap + sl] = damaged ? (int32_t)e : -1;
-            if (damaged) tflag[tile] = 1;
-         }
+         if (ref[k] != 0xffffffffu && (ref[k] & 0x3ffu) != 0x3ffu)
+            tdam[(int64_t)(ref[k] >> 10) * cap + (ref[k] & 0x3ffu)] = damaged ? (int32_t)e : -1;
    }
    double *R = stage[warp] + lane * STRIDE;
    if (damaged)
@@ -363,6 +357,7 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
       for (int k = 4 + 6 * nq; k < RS; ++k) R[k] = 0.;
    }
    const unsigned mask = __ballot_sync(0xffffffffu, damaged);
+   if (lane == 0 && mask && dmg_counter) atomicAdd(dmg_counter, __popc(mask));  // damaged cells of this assembly
    __syncwarp();
    constexpr int UPC = RS / 2;  // 16-byte units per record
    for (int t = lane; t < 32 * UPC; t += 32)
@@ -777,7 +772,7 @@ __device__ __forceinline__ void emit_row_slice(const uint4 raw, unsigned char *s
 // depend on the block and thread index only: the dependent chain of a tile is record -> cell record
 // -> first put (the tile header is needed by the stream-out only), with the cell record one visit
 // and the record two visits ahead.
-template <int ET, bool DMG, bool NORMS, int MINB>
+template <int ET, bool DMG, bool NORMS, int MINB, bool STAGE = false>
 __global__ void __launch_bounds__(kAsmR * 2, MINB)
 assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_out, const __grid_constant__ CUtensorMap tm8,
                      const __grid_constant__ CUtensorMap tm1)
@@ -785,15 +780,10 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    constexpr int R = kAsmR, THREADS = kAsmR * 2;
    extern __shared__ __align__(1024) double2 sv[];
    const int tid = threadIdx.x;
-   // damaged assembly = two launches over the same grid: this kernel without the record stage (7 CTAs per SM) for the
-   // tiles that hold no damaged cell, the DMG variant for the others (tflag, written by the pre-pass); a CTA of the
-   // wrong kind leaves at once.  (CTAs striding over 8 tiles each, to save the launches of the idle ones, lost: 12 %
-   // slower at 100 % damaged cells, 5 % on the linear path.)
-   if (A.tflag && (int)A.tflag[blockIdx.x] != A.tflag_want) return;
    const int64_t tile = blockIdx.x, ntiles = gridDim.x;
    unsigned char *dstage = reinterpret_cast<unsigned char *>(sv) + 16 * (size_t)A.stage_units;
    uint64_t *dbar = reinterpret_cast<uint64_t *>(dstage + kDmgStageBytes);
-   if (DMG)
+   if (STAGE)
    {
       if (tid == 0)
       {
@@ -816,14 +806,14 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    // (slot, unit of the record), completion on the mbarrier.  The records of the tile `prefetch_tiles` ahead are
    // pulled into L2 (thread = (slot, 128-byte line)), its tdam row was prefetched by the tile that far behind.
    constexpr int DCAP = dmg_stage_cap<ET>(), DUPR = dmg_rec_bytes<ET>() / 16, DRS = dmg_rec_doubles<ET>();
-   constexpr int DNR = DMG ? (DCAP + THREADS - 1) / THREADS : 1;                 // row entries per thread
-   constexpr int DNF = DMG ? (DCAP * DUPR + THREADS - 1) / THREADS : 1;          // fill units per thread
+   constexpr int DNR = STAGE ? (DCAP + THREADS - 1) / THREADS : 1;                 // row entries per thread
+   constexpr int DNF = STAGE ? (DCAP * DUPR + THREADS - 1) / THREADS : 1;          // fill units per thread
    constexpr int DLPR = (DRS * 8 + 127) / 128;                                   // 128-byte lines per record
-   const bool dstg = DMG && A.tdam != nullptr;
+   const bool dstg = STAGE && A.tdam != nullptr;
    const bool dpf = dstg && A.prefetch_tiles > 0 && (int64_t)tile + A.prefetch_tiles < ntiles;
    int32_t *drow = reinterpret_cast<int32_t *>(dstage + kDmgStageBytes + 16);    // [DCAP] this tile's row of tdam
    int32_t rcell[DNR], fcell[DNR];
-   if (DMG)
+   if (STAGE)
    {
 #pragma unroll
       for (int k = 0; k < DNR; ++k)
@@ -833,7 +823,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          fcell[k] = (dpf && i < DCAP) ? A.tdam[((int64_t)tile + A.prefetch_tiles) * DCAP + i] : -1;
       }
    }
-   bool staged = !DMG;  // DMG: whether this thread has waited for the record stage
+   bool staged = !STAGE;  // STAGE: whether this thread has waited for the record stage
    {
       const uint4 *rec = A.frec + ((int64_t)tile * A.flevels * R + rank);  // shared by the node's two row threads
       constexpr int LS = R;  // records per level
@@ -864,7 +854,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             if (j < cfut) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + j * LS));
       }
       if (0 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
-      if (DMG)
+      if (STAGE)
       {  // issue the stage fill behind the first loads of the visit pipeline: the row goes through shared memory (one
          // global load per thread instead of one per fill unit; measured 4 % faster than per-thread row loads)
 #pragma unroll
@@ -891,14 +881,14 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          raw = raw1, geo = geo1, raw1 = raw2;
          if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
          raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
-         // damaged cell: NaN marker; its damage record is in the tile's stage (slot in the record), or, where the tile
-         // has more cells than the stage holds (slot 0x3ff), at celld[cell]
+         // damaged cell: NaN marker; STAGE: its damage record is in the tile's stage (slot in the record), or, where the
+         // tile has more cells than the stage holds (slot 0x3ff) and in the kernel without a stage, at celld[cell]
          const bool dam = DMG && geo.g1x != geo.g1x;
          const double *drec = nullptr;
          if (dam)
          {
             if (!staged) mbar_wait(dbar, 0), staged = true;
-            const uint32_t slot = raw.w >> 22;
+            const uint32_t slot = STAGE ? raw.w >> 22 : 0x3ffu;
             drec = slot != 0x3ffu ? reinterpret_cast<const double *>(dstage + slot * dmg_rec_bytes<ET>())
                                   : A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
          }
@@ -931,7 +921,7 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             }
          }
       }
-      if (DMG)
+      if (STAGE)
       {  // L2 prefetch of the damage records of the future tile
 #pragma unroll
          for (int k = 0; k < DNR; ++k)
@@ -1014,24 +1004,12 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
    }
 }
 
-// number of flagged tiles of a damaged assembly -> host-mapped word (read, without synchronisation, by the NEXT damaged
-// assembly on this plan to choose between one launch and two)
-__global__ void __launch_bounds__(1024) tile_flag_count_kernel(const uint8_t *__restrict__ tflag, int64_t ntiles, int *__restrict__ out)
+// damaged cells of this assembly (counted by the pre-pass) -> host-mapped word, read without synchronisation by the
+// NEXT damaged assembly on the plan to choose the kernel; the counter is cleared for the next pre-pass
+__global__ void dmg_count_publish_kernel(int *__restrict__ counter, int *__restrict__ out)
 {
-   __shared__ int sh[32];
-   int c = 0;
-   for (int64_t i = threadIdx.x; i < ntiles; i += 1024) c += tflag[i];
-#pragma unroll
-   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
-   __syncthreads();
-   if (threadIdx.x < 32)
-   {
-      c = sh[threadIdx.x];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (threadIdx.x == 0) *out = c;
-   }
+   *out = *counter;
+   *counter = 0;
 }
 
 __global__ void __launch_bounds__(1024) norms_sum_kernel(const double *__restrict__ partials, unsigned n, double *__restrict__ out)
@@ -1387,22 +1365,23 @@ static int launch_assemble_ch(const femb200_plan *p, AsmArgs A, cudaStream_t st)
    return 0;
 }
 
-template <int ET, bool DMG, bool NORMS, int MINB>
+template <int ET, bool DMG, bool NORMS, int MINB, bool STAGE>
 static int launch_fast_kernel(const femb200_plan *p, AsmArgs A, const ReduceScratch &red, double *d_norms, cudaStream_t st)
 {
    femb200_plan *pm = const_cast<femb200_plan *>(p);
-   const size_t smem = 16 * (size_t)A.stage_units + (DMG ? kDmgStageBytes + 16 + 4 * dmg_stage_cap<ET>() : 0);
+   const size_t smem = 16 * (size_t)A.stage_units + (STAGE ? kDmgStageBytes + 16 + 4 * dmg_stage_cap<ET>() : 0);
    const unsigned grid = (unsigned)cdiv(p->nnodes, kAsmR);
    const CUtensorMap &tm8 = *reinterpret_cast<const CUtensorMap *>(pm->tmap[0]), &tm1 = *reinterpret_cast<const CUtensorMap *>(pm->tmap[1]);
-   if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, NORMS, MINB>>(smem)) return rc;
-   assemble_fast_kernel<ET, DMG, NORMS, MINB><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
+   if (int rc = ensure_dynamic_smem<assemble_fast_kernel<ET, DMG, NORMS, MINB, STAGE>>(smem)) return rc;
+   assemble_fast_kernel<ET, DMG, NORMS, MINB, STAGE><<<grid, kAsmR * 2, smem, st>>>(A, red, d_norms, tm8, tm1);
    FEMB_LAUNCH_CHECK();
    return 0;
 }
 
-// DMG: the pre-pass has flagged the tiles with a damaged cell; those go through the variant that holds the damage-record
-// stage next to the image (P2: 55 KB, P1: 40 KB per CTA, compiled for the 4 / 5 CTAs per SM that fit), the others
-// through the plain kernel at 7 CTAs per SM
+// DMG: with A.tdam (the pre-pass wrote the tiles' rows of damaged cells) the variant that stages the damage records in
+// shared memory (P2: 55 KB per CTA, compiled for the 4 CTAs per SM that fit; P1: 40 KB, 5 CTAs), else the variant whose
+// visits read the records from global memory (5 CTAs per SM): faster while few cells are damaged.  assemble_matrix_impl
+// chooses.
 template <int ET, bool DMG, bool NORMS>
 static int launch_assemble_fast_n(const femb200_plan *p, AsmArgs A, cudaStream_t st, double *d_norms)
 {
@@ -1416,23 +1395,12 @@ static int launch_assemble_fast_n(const femb200_plan *p, AsmArgs A, cudaStream_t
    ReduceScratch red{nullptr, nullptr};
    if (NORMS)
       if (int rc = reduce_scratch(grid, st, &red, 2)) return rc;
-   A.tflag = nullptr, A.tflag_want = 0;
-   if (DMG)
-   {
-      A.tdam = pm->tdam;  // built by plan_tile_cells, written by the pre-pass
-      // One launch or two.  Two: the DMG variant for the flagged tiles, the plain kernel (7 CTAs per SM) for the others;
-      // the CTAs of the wrong kind leave at once, but 131 K idle CTAs still cost ~0.1 ms.  When most tiles were flagged
-      // in the PREVIOUS damaged assembly on this plan (count left in host-mapped memory, read without synchronisation:
-      // the choice affects speed only, either way every tile is assembled) the DMG variant takes all tiles.
-      const int64_t ntiles = grid;
-      const bool split = pm->tflag_count && (int64_t)*static_cast<volatile int *>(pm->tflag_count) * 4 < ntiles * 3;
-      tile_flag_count_kernel<<<1, 1024, 0, st>>>(pm->tflag, ntiles, pm->tflag_count_dev);
-      if (split) A.tflag = pm->tflag, A.tflag_want = 1;
-      if (int rc = launch_fast_kernel<ET, true, NORMS, ET == FEMB200_P1 ? 5 : 4>(p, A, red, d_norms, st)) return rc;
-      A.tflag_want = 0;
-      if (!split) return 0;
-   }
-   if (int rc = launch_fast_kernel<ET, false, NORMS, ET == FEMB200_P1 ? 8 : 7>(p, A, red, d_norms, st)) return rc;
+   int rc;
+   if (DMG && A.tdam)
+      rc = launch_fast_kernel<ET, DMG, NORMS, DMG ? (ET == FEMB200_P1 ? 5 : 4) : 7, DMG>(p, A, red, d_norms, st);
+   else
+      rc = launch_fast_kernel<ET, DMG, NORMS, DMG ? 5 : (ET == FEMB200_P1 ? 8 : 7), false>(p, A, red, d_norms, st);
+   if (rc) return rc;
    if (NORMS)
    {
       norms_sum_kernel<<<1, 1024, 0, st>>>(red.partials, grid, d_norms);
@@ -1483,7 +1451,7 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
    // triangles take the per-cell pre-pass + fast kernel (damaged cells through their own per-cell
    // tangent records); Q2 and plans with assembly_path = 2 take the per-quadrature-point kernel
    const bool linear = (p->etype != FEMB200_Q2) && p->opt_assembly_path != 2;
-   A.cellrec = nullptr, A.celld = nullptr, A.tdam = nullptr, A.tflag = nullptr, A.tflag_want = 0;
+   A.cellrec = nullptr, A.celld = nullptr, A.tdam = nullptr;
    if (linear)
    {
       femb200_plan *pm = const_cast<femb200_plan *>(p);  // lazily allocated scratch of the plan
@@ -1509,20 +1477,43 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
                pm->bytes += sizeof(double) * W * (size_t)p->ncells;
             }
          }
-         // the fast kernel stages the damage records of a tile's cells in shared memory: slot map (plan, built on
-         // the first damaged assembly) + the per-assembly row of damaged cells the pre-pass writes through it
+         // The fast kernel can stage the damage records of a tile's cells in shared memory (slot map of the plan, built
+         // when first needed, + the per-assembly rows of damaged cells the pre-pass writes through it): that wins once
+         // about 40 % of the cells are damaged (n = 1448: 1.56 against 1.65 ms at 50 %, 1.89 against 2.39 ms at 100 %)
+         // and loses below (1.30 against 1.09 ms at 10 %: 4 CTAs per SM instead of 5).  The choice follows the share
+         // of damaged cells of the PREVIOUS damaged assembly on this plan, which the pre-pass leaves in host-mapped
+         // memory (read here without synchronisation): it affects speed only, both kernels assemble the same matrix.
          const bool fastk = p->frec && p->opt_assembly_path != 1;
          const int cap = p->etype == FEMB200_P1 ? dmg_stage_cap<FEMB200_P1>() : dmg_stage_cap<FEMB200_P2>();
-         if (fastk)
+         if (!pm->dmg_count)
+         {
+            std::lock_guard<std::mutex> lock(pm->range_mtx);
+            if (!pm->dmg_count)
+            {
+               int *h = nullptr;
+               FEMB_CUDA(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
+               *h = 0;
+               FEMB_CUDA(cudaHostGetDevicePointer(&pm->dmg_count_dev, h, 0));
+               FEMB_CUDA(cudaMalloc(&pm->dmg_counter, sizeof(int)));
+               FEMB_CUDA(cudaMemset(pm->dmg_counter, 0, sizeof(int)));
+               pm->dmg_count = h;
+            }
+         }
+         const int64_t last = *static_cast<volatile int *>(pm->dmg_count);
+         const bool staged = fastk && (p->opt_dmg_stage == 1 || (p->opt_dmg_stage == 0 && last * 5 >= p->ncells * 2));
+         if (staged)
             if (int rc = plan_tile_cells(pm, cap, st)) return rc;
-         const uint4 *cref = (fastk && pm->tdam_refs) ? reinterpret_cast<const uint4 *>(pm->cref) : nullptr;
-         if (fastk) FEMB_CUDA(cudaMemsetAsync(pm->tflag, cref ? 0 : 1, (size_t)cdiv(p->nnodes, kAsmR), st));
+         const uint4 *cref = (staged && pm->tdam_refs) ? reinterpret_cast<const uint4 *>(pm->cref) : nullptr;
          if (p->etype == FEMB200_P1)
             cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
-                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, pm->tflag, cap);
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, cap,
+                                                                       pm->dmg_counter);
          else
             cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
-                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, pm->tflag, cap);
+                                                                       d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, cap,
+                                                                       pm->dmg_counter);
+         dmg_count_publish_kernel<<<1, 1, 0, st>>>(pm->dmg_counter, pm->dmg_count_dev);
+         A.tdam = staged ? pm->tdam : nullptr;
          A.celld = pm->celld;
       }
       else

@@ -558,8 +558,8 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->cellrec);
    cudaFree(p->cref);
    cudaFree(p->tdam);
-   cudaFree(p->tflag);
-   if (p->tflag_count) cudaFreeHost(p->tflag_count);
+   cudaFree(p->dmg_counter);
+   if (p->dmg_count) cudaFreeHost(p->dmg_count);
    cudaFree(p->celld);
    cudaFree(p->celld_count);
    delete p;
@@ -709,16 +709,11 @@ int femb::plan_tile_cells(femb200_plan *p, int cap, cudaStream_t st)
    if (p->tdam_cap == cap) return 0;
    FEMB_CHECK(p->tdam_cap == 0, "plan_tile_cells: the stage capacity of a plan cannot change");
    const int64_t ntiles = cdiv(p->nnodes, kAsmR);
-   // tile numbers are stored in 22 bits: larger plans run without the stage (every slot = 0x3ff, no references: the
-   // pre-pass flags nothing and every tile takes the damaged kernel)
+   // tile numbers are stored in 22 bits: larger plans run without the stage (every slot = 0x3ff, no references)
    const int use_cap = ntiles < (int64_t(1) << 22) ? cap : 0;
    int32_t *crefcnt = nullptr;
    FEMB_CUDA(cudaMalloc(&p->cref, sizeof(uint32_t) * 8 * (size_t)p->ncells));
    FEMB_CUDA(cudaMalloc(&p->tdam, sizeof(int32_t) * (size_t)ntiles * (size_t)cap));
-   FEMB_CUDA(cudaMalloc(&p->tflag, (size_t)ntiles));
-   FEMB_CUDA(cudaHostAlloc(&p->tflag_count, sizeof(int), cudaHostAllocMapped));
-   *p->tflag_count = 0;
-   FEMB_CUDA(cudaHostGetDevicePointer(&p->tflag_count_dev, p->tflag_count, 0));
    FEMB_CUDA(cudaMalloc(&crefcnt, sizeof(int32_t) * (size_t)p->ncells));
    p->bytes += sizeof(uint32_t) * 8 * (size_t)p->ncells + sizeof(int32_t) * (size_t)ntiles * (size_t)cap;
    FEMB_CUDA(cudaMemsetAsync(p->cref, 0xff, sizeof(uint32_t) * 8 * (size_t)p->ncells, st));
@@ -860,6 +855,11 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
    {
       FEMB_CHECK(value >= 0 && value <= 2, "plan_set_option: assembly_path must be 0 (auto), 1 (visit records) or 2 (per point)");
       p->opt_assembly_path = value;
+   }
+   else if (!strcmp(key, "damage_stage"))
+   {
+      FEMB_CHECK(value >= 0 && value <= 2, "plan_set_option: damage_stage must be 0 (auto), 1 (always) or 2 (never)");
+      p->opt_dmg_stage = value;
    }
    else if (!strcmp(key, "spmv_path"))
    {

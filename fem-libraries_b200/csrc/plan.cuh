@@ -135,8 +135,9 @@ struct femb200_plan
    // slot 0x3ff: visited but not staged, 0xffffffff: unused; tdam[tile][slot] = the cell when it is damaged in the current assembly, else -1
    uint32_t *cref = nullptr;   // [ncells][8]
    int32_t *tdam = nullptr;    // [ntiles][tdam_cap]
-   uint8_t *tflag = nullptr;   // [ntiles] 1: the tile has a damaged cell in the current assembly
-   int *tflag_count = nullptr, *tflag_count_dev = nullptr;  // host-mapped word: flagged tiles of the last damaged assembly
+   // damaged cells of the last damaged assembly: device counter (pre-pass), host-mapped word (and its device address)
+   int *dmg_counter = nullptr, *dmg_count = nullptr, *dmg_count_dev = nullptr;
+   int opt_dmg_stage = 0;      // 0 auto (by the share of damaged cells of the previous assembly), 1 always, 2 never
    int32_t tdam_cap = 0;
    bool tdam_refs = false;     // cref is filled (false: more than 2^22 tiles, no stage)
    double *cellrec = nullptr;  // [ncells][4] per-cell sqrt(|T| E) (grad l1, grad l2), fast path, lazily allocated

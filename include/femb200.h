@@ -248,7 +248,10 @@ int femb200_scatter_rows(int64_t n, int width, const int32_t *d_idx, const doubl
  * from the plan, no environment variables.
  *   "assembly_path"  0 auto | 1 visit-record kernel | 2 per-quadrature-point kernel
  *   "spmv_path"      0 auto (bulk-copy staged) | 1 direct kernel
- *   "prefetch_tiles" record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count, 0: off) */
+ *   "prefetch_tiles" record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count, 0: off)
+ *   "stream_out"     0 auto (tensor bulk stores of the finished tile) | 1 store loop
+ *   "damage_stage"   damaged reassembly: 0 auto (damage records staged per tile in shared memory once 40 % of the
+ *                    cells were damaged in the previous assembly on the plan) | 1 always | 2 never */
 int femb200_plan_set_option(femb200_plan *plan, const char *key, int value);
 
 /* ------------------------------------------------------------------------

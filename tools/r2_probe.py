@@ -55,8 +55,10 @@ def main():
             d = torch.clamp(1.0 - (xy[:, 1] - 0.5 - 0.1 * torch.sin(6.0 * xy[:, 0])).abs() / hw, min=0.0, max=0.95)
             for variant, name in ((0, "closed"), (1, "ad")):
                 f2 = fem.ElasticityForm(m, p.E, 0.3, d=d, u=u, variant=variant)
-                ms, mn = timed(lambda: fem.assemble_matrix(A, f2), k=5, w=2)
-                out[f"dmg_{label}_{name}"] = {"ms": ms, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+                for stg in ((0, 1, 2) if "stage" in what else (0,)):
+                    A.set_option("damage_stage", stg)
+                    ms, mn = timed(lambda: fem.assemble_matrix(A, f2), k=5, w=2)
+                    out[f"dmg_{label}_{name}" + (f"_stage{stg}" if "stage" in what else "")] = {"ms": ms, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
     if "p1" in what:
         n1 = 2896
         m1 = fm.jitter(fm.structured_triangles(n1, order=1), 0.2, seed=1234)
