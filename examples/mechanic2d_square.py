@@ -51,7 +51,8 @@ def fixture_msh(path: str) -> None:
 
 
 def run(msh_path: str, max_refine: int = 0, damaged_facet_tags=(4,), verbose: bool = True):
-    mesh = fm.read_gmsh22(msh_path)                                          # 1
+    # 1: the MFEM driver reads the Gmsh file (M.cc:1017-1020), the FEniCSx driver its XDMF conversion (F.cc:155-163)
+    mesh = fm.read_xdmf(msh_path) if msh_path.endswith(".xdmf") else fm.read_gmsh22(msh_path)
     mesh = fm.refine_uniform(mesh, max_refine)                               # 1: the -r loop (M.cc:1037-1038, F.cc:166-185)
     E = fm.young_from_tags(mesh.meta["cell_tags"])                           # 4.1
     d0 = fm.damage_seed(mesh, list(damaged_facet_tags), max_dam=1.0)         # 4.2

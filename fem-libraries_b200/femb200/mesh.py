@@ -308,3 +308,124 @@ def damage_seed(mesh: Mesh, facet_tags, max_dam: float = 1.0) -> np.ndarray:
     sel = np.isin(mesh.meta["facet_tags"], np.asarray(facet_tags))
     d[np.unique(mesh.meta["facets"][sel])] = max_dam
     return d
+
+
+# ---- XDMF (the FEniCSx driver's mesh file) ---------------------------------------------------------------------------
+def _xdmf_item(node, base: str, dtype):
+    """One <DataItem>: Format="XML" (numbers inline) is read here; Format="HDF" (what dolfinx writes by default,
+    "file.h5:/path") needs h5py, which this image does not ship: it is used when importable, else the error says so."""
+    import os
+    item = node if node.tag == "DataItem" else node.find("DataItem")
+    if item is None:
+        raise ValueError("read_xdmf: element without a DataItem")
+    dims = [int(t) for t in item.get("Dimensions", "").split()]
+    fmt = item.get("Format", "XML").upper()
+    if fmt == "XML":
+        a = np.array((item.text or "").split(), dtype=dtype)
+    elif fmt == "HDF":
+        try:
+            import h5py
+        except ImportError as e:
+            raise ValueError("read_xdmf: this file keeps its arrays in HDF5 and h5py is not installed; convert it with "
+                             "write_xdmf (inline XML data) or read the Gmsh 2.2 source with read_gmsh22") from e
+        fname, path = (item.text or "").strip().split(":", 1)
+        with h5py.File(os.path.join(base, fname), "r") as h:
+            a = np.asarray(h[path], dtype=dtype)
+    else:
+        raise ValueError(f"read_xdmf: DataItem Format={fmt!r} is not supported")
+    return a.reshape(dims) if dims else a
+
+
+def read_xdmf(path: str, name: str | None = None) -> Mesh:
+    """XDMF reader for the layout the FEniCSx driver reads (F.cc:155-163: `read_mesh(tria, ..., name)` +
+    `read_meshtags(mesh, name + "_cells")` + `read_meshtags(mesh, name + "_facets")`, written by
+    gmsh_to_xdmf_neper_dam.py:1-16): grid `name` with a Triangle topology and an XY / XYZ geometry, grid
+    `name_cells` = cell topology + one cell-centred attribute, grid `name_facets` = 2-node PolyLine topology + one
+    attribute.  `name` defaults to the first grid of the file.  Returns the same Mesh (P1, meta cell_tags / facets /
+    facet_tags) as read_gmsh22.  Mesh-tag grids list their entities by vertex numbers: cell tags are matched to the
+    mesh cells by their sorted vertex triple, as `read_meshtags` does."""
+    import os
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    base = os.path.dirname(os.path.abspath(path))
+    grids = {g.get("Name"): g for g in root.iter("Grid")}
+    if not grids:
+        raise ValueError(f"{path}: no Grid")
+    if name is None:
+        name = next(iter(grids))
+    if name not in grids:
+        raise ValueError(f"{path}: no grid named {name!r} (has {sorted(grids)})")
+    g = grids[name]
+    topo, geom = g.find("Topology"), g.find("Geometry")
+    if topo is None or geom is None:
+        raise ValueError(f"{path}: grid {name!r} needs a Topology and a Geometry")
+    if topo.get("TopologyType", "").lower() != "triangle":
+        raise ValueError(f"{path}: only Triangle topologies are supported, got {topo.get('TopologyType')!r}")
+    tri = _xdmf_item(topo, base, np.int64).reshape(-1, 3)
+    x = _xdmf_item(geom, base, np.float64)
+    x = np.ascontiguousarray(x.reshape(-1, 3 if geom.get("GeometryType", "XY").upper() == "XYZ" else 2)[:, :2])
+    if tri.size and (tri.min() < 0 or tri.max() >= len(x)):
+        raise ValueError(f"{path}: a cell refers to a vertex outside the geometry")
+    meta = {"kind": "xdmf", "cell_tags": np.zeros(len(tri), dtype=np.int32), "facets": np.zeros((0, 2), dtype=np.int32),
+            "facet_tags": np.zeros(0, dtype=np.int32)}
+
+    def tags(gname, npe):
+        tg = grids.get(gname)
+        if tg is None:
+            return None
+        ent = _xdmf_item(tg.find("Topology"), base, np.int64).reshape(-1, npe)
+        att = tg.find("Attribute")
+        val = _xdmf_item(att, base, np.float64).reshape(-1).astype(np.int32)
+        if len(val) != len(ent):
+            raise ValueError(f"{path}: grid {gname!r} has {len(ent)} entities and {len(val)} values")
+        return ent, val
+
+    ct = tags(name + "_cells", 3)
+    if ct is not None:
+        nv = len(x)
+        key = lambda t: (np.sort(t, axis=1) * np.array([nv * nv, nv, 1], dtype=np.int64)).sum(axis=1)
+        kc = key(tri)
+        order = np.argsort(kc)
+        pos = np.searchsorted(kc[order], key(ct[0]))
+        if np.any(pos >= len(kc)) or np.any(kc[order][np.minimum(pos, len(kc) - 1)] != key(ct[0])):
+            raise ValueError(f"{path}: a tagged cell is not a cell of the mesh")
+        meta["cell_tags"][order[pos]] = ct[1]
+    ft = tags(name + "_facets", 2)
+    if ft is not None:
+        meta["facets"], meta["facet_tags"] = ft[0].astype(np.int32), ft[1]
+    tri = tri.astype(np.int32)
+    return Mesh(P1, x, tri, tri.copy(), 0, 0, meta)
+
+
+def write_xdmf(path: str, mesh: Mesh, name: str = "mesh") -> None:
+    """Writes a P1 triangulation with its cell and facet tags in the layout read_xdmf / the FEniCSx driver reads, arrays
+    inline (Format="XML", repr-exact floats): the role of gmsh_to_xdmf_neper_dam.py without the HDF5 side file."""
+    tri, x = np.asarray(mesh.xdofmap), np.asarray(mesh.x)
+
+    def item(a, fmtf):
+        a = np.asarray(a)
+        dims = " ".join(str(d) for d in a.shape)
+        num = "Float" if a.dtype.kind == "f" else "Int"
+        body = "\n".join(" ".join(fmtf(v) for v in row) for row in a.reshape(len(a), -1))
+        return f'<DataItem Dimensions="{dims}" NumberType="{num}" Precision="8" Format="XML">\n{body}\n</DataItem>'
+
+    fi, ff = (lambda v: str(int(v))), (lambda v: repr(float(v)))
+    geo = f'<Geometry GeometryType="XY">{item(x, ff)}</Geometry>'
+    out = ['<?xml version="1.0"?>', '<Xdmf Version="3.0"><Domain>',
+           f'<Grid Name="{name}" GridType="Uniform"><Topology TopologyType="Triangle" NumberOfElements="{len(tri)}" '
+           f'NodesPerElement="3">{item(tri, fi)}</Topology>{geo}</Grid>']
+    ctag = mesh.meta.get("cell_tags")
+    if ctag is not None:
+        out.append(f'<Grid Name="{name}_cells" GridType="Uniform"><Topology TopologyType="Triangle" '
+                   f'NumberOfElements="{len(tri)}" NodesPerElement="3">{item(tri, fi)}</Topology>{geo}'
+                   f'<Attribute Name="{name}_cells" AttributeType="Scalar" Center="Cell">'
+                   f'{item(np.asarray(ctag).reshape(-1, 1), fi)}</Attribute></Grid>')
+    fac = mesh.meta.get("facets")
+    if fac is not None and len(fac):
+        out.append(f'<Grid Name="{name}_facets" GridType="Uniform"><Topology TopologyType="PolyLine" '
+                   f'NumberOfElements="{len(fac)}" NodesPerElement="2">{item(fac, fi)}</Topology>{geo}'
+                   f'<Attribute Name="{name}_facets" AttributeType="Scalar" Center="Cell">'
+                   f'{item(np.asarray(mesh.meta["facet_tags"]).reshape(-1, 1), fi)}</Attribute></Grid>')
+    out.append("</Domain></Xdmf>")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")

@@ -230,6 +230,65 @@ def test_gmsh_reader_errors_and_sparse_ids(tmp_path):
         fm.read_gmsh22(r)
 
 
+def test_xdmf_roundtrip_and_errors(square, tmp_path):
+    """XDMF ingestion of the FEniCSx driver (F.cc:155-163; gmsh_to_xdmf_neper_dam.py): the reference's mesh written in
+    the mesh + `_cells` + `_facets` grid layout and read back (geometry bit for bit, cell tags matched by vertex
+    triple even when the tag grid lists the cells in another order and orientation), HDF5 data items refused with a
+    message when h5py is absent, unknown grid / topology errors."""
+    m = square_as_mesh(square, str(tmp_path))
+    p = os.path.join(str(tmp_path), "square.xdmf")
+    fm.write_xdmf(p, m, "neper_dam")
+    r = fm.read_xdmf(p, "neper_dam")
+    assert r.etype == fm.P1 and fm.read_xdmf(p).ncells == m.ncells          # default: first grid
+    np.testing.assert_array_equal(r.x, m.x)
+    np.testing.assert_array_equal(r.xdofmap, m.xdofmap)
+    np.testing.assert_array_equal(r.meta["cell_tags"], m.meta["cell_tags"])
+    np.testing.assert_array_equal(r.meta["facets"], m.meta["facets"])
+    np.testing.assert_array_equal(r.meta["facet_tags"], m.meta["facet_tags"])
+    np.testing.assert_array_equal(fm.young_from_tags(r.meta["cell_tags"]), fm.young_from_tags(m.meta["cell_tags"]))
+    np.testing.assert_array_equal(fm.damage_seed(r, [4]), fm.damage_seed(m, [4]))
+    # tag grid in another cell order, vertices rotated: still matched to the mesh cells
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(m.ncells)
+    m2 = fm.Mesh(fm.P1, m.x, m.xdofmap, m.dofmap, 0, 0, dict(m.meta))
+    q = os.path.join(str(tmp_path), "shuffled.xdmf")
+    fm.write_xdmf(q, m2, "g")
+    txt = open(q).read()
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring(txt)
+    tg = [g for g in root.iter("Grid") if g.get("Name") == "g_cells"][0]
+    tg.find("Topology").find("DataItem").text = "\n".join(" ".join(str(v) for v in np.roll(row, 1)) for row in m.xdofmap[perm])
+    tg.find("Attribute").find("DataItem").text = "\n".join(str(v) for v in m.meta["cell_tags"][perm])
+    ET.ElementTree(root).write(q)
+    np.testing.assert_array_equal(fm.read_xdmf(q, "g").meta["cell_tags"], m.meta["cell_tags"])
+    with pytest.raises(ValueError, match="no grid named"):
+        fm.read_xdmf(p, "other")
+    h = os.path.join(str(tmp_path), "h.xdmf")
+    with open(h, "w") as f:
+        f.write('<Xdmf><Domain><Grid Name="a"><Topology TopologyType="Triangle"><DataItem Dimensions="1 3" Format="HDF">'
+                'a.h5:/Mesh/a/topology</DataItem></Topology><Geometry GeometryType="XY"><DataItem Dimensions="3 2" '
+                'Format="XML">0 0 1 0 0 1</DataItem></Geometry></Grid></Domain></Xdmf>')
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ValueError, match="h5py"):
+            fm.read_xdmf(h)
+    t = os.path.join(str(tmp_path), "t.xdmf")
+    with open(t, "w") as f:
+        f.write('<Xdmf><Domain><Grid Name="a"><Topology TopologyType="Quadrilateral"><DataItem Dimensions="1 4" '
+                'Format="XML">0 1 2 3</DataItem></Topology><Geometry GeometryType="XY"><DataItem Dimensions="4 2" '
+                'Format="XML">0 0 1 0 1 1 0 1</DataItem></Geometry></Grid></Domain></Xdmf>')
+    with pytest.raises(ValueError, match="Triangle"):
+        fm.read_xdmf(t)
+    b = os.path.join(str(tmp_path), "bad.xdmf")
+    with open(b, "w") as f:
+        f.write('<Xdmf><Domain><Grid Name="a"><Topology TopologyType="Triangle"><DataItem Dimensions="1 3" '
+                'Format="XML">0 1 7</DataItem></Topology><Geometry GeometryType="XYZ"><DataItem Dimensions="3 3" '
+                'Format="XML">0 0 0 1 0 0 0 1 0</DataItem></Geometry></Grid></Domain></Xdmf>')
+    with pytest.raises(ValueError, match="outside the geometry"):
+        fm.read_xdmf(b)
+
+
 def _areas(m):
     t = m.xdofmap.astype(np.int64)
     a, b, c = m.x[t[:, 0]], m.x[t[:, 1]], m.x[t[:, 2]]
