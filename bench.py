@@ -67,9 +67,9 @@ def spmv_bytes(nnz_blocks: int, nnodes: int) -> int:
 
 
 def cg_iter_bytes(nnz_blocks: int, nnodes: int) -> int:
-    """SpMV + update_xr (read d, Ad, x, r, dinv; write x, r) + update_dir (read r, dinv,
-    d; write d), 16 B per node per vector pass."""
-    return spmv_bytes(nnz_blocks, nnodes) + 11 * 16 * nnodes
+    """SpMV + update_r (read Ad, r, dinv; write r) + update_xdir (read r, dinv, d, x; write d, x: the x update rides
+    with the direction update), 16 B per node per vector pass."""
+    return spmv_bytes(nnz_blocks, nnodes) + 10 * 16 * nnodes
 
 
 class ClockSampler:
@@ -499,9 +499,9 @@ def run_b200(args):
     a_ms = float(np.mean(asm_calls))
     s_ms = float(np.mean(spmv_calls))
     a_gbs, s_gbs, c_gbs = a_bytes / (a_ms * 1e-3) / 1e9, s_bytes / (s_ms * 1e-3) / 1e9, c_bytes / (cg_iter_ms * 1e-3) / 1e9
-    # PCG call: init, scalar, apply, scalar; cg_iters - 1 full iterations of 5 kernels; the last one 2; one ghost-update
-    # kernel per apply on the P2P transport
-    launches_pcg = 4 + 5 * (args.cg_iters - 1) + 2 + (args.cg_iters if (world > 1 and op.transport == "p2p") else 0)
+    # PCG call: init, scalar, apply, scalar; cg_iters - 1 full iterations of 5 kernels (update_r, scalar, update_xdir,
+    # apply, scalar); the last one 3 (update_r, scalar, x update); one ghost-update kernel per apply on the P2P transport
+    launches_pcg = 4 + 5 * (args.cg_iters - 1) + 3 + (args.cg_iters if (world > 1 and op.transport == "p2p") else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",

@@ -265,7 +265,7 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
                          const double *__restrict__ x, int xs, const double *__restrict__ E, LameCoef lc,
                          const double *__restrict__ dnod, const double *__restrict__ u, int variant,
                          double *__restrict__ rec, double *__restrict__ celld, const uint4 *__restrict__ cref,
-                         int32_t *__restrict__ tdam, int cap, int *__restrict__ dmg_counter)
+                         int32_t *__restrict__ tdam, int cap, int *__restrict__ dmg_counter, int spec)
 {
    constexpr int nd = Elem<ET>::nd, nq = Elem<ET>::nq, RS = dmg_rec_doubles<ET>(), STRIDE = RS + 2;
    __shared__ __align__(16) double stage[4][32 * STRIDE];
@@ -275,10 +275,28 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
    const int64_t ec = active ? e : ncells - 1;
    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + 32 * warp;
    const int64_t v0 = xdofmap[3 * ec], v1 = xdofmap[3 * ec + 1], v2 = xdofmap[3 * ec + 2];
+   // the dof map is loaded with the vertex map, not behind the damage test: the chain of dependent global loads of a
+   // damaged cell is (maps) -> (x, d, u) instead of (vertex map) -> (x, d) -> (dof map) -> (u); with `spec` (most cells
+   // were damaged last time) the gather of u is issued before the test as well.  ncu of the round-2 pre-pass at 100 %
+   // damaged cells: 4.3 long-scoreboard stall cycles per issued instruction at 16 warps per SM.
+   int32_t dm[nd];
+#pragma unroll
+   for (int b = 0; b < nd; ++b) dm[b] = u ? dofmap[ec * nd + b] : 0;
    const double dv[3] = {dnod[v0], dnod[v1], dnod[v2]};
    const double xv[3][2] = {{x[v0 * xs], x[v0 * xs + 1]}, {x[v1 * xs], x[v1 * xs + 1]}, {x[v2 * xs], x[v2 * xs + 1]}};
+   double ue[nd][2];
+   if (spec && u)
+   {
+#pragma unroll
+      for (int b = 0; b < nd; ++b)
+      {
+         const int64_t gd = 2 * (int64_t)dm[b];
+         ue[b][0] = u[gd], ue[b][1] = u[gd + 1];
+      }
+   }
    const double det = (xv[1][0] - xv[0][0]) * (xv[2][1] - xv[0][1]) - (xv[2][0] - xv[0][0]) * (xv[1][1] - xv[0][1]);
    const double id = 1. / det;
+   // d at the points of the rule: vertex basis values (2/3 at the point's own vertex, 1/6 elsewhere; P1: the centroid)
    double dq[nq];
    bool damaged = false;
 #pragma unroll
@@ -323,27 +341,51 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
    {
       R[0] = g1x, R[1] = g1y, R[2] = g2x, R[3] = g2y;
       const double lam = Ee * lc.c2, mu = Ee * lc.c3;
-      double ue[nd][2];
-#pragma unroll
-      for (int b = 0; b < nd; ++b)
+      if (!(spec && u))
       {
-         const int64_t gd = 2 * (int64_t)dofmap[e * nd + b];
-         ue[b][0] = u ? u[gd] : 0., ue[b][1] = u ? u[gd + 1] : 0.;
+#pragma unroll
+         for (int b = 0; b < nd; ++b)
+         {
+            if (u)
+            {
+               const int64_t gd = 2 * (int64_t)dm[b];
+               ue[b][0] = u[gd], ue[b][1] = u[gd + 1];
+            }
+            else
+               ue[b][0] = ue[b][1] = 0.;
+         }
       }
+      // straight-sided triangle: J is constant, so grad u at a point is sum_k t_k (x) grad lambda_k with
+      // t_k = (4 L_k - 1) u_k + 4 sum over the edges at vertex k of L_(other end) u_edge  (P1: t_k = u_k), and with
+      // grad lambda_0 = -(grad lambda_1 + grad lambda_2):  grad u = (t_1 - t_0) (x) g1 + (t_2 - t_0) (x) g2
+      // (the same numbers as u_b G_b of M.cc:742 with G = dN J^-1, M.cc:696, without the per-point inverse)
+      const double wq = (ET == FEMB200_P1 ? 0.5 : 1. / 6.) * fabs(det);
 #pragma unroll 1
       for (int q = 0; q < nq; ++q)
       {
-         double G[nd][2], phi[3], D[9];
-         const double w = qp_geometry<ET>(xv, q, G, phi);
+         double D[9];
          if (dq[q] > 0.)
          {
-            double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
-#pragma unroll
-            for (int b = 0; b < nd; ++b)
+            double t[3][2];
+            if (ET == FEMB200_P1)
             {
-               g00 += ue[b][0] * G[b][0], g01 += ue[b][0] * G[b][1];
-               g10 += ue[b][1] * G[b][0], g11 += ue[b][1] * G[b][1];
+#pragma unroll
+               for (int k = 0; k < 3; ++k) t[k][0] = ue[k][0], t[k][1] = ue[k][1];
             }
+            else
+            {
+               const double L0 = q == 0 ? 2. / 3. : 1. / 6., L1 = q == 1 ? 2. / 3. : 1. / 6., L2 = q == 2 ? 2. / 3. : 1. / 6.;
+#pragma unroll
+               for (int c = 0; c < 2; ++c)
+               {  // edge 3 + i is opposite vertex i
+                  t[0][c] = (4. * L0 - 1.) * ue[0][c] + 4. * (L2 * ue[nd > 3 ? 4 : 0][c] + L1 * ue[nd > 3 ? 5 : 0][c]);
+                  t[1][c] = (4. * L1 - 1.) * ue[1][c] + 4. * (L2 * ue[nd > 3 ? 3 : 0][c] + L0 * ue[nd > 3 ? 5 : 0][c]);
+                  t[2][c] = (4. * L2 - 1.) * ue[2][c] + 4. * (L1 * ue[nd > 3 ? 3 : 0][c] + L0 * ue[nd > 3 ? 4 : 0][c]);
+               }
+            }
+            const double a0 = t[1][0] - t[0][0], a1 = t[1][1] - t[0][1], b0 = t[2][0] - t[0][0], b1 = t[2][1] - t[0][1];
+            const double g00 = a0 * g1x + b0 * g2x, g01 = a0 * g1y + b0 * g2y;  // grad u (M.cc:742)
+            const double g10 = a1 * g1x + b1 * g2x, g11 = a1 * g1y + b1 * g2y;
             const double sh = 0.5 * (g01 + g10);
             const double eps[4] = {g00, sh, sh, g11};
             tangent(variant, lam, mu, dq[q], eps, D);
@@ -351,7 +393,7 @@ cell_setup_damage_kernel(int64_t ncells, const int32_t *__restrict__ xdofmap, co
          else
             hooke_scaled(lam, mu, 1., D);
          double *Rq = R + 4 + 6 * q;
-         Rq[0] = D[0] * w, Rq[1] = D[1] * w, Rq[2] = D[2] * w, Rq[3] = D[4] * w, Rq[4] = D[5] * w, Rq[5] = D[8] * w;
+         Rq[0] = D[0] * wq, Rq[1] = D[1] * wq, Rq[2] = D[2] * wq, Rq[3] = D[4] * wq, Rq[4] = D[5] * wq, Rq[5] = D[8] * wq;
       }
 #pragma unroll
       for (int k = 4 + 6 * nq; k < RS; ++k) R[k] = 0.;
@@ -876,34 +918,31 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
          if (dpf && (int64_t)tile + 2 * A.prefetch_tiles < ntiles && tid < (DCAP * 4 + 127) / 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A.tdam + ((int64_t)tile + 2 * A.prefetch_tiles) * DCAP) + 128 * tid));
       }
-      for (int c = 0; c < cnt; ++c)
-      {
-         raw = raw1, geo = geo1, raw1 = raw2;
-         if (c + 1 < cnt) ld_d4(A.cellrec + 4 * (int64_t)(raw1.x & 0x0fffffffu), geo1.g1x, geo1.g1y, geo1.g2x, geo1.g2y);
-         raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
+      // One visit: the row slice of cell (R.x & 0x0fffffff) with its cell record G.
+      auto visit = [&](const uint4 &R, const FastGeo &G) {
          // damaged cell: NaN marker; STAGE: its damage record is in the tile's stage (slot in the record), or, where the
          // tile has more cells than the stage holds (slot 0x3ff) and in the kernel without a stage, at celld[cell]
-         const bool dam = DMG && geo.g1x != geo.g1x;
+         const bool dam = DMG && G.g1x != G.g1x;
          const double *drec = nullptr;
          if (dam)
          {
             if (!staged) mbar_wait(dbar, 0), staged = true;
-            const uint32_t slot = STAGE ? raw.w >> 22 : 0x3ffu;
+            const uint32_t slot = STAGE ? R.w >> 22 : 0x3ffu;
             drec = slot != 0x3ffu ? reinterpret_cast<const double *>(dstage + slot * dmg_rec_bytes<ET>())
-                                  : A.celld + (int64_t)(raw.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
+                                  : A.celld + (int64_t)(R.x & 0x0fffffffu) * dmg_rec_doubles<ET>();
          }
-         if (!rec_edge(raw))
+         if (!rec_edge(R))
          {  // vertex row
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET, false>(drec, raw, half, v);
-               emit_row_slice<ET, false>(raw, img, half, C, v);
+               damaged_values<ET, false>(drec, R, half, v);
+               emit_row_slice<ET, false>(R, img, half, C, v);
             }
             else
             {
-               fast_values<ET, false>(A, raw, geo, half, v);
-               emit_row_slice<ET, false>(raw, img, half, C, v);
+               fast_values<ET, false>(A, R, G, half, v);
+               emit_row_slice<ET, false>(R, img, half, C, v);
             }
          }
          else if (ET != FEMB200_P1)
@@ -911,15 +950,27 @@ assemble_fast_kernel(AsmArgs A, ReduceScratch red, double *__restrict__ norms_ou
             double v[Elem<ET>::nd][2];
             if (dam)
             {
-               damaged_values<ET, true>(drec, raw, half, v);
-               emit_row_slice<ET, true>(raw, img, half, C, v);
+               damaged_values<ET, true>(drec, R, half, v);
+               emit_row_slice<ET, true>(R, img, half, C, v);
             }
             else
             {
-               fast_values<ET, true>(A, raw, geo, half, v);
-               emit_row_slice<ET, true>(raw, img, half, C, v);
+               fast_values<ET, true>(A, R, G, half, v);
+               emit_row_slice<ET, true>(R, img, half, C, v);
             }
          }
+      };
+      auto ld_geo = [&](const uint4 &R, FastGeo &G) { ld_d4(A.cellrec + 4 * (int64_t)(R.x & 0x0fffffffu), G.g1x, G.g1y, G.g2x, G.g2y); };
+      // (Three named register sets used round robin with the loop unrolled by three would remove the 16 register moves
+      // per visit of this rotation -- 14 % of the kernel's instructions are IMAD.MOV -- but spills at the 72 registers
+      // of 7 CTAs per SM: 0.669 -> 1.165 ms at n = 1448; a carry flag as a 0 / 1 multiplier instead of the conditional
+      // zeroing of the carry registers, another 16 moves per visit: 0.669 -> 0.703 ms; profiles/r2_experiments.md.)
+      for (int c = 0; c < cnt; ++c)
+      {
+         raw = raw1, geo = geo1, raw1 = raw2;
+         if (c + 1 < cnt) ld_geo(raw1, geo1);
+         raw2 = (c + 2 < cnt) ? rec[(c + 2) * LS] : none;
+         visit(raw, geo);
       }
       if (STAGE)
       {  // L2 prefetch of the damage records of the future tile
@@ -1504,14 +1555,15 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
          if (staged)
             if (int rc = plan_tile_cells(pm, cap, st)) return rc;
          const uint4 *cref = (staged && pm->tdam_refs) ? reinterpret_cast<const uint4 *>(pm->cref) : nullptr;
+         const int spec = last * 5 >= p->ncells * 2;  // most cells damaged last time: the pre-pass gathers u before it tests d
          if (p->etype == FEMB200_P1)
             cell_setup_damage_kernel<FEMB200_P1><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
                                                                        d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, cap,
-                                                                       pm->dmg_counter);
+                                                                       pm->dmg_counter, spec);
          else
             cell_setup_damage_kernel<FEMB200_P2><<<grid, 128, 0, st>>>(p->ncells, p->xdofmap, p->dofmap, d_x, x_stride, d_E, A.lc,
                                                                        d_dnod, d_u, variant, pm->cellrec, pm->celld, cref, pm->tdam, cap,
-                                                                       pm->dmg_counter);
+                                                                       pm->dmg_counter, spec);
          dmg_count_publish_kernel<<<1, 1, 0, st>>>(pm->dmg_counter, pm->dmg_count_dev);
          A.tdam = staged ? pm->tdam : nullptr;
          A.celld = pm->celld;

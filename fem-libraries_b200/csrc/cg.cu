@@ -11,7 +11,8 @@
 //    alpha = nom / den;  x += alpha d;  r -= alpha A d;  betanom = <B r, r>;
 //    stop if betanom <= r0;  beta = betanom / nom;  d = B r + beta d;
 //    den = <d, A d>;  nom = betanom.
-// One iteration is 3 vector kernels (update_xr, update_dir, spmv+dot) and 2
+// One iteration is 3 vector kernels (update_r, update_xdir, spmv+dot: x += alpha d rides with the direction update, which
+// reads d anyway -- 10 vector passes instead of 11 next to the operator apply) and 2
 // one-thread scalar kernels; the host never reads a scalar inside the loop except
 // for the convergence poll every `check_every` iterations.  After convergence the
 // remaining queued kernels see flag != 0 and return immediately.
@@ -48,6 +49,8 @@ enum
    SC_RED_DEN = 10,
    SC_RED_BETA = 11,
    SC_BETA = 12,
+   SC_ALPHA = 13,  // nom / den of the current iteration (cg_core: the x update is deferred to the direction kernel)
+   SC_XPEND = 14,  // 1 while x += alpha d of the current iteration has not been applied yet
    SC_COUNT = 16
 };
 
@@ -86,17 +89,17 @@ cg_update_xr_kernel(int64_t n2, const double *__restrict__ scal, const double2 *
    {
       const double2 di = d[i], zi = z[i];
       double2 xi = x[i], ri = r[i];
-      xi.x += alpha * di.x, xi.y += alpha * di.y;
-      ri.x -= alpha * zi.x, ri.y -= alpha * zi.y;
+      xi.x = __fma_rn(alpha, di.x, xi.x), xi.y = __fma_rn(alpha, di.y, xi.y);
+      ri.x = __fma_rn(-alpha, zi.x, ri.x), ri.y = __fma_rn(-alpha, zi.y, ri.y);
       x[i] = xi;
       r[i] = ri;
       if (dinv)
       {
          const double2 pi = dinv[i];
-         part += (pi.x * ri.x) * ri.x + (pi.y * ri.y) * ri.y;
+         part = __fma_rn(__dmul_rn(pi.x, ri.x), ri.x, part), part = __fma_rn(__dmul_rn(pi.y, ri.y), ri.y, part);
       }
       else
-         part += ri.x * ri.x + ri.y * ri.y;
+         part = __fma_rn(ri.x, ri.x, part), part = __fma_rn(ri.y, ri.y, part);
    }
    block_reduce_finish<kVecThreads>(part, red, out);
 }
@@ -115,12 +118,77 @@ cg_update_dir_kernel(int64_t n2, const double *__restrict__ scal, const double2 
       if (dinv)
       {
          const double2 pi = dinv[i];
-         ri.x *= pi.x, ri.y *= pi.y;
+         ri.x = __dmul_rn(ri.x, pi.x), ri.y = __dmul_rn(ri.y, pi.y);
       }
       double2 di = d[i];
-      di.x = ri.x + beta * di.x;
-      di.y = ri.y + beta * di.y;
+      di.x = __fma_rn(beta, di.x, ri.x);
+      di.y = __fma_rn(beta, di.y, ri.y);
       d[i] = di;
+   }
+}
+
+// The loop of cg_core splits the updates differently: r first (the stopping test needs it), x together with the
+// direction, which reads d anyway: 4 + 6 vector passes per iteration instead of 7 + 4.  Same operations on the same
+// operands in the same order as cg_update_xr_kernel + cg_update_dir_kernel, with the roundings pinned by explicit
+// __dmul_rn / __fma_rn in all four kernels (left to the compiler, the contraction of B r + beta d differed between the
+// two forms): x, r, d are bit-identical (tests/test_gpu_parity.py::test_pcg_matches_building_blocks_bitwise).
+// r -= alpha z;  partial <B r, r>
+__global__ void __launch_bounds__(kVecThreads)
+cg_update_r_kernel(int64_t n2, const double *__restrict__ scal, const double2 *__restrict__ z,
+                   const double2 *__restrict__ dinv, double2 *__restrict__ r, ReduceScratch red, double *__restrict__ out)
+{
+   if (scal[SC_FLAG] != 0.) return;
+   const double alpha = scal[SC_ALPHA];
+   double part = 0.;
+   const int64_t stride = (int64_t)gridDim.x * kVecThreads;
+   for (int64_t i = (int64_t)blockIdx.x * kVecThreads + threadIdx.x; i < n2; i += stride)
+   {
+      const double2 zi = z[i];
+      double2 ri = r[i];
+      ri.x = __fma_rn(-alpha, zi.x, ri.x), ri.y = __fma_rn(-alpha, zi.y, ri.y);
+      r[i] = ri;
+      if (dinv)
+      {
+         const double2 pi = dinv[i];
+         part = __fma_rn(__dmul_rn(pi.x, ri.x), ri.x, part), part = __fma_rn(__dmul_rn(pi.y, ri.y), ri.y, part);
+      }
+      else
+         part = __fma_rn(ri.x, ri.x, part), part = __fma_rn(ri.y, ri.y, part);
+   }
+   block_reduce_finish<kVecThreads>(part, red, out);
+}
+
+// x += alpha d when that update is pending (it is applied even when the iteration stopped: mfem::CGSolver updates x
+// before it tests <B r, r>);  then, unless the solve has stopped or x_only, d = B r + beta d
+__global__ void __launch_bounds__(kVecThreads)
+cg_update_xdir_kernel(int64_t n2, const double *__restrict__ scal, const double2 *__restrict__ r,
+                      const double2 *__restrict__ dinv, double2 *__restrict__ x, double2 *__restrict__ d, int x_only)
+{
+   const bool pend = scal[SC_XPEND] != 0., go = !x_only && scal[SC_FLAG] == 0.;
+   if (!pend && !go) return;
+   const double alpha = scal[SC_ALPHA], beta = scal[SC_BETA];
+   const int64_t stride = (int64_t)gridDim.x * kVecThreads;
+   for (int64_t i = (int64_t)blockIdx.x * kVecThreads + threadIdx.x; i < n2; i += stride)
+   {
+      double2 di = d[i];
+      if (pend)
+      {
+         double2 xi = x[i];
+         xi.x = __fma_rn(alpha, di.x, xi.x), xi.y = __fma_rn(alpha, di.y, xi.y);
+         x[i] = xi;
+      }
+      if (go)
+      {
+         double2 ri = r[i];
+         if (dinv)
+         {
+            const double2 pi = dinv[i];
+            ri.x = __dmul_rn(ri.x, pi.x), ri.y = __dmul_rn(ri.y, pi.y);
+         }
+         di.x = __fma_rn(beta, di.x, ri.x);
+         di.y = __fma_rn(beta, di.y, ri.y);
+         d[i] = di;
+      }
    }
 }
 
@@ -167,12 +235,19 @@ __global__ void __launch_bounds__(32) cg_scalar_kernel(double *__restrict__ s, i
       s[SC_FLAG] = (nom < 0.) ? 2. : ((nom <= s[SC_R0]) ? 1. : 0.);
       return;
    }
-   if (s[SC_FLAG] != 0.) return;
+   if (s[SC_FLAG] != 0.)
+   {  // stopped: the direction kernel before this apply has brought x up to date
+      if (phase == 1) s[SC_XPEND] = 0.;
+      return;
+   }
    if (phase == 1)
    {
       const double den = s[SC_RED_DEN];
       s[SC_DEN] = den;
-      if (!(den > 0.)) s[SC_FLAG] = 2.;  // not positive definite: mfem leaves the loop
+      if (!(den > 0.))
+         s[SC_FLAG] = 2., s[SC_XPEND] = 0.;  // not positive definite: mfem leaves the loop before it touches x
+      else
+         s[SC_ALPHA] = s[SC_NOM] / den, s[SC_XPEND] = 1.;
    }
    else
    {
@@ -310,8 +385,8 @@ static int cg_apply_rows(const femb200_plan *plan, int op_kind, const void *op, 
 // The PCG loop of femb200_pcg and femb200_dist_pcg.  Vector kernels run on the owned dofs [2 own_lo,
 // 2 own_hi) of the local vectors; with a communicator the search direction gets its ghost update before
 // every operator apply and the three dot products are all-reduced (fused into the scalar kernels on the P2P
-// transport, ncclAllReduce on the NCCL transport).  With use_graph the full iteration (update_xr, scalar,
-// update_dir, ghost update, apply + dot, scalar) is captured once into a CUDA graph cached in the
+// transport, ncclAllReduce on the NCCL transport).  With use_graph the full iteration (update_r, scalar,
+// update_xdir, ghost update, apply + dot, scalar) is captured once into a CUDA graph cached in the
 // communicator and replayed; everything it needs (scalars, sequence numbers) lives in device memory.
 int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, cudaStream_t st)
 {
@@ -342,27 +417,25 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
       if (int e = cg_apply_rows(P.plan, P.op_kind, P.op, P.values, rr, P.own_lo, P.own_hi, P.d, P.z, scal, s)) return e;
       return scalar(1, SC_RED_DEN, s);
    };
-   auto update_xr = [&](cudaStream_t s) -> int {
+   auto update_r = [&](cudaStream_t s) -> int {
       ReduceScratch rs;
       if (int e = reduce_scratch(gv, s, &rs)) return e;
-      cg_update_xr_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.d + o),
-                                                     reinterpret_cast<const double2 *>(P.z + o),
-                                                     reinterpret_cast<const double2 *>(dinv_o),
-                                                     reinterpret_cast<double2 *>(P.x + o), reinterpret_cast<double2 *>(P.r + o),
-                                                     rs, scal + SC_RED_BETA);
+      cg_update_r_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.z + o),
+                                                    reinterpret_cast<const double2 *>(dinv_o), reinterpret_cast<double2 *>(P.r + o),
+                                                    rs, scal + SC_RED_BETA);
       FEMB_LAUNCH_CHECK();
       return scalar(2, SC_RED_BETA, s);
    };
-   auto update_dir = [&](cudaStream_t s) -> int {
-      cg_update_dir_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.r + o),
-                                                      reinterpret_cast<const double2 *>(dinv_o),
-                                                      reinterpret_cast<double2 *>(P.d + o));
+   auto update_xdir = [&](cudaStream_t s, int x_only) -> int {
+      cg_update_xdir_kernel<<<gv, kVecThreads, 0, s>>>(n / 2, scal, reinterpret_cast<const double2 *>(P.r + o),
+                                                       reinterpret_cast<const double2 *>(dinv_o), reinterpret_cast<double2 *>(P.x + o),
+                                                       reinterpret_cast<double2 *>(P.d + o), x_only);
       FEMB_LAUNCH_CHECK();
       return 0;
    };
    auto full_iteration = [&](cudaStream_t s) -> int {
-      if (int e = update_xr(s)) return e;
-      if (int e = update_dir(s)) return e;
+      if (int e = update_r(s)) return e;
+      if (int e = update_xdir(s, 0)) return e;
       return apply(s);
    };
 
@@ -382,7 +455,8 @@ int cg_core(const CgProblem &P, int *iters, double *final_norm, int *converged, 
    {
       if (i == nit)
       {
-         if ((rc = update_xr(st))) return rc;
+         if ((rc = update_r(st))) return rc;
+         if ((rc = update_xdir(st, 1))) return rc;
       }
       else if (G && i >= 2)
       {  // iteration 1 ran eagerly (warm kernels, NCCL connections); capture on first use, then replay

@@ -536,6 +536,55 @@ def test_pcg_edge_cases():
     assert cg2.GetNumIterations() == cg3.GetNumIterations()
 
 
+def test_pcg_matches_building_blocks_bitwise():
+    """femb200_pcg defers x += alpha d to the direction kernel (10 vector passes per iteration instead of 11); the
+    exported building blocks (cg_init / cg_apply / cg_scalar_step / cg_update_xr / cg_update_dir: the textbook split of
+    mfem::CGSolver::Mult, M.cc:1502) driven one by one from the host must give the same x bit for bit: stop at the
+    iteration limit, stop on convergence with queued no-op iterations behind it, CSR and matrix-free operators."""
+    import torch
+    m = make_mesh("P2", 10)
+    E = fm.young_per_cell(m.ncells)
+    bc, g, rowptr, colidx, vals, b = linear_problem(m, E)
+    f = fem()
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form, bcs=[f.DirichletBC(bc)])
+    n = m.ndofs
+    bd = f.to_device(b, np.float64)
+    call, p, st = f.capi.call, f._p, f._stream
+    for maxit, rtol in ((7, 1e-12), (4000, 1e-12), (4000, 1e-3)):
+        cg = f.CGSolver(rel_tol=rtol, max_iter=maxit, check_every=40)
+        cg.SetOperator(A)
+        cg.SetPreconditioner("jacobi")
+        x = cg.Mult(bd).clone()
+        its = cg.GetNumIterations()
+        # the same solve from the blocks
+        xb, r, d, z = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(4))
+        scal = torch.zeros(16, dtype=torch.float64, device="cuda")
+        call("femb200_cg_set_tolerances", p(scal), rtol, 0.0, st())
+        call("femb200_cg_init", n, p(bd), p(cg.dinv), p(xb), p(r), p(d), p(scal), st())
+        call("femb200_cg_scalar_step", p(scal), 0, st())
+        call("femb200_cg_apply", A.plan, 0, None, p(A.values), p(d), p(z), p(scal), st())
+        call("femb200_cg_scalar_step", p(scal), 1, st())
+        for i in range(1, maxit + 1):
+            call("femb200_cg_update_xr", n, p(scal), p(d), p(z), p(cg.dinv), p(xb), p(r), st())
+            call("femb200_cg_scalar_step", p(scal), 2, st())
+            if i == maxit or scal[4].item() != 0.0:
+                break
+            call("femb200_cg_update_dir", n, p(scal), p(r), p(cg.dinv), p(d), st())
+            call("femb200_cg_apply", A.plan, 0, None, p(A.values), p(d), p(z), p(scal), st())
+            call("femb200_cg_scalar_step", p(scal), 1, st())
+        assert int(scal[5].item()) == its
+        assert torch.equal(x, xb), (maxit, rtol, float((x - xb).abs().max()))
+    # matrix-free operator, both stopping modes, against the assembled operator's iterate count and the oracle
+    pa = f.PAOperator(form, bcs=[f.DirichletBC(bc)])
+    want, it_o, _, _ = oracle.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=9, jacobi=True)
+    cg = f.CGSolver(rel_tol=1e-12, max_iter=9)
+    cg.SetOperator(pa)
+    cg.SetPreconditioner("jacobi")
+    x9 = cg.Mult(bd).cpu().numpy()
+    assert cg.GetNumIterations() == it_o == 9 and relfro(x9, want) < 1e-12
+
+
 def test_error_behaviour():
     """No exceptions cross the C ABI: status + femb200_last_error, raised here as Femb200Error."""
     import ctypes as C

@@ -17,7 +17,7 @@ PEAK = 6451.2
 def timed(fn, k=10, w=3):
     for _ in range(w):
         fn()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()  # the damaged schedule follows the previous assembly's damage share (host-mapped word)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
     for a, b in evs:
         a.record(); fn(); b.record()
