@@ -487,7 +487,10 @@ def run_b200(args):
     plan_bytes = A.plan_bytes
     a_bytes = assembly_bytes(A.nnz, m.ncells, m.nnodes)            # this rank's launch (ghost cell row included)
     s_bytes = spmv_bytes(nnzb_owned, owned_nodes)
-    c_bytes = cg_iter_bytes(nnzb_owned, owned_nodes)
+    col_bits = A.get_option("spmv_col_bits")                       # 16: column offsets from the row's node, 2 B per block
+    s_moved = s_bytes - (4 - col_bits // 8) * nnzb_owned           # bytes the kernel is designed to move
+    c_bytes = cg_iter_bytes(nnzb_owned, owned_nodes) - (s_bytes - s_moved)   # bytes the iteration's kernels move
+    c_bytes_survey = s_bytes + 56 * 2 * owned_nodes                # SpMV + 7 vector passes (56 B per dof)
     if rank != 0:
         if world == 1:
             pass
@@ -516,8 +519,12 @@ def run_b200(args):
         "roofline": {"kernel": "spmv_tma_kernel<DOT,64,2,4> (dominant: cg_iters + 1 launches per step)", "bound": "hbm",
                      "achieved": s_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": s_gbs / peak,
                      "algorithmic_bytes_per_launch": s_bytes, "kernel_ms": s_ms,
+                     "bytes_moved_by_design": s_moved, "frac_of_bytes_moved": s_moved / (s_ms * 1e-3) / 1e9 / peak,
+                     "column_index_bits": col_bits,
                      "traffic": traffic_from_profile("spmv", n, world), "note": "rank 0's owned rows; timed alone over "
-                     f"{ks} launches (with the ghost update at N > 1)"},
+                     f"{ks} launches (with the ghost update at N > 1); achieved = SURVEY 8(d)'s algorithmic bytes "
+                     "(36 B per node block + 40 B per node) / time; the kernel reads 16-bit column offsets where the "
+                     "pattern allows (34 B per block): bytes_moved_by_design / frac_of_bytes_moved"},
         "assembly": {"ms": asm_ms, "gdofs": total_dofs / (asm_ms * 1e-3) / 1e9,
                      "roofline": {"kernel": "assemble_fast_kernel<P2> (+ cell_setup_kernel, dirichlet_kernel)", "bound": "hbm",
                                   "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak,
@@ -525,6 +532,10 @@ def run_b200(args):
                                   "traffic": traffic_from_profile("assemble", n, world)}},
         "cg": {"spmv_ms": spmv_ms, "spmv_gbs": s_gbs, "spmv_frac": s_gbs / peak, "spmv_gdofs": total_dofs / (spmv_ms * 1e-3) / 1e9,
                "cg_iter_ms": cg_iter_ms, "cg_iter_gbs": c_gbs, "cg_iter_frac": c_gbs / peak,
+               "cg_iter_bytes": c_bytes, "cg_iter_frac_at_survey_bytes": c_bytes_survey / (cg_iter_ms * 1e-3) / 1e9 / peak,
+               "cg_iter_what": "bytes moved by design: SpMV (34 or 36 B per block + 40 B per node) + 10 vector passes "
+                               "(update_r: 3 reads 1 write; update_xdir: 4 reads 2 writes, Jacobi included); "
+                               "SURVEY 8(d) counts SpMV at 36 B per block + 7 passes",
                "cg_iter_gdofs": total_dofs / (cg_iter_ms * 1e-3) / 1e9, "precond": "jacobi", "iters": args.cg_iters,
                "comm": comm},
         "e2e": e2e,

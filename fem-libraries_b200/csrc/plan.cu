@@ -490,6 +490,23 @@ __global__ void k_range_tile_max(int64_t lo, int64_t hi, int R, const int64_t *_
 }
 
 // --- scalar CSR expansion ---------------------------------------------------------
+// 16-bit relative column indices of the block pattern for the SpMV (spmv.cu): bcol16[k] = bcol[k] - I for the blocks
+// of node row I; *bad is set when an offset does not fit (the plan then keeps the 32-bit indices only)
+__global__ void k_cols16(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
+                         int16_t *__restrict__ bcol16, int32_t *__restrict__ bad)
+{
+   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // eight lanes per node row
+   const int lane = threadIdx.x & 7;
+   if (w >= nnodes) return;
+   const int64_t b0 = brp[w], b1 = brp[w + 1];
+   for (int64_t k = b0 + lane; k < b1; k += 8)
+   {
+      const int64_t d = (int64_t)bcol[k] - w;
+      if (d < -32768 || d > 32767) *bad = 1;
+      bcol16[k] = (int16_t)d;
+   }
+}
+
 __global__ void k_scalar_csr(int64_t nnodes, const int64_t *__restrict__ brp, const int32_t *__restrict__ bcol,
                              int64_t *__restrict__ rowptr, int32_t *__restrict__ colidx)
 {
@@ -551,6 +568,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->voff);
    cudaFree(p->brp);
    cudaFree(p->bcol);
+   cudaFree(p->bcol16);
    cudaFree(p->dslot);
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
@@ -640,6 +658,23 @@ extern "C" int femb200_plan_create(int etype, int64_t nnodes, int64_t ncells, co
       return fail(1);
    k_fill_cols<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
                                                             p->dslot);
+
+   {  // 16-bit relative column indices for the SpMV, when every offset fits
+      if (dev_alloc(&p->bcol16, (size_t)p->nnzb + 16, &p->bytes)) return fail(1);
+      cudaMemsetAsync(flags, 0, sizeof(int32_t), st);
+      k_cols16<<<(unsigned)cdiv(nnodes * 8, 256), 256, 0, st>>>(nnodes, p->brp, p->bcol, p->bcol16, flags);
+      int32_t bad = 0;
+      if (cudaMemcpyAsync(&bad, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+         return fail(set_error("plan_create: column offsets failed: %s", cudaGetErrorString(cudaGetLastError())));
+      if (bad)
+      {
+         cudaFree(p->bcol16);
+         p->bcol16 = nullptr;
+         p->bytes -= sizeof(int16_t) * ((size_t)p->nnzb + 16);
+      }
+      cudaMemsetAsync(flags, 0, sizeof(int32_t) * 2, st);
+   }
 
    // 3. slot map + staging-tile sizes
    k_fill_slots<<<(unsigned)cdiv(nnodes, 128), 128, 0, st>>>(nnodes, nd, d_dofmap, p->nptr, tmpvis, p->brp, p->bcol,
@@ -866,6 +901,11 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
       FEMB_CHECK(value == 0 || value == 1, "plan_set_option: spmv_path must be 0 (auto) or 1 (direct)");
       p->opt_spmv_path = value;
    }
+   else if (!strcmp(key, "spmv_cols"))
+   {
+      FEMB_CHECK(value == 0 || value == 1, "plan_set_option: spmv_cols must be 0 (auto: 16-bit relative indices) or 1 (32-bit)");
+      p->opt_spmv_cols = value;
+   }
    else if (!strcmp(key, "prefetch_tiles"))
       p->opt_prefetch_tiles = value;
    else if (!strcmp(key, "stream_out"))
@@ -876,5 +916,29 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
 
    else
       return set_error("plan_set_option: unknown key '%s'", key);
+   return 0;
+}
+
+extern "C" int femb200_plan_get_option(const femb200_plan *p, const char *key, int *value)
+{
+   FEMB_CHECK(p && key && value, "plan_get_option: null argument");
+   if (!strcmp(key, "assembly_path"))
+      *value = p->opt_assembly_path;
+   else if (!strcmp(key, "damage_stage"))
+      *value = p->opt_dmg_stage;
+   else if (!strcmp(key, "spmv_path"))
+      *value = p->opt_spmv_path;
+   else if (!strcmp(key, "spmv_cols"))
+      *value = p->opt_spmv_cols;
+   else if (!strcmp(key, "prefetch_tiles"))
+      *value = p->opt_prefetch_tiles;
+   else if (!strcmp(key, "stream_out"))
+      *value = p->opt_stream_out;
+   else if (!strcmp(key, "spmv_col_bits"))
+      *value = (p->bcol16 && p->opt_spmv_cols != 1) ? 16 : 32;
+   else if (!strcmp(key, "fast_records"))
+      *value = p->frec ? 1 : 0;
+   else
+      return set_error("plan_get_option: unknown key '%s'", key);
    return 0;
 }

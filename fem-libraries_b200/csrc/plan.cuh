@@ -120,6 +120,7 @@ struct femb200_plan
    uint16_t *voff = nullptr;                              // [ntiles * kAsmLevels] level offsets in a tile
    int64_t *brp = nullptr;                                // [nnodes+1]
    int32_t *bcol = nullptr;                               // [nnzb]
+   int16_t *bcol16 = nullptr;                             // [nnzb] bcol[k] - (node of the row), or null when one does not fit
    uint8_t *dslot = nullptr;                              // [nnodes] slot of the diagonal block in its row (255: none)
    int32_t tile_max_blocks[femb::kNumTileR] = {0, 0, 0, 0, 0, 0};
    // Dirichlet
@@ -149,6 +150,7 @@ struct femb200_plan
    // fast records / oversized SpMV tiles can be forced, so that the tests cover them on any mesh.
    int opt_assembly_path = 0;    // 0 auto; 1 visit-record kernel; 2 per-quadrature-point kernel
    int opt_spmv_path = 0;        // 0 auto (bulk-copy staged, persistent); 1 direct kernel
+   int opt_spmv_cols = 0;        // 0 auto (16-bit relative column indices when the pattern allows); 1 32-bit indices
    int opt_prefetch_tiles = -1;  // record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count)
    // largest 32- / 64-row SpMV tile (in node blocks) of the tiling that starts at row_lo, per row range
    // [row_lo, row_hi) that has been applied (the owned rows of a rank; measured once, on first use)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "femb200_gather": [i64, vp, vp, vp, vp],
     "femb200_scatter_rows": [i64, i32, vp, vp, vp, vp],
     "femb200_plan_set_option": [vp, C.c_char_p, i32],
+    "femb200_plan_get_option": [vp, C.c_char_p, C.POINTER(C.c_int)],
     "femb200_dist_create": [vp, i32, i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, C.POINTER(vp)],
     "femb200_dist_nccl_unique_id": [vp],
     "femb200_dist_nccl_comm_create": [vp, i32, i32, C.POINTER(vp)],

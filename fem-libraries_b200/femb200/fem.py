@@ -224,9 +224,15 @@ class Matrix:
         self._bc_marker = m
 
     def set_option(self, key: str, value: int):
-        """Kernel selection of the plan (femb200_plan_set_option): "assembly_path", "spmv_path", "prefetch_tiles",
+        """Kernel selection of the plan (femb200_plan_set_option): "assembly_path", "spmv_path", "spmv_cols", "prefetch_tiles",
         "stream_out", "damage_stage"."""
         capi.call("femb200_plan_set_option", self._plan, key.encode(), int(value))
+
+    def get_option(self, key: str) -> int:
+        """An option read back, or a read-only fact of the plan ("spmv_col_bits", "fast_records"): femb200_plan_get_option."""
+        v = C.c_int()
+        capi.call("femb200_plan_get_option", self._plan, key.encode(), C.byref(v))
+        return v.value
 
     def mult_rows(self, x: torch.Tensor, y: torch.Tensor, lo: int, hi: int, dot: torch.Tensor | None = None,
                   accumulate: bool = False) -> torch.Tensor:

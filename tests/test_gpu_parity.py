@@ -431,6 +431,46 @@ def test_spmv_and_pa_apply(kind, n):
         np.testing.assert_allclose(pa.diagonal().cpu().numpy(), K.diagonal(), rtol=1e-11)
 
 
+def test_spmv_column_index_widths():
+    """The staged SpMV reads 16-bit column offsets from the row's node when every offset of the pattern fits, 32-bit
+    indices otherwise: both give the same y bit for bit (same products, same order); a numbering without locality
+    (random node permutation of a 40 401-node P1 mesh: offsets beyond 2^15) takes the 32-bit path by itself."""
+    import torch
+    f = fem()
+    m = make_mesh("P2", 40, ny=23)
+    E = fm.young_per_cell(m.ncells)
+    form = f.ElasticityForm(m, E)
+    A = f.assemble_matrix(f.create_matrix(form), form)
+    rowptr, colidx, vals = oracle_assemble(m, E)
+    v = np.random.default_rng(5).standard_normal(m.ndofs)
+    vd = f.to_device(v, np.float64)
+    want = oracle.spmv(rowptr, colidx, vals, v)
+    y16 = A.mult(vd).clone()
+    A.set_option("spmv_cols", 1)
+    y32 = A.mult(vd).clone()
+    A.set_option("spmv_cols", 0)
+    assert relfro(y16.cpu().numpy(), want) < 1e-13
+    assert torch.equal(y16, y32)
+    for lo, hi in ((1, m.nnodes - 1), (163, 1000), (m.nnodes - 5, m.nnodes)):   # ragged tile starts: other alignments
+        ya = torch.zeros(m.ndofs, dtype=torch.float64, device="cuda")
+        A.mult_rows(vd, ya, lo, hi)
+        assert torch.equal(ya[2 * lo:2 * hi], y32[2 * lo:2 * hi])
+    # no locality: node ids permuted at random
+    m1 = make_mesh("P1", 200)
+    perm = np.random.default_rng(7).permutation(m1.nnodes).astype(np.int32)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(m1.nnodes, dtype=np.int32)
+    mp = fm.Mesh(m1.etype, np.ascontiguousarray(m1.x[inv]), perm[m1.xdofmap], perm[m1.dofmap], 0, 0, {})
+    E1 = fm.young_per_cell(mp.ncells)
+    form1 = f.ElasticityForm(mp, E1)
+    A1 = f.assemble_matrix(f.create_matrix(form1), form1)
+    r1, c1, v1 = oracle_assemble(mp, E1)
+    w = np.random.default_rng(9).standard_normal(mp.ndofs)
+    assert np.abs(c1[r1[0]:r1[1]] // 2).max() >= 0 and (np.abs(np.repeat(np.arange(mp.ndofs), np.diff(r1)) // 2 - c1 // 2).max() > 32767)
+    y1 = A1.mult(f.to_device(w, np.float64)).cpu().numpy()
+    assert relfro(y1, oracle.spmv(r1, c1, v1, w)) < 1e-13
+
+
 @pytest.mark.parametrize("direct", [False, True])
 def test_spmv_variants_and_row_ranges(direct, monkeypatch):
     """TMA-staged and direct kernels; owned-row ranges (multi-GPU) incl. odd and ragged bounds."""
