@@ -16,10 +16,10 @@ cap() {  # name, kernel regex, launch-skip, probe args...
    shift 3
    $NCU -k "regex:$rx" --launch-skip $skip -c 1 -f -o $OUT/${TAG}_$name python tools/r2_probe.py "$@" > $OUT/${TAG}_$name.log 2>&1 || echo "capture $name failed"
 }
-cap asm_p2_n1448 'assemble_fast_kernel' 5 asm
+cap asm_p2_n1448 'assemble_fast_kernel' 20 asm
 cap dmg_gather_100pct 'assemble_fast_kernel' 4 dmg100
 cap dmg_prepass_100pct 'cell_setup_damage_kernel' 3 dmg100
-cap asm_p1_n2896 'assemble_fast_kernel' 5 p1
+cap asm_p1_n2896 'assemble_fast_kernel' 20 p1
 cap pa_q2_n2048 'pa_tile_kernel' 5 pa
 
 # config 4 (n = 5792): launch list of the bench step, then the two dominant kernels
