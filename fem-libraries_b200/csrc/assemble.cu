@@ -1518,16 +1518,9 @@ static int assemble_matrix_impl(const femb200_plan *p, const double *d_x, int x_
       const unsigned grid = (unsigned)cdiv(p->ncells, 128);
       if (d_dnod)
       {
-         const size_t W = p->etype == FEMB200_P1 ? dmg_rec_doubles<FEMB200_P1>() : dmg_rec_doubles<FEMB200_P2>();
-         if (!pm->celld)
-         {  // one damage record per cell at worst (256 B for P2); allocated on the first damaged assembly
-            std::lock_guard<std::mutex> lock(pm->range_mtx);
-            if (!pm->celld)
-            {
-               FEMB_CUDA(cudaMalloc(&pm->celld, sizeof(double) * W * (size_t)p->ncells));
-               pm->bytes += sizeof(double) * W * (size_t)p->ncells;
-            }
-         }
+         // one damage record per cell at worst (192-byte slots for P2): the plan's per-cell scratch, allocated on first use
+         static_assert(dmg_rec_doubles<FEMB200_P1>() == 12 && dmg_rec_doubles<FEMB200_P2>() == 24, "plan_cell_scratch_doubles");
+         if (int rc = plan_cell_scratch(pm)) return rc;
          // The fast kernel can stage the damage records of a tile's cells in shared memory (slot map of the plan, built
          // when first needed, + the per-assembly rows of damaged cells the pre-pass writes through it): that wins once
          // about 40 % of the cells are damaged (n = 1448: 1.56 against 1.65 ms at 50 %, 1.89 against 2.39 ms at 100 %)

@@ -168,6 +168,38 @@ __device__ __forceinline__ double qp_geometry(const double (*xv)[2], int q, doub
    return wq * point_geometry<ET>(xv, xi, eta, G, phi);
 }
 
+// Straight-sided triangles: J is constant, so the physical gradients at point q of the rule are fixed combinations of
+// the barycentric gradients gl[v] = grad lambda_v (one reciprocal per cell instead of the per-point inverse of
+// point_geometry): P1 G_v = gl[v]; P2 G_v = (4 L_v - 1) gl[v], G_(3+i) = 4 (L_j gl[k] + L_k gl[j]) for the edge (j, k)
+// opposite vertex i, with L = (2/3 at the point's own vertex, 1/6 elsewhere).  Returns the vertex basis in phi.
+template <int ET>
+__device__ __forceinline__ void tri_point_grads(int q, const double (*gl)[2], double (*G)[2], double *phi)
+{
+   static_assert(ET == FEMB200_P1 || ET == FEMB200_P2, "triangles only");
+   if (ET == FEMB200_P1)
+   {
+      phi[0] = phi[1] = phi[2] = 1. / 3.;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) G[v][0] = gl[v][0], G[v][1] = gl[v][1];
+      return;
+   }
+   const double L0 = q == 0 ? 2. / 3. : 1. / 6., L1 = q == 1 ? 2. / 3. : 1. / 6., L2 = q == 2 ? 2. / 3. : 1. / 6.;
+   phi[0] = L0, phi[1] = L1, phi[2] = L2;
+#pragma unroll
+   for (int c = 0; c < 2; ++c)
+   {
+      G[0][c] = (4. * L0 - 1.) * gl[0][c];
+      G[1][c] = (4. * L1 - 1.) * gl[1][c];
+      G[2][c] = (4. * L2 - 1.) * gl[2][c];
+      if (ET == FEMB200_P2)
+      {
+         G[Elem<ET>::nd > 3 ? 3 : 0][c] = 4. * (L1 * gl[2][c] + L2 * gl[1][c]);
+         G[Elem<ET>::nd > 3 ? 4 : 0][c] = 4. * (L0 * gl[2][c] + L2 * gl[0][c]);
+         G[Elem<ET>::nd > 3 ? 5 : 0][c] = 4. * (L0 * gl[1][c] + L1 * gl[0][c]);
+      }
+   }
+}
+
 // 2x2 block  w * B_a D B_b^t  with B rows (a,0) = [Gx, 0, Gy], (a,1) = [0, Gy, Gx]
 // (M.cc:699-704, 885-887); D row-major 3x3.
 __device__ __forceinline__ void bdb_block(const double *ga, const double *gb, const double *D, double w, double *k)

@@ -883,6 +883,19 @@ int plan_row_range(const femb200_plan *p, int64_t lo, int64_t hi, RowRange *out)
 }
 }  // namespace femb
 
+namespace femb {
+int plan_cell_scratch(femb200_plan *p)
+{
+   if (p->celld) return 0;
+   std::lock_guard<std::mutex> lock(p->range_mtx);
+   if (p->celld) return 0;
+   const size_t bytes = sizeof(double) * plan_cell_scratch_doubles(p->etype) * (size_t)p->ncells;
+   FEMB_CUDA(cudaMalloc(&p->celld, bytes));
+   p->bytes += bytes;
+   return 0;
+}
+}  // namespace femb
+
 extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int value)
 {
    FEMB_CHECK(p && key, "plan_set_option: null argument");
@@ -905,6 +918,11 @@ extern "C" int femb200_plan_set_option(femb200_plan *p, const char *key, int val
    {
       FEMB_CHECK(value == 0 || value == 1, "plan_set_option: spmv_cols must be 0 (auto: 16-bit relative indices) or 1 (32-bit)");
       p->opt_spmv_cols = value;
+   }
+   else if (!strcmp(key, "vector_path"))
+   {
+      FEMB_CHECK(value == 0 || value == 1, "plan_set_option: vector_path must be 0 (two passes) or 1 (single-pass gather)");
+      p->opt_vector_path = value;
    }
    else if (!strcmp(key, "prefetch_tiles"))
       p->opt_prefetch_tiles = value;
@@ -930,6 +948,8 @@ extern "C" int femb200_plan_get_option(const femb200_plan *p, const char *key, i
       *value = p->opt_spmv_path;
    else if (!strcmp(key, "spmv_cols"))
       *value = p->opt_spmv_cols;
+   else if (!strcmp(key, "vector_path"))
+      *value = p->opt_vector_path;
    else if (!strcmp(key, "prefetch_tiles"))
       *value = p->opt_prefetch_tiles;
    else if (!strcmp(key, "stream_out"))

@@ -151,6 +151,7 @@ struct femb200_plan
    int opt_assembly_path = 0;    // 0 auto; 1 visit-record kernel; 2 per-quadrature-point kernel
    int opt_spmv_path = 0;        // 0 auto (bulk-copy staged, persistent); 1 direct kernel
    int opt_spmv_cols = 0;        // 0 auto (16-bit relative column indices when the pattern allows); 1 32-bit indices
+   int opt_vector_path = 0;      // residual vector: 0 two passes (per-cell r_e + gather); 1 single-pass gather
    int opt_prefetch_tiles = -1;  // record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count)
    // largest 32- / 64-row SpMV tile (in node blocks) of the tiling that starts at row_lo, per row range
    // [row_lo, row_hi) that has been applied (the owned rows of a rank; measured once, on first use)
@@ -169,6 +170,11 @@ struct RowRange
 // fast records
 int plan_tile_cells(femb200_plan *p, int cap, cudaStream_t st);
 int plan_row_range(const femb200_plan *p, int64_t lo, int64_t hi, RowRange *out);
+// doubles per cell of the plan's per-cell scratch p->celld: the damage records of the matrix assembly (P1: 96-byte
+// slots, P2: 192-byte slots) and the element vectors of the residual assembly (2 nd doubles: 6 / 12 / 18)
+inline size_t plan_cell_scratch_doubles(int etype) { return etype == FEMB200_P1 ? 12 : 24; }
+// allocates p->celld on first use
+int plan_cell_scratch(femb200_plan *p);
 int spmv_launch(const femb200_plan *p, const RowRange &rr, const double *d_values, const double *d_x, double *d_y,
                 const double *d_flag, double *d_dot_out, bool accumulate, cudaStream_t st);
 }  // namespace femb

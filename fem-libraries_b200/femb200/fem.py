@@ -224,7 +224,7 @@ class Matrix:
         self._bc_marker = m
 
     def set_option(self, key: str, value: int):
-        """Kernel selection of the plan (femb200_plan_set_option): "assembly_path", "spmv_path", "spmv_cols", "prefetch_tiles",
+        """Kernel selection of the plan (femb200_plan_set_option): "assembly_path", "spmv_path", "spmv_cols", "vector_path", "prefetch_tiles",
         "stream_out", "damage_stage"."""
         capi.call("femb200_plan_set_option", self._plan, key.encode(), int(value))
 

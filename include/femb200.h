@@ -249,6 +249,7 @@ int femb200_scatter_rows(int64_t n, int width, const int32_t *d_idx, const doubl
  *   "assembly_path"  0 auto | 1 visit-record kernel | 2 per-quadrature-point kernel
  *   "spmv_path"      0 auto (bulk-copy staged) | 1 direct kernel
  *   "spmv_cols"      0 auto (16-bit column offsets from the row's node when every offset of the pattern fits) | 1 32-bit
+ *   "vector_path"    residual vector: 0 two passes (element vectors per cell, then a gather per node) | 1 single-pass gather
  *   "prefetch_tiles" record prefetch distance of the assembly kernel in tiles (-1: 8 x SM count, 0: off)
  *   "stream_out"     0 auto (tensor bulk stores of the finished tile) | 1 store loop
  *   "damage_stage"   damaged reassembly: 0 auto (damage records staged per tile in shared memory once 40 % of the

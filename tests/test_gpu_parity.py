@@ -841,6 +841,11 @@ def test_residual_vector_and_lifting(kind, n, damaged):
                                       fnod=None if load is None else load.ravel())
         got = f.assemble_vector(A, form, load).cpu().numpy()
         assert relfro(got, want) < 1e-12
+        # the single-pass gather (plan option vector_path = 1) computes the same entries per visit instead of per cell
+        A.set_option("vector_path", 1)
+        got1 = f.assemble_vector(A, form, load).cpu().numpy()
+        A.set_option("vector_path", 0)
+        assert relfro(got1, want) < 1e-12 and relfro(got1, got) < 1e-14
     # lifting + set_bc (F.cc:826-836): b += J[:, bc] (g - u)_bc on free dofs, b[bc] = -(g - u)[bc]
     bc, g = fm.dirichlet_markers(m)
     A.set_bcs([f.DirichletBC(bc, g)])

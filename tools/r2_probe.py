@@ -47,6 +47,15 @@ def main():
             A.set_option("stream_out", so)
             ms, mn = timed(lambda: fem.assemble_matrix(A, form))
             out[f"assemble_p2_stream_out{so}" + ("b" if f"assemble_p2_stream_out{so}" in out else "")] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+    if "vec" in what:
+        u0 = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+        fl = torch.ones(2 * m.nnodes, dtype=torch.float64, device="cuda")
+        bout = torch.empty(2 * m.nnodes, dtype=torch.float64, device="cuda")
+        dband = torch.clamp(1.0 - (m.x[:, 1] - 0.5 - 0.1 * torch.sin(6.0 * m.x[:, 0])).abs() / 10.0, min=0.0, max=0.95)
+        for label, dd, ff in (("linear", None, None), ("linear_load", None, fl), ("damaged100_load", dband, fl)):
+            fv = fem.ElasticityForm(m, p.E, 0.3, d=dd, u=u0)
+            ms, mn = timed(lambda: fem.assemble_vector(A, fv, ff, out=bout), k=5, w=2)
+            out[f"vector_{label}"] = {"ms": ms, "min": mn}
     if "dmg" in what or "dmg100" in what:
         xy = m.x
         u = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
