@@ -209,6 +209,12 @@ def damage_band(mesh: Mesh) -> np.ndarray:
     return np.minimum(d, 0.95)
 
 
+def _remap_checked(remap: np.ndarray, ids: np.ndarray, path: str) -> np.ndarray:
+    if ids.size and (ids.min() < 0 or ids.max() >= len(remap) or (remap[ids] < 0).any()):
+        raise ValueError(f"{path}: an element refers to a node id that $Nodes does not define")
+    return remap[ids]
+
+
 def read_gmsh22(path: str) -> Mesh:
     """Gmsh 2.2 ASCII reader for triangulations (role of `Mesh(mesh_file, 1, 0, true)`, M.cc:1017-1020,
     and of the gmsh -> XDMF conversion + `read_mesh` / `read_meshtags`, gmsh_to_xdmf_neper_dam.py:1-16,
@@ -249,9 +255,12 @@ def read_gmsh22(path: str) -> Mesh:
             lines.append(nodes), ltag.append(tag)
     if not tris:
         raise ValueError(f"{path}: no triangles")
-    tri = remap[np.array(tris, dtype=np.int64)].astype(np.int32)
+    tri_ids = np.array(tris, dtype=np.int64)
+    if tri_ids.min() < 0 or tri_ids.max() >= len(remap) or (remap[tri_ids] < 0).any():
+        raise ValueError(f"{path}: an element refers to a node id that $Nodes does not define")
+    tri = remap[tri_ids].astype(np.int32)
     meta = {"kind": "gmsh22", "cell_tags": np.array(ttag, dtype=np.int32),
-            "facets": remap[np.array(lines, dtype=np.int64).reshape(-1, 2)].astype(np.int32),
+            "facets": _remap_checked(remap, np.array(lines, dtype=np.int64).reshape(-1, 2), path).astype(np.int32),
             "facet_tags": np.array(ltag, dtype=np.int32)}
     return Mesh(P1, x, tri, tri.copy(), 0, 0, meta)
 

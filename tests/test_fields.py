@@ -223,6 +223,11 @@ def test_gmsh_reader_errors_and_sparse_ids(tmp_path):
         f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n2\n1 0 0 0\n2 1 0 0\n$EndNodes\n$Elements\n1\n1 1 2 1 1 1 2\n$EndElements\n")
     with pytest.raises(ValueError, match="no triangles"):
         fm.read_gmsh22(q)
+    u = os.path.join(str(tmp_path), "u.msh")   # an element names a node that $Nodes does not define
+    with open(u, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n3\n1 0 0 0\n2 1 0 0\n4 0 1 0\n$EndNodes\n$Elements\n1\n1 2 2 1 1 1 2 3\n$EndElements\n")
+    with pytest.raises(ValueError, match="does not define"):
+        fm.read_gmsh22(u)
     r = os.path.join(str(tmp_path), "c.msh")
     with open(r, "w") as f:
         f.write("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n$Nodes\n0\n$EndNodes\n$Elements\n0\n$EndElements\n")
