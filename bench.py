@@ -577,7 +577,6 @@ def e2e_newton(env, fem, dist, form, part, op, A, args, total_dofs):
     ns.cg = dist.DistCG(A, part, rel_tol=0.0, abs_tol=0.0, max_iter=args.cg_iters, op=op, jacobi=False,
                         use_graph=not args.no_graph)
     ns._lo, ns._hi = 2 * part.own_lo, 2 * part.own_hi
-    ns._work = torch.empty(2 * A.ndofs, dtype=torch.float64, device="cuda")
     ns._b = torch.empty(A.ndofs, dtype=torch.float64, device="cuda")
     ns._du = torch.zeros(A.ndofs, dtype=torch.float64, device="cuda")
     ns._nrm = torch.zeros(1, dtype=torch.float64, device="cuda")

@@ -542,6 +542,24 @@ __global__ void k_bc_nodes(int64_t nnodes, const uint8_t *__restrict__ bc, int32
    }
 }
 
+// mark[I] = 1 for every node I in the row of a constrained node J (symmetric pattern: the rows that have column J)
+__global__ void k_mark_lift_rows(int nbc, const int32_t *__restrict__ bc_nodes, const int64_t *__restrict__ brp,
+                                 const int32_t *__restrict__ bcol, uint8_t *__restrict__ mark)
+{
+   const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+   if (w >= nbc) return;
+   const int64_t J = bc_nodes[w], b0 = brp[J], b1 = brp[J + 1];
+   for (int64_t k = b0 + lane; k < b1; k += 32) mark[bcol[k]] = 1;
+}
+__global__ void k_compact_marked(int64_t nnodes, const uint8_t *__restrict__ mark, int32_t *__restrict__ list,
+                                 int32_t *__restrict__ count)
+{
+   const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (I >= nnodes || !mark[I]) return;
+   const int32_t p = atomicAdd(count, 1);
+   if (list) list[p] = (int32_t)I;
+}
+
 template <typename T>
 static int dev_alloc(T **p, size_t n, size_t *acc)
 {
@@ -572,6 +590,7 @@ extern "C" void femb200_plan_destroy(femb200_plan *p)
    cudaFree(p->dslot);
    cudaFree(p->bc);
    cudaFree(p->bc_nodes);
+   cudaFree(p->lift_nodes);
    cudaFree(p->norm_partials);
    cudaFree(p->cellrec);
    cudaFree(p->cref);
@@ -812,6 +831,9 @@ extern "C" int femb200_plan_set_dirichlet(femb200_plan *p, const uint8_t *d_bc, 
    cudaFree(p->bc_nodes);
    p->bc_nodes = nullptr;
    p->nbc = 0;
+   cudaFree(p->lift_nodes);
+   p->lift_nodes = nullptr;
+   p->nlift = 0;
    if (!d_bc)
    {
       cudaFree(p->bc);
@@ -840,9 +862,34 @@ extern "C" int femb200_plan_set_dirichlet(femb200_plan *p, const uint8_t *d_bc, 
    }
    cudaMemsetAsync(count, 0, sizeof(int32_t), st);
    k_bc_nodes<<<(unsigned)cdiv(p->nnodes, T), T, 0, st>>>(p->nnodes, p->bc, p->bc_nodes, count);
+   p->nbc = n;
+   // the node rows apply_lifting touches: every row with a constrained column (the constrained nodes among them)
+   uint8_t *mark = nullptr;
+   int32_t nl = 0;
+   if (n > 0)
+   {
+      if (dev_alloc(&mark, (size_t)p->nnodes, &acc))
+      {
+         cudaFree(count);
+         return 1;
+      }
+      cudaMemsetAsync(mark, 0, (size_t)p->nnodes, st);
+      k_mark_lift_rows<<<(unsigned)cdiv((int64_t)n * 32, T), T, 0, st>>>(n, p->bc_nodes, p->brp, p->bcol, mark);
+      cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+      k_compact_marked<<<(unsigned)cdiv(p->nnodes, T), T, 0, st>>>(p->nnodes, mark, nullptr, count);
+      cudaMemcpyAsync(&nl, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess || dev_alloc(&p->lift_nodes, (size_t)nl, &acc))
+      {
+         cudaFree(count), cudaFree(mark);
+         return set_error("plan_set_dirichlet: lifting rows: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+      cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+      k_compact_marked<<<(unsigned)cdiv(p->nnodes, T), T, 0, st>>>(p->nnodes, mark, p->lift_nodes, count);
+   }
    cudaStreamSynchronize(st);
    cudaFree(count);
-   p->nbc = n;
+   cudaFree(mark);
+   p->nlift = nl;
    FEMB_LAUNCH_CHECK();
    return 0;
 }

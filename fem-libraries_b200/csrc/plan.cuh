@@ -127,6 +127,8 @@ struct femb200_plan
    uint8_t *bc = nullptr;        // [2*nnodes] or null
    int32_t *bc_nodes = nullptr;  // compact list of constrained nodes
    int32_t nbc = 0;
+   int32_t *lift_nodes = nullptr;  // compact list of the node rows with a constrained column (the rows apply_lifting changes)
+   int32_t nlift = 0;
    double *norm_partials = nullptr;  // [3 nbc] scratch of femb200_assemble_matrix_norms
    size_t bytes = 0;
    double *celld = nullptr;    // damage records of the cells (assemble.cu, cell_setup_damage_kernel), lazily allocated

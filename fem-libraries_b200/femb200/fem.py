@@ -323,8 +323,7 @@ def apply_lifting(A: Matrix, b: torch.Tensor, g: torch.Tensor, u: torch.Tensor, 
     """apply_lifting(b, {J}, {bcs}, {u}, scale) + set_bc(b, bcs, u, scale) of the setF lambda
     (F.cc:826-836): b -= scale * J[:, bc] (g - u)_bc on the free dofs, b[bc] = scale * (g - u)[bc].
     A.values must hold the UNCONSTRAINED tangent (assemble_matrix_nobc)."""
-    work = torch.empty(2 * b.numel(), dtype=torch.float64, device="cuda")
-    capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(g), _p(u), float(scale), _p(b), _p(work), _stream())
+    capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(g), _p(u), float(scale), _p(b), None, _stream())
     return b
 
 
@@ -367,7 +366,6 @@ class NewtonSolver:
         self.cg = dist.DistCG(self.A, self.part, rel_tol=cg_rel_tol, max_iter=cg_max_iter, jacobi=False,
                               transport=transport, group=group)
         self._lo, self._hi = 2 * self.part.own_lo, 2 * self.part.own_hi
-        self._work = torch.empty(2 * self.A.ndofs, dtype=torch.float64, device="cuda")
         self._b = torch.empty(self.A.ndofs, dtype=torch.float64, device="cuda")
         self._du = torch.zeros(self.A.ndofs, dtype=torch.float64, device="cuda")
         self._nrm = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -390,7 +388,7 @@ class NewtonSolver:
         else:
             assemble_matrix_nobc(A, form)
             self._tangent_ready = True
-            capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(self.g), _p(u), -1.0, _p(b), _p(self._work), _stream())
+            capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(self.g), _p(u), -1.0, _p(b), None, _stream())
         return b
 
     def norm(self, v: torch.Tensor) -> float:

@@ -154,7 +154,8 @@ int femb200_matrix_norms(const femb200_plan *plan, const double *d_values, doubl
  *   d_u current iterate (required); d_fnod nodal body force (nnodes x 2) or NULL.
  * apply_lifting: b -= scale * K[:, bc] (g - u)_bc on the free dofs and
  *   b[bc] = scale * (g - u)[bc]  (dolfinx: scale = -1), with K the
- *   UNCONSTRAINED tangent (femb200_assemble_matrix_nobc); d_work: 4*nnodes doubles.
+ *   UNCONSTRAINED tangent (femb200_assemble_matrix_nobc); only the node rows with a constrained
+ *   column are touched (O(boundary) work); d_work: unused (may be NULL), kept in the signature.
  * ------------------------------------------------------------------------ */
 int femb200_assemble_vector(const femb200_plan *plan, const double *d_x, int x_stride, const double *d_E, double nu,
                             const double *d_dnod, const double *d_u, const double *d_fnod, double *d_b, void *stream);
