@@ -638,12 +638,32 @@ def extras(env, fem, peak, args):
         fem.tabulate_tensor_batched(form, out=Ae)
     tot, calls = env.timed(lambda: fem.tabulate_tensor_batched(form, out=Ae), 10)
     ms = float(np.mean(calls))
-    FL_TAB = 36 * 3 * 38 + 3 * 70     # 36 block pairs x 3 points x bdb_block (38 flops) + 3 x point geometry (~70)
+    # undamaged straight-sided triangles: closed form from the nine P1 blocks: 9 x bdb_block (38 flops) + the 36 blocks
+    # (9 x 4 + 12 x 4 + 9 x 4 x 8 flops) + geometry (~30)
+    FL_CLOSED = 9 * 38 + 36 + 48 + 288 + 30
     out["fp64"]["tabulate_kernel_p2"] = {
-        "ms": ms, "cells": m.ncells, "flops_per_element": FL_TAB, "tflops": FL_TAB * m.ncells / (ms * 1e-3) / 1e12,
-        "frac_fp64": FL_TAB * m.ncells / (ms * 1e-3) / 1e12 / fp64_peak, "bytes_written_per_element": 1152,
+        "ms": ms, "cells": m.ncells, "flops_per_element": FL_CLOSED, "tflops": FL_CLOSED * m.ncells / (ms * 1e-3) / 1e12,
+        "frac_fp64": FL_CLOSED * m.ncells / (ms * 1e-3) / 1e12 / fp64_peak, "bytes_written_per_element": 1152,
         "frac_hbm": (1152 + 40) * m.ncells / (ms * 1e-3) / 1e9 / peak,
-        "what": "femb200_tabulate_tensor_batched (ufcx / AssembleElementGrad surface): all 12 x 12 element tangents to HBM"}
+        "what": "femb200_tabulate_tensor_batched (ufcx / AssembleElementGrad surface), undamaged cells: all 12 x 12 element "
+                "tangents to HBM from the closed form (exact for the 3-point rule on straight-sided triangles): HBM-bound"}
+    # the same kernel on damaged cells (d > 0 at every point): per-point integration, B_q D_q B_q^t with the reference's
+    # closed-form tangent (M.cc:736-872): the FP64-heavy form of the element kernel
+    xy = m.x
+    dfull = torch.full((m.nnodes,), 0.5, dtype=torch.float64, device="cuda")
+    ufull = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    formd = fem.ElasticityForm(m, p.E, 0.3, d=dfull, u=ufull)
+    for _ in range(2):
+        fem.tabulate_tensor_batched(formd, out=Ae)
+    tot, calls = env.timed(lambda: fem.tabulate_tensor_batched(formd, out=Ae), 10)
+    msd = float(np.mean(calls))
+    FL_TAB = 36 * 3 * 38 + 3 * 70 + 3 * 150   # 36 block pairs x 3 points x bdb_block (38) + 3 x point geometry (~70) + 3 x tangent (~150)
+    out["fp64"]["tabulate_kernel_p2_damaged"] = {
+        "ms": msd, "cells": m.ncells, "flops_per_element": FL_TAB, "tflops": FL_TAB * m.ncells / (msd * 1e-3) / 1e12,
+        "frac_fp64": FL_TAB * m.ncells / (msd * 1e-3) / 1e12 / fp64_peak,
+        "frac_hbm": (1152 + 40 + 6 * 16 + 24) * m.ncells / (msd * 1e-3) / 1e9 / peak,
+        "what": "the same kernel with every cell damaged: per-point triple products + the closed-form damaged tangent"}
+    del formd, dfull, ufull
     del Ae
     A = fem.create_matrix(form)
     for _ in range(3):

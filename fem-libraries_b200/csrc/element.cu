@@ -8,6 +8,53 @@
 
 namespace femb {
 
+// Block (a, b) of the element matrix of an undamaged straight-sided triangle from the nine P1 blocks
+// W[c][d] = |T| B_c D B_d^t (c, d = vertices; M.cc:699-704, 885-887 with w = |T|): what the 3-point rule integrates
+// exactly (derivation in assemble.cu), at ~0.6 kflop per P2 element instead of 4.3 kflop for the
+// triple product per point:
+//   vertex / vertex          W^{aa}, or -W^{ab} / 3
+//   vertex a / edge (r, s)   4/3 W^{as} if a = r, 4/3 W^{ar} if a = s, 0 if a is opposite; edge / vertex likewise
+//   edge (p, q) / edge (r, s)  4/3 [(1 + d_qs) W^{pr} + (1 + d_qr) W^{ps} + (1 + d_ps) W^{qr} + (1 + d_pr) W^{qs}]
+// a, b are compile-time constants at every call site (unrolled loops): W stays in registers.
+template <int ET>
+__device__ __forceinline__ void closed_block(int a, int b, const double (*W)[3][4], double *k)
+{
+   if (ET == FEMB200_P1)
+   {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = W[a][b][j];
+      return;
+   }
+   const double c43 = 4. / 3.;
+   // edge 3 + i joins the two vertices other than i
+   const int p = (a - 3 + 1) % 3, q = (a - 3 + 2) % 3, r = (b - 3 + 1) % 3, t = (b - 3 + 2) % 3;
+   if (a < 3 && b < 3)
+   {
+      const double c = a == b ? 1. : -1. / 3.;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = c * W[a][b][j];
+   }
+   else if (a < 3)
+   {
+      const int o = a == r ? t : r;  // the other end of the edge, when a is one of its ends
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = (a == r || a == t) ? c43 * W[a][o][j] : 0.;
+   }
+   else if (b < 3)
+   {
+      const int o = b == p ? q : p;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = (b == p || b == q) ? c43 * W[o][b][j] : 0.;
+   }
+   else
+   {
+      const double cpr = q == t ? 2. : 1., cps = q == r ? 2. : 1., cqr = p == t ? 2. : 1., cqs = p == r ? 2. : 1.;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+         k[j] = c43 * (cpr * W[p][r][j] + cps * W[p][t][j] + cqr * W[q][r][j] + cqs * W[q][t][j]);
+   }
+}
+
 // One thread integrates one cell; the 2 x n slabs of the element matrix (a row pair in the ufcx layout, a column
 // pair in the MFEM layout) go through a per-warp shared-memory stage (padded: conflict-free 16-byte accesses) and
 // leave as contiguous n-double chunks, 12 lanes per 96-byte chunk for P2: every 32-byte sector written whole,
@@ -40,59 +87,115 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
    const double Ee = E[ec];
    const double lam = Ee * lc.c2, mu = Ee * lc.c3;  // M.cc:1093-1098
 
-   double G[nq][nd][2], w[nq], D[nq][9];
-#pragma unroll
-   for (int q = 0; q < nq; ++q)
+   // undamaged straight-sided triangle: closed form from the nine P1 blocks (the cells of a linear problem, and the
+   // undamaged cells of a damaged one); everything else integrates point by point
+   bool lin = false;
+   double W[3][3][4];
+   if (ET != FEMB200_Q2)
    {
-      double phi[nv];
-      w[q] = qp_geometry<ET>(xv, q, G[q], phi);
-      double d = 0.;
+      lin = true;
 #pragma unroll
-      for (int v = 0; v < nv; ++v) d += phi[v] * dv[v];
-      if (d > 0.)
+      for (int q = 0; q < nq; ++q)
       {
-         double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
-         if (u)
-#pragma unroll
-            for (int a = 0; a < nd; ++a)
-            {
-               const int64_t gd = 2 * (int64_t)dofmap[ec * nd + a];
-               const double ux = u[gd], uy = u[gd + 1];
-               g00 += ux * G[q][a][0];
-               g01 += ux * G[q][a][1];
-               g10 += uy * G[q][a][0];
-               g11 += uy * G[q][a][1];
-            }
-         const double s = 0.5 * (g01 + g10);
-         const double eps[4] = {g00, s, s, g11};
-         tangent(variant, lam, mu, d, eps, D[q]);
+         double dN[nd][2], phi[3], w2;
+         double xi, eta, wq;
+         quad_point<ET>(q, xi, eta, wq);
+         (void)dN, (void)w2, (void)wq;
+         phi[0] = 1. - xi - eta, phi[1] = xi, phi[2] = eta;
+         lin = lin && !(phi[0] * dv[0] + phi[1] * dv[1] + phi[2] * dv[2] > 0.);
       }
-      else
-         hooke_scaled(lam, mu, 1., D[q]);
+      if (lin)
+      {
+         const double det = (xv[1][0] - xv[0][0]) * (xv[2][1] - xv[0][1]) - (xv[2][0] - xv[0][0]) * (xv[1][1] - xv[0][1]);
+         const double id = 1. / det;
+         double gl[3][2], Dh[9];
+         gl[1][0] = (xv[2][1] - xv[0][1]) * id, gl[1][1] = -(xv[2][0] - xv[0][0]) * id;
+         gl[2][0] = -(xv[1][1] - xv[0][1]) * id, gl[2][1] = (xv[1][0] - xv[0][0]) * id;
+         gl[0][0] = -gl[1][0] - gl[2][0], gl[0][1] = -gl[1][1] - gl[2][1];
+         hooke_scaled(lam, mu, 1., Dh);
+         const double wT = 0.5 * fabs(det);
+#pragma unroll
+         for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+               W[c][d][0] = W[c][d][1] = W[c][d][2] = W[c][d][3] = 0.;
+               bdb_block(gl[c], gl[d], Dh, wT, W[c][d]);
+            }
+      }
+   }
+   double G[nq][nd][2], w[nq], D[nq][9];
+   if (!lin)
+   {
+#pragma unroll
+      for (int q = 0; q < nq; ++q)
+      {
+         double phi[nv];
+         w[q] = qp_geometry<ET>(xv, q, G[q], phi);
+         double d = 0.;
+#pragma unroll
+         for (int v = 0; v < nv; ++v) d += phi[v] * dv[v];
+         if (d > 0.)
+         {
+            double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+            if (u)
+#pragma unroll
+               for (int a = 0; a < nd; ++a)
+               {
+                  const int64_t gd = 2 * (int64_t)dofmap[ec * nd + a];
+                  const double ux = u[gd], uy = u[gd + 1];
+                  g00 += ux * G[q][a][0];
+                  g01 += ux * G[q][a][1];
+                  g10 += uy * G[q][a][0];
+                  g11 += uy * G[q][a][1];
+               }
+            const double s = 0.5 * (g01 + g10);
+            const double eps[4] = {g00, s, s, g11};
+            tangent(variant, lam, mu, d, eps, D[q]);
+         }
+         else
+            hooke_scaled(lam, mu, 1., D[q]);
+      }
    }
 
    constexpr bool rowmajor = ROWMAJOR;
    double *st = stage[warp] + lane * STRIDE;
-   constexpr int UNR = 1;  // rolled loops (G indexed in local memory, L1 hits): 154 registers for P2 against 254 unrolled
-#pragma unroll 1
-   for (int o = 0; o < nd; ++o)
-   {  // slab o: rows (2o, 2o+1) of the ufcx layout / columns (o, nd + o) of the MFEM layout
-#pragma unroll UNR
-      for (int i = 0; i < nd; ++i)
+   auto put = [&](int a, int b, const double *k) {
+      if (rowmajor)
+      {  // chunk r = row 2a + r: entries (2b, 2b + 1)
+         reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
+         reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
+      }
+      else
+      {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
+         st[a] = k[0], st[nd + a] = k[2];
+         st[n + a] = k[1], st[n + nd + a] = k[3];
+      }
+   };
+   // the slab loop is unrolled for triangles (closed_block needs constant node numbers), rolled for Q2 (G indexed in
+   // local memory, L1 hits: 154 registers against 254 unrolled)
+   auto slab = [&](const int o) {  // slab o: rows (2o, 2o+1) of the ufcx layout / columns (o, nd + o) of the MFEM layout
+      if (ET != FEMB200_Q2 && lin)
       {
-         const int a = rowmajor ? o : i, b = rowmajor ? i : o;
-         double k[4] = {0., 0., 0., 0.};
 #pragma unroll
-         for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], w[q], k);
-         if (rowmajor)
-         {  // chunk r = row 2a + r: entries (2b, 2b + 1)
-            reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
-            reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
+         for (int i = 0; i < nd; ++i)
+         {
+            const int a = rowmajor ? o : i, b = rowmajor ? i : o;
+            double k[4];
+            closed_block<ET>(a, b, W, k);
+            put(a, b, k);
          }
-         else
-         {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
-            st[a] = k[0], st[nd + a] = k[2];
-            st[n + a] = k[1], st[n + nd + a] = k[3];
+      }
+      else
+      {
+#pragma unroll 1
+         for (int i = 0; i < nd; ++i)
+         {
+            const int a = rowmajor ? o : i, b = rowmajor ? i : o;
+            double k[4] = {0., 0., 0., 0.};
+#pragma unroll
+            for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], w[q], k);
+            put(a, b, k);
          }
       }
       __syncwarp();
@@ -106,6 +209,16 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
          reinterpret_cast<double2 *>(dst)[j] = val;
       }
       __syncwarp();
+   };
+   if (ET == FEMB200_Q2)
+   {
+#pragma unroll 1
+      for (int o = 0; o < nd; ++o) slab(o);
+   }
+   else
+   {
+#pragma unroll
+      for (int o = 0; o < nd; ++o) slab(o);
    }
 }
 
