@@ -58,7 +58,8 @@ __device__ __forceinline__ void closed_block(int a, int b, const double (*W)[3][
 // One thread integrates one cell; the 2 x n slabs of the element matrix (a row pair in the ufcx layout, a column
 // pair in the MFEM layout) go through a per-warp shared-memory stage (padded: conflict-free 16-byte accesses) and
 // leave as contiguous n-double chunks, 12 lanes per 96-byte chunk for P2: every 32-byte sector written whole,
-// instead of 32 lanes storing 1152 bytes apart (5.1 -> ~0.9 ms for 4.19 M P2 cells).
+// instead of 32 lanes storing 1152 bytes apart (5.1 -> 1.46 ms for 4.19 M P2 cells; with the closed form of the undamaged
+// cells 0.84 ms = 0.92 of the HBM roofline; compiled for 4 CTAs per SM, 128 registers: 0.87 ms, not kept).
 template <int ET, bool ROWMAJOR>
 __global__ void __launch_bounds__(128)
 tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict__ x, int xs,
@@ -124,8 +125,54 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
             }
       }
    }
+   constexpr bool rowmajor = ROWMAJOR;
+   double *st = stage[warp] + lane * STRIDE;
+   auto put = [&](int a, int b, const double *k) {
+      if (rowmajor)
+      {  // chunk r = row 2a + r: entries (2b, 2b + 1)
+         reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
+         reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
+      }
+      else
+      {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
+         st[a] = k[0], st[nd + a] = k[2];
+         st[n + a] = k[1], st[n + nd + a] = k[3];
+      }
+   };
+   auto flush = [&](const int o) {  // slab o of the warp's cells leaves: 2 chunks of n doubles per cell, n double2 units per cell
+      __syncwarp();
+      for (int t = lane; t < nwarp * n; t += 32)
+      {
+         const int c = t / n, r = t - c * n;       // cell of the warp, unit in its slab
+         const int ch = r / nd, j = r - ch * nd;   // chunk, double2 inside the chunk
+         const double2 val = reinterpret_cast<const double2 *>(stage[warp] + c * STRIDE + ch * n)[j];
+         double *dst = A + (e0 + c) * (int64_t)(n * n) + (rowmajor ? (int64_t)(2 * o + ch) * n : (int64_t)(ch * nd + o) * n);
+         reinterpret_cast<double2 *>(dst)[j] = val;
+      }
+      __syncwarp();
+   };
+   // slab o: rows (2o, 2o+1) of the ufcx layout / columns (o, nd + o) of the MFEM layout.  A warp whose 32 cells are all
+   // undamaged triangles takes the closed form with the slab loop unrolled (closed_block needs constant node numbers);
+   // any other warp integrates all its cells point by point with rolled loops (G indexed in local memory, L1 hits).
+   if (ET != FEMB200_Q2 && __all_sync(0xffffffffu, lin))
+   {
+#pragma unroll
+      for (int o = 0; o < nd; ++o)
+      {
+#pragma unroll
+         for (int i = 0; i < nd; ++i)
+         {
+            const int a = rowmajor ? o : i, b = rowmajor ? i : o;
+            double k[4];
+            closed_block<ET>(a, b, W, k);
+            put(a, b, k);
+         }
+         flush(o);
+      }
+      return;
+   }
    double G[nq][nd][2], w[nq], D[nq][9];
-   if (!lin)
+   if constexpr (ET == FEMB200_Q2)
    {
 #pragma unroll
       for (int q = 0; q < nq; ++q)
@@ -157,68 +204,65 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
             hooke_scaled(lam, mu, 1., D[q]);
       }
    }
-
-   constexpr bool rowmajor = ROWMAJOR;
-   double *st = stage[warp] + lane * STRIDE;
-   auto put = [&](int a, int b, const double *k) {
-      if (rowmajor)
-      {  // chunk r = row 2a + r: entries (2b, 2b + 1)
-         reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
-         reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
-      }
-      else
-      {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
-         st[a] = k[0], st[nd + a] = k[2];
-         st[n + a] = k[1], st[n + nd + a] = k[3];
-      }
-   };
-   // the slab loop is unrolled for triangles (closed_block needs constant node numbers), rolled for Q2 (G indexed in
-   // local memory, L1 hits: 154 registers against 254 unrolled)
-   auto slab = [&](const int o) {  // slab o: rows (2o, 2o+1) of the ufcx layout / columns (o, nd + o) of the MFEM layout
-      if (ET != FEMB200_Q2 && lin)
-      {
-#pragma unroll
-         for (int i = 0; i < nd; ++i)
-         {
-            const int a = rowmajor ? o : i, b = rowmajor ? i : o;
-            double k[4];
-            closed_block<ET>(a, b, W, k);
-            put(a, b, k);
-         }
-      }
-      else
-      {
-#pragma unroll 1
-         for (int i = 0; i < nd; ++i)
-         {
-            const int a = rowmajor ? o : i, b = rowmajor ? i : o;
-            double k[4] = {0., 0., 0., 0.};
-#pragma unroll
-            for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], w[q], k);
-            put(a, b, k);
-         }
-      }
-      __syncwarp();
-      // 2 chunks of n doubles per cell, n double2 units per cell
-      for (int t = lane; t < nwarp * n; t += 32)
-      {
-         const int c = t / n, r = t - c * n;       // cell of the warp, unit in its slab
-         const int ch = r / nd, j = r - ch * nd;   // chunk, double2 inside the chunk
-         const double2 val = reinterpret_cast<const double2 *>(stage[warp] + c * STRIDE + ch * n)[j];
-         double *dst = A + (e0 + c) * (int64_t)(n * n) + (rowmajor ? (int64_t)(2 * o + ch) * n : (int64_t)(ch * nd + o) * n);
-         reinterpret_cast<double2 *>(dst)[j] = val;
-      }
-      __syncwarp();
-   };
-   if (ET == FEMB200_Q2)
-   {
-#pragma unroll 1
-      for (int o = 0; o < nd; ++o) slab(o);
-   }
    else
-   {
+   {  // triangles: u gathered once per cell, before the points
+      bool dam = false;  // d > 0 at some point of the cell: the tangent needs grad u
+      double dq[nq];
 #pragma unroll
-      for (int o = 0; o < nd; ++o) slab(o);
+      for (int q = 0; q < nq; ++q)
+      {
+         double phi[nv];
+         w[q] = qp_geometry<ET>(xv, q, G[q], phi);
+         dq[q] = 0.;
+#pragma unroll
+         for (int v = 0; v < nv; ++v) dq[q] += phi[v] * dv[v];
+         dam = dam || dq[q] > 0.;
+      }
+      double ue[nd][2];
+      if (dam)
+      {
+#pragma unroll
+         for (int a = 0; a < nd; ++a)
+         {
+            const int64_t gd = 2 * (int64_t)dofmap[ec * nd + a];
+            ue[a][0] = u ? u[gd] : 0., ue[a][1] = u ? u[gd + 1] : 0.;
+         }
+      }
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q)
+      {
+         if (dq[q] > 0.)
+         {
+            double g00 = 0., g01 = 0., g10 = 0., g11 = 0.;  // grad u (M.cc:742)
+#pragma unroll
+            for (int a = 0; a < nd; ++a)
+            {
+               g00 += ue[a][0] * G[q][a][0];
+               g01 += ue[a][0] * G[q][a][1];
+               g10 += ue[a][1] * G[q][a][0];
+               g11 += ue[a][1] * G[q][a][1];
+            }
+            const double s = 0.5 * (g01 + g10);
+            const double eps[4] = {g00, s, s, g11};
+            tangent(variant, lam, mu, dq[q], eps, D[q]);
+         }
+         else
+            hooke_scaled(lam, mu, 1., D[q]);
+      }
+   }
+#pragma unroll 1
+   for (int o = 0; o < nd; ++o)
+   {
+#pragma unroll 1
+      for (int i = 0; i < nd; ++i)
+      {
+         const int a = rowmajor ? o : i, b = rowmajor ? i : o;
+         double k[4] = {0., 0., 0., 0.};
+#pragma unroll
+         for (int q = 0; q < nq; ++q) bdb_block(G[q][a], G[q][b], D[q], w[q], k);
+         put(a, b, k);
+      }
+      flush(o);
    }
 }
 

@@ -39,6 +39,12 @@ def main():
             ms, mn = timed(lambda: fem.tabulate_tensor_batched(form, layout=lay, out=Ae))
             out[f"tabulate_p2_layout{lay}"] = {"ms": ms, "min": mn, "frac_hbm": 1192 * m.ncells / (ms * 1e-3) / 1e9 / PEAK,
                                                "tflops": 4314 * m.ncells / (ms * 1e-3) / 1e12}
+        dfull = torch.full((m.nnodes,), 0.5, dtype=torch.float64, device="cuda")
+        ufull = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+        for var, nm in ((0, "closed"), (1, "ad")):
+            fd = fem.ElasticityForm(m, p.E, 0.3, d=dfull, u=ufull, variant=var)
+            ms, mn = timed(lambda: fem.tabulate_tensor_batched(fd, layout=0, out=Ae))
+            out[f"tabulate_p2_damaged_{nm}"] = {"ms": ms, "min": mn}
         del Ae
     A = fem.create_matrix(form)
     abytes = 8 * A.nnz + m.ncells * 32 + m.nnodes * 16
