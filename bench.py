@@ -664,6 +664,22 @@ def extras(env, fem, peak, args):
         "frac_hbm": (1152 + 40 + 6 * 16 + 24) * m.ncells / (msd * 1e-3) / 1e9 / peak,
         "what": "the same kernel with every cell damaged: per-point triple products + the closed-form damaged tangent"}
     del formd, dfull, ufull
+    # the reference's own element: P1, one point (damIntegrator::AssembleElementGrad, M.cc:639-916; the CPU figure of the
+    # same kernel compiled from the reference's source is in cpu_baseline.reference_element_kernel)
+    from femb200 import mesh as _fm
+    m1 = _fm.jitter(_fm.structured_triangles(2896, order=1), 0.2, seed=1234)
+    f1 = fem.ElasticityForm(m1, _fm.young_per_cell(m1.ncells), 0.3)
+    A1 = torch.empty((m1.ncells, 6, 6), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        fem.tabulate_tensor_batched(f1, layout=fem.capi.COLMAJOR_BYNODES, out=A1)
+    tot, calls = env.timed(lambda: fem.tabulate_tensor_batched(f1, layout=fem.capi.COLMAJOR_BYNODES, out=A1), 10)
+    ms1 = float(np.mean(calls))
+    out["fp64"]["element_grad_p1"] = {
+        "ms": ms1, "cells": m1.ncells, "gelems_per_s": m1.ncells / (ms1 * 1e-3) / 1e9, "bytes_written_per_element": 288,
+        "frac_hbm": (288 + 12 + 8 + 8) * m1.ncells / (ms1 * 1e-3) / 1e9 / peak,
+        "what": "femb200_element_grad_batched on 16.8 M P1 triangles, MFEM layout (column-major, byNODES): the batched "
+                "form of the reference's AssembleElementGrad, d = 0"}
+    del A1, f1, m1
     del Ae
     A = fem.create_matrix(form)
     for _ in range(3):

@@ -67,7 +67,10 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
                 LameCoef lc, const double *__restrict__ dnod, const double *__restrict__ u, int variant)
 {
    constexpr int nd = Elem<ET>::nd, nv = Elem<ET>::nv, nq = Elem<ET>::nq, n = 2 * nd;
-   constexpr int STRIDE = 2 * n + 2;  // doubles per lane in the stage
+   // P1: the whole 6 x 6 matrix of a cell is staged, the 32 matrices of a warp leave as one contiguous 9 KB range;
+   // P2 / Q2: one slab (2 x n) at a time
+   constexpr bool FULL = ET == FEMB200_P1;
+   constexpr int STRIDE = FULL ? n * n + 2 : 2 * n + 2;  // doubles per lane in the stage
    __shared__ __align__(16) double stage[4][32 * STRIDE];
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,16 +133,31 @@ tabulate_kernel(int64_t ncells, double *__restrict__ A, const double *__restrict
    auto put = [&](int a, int b, const double *k) {
       if (rowmajor)
       {  // chunk r = row 2a + r: entries (2b, 2b + 1)
-         reinterpret_cast<double2 *>(st)[b] = make_double2(k[0], k[1]);
-         reinterpret_cast<double2 *>(st + n)[b] = make_double2(k[2], k[3]);
+         double *s0 = FULL ? st + 2 * a * n : st;
+         reinterpret_cast<double2 *>(s0)[b] = make_double2(k[0], k[1]);
+         reinterpret_cast<double2 *>(s0 + n)[b] = make_double2(k[2], k[3]);
       }
       else
       {  // chunk c = column c * nd + b: rows a and nd + a (elmat(i, j) at i + j n, M.cc:647,673)
-         st[a] = k[0], st[nd + a] = k[2];
-         st[n + a] = k[1], st[n + nd + a] = k[3];
+         double *s0 = FULL ? st + b * n : st, *s1 = FULL ? st + (nd + b) * n : st + n;
+         s0[a] = k[0], s0[nd + a] = k[2];
+         s1[a] = k[1], s1[nd + a] = k[3];
       }
    };
    auto flush = [&](const int o) {  // slab o of the warp's cells leaves: 2 chunks of n doubles per cell, n double2 units per cell
+      if (FULL)
+      {
+         if (o != nd - 1) return;
+         __syncwarp();
+         constexpr int UPC = n * n / 2;  // 16-byte units per cell
+         double2 *dst = reinterpret_cast<double2 *>(A + e0 * (int64_t)(n * n));
+         for (int t = lane; t < nwarp * UPC; t += 32)
+         {
+            const int c = t / UPC, r = t - c * UPC;
+            dst[t] = reinterpret_cast<const double2 *>(stage[warp] + c * STRIDE)[r];
+         }
+         return;
+      }
       __syncwarp();
       for (int t = lane; t < nwarp * n; t += 32)
       {

@@ -46,6 +46,14 @@ def main():
             ms, mn = timed(lambda: fem.tabulate_tensor_batched(fd, layout=0, out=Ae))
             out[f"tabulate_p2_damaged_{nm}"] = {"ms": ms, "min": mn}
         del Ae
+        m1 = fm.jitter(fm.structured_triangles(2896, order=1), 0.2, seed=1234)
+        f1 = fem.ElasticityForm(m1, fm.young_per_cell(m1.ncells), 0.3)
+        A1 = torch.empty((m1.ncells, 6, 6), dtype=torch.float64, device="cuda")
+        for lay in (0, 1):
+            ms, mn = timed(lambda: fem.tabulate_tensor_batched(f1, layout=lay, out=A1))
+            out[f"tabulate_p1_layout{lay}"] = {"ms": ms, "min": mn, "frac_hbm": 316 * m1.ncells / (ms * 1e-3) / 1e9 / PEAK,
+                                               "gelems": m1.ncells / ms / 1e6}
+        del A1, f1, m1
     A = fem.create_matrix(form)
     abytes = 8 * A.nnz + m.ncells * 32 + m.nnodes * 16
     if "asm" in what:
