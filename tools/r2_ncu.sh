@@ -8,7 +8,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --set full --clock-control none --import-source on"
 
-python tools/r2_probe.py asm dmg p1 pa > $OUT/${TAG}_probe.json 2> $OUT/${TAG}_probe.err || { echo "probe failed"; tail -5 $OUT/${TAG}_probe.err; exit 1; }
+python tools/r2_probe.py asm dmg p1 pa tab vec > $OUT/${TAG}_probe.json 2> $OUT/${TAG}_probe.err || { echo "probe failed"; tail -5 $OUT/${TAG}_probe.err; exit 1; }
 cat $OUT/${TAG}_probe.json
 
 cap() {  # name, kernel regex, launch-skip, probe args...
@@ -21,6 +21,9 @@ cap dmg_gather_100pct 'assemble_fast_kernel' 4 dmg100
 cap dmg_prepass_100pct 'cell_setup_damage_kernel' 3 dmg100
 cap asm_p1_n2896 'assemble_fast_kernel' 20 p1
 cap pa_q2_n2048 'pa_tile_kernel' 5 pa
+cap tabulate_p2 'tabulate_kernel' 4 tab
+cap residual_cells 'cell_residual_kernel' 4 vec
+cap residual_gather 'vector_gather_kernel' 4 vec
 
 # config 4 (n = 5792): launch list of the bench step, then the two dominant kernels
 B="python bench.py --steps 2 --warmup 3 --skip-extras --no-cpu-baseline --e2e-steps 1"
