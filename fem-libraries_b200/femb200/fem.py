@@ -377,17 +377,29 @@ class NewtonSolver:
         self.cg.close()
 
     # -- building blocks (one Newton linearisation = residual() + increment()) -----------------
+    def prepare_tangent(self) -> bool:
+        """Assembles the unconstrained tangent ahead of residual() when it does not depend on the iterate (a form
+        without damage: J is the linear stiffness, M.cc:873-881), e.g. while u is still on its way to the device;
+        returns False (and does nothing) for a form whose tangent needs u."""
+        if self.form.d is not None:
+            return False
+        assemble_matrix_nobc(self.A, self.form)
+        self._tangent_ready = True
+        return True
+
     def residual(self, u: torch.Tensor) -> torch.Tensor:
         """b = F(u) with apply_lifting + set_bc (scale -1), setF lambda F.cc:817-845."""
         form, A, b = self.form, self.A, self._b
         form.u = u
         assemble_vector(A, form, self.f, out=b)
-        self._tangent_ready = False
+        if form.d is not None:
+            self._tangent_ready = False     # the tangent of a damaged form depends on u
         if self._lifted:
             capi.call("femb200_set_bc", A.plan, _p(self.g), _p(u), -1.0, _p(b), _stream())
         else:
-            assemble_matrix_nobc(A, form)
-            self._tangent_ready = True
+            if not self._tangent_ready:
+                assemble_matrix_nobc(A, form)
+                self._tangent_ready = True
             capi.call("femb200_apply_lifting", A.plan, _p(A.values), _p(self.g), _p(u), -1.0, _p(b), None, _stream())
         return b
 
