@@ -61,6 +61,13 @@ def main():
             A.set_option("stream_out", so)
             ms, mn = timed(lambda: fem.assemble_matrix(A, form))
             out[f"assemble_p2_stream_out{so}" + ("b" if f"assemble_p2_stream_out{so}" in out else "")] = {"ms": ms, "min": mn, "frac": abytes / (ms * 1e-3) / 1e9 / PEAK}
+    if "spmv" in what:
+        fem.assemble_matrix(A, form)
+        v = torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda")
+        y = torch.empty_like(v)
+        sb = 34 * A.nnz_blocks + 40 * m.nnodes
+        ms, mn = timed(lambda: fem.capi.call("femb200_spmv", A.plan, fem._p(A.values), fem._p(v), fem._p(y), fem._stream()), k=20, w=3)
+        out["spmv_p2_n1448"] = {"ms": ms, "min": mn, "frac_moved": sb / (ms * 1e-3) / 1e9 / PEAK}
     if "vec" in what:
         u0 = 1e-3 * torch.randn(2 * m.nnodes, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
         fl = torch.ones(2 * m.nnodes, dtype=torch.float64, device="cuda")
