@@ -321,8 +321,9 @@ def damage_seed(mesh: Mesh, facet_tags, max_dam: float = 1.0) -> np.ndarray:
 
 # ---- XDMF (the FEniCSx driver's mesh file) ---------------------------------------------------------------------------
 def _xdmf_item(node, base: str, dtype):
-    """One <DataItem>: Format="XML" (numbers inline) is read here; Format="HDF" (what dolfinx writes by default,
-    "file.h5:/path") needs h5py, which this image does not ship: it is used when importable, else the error says so."""
+    """One <DataItem>: Format="XML" (numbers inline) and Format="Binary" (raw side file) are read here; Format="HDF"
+    (what dolfinx writes by default, "file.h5:/path") needs h5py, which this image does not ship: it is used when
+    importable, else the error says so."""
     import os
     item = node if node.tag == "DataItem" else node.find("DataItem")
     if item is None:
@@ -340,6 +341,16 @@ def _xdmf_item(node, base: str, dtype):
         fname, path = (item.text or "").strip().split(":", 1)
         with h5py.File(os.path.join(base, fname), "r") as h:
             a = np.asarray(h[path], dtype=dtype)
+    elif fmt == "BINARY":
+        # raw side file (XDMF "Binary" format): NumberType / Precision / Endian / Seek attributes
+        kind = {"FLOAT": "f", "INT": "i", "UINT": "u", "CHAR": "i", "UCHAR": "u"}.get(item.get("NumberType", "Float").upper())
+        if kind is None:
+            raise ValueError(f"read_xdmf: NumberType={item.get('NumberType')!r} is not supported")
+        prec = int(item.get("Precision", "4"))
+        order = {"BIG": ">", "LITTLE": "<"}.get(item.get("Endian", "Native").upper(), "=")
+        count = int(np.prod(dims)) if dims else -1
+        a = np.fromfile(os.path.join(base, (item.text or "").strip()), dtype=np.dtype(f"{order}{kind}{prec}"), count=count,
+                        offset=int(item.get("Seek", "0"))).astype(dtype)
     else:
         raise ValueError(f"read_xdmf: DataItem Format={fmt!r} is not supported")
     return a.reshape(dims) if dims else a

@@ -266,6 +266,19 @@ def test_xdmf_roundtrip_and_errors(square, tmp_path):
     tg.find("Attribute").find("DataItem").text = "\n".join(str(v) for v in m.meta["cell_tags"][perm])
     ET.ElementTree(root).write(q)
     np.testing.assert_array_equal(fm.read_xdmf(q, "g").meta["cell_tags"], m.meta["cell_tags"])
+    # the geometry in a raw binary side file (XDMF "Binary" data item, big-endian float64 after a 16-byte header)
+    bx = os.path.join(str(tmp_path), "geom.bin")
+    with open(bx, "wb") as fb:
+        fb.write(b"\0" * 16)
+        fb.write(m.x.astype(">f8").tobytes())
+    root = ET.fromstring(open(p).read())
+    g0 = [g for g in root.iter("Grid") if g.get("Name") == "neper_dam"][0]
+    di = g0.find("Geometry").find("DataItem")
+    di.set("Format", "Binary"), di.set("Endian", "Big"), di.set("Precision", "8"), di.set("Seek", "16")
+    di.text = "geom.bin"
+    pb = os.path.join(str(tmp_path), "square_bin.xdmf")
+    ET.ElementTree(root).write(pb)
+    np.testing.assert_array_equal(fm.read_xdmf(pb, "neper_dam").x, m.x)
     with pytest.raises(ValueError, match="no grid named"):
         fm.read_xdmf(p, "other")
     h = os.path.join(str(tmp_path), "h.xdmf")
